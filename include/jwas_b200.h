@@ -1,0 +1,151 @@
+/*
+ * jwas_b200.h -- C ABI of libjwasb200.so, the B200 (sm_100a) backend for the JWAS
+ * marker-effects Gibbs sweep.
+ *
+ * JWAS.jl has no plugin interface; the seam it used for its own second backend is
+ * Genotypes.storage_mode / Genotypes.stream_backend plus a per-backend sampler picked
+ * in the MCMC loop (types.jl:149-150; MCMC/MCMC_BayesianAlphabet.jl:53-65, 243-251;
+ * markers/readgenotypes.jl:236-295).  These entry points are what a third
+ * `storage=:gpu` branch binds with `ccall`; each one cites the
+ * reference routine it replaces.  Paths are relative to src/1.JWAS/src/.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every call returns 0 on success, non-zero on error,
+ *     and jwas_last_error() describes the last failure of the calling thread
+ *     (the reference raises ErrorException via error("..."); wrappers re-raise).
+ *   - the library owns device memory behind the handle; host buffers are borrowed only
+ *     for the duration of the (synchronous) call.
+ *   - one host thread per handle; no callbacks into the host language.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *   - markers are 0-based here; block starts are 0-based boundaries (nblocks+1 entries).
+ *   - unit residual weights only (Rinv == 1): heterogeneous_residuals is rejected by the
+ *     host wrapper before it gets here.
+ */
+#ifndef JWAS_B200_H
+#define JWAS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jwas_handle jwas_handle;
+
+/* sweep schedule -- which reference sampler the call reproduces */
+#define JWAS_SCHED_EXACT        0  /* BayesABC! / BayesR! / _MTBayesABC_samplerI!: one pass, marker by marker.
+                                      Runs as look-ahead panels with one repetition (the in-block Gram
+                                      identity of BayesABC_block!, BayesABC.jl:157,169). */
+#define JWAS_SCHED_BLOCK        1  /* BayesABC_block! etc. with independent_blocks=false: nreps = block size */
+#define JWAS_SCHED_INDEPENDENT  2  /* BayesABC_block_independent! etc.: all blocks read a ycorr snapshot */
+
+/* reductions a sweep returns so the host-side hyper-parameter draws need no extra pass
+ * (variance_components.jl:60-79, 82-112, 151-189; Pi.jl:7-42; MCMC_BayesianAlphabet.jl:357-365) */
+typedef struct {
+    double ycorr_ss[16];     /* t*t row-major: ycorr_i' ycorr_j                       */
+    double ycorr_sum[4];     /* per trait sum(ycorr)                                  */
+    double alpha_ss[16];     /* t*t: alpha_i' alpha_j (BayesC single trait: alpha'alpha) */
+    double beta_ss[16];      /* t*t: beta_i' beta_j (multi-trait BayesC variance update) */
+    double nnz_alpha[4];     /* per trait #(alpha != 0)                               */
+    double sum_delta[4];     /* per trait sum(delta) (ABC); BayesR: #(delta > 1)      */
+    double class_counts[16]; /* BayesR: counts per class; MT: counts per joint state  */
+    double bayesr_ssq;       /* sum alpha_j^2 / gamma[delta_j] over delta_j > 1       */
+    double ycorr_maxabs;     /* max |ycorr| (next sweep's fixed-point scale)          */
+    int32_t scale_exp;       /* S used by this sweep's fixed-point dots               */
+    int32_t overflow;        /* 1 if the fixed-point clamp was hit (call also fails)  */
+    int64_t n_active;        /* marker updates with delta-alpha != 0 (sequential depth) */
+    int64_t n_rounds;        /* speculative rounds executed by the chain              */
+} jwas_sweep_stats;
+
+/* ---- lifetime: replaces GibbsMats(...) (markers/tools4genotypes.jl:237-275) and
+ *      load_streaming_backend (markers/streaming_genotypes.jl:884-971) -------------- */
+/* packed: marker-major 2-bit codes exactly as in a .jgb2 file (p columns of `stride`
+ * bytes; individual i in byte i>>2, bits (i&3)<<1; code 3 = missing).  Column means and
+ * xpRinvx are computed on the device. */
+int jwas_create(int64_t n_obs, int64_t n_markers, int n_traits,
+                const uint8_t* packed, int64_t stride_bytes, int device, jwas_handle** out);
+/* Synthetic genotypes generated directly as packed bytes on the device (never materialised
+ * dense): f_j ~ U(0.05,0.5), code = Bernoulli(f_j)+Bernoulli(f_j), optional missing rate;
+ * Philox keyed by `seed` (benchmarks/bayesr_parity_common.jl:28-59 is the model). */
+int jwas_create_synthetic(int64_t n_obs, int64_t n_markers, int n_traits, uint64_t seed,
+                          double missing_rate, int device, jwas_handle** out);
+/* copy of the packed image back to the host (p * stride bytes, stride = cld(n,4)) */
+int jwas_get_packed(jwas_handle* h, uint8_t* packed, int64_t stride_bytes);
+int jwas_destroy(jwas_handle* h);
+const char* jwas_last_error(void);
+int jwas_device_count(void);
+
+/* marker_means / xpRinvx (Packed2BitBackend fields, streaming_genotypes.jl:16-17) */
+int jwas_get_marker_stats(jwas_handle* h, float* means, float* xpx);
+
+/* block partition + Gram blocks X_b'X_b: GibbsMats(...; fast_blocks) (tools4genotypes.jl:259-269).
+ * Must be called before any sweep (JWAS_SCHED_EXACT uses it as the look-ahead panel partition). */
+int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nblocks);
+
+/* ---- ycorr lifecycle (MCMC/MCMC_BayesianAlphabet.jl:131-147, 207-220, 365) ---------- */
+int jwas_put_ycorr(jwas_handle* h, const float* ycorr /* t*n */);
+int jwas_get_ycorr(jwas_handle* h, float* ycorr);
+/* ycorr[trait] -= M * alpha[trait] for the current device alpha (:137-143, streaming_mul_alpha!) */
+int jwas_ycorr_sub_malpha(jwas_handle* h);
+/* ycorr[trait] += shift (intercept-only location update :207-220 without moving ycorr);
+ * returns sum and sum of squares after the shift */
+int jwas_shift_ycorr(jwas_handle* h, int trait, float shift, double* sum, double* sumsq);
+/* out = M * alpha[trait] (getEBV, output.jl:281-306) */
+int jwas_mul_alpha(jwas_handle* h, int trait, float* out /* n */);
+
+/* ---- sampler state alpha, beta, delta (Genotypes fields, types.jl:124-131) ----------- */
+int jwas_put_state(jwas_handle* h, const float* alpha, const float* beta, const int32_t* delta);
+int jwas_get_state(jwas_handle* h, float* alpha, float* beta, int32_t* delta);
+
+/* ---- sweeps.  u/z: optional replayed draw tables indexed [(rep*t + trait)*p + marker]
+ *      (host generates them in reference order); NULL -> native Philox stream
+ *      keyed (seed; marker, iter, slot, rep) of include/jwas_contract.h ---------------- */
+/* BayesABC! (BayesABC.jl:60-80), BayesABC_block! (:118-188), _independent! (:190-255).
+ * var_effects: p entries (BayesC passes fill(G.val,p), MCMC_BayesianAlphabet.jl:231);
+ * pi: p entries = P(effect is zero) (BayesABC.jl:66-68). */
+int jwas_sweep_bayesabc(jwas_handle* h, int schedule, double vare,
+                        const double* var_effects, const double* pi,
+                        uint64_t seed, uint32_t iter, const double* u, const double* z,
+                        jwas_sweep_stats* stats);
+/* scalar convenience forms (device-side fill) */
+int jwas_sweep_bayesc(jwas_handle* h, int schedule, double vare, double var_effect, double pi,
+                      uint64_t seed, uint32_t iter, jwas_sweep_stats* stats);
+/* BayesR! (BayesR.jl:45-97), BayesR_block! (:111-193), _independent! (:195-273).
+ * full_reps: the burn-in gate of bayesr_block_nreps (:22-25) evaluated by the caller. */
+int jwas_sweep_bayesr(jwas_handle* h, int schedule, int full_reps, double vare, double sigma_sq,
+                      const double* pi, int per_marker_pi, const double* gamma, int nclasses,
+                      uint64_t seed, uint32_t iter, const double* u, const double* z,
+                      jwas_sweep_stats* stats);
+/* _MTBayesABC_samplerI! (MTBayesABC.jl:57-127), block (:243-333), independent (:335-437).
+ * R, G: t*t row-major covariances (G: p*t*t if per_marker_G);
+ * big_pi: 2^t joint-state priors indexed sum(delta_k << k) (or p*2^t if per_marker_pi). */
+int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, const double* G, int per_marker_G,
+                   const double* big_pi, int per_marker_pi,
+                   uint64_t seed, uint32_t iter, const double* u, const double* z,
+                   jwas_sweep_stats* stats);
+
+/* BayesB per-marker variance update on device (variance_components.jl:169-172):
+ * var_j = (beta_j^2 + df*scale) / chisq(df+1), chi-square from the native stream. */
+int jwas_sample_bayesb_variances(jwas_handle* h, double df, double scale, uint64_t seed,
+                                 uint32_t iter, double* var_effects_out /* p, may be NULL */);
+
+/* ---- posterior accumulators (output.jl:556-577) --------------------------------------- */
+int jwas_accumulate(jwas_handle* h, double nsamples, int bayesr /* meanDelta tracks delta>1 */);
+int jwas_get_means(jwas_handle* h, float* mean_alpha, float* mean_alpha2, float* mean_delta);
+
+/* Gram block of block `ib` (b*b floats, row-major) -- XpRinvX[ib] of GibbsMats */
+int jwas_get_gram(jwas_handle* h, int64_t ib, float* out);
+
+/* ---- introspection used by bench.py / tests ------------------------------------------- */
+int64_t jwas_kernel_launches(jwas_handle* h);     /* kernels launched by this handle so far */
+int jwas_set_option(jwas_handle* h, const char* key, int64_t value);
+/* last sweep's device time in milliseconds (CUDA events on the handle's stream) */
+double jwas_last_sweep_ms(jwas_handle* h);
+/* device time (ms, CUDA events on the handle's stream) and launch count of the dominant
+ * genotype-streaming kernel(s) of the last sweep; needs jwas_set_option(h,"profile",1) */
+double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches);
+/* raw CUDA stream of the handle (cudaStream_t) so callers can time on it */
+void* jwas_stream(jwas_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,11 @@
+"""jwas_b200 -- B200-native backend for the JWAS.jl marker-effects Gibbs sweep.
+
+Host-side mirror of the reference interface for this path (get_genotypes / build_model /
+set_random / runMCMC with Genotypes / MME types), driving hand-written sm_100a CUDA kernels
+through the C ABI in include/jwas_b200.h.  There is no CPU fallback.
+"""
+from ._lib import (GpuSweeper, JwasError, SweepStats, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT,
+                   device_count, SO_PATH)
+
+__all__ = ["GpuSweeper", "JwasError", "SweepStats", "SCHED_EXACT", "SCHED_BLOCK", "SCHED_INDEPENDENT",
+           "device_count", "SO_PATH"]

@@ -1,0 +1,34 @@
+"""Builds libjwasb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libjwasb200.so")
+SRC = os.path.join(HERE, "csrc", "jwas_b200.cu")
+
+
+def _newest_source_mtime():
+    m = 0.0
+    for d in (os.path.join(HERE, "csrc"), os.path.join(os.path.dirname(HERE), "include")):
+        for f in os.listdir(d):
+            m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _newest_source_mtime():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
+           "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
+           "-o", SO, SRC]
+    if verbose:
+        cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(SO)

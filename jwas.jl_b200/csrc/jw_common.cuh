@@ -1,0 +1,97 @@
+// jw_common.cuh -- handle layout, error plumbing and small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/jwas_b200.h"
+#include "../../include/jwas_contract.h"
+
+#define JW_MAX_TRAITS 4
+#define JW_MAX_BLOCK 1024      // one chain thread per marker of a block
+#define JW_MAX_CLASSES 8
+
+void jw_set_error(const std::string& s);
+
+#define JW_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            jw_set_error(std::string(#call) + ": " + cudaGetErrorString(e__));          \
+            return 10;                                                                  \
+        }                                                                               \
+    } while (0)
+
+#define JW_REQUIRE(cond, msg)                                                           \
+    do {                                                                                \
+        if (!(cond)) { jw_set_error(msg); return 2; }                                   \
+    } while (0)
+
+struct jwas_handle {
+    int device = 0;
+    int64_t n = 0, p = 0, stride = 0, stride_d = 0;   // stride_d: device column pitch (16B multiple)
+    int t = 1;
+    int has_missing = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_sweep_ms = 0.0;
+    int64_t launches = 0;
+
+    // genotypes (marker-major .jgb2 image) and per-marker statistics
+    uint8_t* d_packed = nullptr;
+    float* d_means = nullptr;
+    float* d_xpx = nullptr;
+    int32_t* d_colsum = nullptr;   // sum of codes over observed rows
+    int32_t* d_nvalid = nullptr;   // observed rows
+
+    // sampler state
+    float* d_ycorr = nullptr;      // t * n
+    float* d_alpha = nullptr;      // t * p
+    float* d_beta = nullptr;       // t * p
+    int32_t* d_delta = nullptr;    // t * p
+    float* d_mean_alpha = nullptr; // posterior accumulators, t * p each
+    float* d_mean_alpha2 = nullptr;
+    float* d_mean_delta = nullptr;
+
+    // hyper-parameter vectors resident on the device
+    double* d_ve = nullptr;        // p (or p*t*t for per-marker G)
+    double* d_pi = nullptr;        // p  (BayesR per-marker: p*nclasses; MT per-marker: p*2^t)
+    double* d_u = nullptr;         // replay tables (allocated on demand)
+    double* d_z = nullptr;
+    size_t cap_ve = 0, cap_pi = 0, cap_u = 0, cap_z = 0;
+
+    // block partition and Gram blocks
+    std::vector<int64_t> starts;   // nblocks+1, 0-based
+    std::vector<int64_t> gram_off; // float offset of each block's b*b Gram
+    int64_t* d_starts = nullptr;
+    int64_t* d_gram_off = nullptr;
+    float* d_gram = nullptr;
+    int64_t nblocks = 0, maxb = 0;
+
+    // sweep workspace
+    int32_t* d_yq = nullptr;       // t * n fixed-point image of ycorr
+    long long* d_sq = nullptr;     // t
+    long long* d_dq = nullptr;     // t * p  (indexed by marker)
+    long long* d_mq = nullptr;     // t * p
+    float* d_dalpha = nullptr;     // t * p  net (old - new) per marker of the current block(s)
+    int32_t* d_act_idx = nullptr;  // p   ordered list of markers with any dalpha != 0
+    int32_t* d_act_cnt = nullptr;  // 1
+    int32_t* d_flags = nullptr;    // [0] overflow
+    unsigned long long* d_counters = nullptr; // [0] n_active, [1] n_rounds
+    float* d_maxabs = nullptr;     // 1 (as uint bits)
+    double* d_stats = nullptr;     // reduction scratch
+    double* d_partials = nullptr;
+    size_t cap_partials = 0;
+
+    // options
+    int64_t opt_profile = 0;       // 1 = time the genotype-streaming kernel(s) with CUDA events
+    std::vector<cudaEvent_t> prof_events;
+    double prof_ms = 0.0; int64_t prof_launches = 0;
+    int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
+    float next_maxabs = -1.0f;     // carried from the previous sweep's stats when ycorr untouched
+};
+
+__device__ __forceinline__ unsigned jw_dcode(const uint8_t* col, int64_t i) {
+    return (col[i >> 2] >> ((i & 3) << 1)) & 3u;
+}

@@ -1,0 +1,615 @@
+// jw_sweep_kernels.cuh -- multi-kernel sweep engine ("engine 0"): one launch per phase.
+//   quantise ycorr -> block rhs (packed GEMV, exact int64) -> in-block Gibbs chain on the Gram
+//   block (speculative parallel rounds) -> block exit ycorr += X_b * d_alpha.
+// Replaces bayesabc_update_marker!/BayesABC!/BayesABC_block!/_independent! (BayesABC.jl:24-255),
+// BayesR!/BayesR_block!/_independent! (BayesR.jl:45-273), _MTBayesABC_samplerI! + block +
+// independent (MTBayesABC.jl:57-127, 243-437), block_rhs! (tools4genotypes.jl:59-78).
+// Arithmetic contract: include/jwas_contract.h; bit-for-bit twin: oracle/jwas_oracle.c
+// (jwo_sweep_contract).
+#pragma once
+#include "jw_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// ycorr -> fixed point.  yq = rint(y * 2^S); sq[k] = sum_i yq (exact, atomics commute).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+jw_k_quantize(const float* __restrict__ y, int64_t n, int t, float scale,
+              int32_t* __restrict__ yq, long long* __restrict__ sq, int32_t* __restrict__ flags) {
+    int k = blockIdx.y;
+    long long acc = 0;
+    int ovf = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t q = jw_quantize(y[k * n + i], scale, &ovf);
+        yq[k * n + i] = q;
+        acc += q;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd((unsigned long long*)&sq[k], (unsigned long long)acc);
+    if (ovf) atomicOr(&flags[0], 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// block rhs: dq[k][j] = sum_i value(code_ij) * yq[k][i], mq[k][j] = sum over missing calls.
+// One warp per (marker, row slab); each lane decodes one 32-bit word (16 individuals).
+// ------------------------------------------------------------------------------------------
+#define JW_DOT_SLAB_WORDS 256   // 4096 individuals per slab
+template <int T, bool MISSING>
+__global__ void __launch_bounds__(256)
+jw_k_block_dot(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
+               int64_t j0, int64_t nj, const int32_t* __restrict__ yq,
+               long long* __restrict__ dq, long long* __restrict__ mq) {
+    int64_t jj = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (jj >= nj) return;
+    int64_t j = j0 + jj;
+    int lane = threadIdx.x & 31;
+    const uint32_t* col = reinterpret_cast<const uint32_t*>(packed + j * stride_d);
+    int64_t nwords = (n + 15) >> 4;
+    int64_t wbeg = (int64_t)blockIdx.y * JW_DOT_SLAB_WORDS;
+    int64_t wend = min(wbeg + JW_DOT_SLAB_WORDS, nwords);
+    long long acc[T], macc[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) { acc[k] = 0; macc[k] = 0; }
+    for (int64_t w = wbeg + lane; w < wend; w += 32) {
+        uint32_t v = __ldg(col + w);
+        int64_t i0 = w << 4;
+        if (i0 + 16 <= n) {
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const int4* yp = reinterpret_cast<const int4*>(yq + k * n + i0);
+                int part = 0, mpart = 0;
+                bool al = ((k * n + i0) & 3) == 0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    int4 q;
+                    if (al) q = __ldg(yp + g);
+                    else { const int32_t* s = yq + k * n + i0 + 4 * g; q = make_int4(s[0], s[1], s[2], s[3]); }
+                    uint32_t c0 = (v >> (8 * g)) & 3u, c1 = (v >> (8 * g + 2)) & 3u,
+                             c2 = (v >> (8 * g + 4)) & 3u, c3 = (v >> (8 * g + 6)) & 3u;
+                    if (MISSING) {
+                        mpart = 0;
+                        long long m = 0;
+                        if (c0 == 3u) { m += q.x; c0 = 0; }
+                        if (c1 == 3u) { m += q.y; c1 = 0; }
+                        if (c2 == 3u) { m += q.z; c2 = 0; }
+                        if (c3 == 3u) { m += q.w; c3 = 0; }
+                        macc[k] += m;
+                    }
+                    // 4 products of magnitude <= 2^27 fit an int; widen once per group
+                    long long s4 = (long long)((int)c0 * q.x) + (long long)((int)c1 * q.y)
+                                 + (long long)((int)c2 * q.z) + (long long)((int)c3 * q.w);
+                    acc[k] += s4;
+                    (void)part; (void)mpart;
+                }
+            }
+        } else {
+            for (int e = 0; e < 16 && i0 + e < n; ++e) {
+                uint32_t c = (v >> (2 * e)) & 3u;
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    int q = yq[k * n + i0 + e];
+                    if (c == 3u) macc[k] += q; else acc[k] += (long long)((int)c * q);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        long long a = acc[k], m = macc[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (MISSING) m += __shfl_xor_sync(0xffffffffu, m, o);
+        }
+        if (lane == 0) {
+            if (a != 0) atomicAdd((unsigned long long*)&dq[k * p + j], (unsigned long long)a);
+            if (MISSING && m != 0) atomicAdd((unsigned long long*)&mq[k * p + j], (unsigned long long)m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// In-block Gibbs chain.  One CTA per block, one thread per marker.  The sequential chain of the
+// reference is executed as speculative rounds: every uncommitted marker evaluates its draw with
+// the current rhs; markers that neither hold nor acquire an effect do not touch the rhs
+// (BayesABC.jl:50-52), so everything before the first "active" marker commits at once, the
+// active marker commits, its Gram row is applied, and the rest re-evaluate.  Draws are indexed
+// by (marker, iter, trait, rep), so the result is exactly the sequential one.
+// ------------------------------------------------------------------------------------------
+struct jw_chain_args {
+    int64_t n, p;
+    int t, method, nreps_mode, nclasses;
+    int per_marker_pi, per_marker_G;
+    int block0;                    // first block handled by blockIdx.x == 0
+    const int64_t* starts;
+    const int64_t* gram_off;
+    const float* gram;
+    const float* means;
+    const float* xpx;
+    const long long* dq; const long long* mq; const long long* sq;
+    double invscale;
+    float* alpha; float* beta; int32_t* delta; float* dalpha;
+    double vare, sigmaSq;
+    const double* ve; const double* pi;
+    double gamma[JW_MAX_CLASSES];
+    double Rinv[16]; double Ginv[16];
+    const double* Gmat;            // per-marker covariance (p*t*t) when per_marker_G
+    const double* bigPi;
+    uint64_t seed; uint32_t iter;
+    const double* u; const double* z;
+    int32_t* act_idx; int32_t* act_cnt;     // ordered active list of this launch (single-block mode)
+    int write_active_list;
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ double jw_get_u(const jw_chain_args& A, int64_t j, int trait, int rep) {
+    if (A.u) return A.u[((int64_t)rep * A.t + trait) * A.p + j];
+    return jw_draw_uniform(A.seed, (uint32_t)j, A.iter, (uint32_t)trait, (uint32_t)rep);
+}
+__device__ __forceinline__ double jw_get_z(const jw_chain_args& A, int64_t j, int trait, int rep) {
+    if (A.z) return A.z[((int64_t)rep * A.t + trait) * A.p + j];
+    return jw_draw_normal(A.seed, (uint32_t)j, A.iter, (uint32_t)trait, (uint32_t)rep);
+}
+
+// fixed-order Gauss-Jordan, twin of inv_spd_fixed in the oracle
+__host__ __device__ inline void jw_inv_spd_fixed(const double* A, int t, double* Ai) {
+    double M[JW_MAX_TRAITS][2 * JW_MAX_TRAITS];
+    for (int i = 0; i < t; ++i)
+        for (int j = 0; j < t; ++j) { M[i][j] = A[i * t + j]; M[i][t + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < t; ++c) {
+        double d = 1.0 / M[c][c];
+        for (int j = 0; j < 2 * t; ++j) M[c][j] = M[c][j] * d;
+        for (int r = 0; r < t; ++r) if (r != c) {
+            double f = M[r][c];
+            for (int j = 0; j < 2 * t; ++j) M[r][j] = M[r][j] - f * M[c][j];
+        }
+    }
+    for (int i = 0; i < t; ++i) for (int j = 0; j < t; ++j) Ai[i * t + j] = M[i][t + j];
+}
+
+__device__ __forceinline__ int jw_categorical(const double* probs, int k, double u) {
+    double cp = probs[0]; int i = 0;
+    while (cp <= u && i < k - 1) { i += 1; cp += probs[i]; }
+    return i;
+}
+
+template <int METHOD, int T>
+__global__ void __launch_bounds__(JW_MAX_BLOCK)
+jw_k_chain(jw_chain_args A) {
+    __shared__ int s_wmin[32];
+    __shared__ int s_first;
+    __shared__ float s_d[JW_MAX_TRAITS];
+    __shared__ int s_cnt[33];
+
+    const int ib = A.block0 + blockIdx.x;
+    const int64_t s = A.starts[ib];
+    const int b = (int)(A.starts[ib + 1] - s);
+    const int m = threadIdx.x;
+    const bool valid = m < b;
+    const int64_t j = s + (valid ? m : 0);
+    const int lane = m & 31, warp = m >> 5;
+    const int64_t p = A.p;
+    const float* G = A.gram + A.gram_off[ib];
+    const double x = (double)A.xpx[j];
+
+    // rhs of this marker for every trait, state at block entry
+    double r[T];
+    float a_entry[T], a_cur[T], b_cur[T];
+    int d_cur[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        long long dq = A.dq[k * p + j], mq = A.mq ? A.mq[k * p + j] : 0ll;
+        double mu = (double)A.means[j];
+        r[k] = ((double)dq - mu * (double)(A.sq[k] - mq)) * A.invscale;
+        a_entry[k] = a_cur[k] = A.alpha[k * p + j];
+        b_cur[k] = (METHOD == 1) ? 0.0f : A.beta[k * p + j];
+        d_cur[k] = A.delta[k * p + j];
+    }
+    double Ginv[T * T];
+    if (METHOD == 2) {
+        if (A.per_marker_G) jw_inv_spd_fixed(A.Gmat + j * T * T, T, Ginv);
+        else for (int q = 0; q < T * T; ++q) Ginv[q] = A.Ginv[q];
+    }
+    const double invVarRes = (METHOD == 2) ? 0.0 : 1.0 / A.vare;
+
+    // draw-independent constants
+    double c_lhs = 0, c_invLhs = 0, c_L = 0, c_lpc = 0, c_lp0 = 0, c_ve = 1;
+    if (METHOD == 0) {
+        c_ve = A.ve[j];
+        double pi = A.pi[j];
+        c_lhs = x * invVarRes + 1.0 / c_ve;
+        c_invLhs = 1.0 / c_lhs;
+        c_L = jw_log(c_lhs) + jw_log(c_ve);
+        c_lpc = jw_log(1.0 - pi);
+        c_lp0 = jw_log(pi);
+    }
+
+    const int nreps = A.nreps_mode ? b : 1;
+    unsigned long long my_active = 0, my_rounds = 0;
+
+    for (int rep = 0; rep < nreps; ++rep) {
+        double u[T], z[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) { u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep); }
+        int pos = 0;
+        while (true) {
+            // ---- evaluate this marker against the current rhs ----
+            bool pending = valid && m >= pos;
+            float newA[T], newB[T]; int newD[T];
+            bool active = false;
+            if (pending) {
+                if (METHOD == 0) {
+                    double aold = (double)a_cur[0];
+                    double rhs = (r[0] + x * aold) * invVarRes;
+                    double gHat = rhs * c_invLhs;
+                    double logDelta1 = -0.5 * (c_L - gHat * rhs) + c_lpc;
+                    double prob1 = 1.0 / (1.0 + jw_exp(c_lp0 - logDelta1));
+                    if (u[0] < prob1) {
+                        newD[0] = 1;
+                        newA[0] = (float)(gHat + z[0] * jw_sqrt(c_invLhs));
+                        newB[0] = newA[0];
+                    } else {
+                        newD[0] = 0;
+                        newB[0] = (float)(z[0] * jw_sqrt(c_ve));
+                        newA[0] = 0.0f;
+                    }
+                    active = (a_cur[0] - newA[0]) != 0.0f;
+                } else if (METHOD == 1) {
+                    double aold = (double)a_cur[0];
+                    double rhs = (r[0] + x * aold) * invVarRes;
+                    const double* pij = A.per_marker_pi ? A.pi + j * A.nclasses : A.pi;
+                    double lp[JW_MAX_CLASSES], pr[JW_MAX_CLASSES];
+                    lp[0] = jw_log(pij[0]);
+                    for (int c = 1; c < A.nclasses; ++c) {
+                        double varEffect = A.gamma[c] * A.sigmaSq;
+                        double lhs = x * invVarRes + 1.0 / varEffect;
+                        double invLhs = 1.0 / lhs;
+                        double betaHat = invLhs * rhs;
+                        lp[c] = 0.5 * (jw_log(invLhs) - jw_log(varEffect) + betaHat * rhs) + jw_log(pij[c]);
+                    }
+                    double mx = lp[0];
+                    for (int c = 1; c < A.nclasses; ++c) if (lp[c] > mx) mx = lp[c];
+                    double se = 0.0;
+                    for (int c = 0; c < A.nclasses; ++c) se += jw_exp(lp[c] - mx);
+                    double log_norm = mx + jw_log(se);
+                    for (int c = 0; c < A.nclasses; ++c) pr[c] = jw_exp(lp[c] - log_norm);
+                    int cls = jw_categorical(pr, A.nclasses, u[0]);
+                    newD[0] = cls + 1;
+                    newA[0] = 0.0f;
+                    if (cls > 0) {
+                        double varEffect = A.gamma[cls] * A.sigmaSq;
+                        double lhs = x * invVarRes + 1.0 / varEffect;
+                        double invLhs = 1.0 / lhs;
+                        double betaHat = invLhs * rhs;
+                        newA[0] = (float)(betaHat + z[0] * jw_sqrt(invLhs));
+                    }
+                    newB[0] = 0.0f;
+                    active = (a_cur[0] - newA[0]) != 0.0f;
+                } else {
+                    // MTBayesABC.jl:78-125
+                    double bb[T], olda[T], w[T]; int dd[T];
+                    const double* Pi = A.per_marker_pi ? A.bigPi + j * (1 << T) : A.bigPi;
+#pragma unroll
+                    for (int k = 0; k < T; ++k) {
+                        bb[k] = (double)b_cur[k]; olda[k] = (double)a_cur[k]; dd[k] = d_cur[k] != 0;
+                        w[k] = r[k] + x * olda[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < T; ++k) {
+                        double Ginv11 = Ginv[k * T + k];
+                        double C11 = Ginv11 + A.Rinv[k * T + k] * x;
+                        double rhs0 = 0.0, c12b = 0.0;
+#pragma unroll
+                        for (int q = 0; q < T; ++q) if (q != k) {
+                            double Ginv12 = Ginv[k * T + q];
+                            double C12 = Ginv12 + x * (double)dd[q] * A.Rinv[k * T + q];
+                            rhs0 = rhs0 - Ginv12 * bb[q];
+                            c12b = c12b + C12 * bb[q];
+                        }
+                        double invLhs0 = 1.0 / Ginv11, gHat0 = rhs0 * invLhs0;
+                        double invLhs1 = 1.0 / C11;
+                        double wr = 0.0;
+#pragma unroll
+                        for (int q = 0; q < T; ++q) wr = wr + w[q] * A.Rinv[q * T + k];
+                        double gHat1 = (wr - c12b) * invLhs1;
+                        int s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int q = 0; q < T; ++q) {
+                            int dqq = (q == k) ? 0 : dd[q];
+                            s0 |= dqq << q; s1 |= ((q == k) ? 1 : dqq) << q;
+                        }
+                        double logDelta0 = -0.5 * (jw_log(Ginv11) - gHat0 * gHat0 * Ginv11) + jw_log(Pi[s0]);
+                        double logDelta1 = -0.5 * (jw_log(C11) - gHat1 * gHat1 * C11) + jw_log(Pi[s1]);
+                        double prob1 = 1.0 / (1.0 + jw_exp(logDelta0 - logDelta1));
+                        if (u[k] < prob1) {
+                            dd[k] = 1;
+                            newA[k] = (float)(gHat1 + z[k] * jw_sqrt(invLhs1));
+                            bb[k] = (double)newA[k];
+                        } else {
+                            dd[k] = 0;
+                            bb[k] = (double)(float)(gHat0 + z[k] * jw_sqrt(invLhs0));
+                            newA[k] = 0.0f;
+                        }
+                        newB[k] = (float)bb[k]; newD[k] = dd[k];
+                        if ((a_cur[k] - newA[k]) != 0.0f) active = true;
+                    }
+                }
+            }
+            // ---- first active marker among the pending ones ----
+            int key = (pending && active) ? m : 0x7fffffff;
+            int wmin = __reduce_min_sync(0xffffffffu, key);
+            if (lane == 0) s_wmin[warp] = wmin;
+            __syncthreads();
+            if (warp == 0) {
+                int v = s_wmin[lane];
+                v = __reduce_min_sync(0xffffffffu, v);
+                if (lane == 0) s_first = v;
+            }
+            __syncthreads();
+            const int first = s_first;
+            my_rounds += (m == 0);
+            // ---- commit everything up to and including `first` ----
+            if (pending && m <= first) {
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    if (m == first) s_d[k] = a_cur[k] - newA[k];
+                    a_cur[k] = newA[k]; b_cur[k] = newB[k]; d_cur[k] = newD[k];
+                }
+                if (m == first) my_active += 1;
+            }
+            if (first == 0x7fffffff) break;
+            __syncthreads();
+            // ---- apply the committed marker's Gram row to the rhs ----
+            if (valid && (A.nreps_mode || m > first)) {
+                float g = G[(int64_t)first * b + m];
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    float d = s_d[k];
+                    if (d != 0.0f) r[k] += (double)d * (double)g;
+                }
+            }
+            pos = first + 1;
+            if (pos >= b) break;
+        }
+    }
+
+    // ---- block exit: publish state and the net delta-alpha of every marker ----
+    bool any = false;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            A.alpha[k * p + j] = a_cur[k];
+            if (METHOD != 1) A.beta[k * p + j] = b_cur[k];
+            A.delta[k * p + j] = d_cur[k];
+            float d = a_entry[k] - a_cur[k];
+            A.dalpha[k * p + j] = d;
+            any = any || (d != 0.0f);
+        }
+    }
+    if (A.write_active_list) {
+        // ordered compaction of this block's markers with any non-zero delta
+        unsigned bal = __ballot_sync(0xffffffffu, any);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        if (m == 0) {
+            int acc = 0;
+            for (int w = 0; w < 32; ++w) { int c = s_cnt[w]; s_cnt[w] = acc; acc += c; }
+            s_cnt[32] = acc;
+        }
+        __syncthreads();
+        if (any) A.act_idx[s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
+        if (m == 0) *A.act_cnt = s_cnt[32];
+    }
+    if (A.counters) {
+        if (my_active) atomicAdd(&A.counters[0], my_active);
+        if (my_rounds) atomicAdd(&A.counters[1], my_rounds);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ordered compaction of all markers with a non-zero delta (independent-block reconcile,
+// BayesABC.jl:251-253): single CTA, contiguous chunk per thread, so the list is ascending.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+jw_k_compact_active(const float* __restrict__ dalpha, int64_t p, int t,
+                    int32_t* __restrict__ act_idx, int32_t* __restrict__ act_cnt) {
+    __shared__ int s_cnt[1025];
+    int64_t chunk = (p + 1023) / 1024;
+    int64_t beg = (int64_t)threadIdx.x * chunk, end = min(beg + chunk, p);
+    int c = 0;
+    for (int64_t j = beg; j < end; ++j) {
+        bool any = false;
+        for (int k = 0; k < t; ++k) any = any || (dalpha[k * p + j] != 0.0f);
+        c += any;
+    }
+    s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < 1024; ++i) { int v = s_cnt[i]; s_cnt[i] = acc; acc += v; }
+        s_cnt[1024] = acc;
+        *act_cnt = acc;
+    }
+    __syncthreads();
+    int o = s_cnt[threadIdx.x];
+    for (int64_t j = beg; j < end; ++j) {
+        bool any = false;
+        for (int k = 0; k < t; ++k) any = any || (dalpha[k * p + j] != 0.0f);
+        if (any) act_idx[o++] = (int32_t)j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// block exit  ycorr[k] += X_b * dalpha[k]  (BayesABC.jl:181-185): one thread per individual,
+// active columns applied in ascending marker order with one fused multiply-add each, exactly as
+// the oracle does.  x = code - mean, 0 where the call is missing (decode_marker!).
+// ------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(256)
+jw_k_apply(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
+           const float* __restrict__ means, const float* __restrict__ dalpha,
+           const int32_t* __restrict__ act_idx, const int32_t* __restrict__ act_cnt,
+           float* __restrict__ y) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = *act_cnt;
+    if (i >= n || cnt == 0) return;
+    float v[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) v[k] = y[k * n + i];
+    const int sh = (int)(i & 3) << 1;
+    const int64_t byte = i >> 2;
+    for (int a = 0; a < cnt; ++a) {
+        int64_t j = act_idx[a];
+        unsigned code = (packed[j * stride_d + byte] >> sh) & 3u;
+        float mu = means[j];
+        float xv = (code == 3u ? mu : (float)code) - mu;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            float d = dalpha[k * p + j];
+            if (d != 0.0f) v[k] = fmaf(d, xv, v[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) y[k * n + i] = v[k];
+}
+
+// out = M * alpha (getEBV / ycorr init): same column walk, alpha as the coefficient, no list
+__global__ void __launch_bounds__(256)
+jw_k_mul_alpha(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
+               const float* __restrict__ means, const float* __restrict__ alpha,
+               float sign, float* __restrict__ out, int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = accumulate ? out[i] : 0.0f;
+    const int sh = (int)(i & 3) << 1;
+    const int64_t byte = i >> 2;
+    for (int64_t j = 0; j < p; ++j) {
+        float a = alpha[j];
+        if (a != 0.0f) {
+            unsigned code = (packed[j * stride_d + byte] >> sh) & 3u;
+            float mu = means[j];
+            float xv = (code == 3u ? mu : (float)code) - mu;
+            v = fmaf(sign * a, xv, v);
+        }
+    }
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// canonical reductions: chunks of 256 consecutive elements summed in index order by one thread,
+// chunk sums then added in order by a single thread.  Same order in tests/ (canonical_sum).
+// ------------------------------------------------------------------------------------------
+#define JW_CHUNK 256
+__global__ void __launch_bounds__(128)
+jw_k_chunk_prod(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                double* __restrict__ partials) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t beg = c * JW_CHUNK;
+    if (beg >= n) return;
+    int64_t end = min(beg + JW_CHUNK, n);
+    double s = 0.0;
+    for (int64_t i = beg; i < end; ++i) s += (double)a[i] * (double)b[i];
+    partials[c] = s;
+}
+__global__ void jw_k_chunk_final(const double* __restrict__ partials, int64_t nchunks, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int64_t c = 0; c < nchunks; ++c) s += partials[c];
+        *out = s;
+    }
+}
+// BayesR: sum alpha^2 / gamma[delta] over delta > 1 (variance_components.jl:68-79)
+__global__ void __launch_bounds__(128)
+jw_k_chunk_bayesr(const float* __restrict__ alpha, const int32_t* __restrict__ delta, int64_t n,
+                  double g1, double g2, double g3, double g4, double g5, double g6, double g7,
+                  double* __restrict__ partials) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t beg = c * JW_CHUNK;
+    if (beg >= n) return;
+    int64_t end = min(beg + JW_CHUNK, n);
+    double g[8] = {0.0, g1, g2, g3, g4, g5, g6, g7};
+    double s = 0.0;
+    for (int64_t i = beg; i < end; ++i) {
+        int d = delta[i];
+        if (d > 1) s += (double)alpha[i] * (double)alpha[i] / g[d - 1];
+    }
+    partials[c] = s;
+}
+// integer statistics: counts are exact under any order
+__global__ void __launch_bounds__(256)
+jw_k_counts(const float* __restrict__ alpha, const int32_t* __restrict__ delta, int64_t p, int t,
+            int method, unsigned long long* __restrict__ out /* [0..3] nnz, [4..7] sumdelta, [8..23] classes */) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    int state = 0;
+    for (int k = 0; k < t; ++k) {
+        if (alpha[k * p + j] != 0.0f) atomicAdd(&out[k], 1ull);
+        int d = delta[k * p + j];
+        if (method == 1) { if (d > 1) atomicAdd(&out[4 + k], 1ull); }
+        else if (d != 0) atomicAdd(&out[4 + k], 1ull);
+        state |= (d != 0) << k;
+    }
+    if (method == 1) atomicAdd(&out[8 + (delta[j] - 1)], 1ull);
+    else atomicAdd(&out[8 + state], 1ull);
+}
+// sum / max|.| of ycorr (order-free: integer-like max; the sum is informational)
+__global__ void __launch_bounds__(256)
+jw_k_maxabs(const float* __restrict__ y, int64_t n, unsigned* __restrict__ out) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(y[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+__global__ void __launch_bounds__(256)
+jw_k_shift(float* __restrict__ y, int64_t n, float shift) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = y[i] + shift;
+}
+__global__ void __launch_bounds__(256)
+jw_k_fill_double(double* __restrict__ a, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// posterior running means (output.jl:568-577): Float32 state, binary64 update
+__global__ void __launch_bounds__(256)
+jw_k_accumulate(const float* __restrict__ alpha, const int32_t* __restrict__ delta, int64_t tp,
+                double nsamples, int bayesr, float* __restrict__ ma, float* __restrict__ ma2,
+                float* __restrict__ md) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tp) return;
+    double a = (double)alpha[i];
+    double d = bayesr ? (delta[i] > 1 ? 1.0 : 0.0) : (double)delta[i];
+    ma[i] = (float)((double)ma[i] + (a - (double)ma[i]) / nsamples);
+    ma2[i] = (float)((double)ma2[i] + (a * a - (double)ma2[i]) / nsamples);
+    md[i] = (float)((double)md[i] + (d - (double)md[i]) / nsamples);
+}
+
+// BayesB: var_j = (beta_j^2 + df*scale)/chisq(df+1) (variance_components.jl:60-66, 169-172).
+// chisq(k) = 2*Gamma(k/2) by Marsaglia-Tsang with draws from the native stream
+// (slot 254/255 of the marker's counter space, attempt number in `rep`).
+__global__ void __launch_bounds__(256)
+jw_k_bayesb_var(const float* __restrict__ beta, int64_t p, double df, double scale,
+                uint64_t seed, uint32_t iter, double* __restrict__ ve) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double shape = 0.5 * (df + 1.0);        // >= 0.5; boost when < 1
+    double boost = 1.0;
+    if (shape < 1.0) {
+        double uu = jw_draw_uniform(seed, (uint32_t)j, iter, 126u, 0u);
+        boost = jw_exp(jw_log(uu) / shape);
+        shape += 1.0;
+    }
+    double d = shape - 1.0 / 3.0, c = 1.0 / jw_sqrt(9.0 * d);
+    double g = d;
+    for (uint32_t att = 0; att < 64u; ++att) {
+        double zz = jw_draw_normal(seed, (uint32_t)j, iter, 127u, att);
+        double uu = jw_draw_uniform(seed, (uint32_t)j, iter, 127u, att);
+        double v = 1.0 + c * zz;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (jw_log(uu) < 0.5 * zz * zz + d - d * v + d * jw_log(v)) { g = d * v; break; }
+    }
+    double chisq = 2.0 * g * boost;
+    double b = (double)beta[j];
+    ve[j] = (b * b + df * scale) / chisq;
+}

@@ -1,0 +1,733 @@
+// jwas_b200.cu -- C ABI of libjwasb200.so (see include/jwas_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false ...
+//        (--fmad=false is part of the arithmetic contract: no implicit contraction).
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <cmath>
+#include "jw_common.cuh"
+#include "jw_setup_kernels.cuh"
+#include "jw_sweep_kernels.cuh"
+#include "jw_fused_sweep.cuh"
+
+static thread_local std::string g_err;
+void jw_set_error(const std::string& s) { g_err = s; }
+extern "C" const char* jwas_last_error(void) { return g_err.c_str(); }
+
+extern "C" int jwas_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+#define JW_LAUNCH_CHECK(h)                                                              \
+    do {                                                                                \
+        (h)->launches += 1;                                                             \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess) {                                                       \
+            jw_set_error(std::string("kernel launch failed: ") + cudaGetErrorString(e__)); \
+            return 11;                                                                  \
+        }                                                                               \
+    } while (0)
+
+extern "C" int jwas_destroy(jwas_handle* h);
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <typename T>
+static int ensure_cap(T** ptr, size_t* cap, size_t need) {
+    if (*cap >= need && *ptr) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    JW_CUDA(cudaMalloc((void**)ptr, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+static int create_common(int64_t n, int64_t p, int t, int device, jwas_handle** out) {
+    JW_REQUIRE(out != nullptr, "jwas_create: out is NULL");
+    *out = nullptr;
+    JW_REQUIRE(n > 0 && p > 0, "Genotype data is empty.");
+    JW_REQUIRE(p < (int64_t)2147483647, "jwas_create: too many markers for 32-bit marker ids");
+    JW_REQUIRE(t >= 1 && t <= JW_MAX_TRAITS, "jwas_create: number of traits must be 1..4");
+    int ndev = jwas_device_count();
+    JW_REQUIRE(ndev > 0, "no CUDA device is visible: libjwasb200 has no CPU fallback");
+    JW_REQUIRE(device >= 0 && device < ndev, "jwas_create: device index out of range");
+    JW_CUDA(cudaSetDevice(device));
+
+    jwas_handle* h = new jwas_handle();
+    h->device = device; h->n = n; h->p = p; h->t = t; h->stride = (n + 3) / 4;
+    h->stride_d = ceil_div((n + 3) / 4, 16) * 16;
+    cudaDeviceProp prop;
+    JW_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    JW_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    JW_CUDA(cudaEventCreate(&h->ev0));
+    JW_CUDA(cudaEventCreate(&h->ev1));
+
+    size_t tp = (size_t)t * p, tn = (size_t)t * n;
+    JW_CUDA(cudaMalloc((void**)&h->d_packed, (size_t)p * h->stride_d));
+    JW_CUDA(cudaMemsetAsync(h->d_packed, 0, (size_t)p * h->stride_d, h->stream));
+    JW_CUDA(cudaMalloc((void**)&h->d_means, p * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_xpx, p * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_colsum, p * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_nvalid, p * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_ycorr, tn * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_alpha, tp * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_beta, tp * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_delta, tp * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_mean_alpha, tp * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_mean_alpha2, tp * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_mean_delta, tp * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_yq, tn * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_sq, JW_MAX_TRAITS * sizeof(long long)));
+    JW_CUDA(cudaMalloc((void**)&h->d_dq, tp * sizeof(long long)));
+    JW_CUDA(cudaMalloc((void**)&h->d_mq, tp * sizeof(long long)));
+    JW_CUDA(cudaMalloc((void**)&h->d_dalpha, tp * sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_act_idx, p * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_act_cnt, sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_flags, 4 * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_counters, 32 * sizeof(unsigned long long)));
+    JW_CUDA(cudaMalloc((void**)&h->d_maxabs, sizeof(float)));
+    JW_CUDA(cudaMalloc((void**)&h->d_stats, 64 * sizeof(double)));
+    for (void* z : {(void*)h->d_ycorr, (void*)h->d_yq}) JW_CUDA(cudaMemsetAsync(z, 0, tn * 4, h->stream));
+    for (void* z : {(void*)h->d_alpha, (void*)h->d_beta, (void*)h->d_delta, (void*)h->d_mean_alpha,
+                    (void*)h->d_mean_alpha2, (void*)h->d_mean_delta, (void*)h->d_dalpha})
+        JW_CUDA(cudaMemsetAsync(z, 0, tp * 4, h->stream));
+    JW_CUDA(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int32_t), h->stream));
+    *out = h;
+    return 0;
+}
+
+// per-marker statistics (GibbsMats: xpRinvx, tools4genotypes.jl:28-36, 247-250)
+static int finish_create(jwas_handle* h) {
+    int* d_hm = (int*)&h->d_flags[1];
+    jw_k_marker_stats<<<(unsigned)ceil_div(h->p, 8), 256, 0, h->stream>>>(
+        h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, d_hm);
+    JW_LAUNCH_CHECK(h);
+    JW_CUDA(cudaMemcpyAsync(&h->has_missing, d_hm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int jwas_create(int64_t n, int64_t p, int t, const uint8_t* packed, int64_t stride,
+                           int device, jwas_handle** out) {
+    JW_REQUIRE(n > 0 && p > 0, "Genotype data is empty.");
+    JW_REQUIRE(stride >= (n + 3) / 4, "jwas_create: stride_bytes is smaller than cld(nObs,4)");
+    JW_REQUIRE(packed != nullptr, "jwas_create: packed is NULL");
+    int rc = create_common(n, p, t, device, out);
+    if (rc) return rc;
+    jwas_handle* h = *out;
+    JW_CUDA(cudaMemcpy2DAsync(h->d_packed, h->stride_d, packed, stride, (n + 3) / 4, p,
+                              cudaMemcpyHostToDevice, h->stream));
+    rc = finish_create(h);
+    if (rc) { jwas_destroy(h); *out = nullptr; }
+    return rc;
+}
+
+// synthetic genotypes: one thread per packed byte (4 individuals)
+__global__ void __launch_bounds__(256)
+jw_k_synth(uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p, uint64_t seed,
+           uint32_t miss_thr) {
+    int64_t nbytes = (n + 3) >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nbytes * p) return;
+    int64_t j = idx / nbytes, b = idx % nbytes;
+    jw_u32x4 rf = jw_philox4x32_10((uint32_t)j, 0u, 0xF00Du, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double f = 0.05 + 0.45 * jw_u53(rf.v[0], rf.v[1]);
+    uint32_t thr = (uint32_t)(f * 65536.0);
+    jw_u32x4 r = jw_philox4x32_10((uint32_t)b, (uint32_t)j, 0xC0DEu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    jw_u32x4 rm;
+    if (miss_thr) rm = jw_philox4x32_10((uint32_t)b, (uint32_t)j, 0xC0DFu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    unsigned byte = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (4 * b + k >= n) break;
+        uint32_t w = r.v[k];
+        unsigned code = ((w & 0xffffu) < thr) + ((w >> 16) < thr);
+        if (miss_thr && (rm.v[k] >> 16) < miss_thr) code = 3u;
+        byte |= code << (2 * k);
+    }
+    packed[j * stride_d + b] = (uint8_t)byte;
+}
+
+extern "C" int jwas_create_synthetic(int64_t n, int64_t p, int t, uint64_t seed, double missing_rate,
+                                     int device, jwas_handle** out) {
+    JW_REQUIRE(missing_rate >= 0.0 && missing_rate < 0.5, "missing_rate must be in [0,0.5)");
+    int rc = create_common(n, p, t, device, out);
+    if (rc) return rc;
+    jwas_handle* h = *out;
+    int64_t total = ((n + 3) / 4) * p;
+    jw_k_synth<<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, p, seed,
+                                                                     (uint32_t)(missing_rate * 65536.0));
+    JW_LAUNCH_CHECK(h);
+    rc = finish_create(h);
+    if (rc) { jwas_destroy(h); *out = nullptr; }
+    return rc;
+}
+
+extern "C" int jwas_get_packed(jwas_handle* h, uint8_t* packed, int64_t stride) {
+    JW_REQUIRE(h && packed, "jwas_get_packed: null argument");
+    JW_REQUIRE(stride >= (h->n + 3) / 4, "jwas_get_packed: stride too small");
+    JW_CUDA(cudaSetDevice(h->device));
+    JW_CUDA(cudaMemcpy2DAsync(packed, stride, h->d_packed, h->stride_d, (h->n + 3) / 4, h->p,
+                              cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int jwas_get_gram(jwas_handle* h, int64_t ib, float* out) {
+    JW_REQUIRE(h && out, "jwas_get_gram: null argument");
+    JW_REQUIRE(ib >= 0 && ib < h->nblocks, "jwas_get_gram: block out of range");
+    JW_CUDA(cudaSetDevice(h->device));
+    int64_t b = h->starts[ib + 1] - h->starts[ib];
+    JW_CUDA(cudaMemcpyAsync(out, h->d_gram + h->gram_off[ib], b * b * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int jwas_destroy(jwas_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_ycorr, h->d_alpha,
+                    h->d_beta, h->d_delta, h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta, h->d_ve,
+                    h->d_pi, h->d_u, h->d_z, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
+                    h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
+                    h->d_maxabs, h->d_stats, h->d_partials};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    jw_fused_free(h);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int jwas_get_marker_stats(jwas_handle* h, float* means, float* xpx) {
+    JW_REQUIRE(h, "null handle");
+    JW_CUDA(cudaSetDevice(h->device));
+    if (means) JW_CUDA(cudaMemcpyAsync(means, h->d_means, h->p * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (xpx) JW_CUDA(cudaMemcpyAsync(xpx, h->d_xpx, h->p * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// block partition + Gram blocks (JWAS.jl:73-79 validation; tools4genotypes.jl:259-269)
+// ------------------------------------------------------------------------------------------
+extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nblocks) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(starts && nblocks > 0, "fast_blocks block start vector cannot be empty.");
+    JW_REQUIRE(starts[0] == 0, "fast_blocks block starts must begin with 1.");
+    JW_REQUIRE(starts[nblocks] == h->p, "fast_blocks block boundaries must end at nMarkers.");
+    int64_t maxb = 0, total = 0;
+    std::vector<int64_t> off(nblocks);
+    for (int64_t i = 0; i < nblocks; ++i) {
+        int64_t b = starts[i + 1] - starts[i];
+        JW_REQUIRE(b > 0, "fast_blocks block starts must be sorted and unique.");
+        JW_REQUIRE(starts[i] >= 0 && starts[i] < h->p, "fast_blocks block starts must be within 1:nMarkers.");
+        JW_REQUIRE(b <= JW_MAX_BLOCK, "fast_blocks: block size above 1024 is not supported by the GPU backend.");
+        off[i] = total; total += b * b; maxb = std::max(maxb, b);
+    }
+    JW_CUDA(cudaSetDevice(h->device));
+    for (void* q : {(void*)h->d_starts, (void*)h->d_gram_off, (void*)h->d_gram}) if (q) cudaFree(q);
+    h->d_starts = nullptr; h->d_gram_off = nullptr; h->d_gram = nullptr;
+    h->starts.assign(starts, starts + nblocks + 1);
+    h->gram_off = off; h->nblocks = nblocks; h->maxb = maxb;
+    JW_CUDA(cudaMalloc((void**)&h->d_starts, (nblocks + 1) * sizeof(int64_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_gram_off, nblocks * sizeof(int64_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_gram, (size_t)total * sizeof(float)));
+    JW_CUDA(cudaMemcpyAsync(h->d_starts, starts, (nblocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(h->d_gram_off, off.data(), nblocks * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    // tile list: every 64x64 tile of every block
+    std::vector<int32_t> tb, tab;
+    for (int64_t i = 0; i < nblocks; ++i) {
+        int nt = (int)ceil_div(starts[i + 1] - starts[i], JW_GT);
+        for (int a = 0; a < nt; ++a) for (int c = 0; c < nt; ++c) { tb.push_back((int32_t)i); tab.push_back(a); tab.push_back(c); }
+    }
+    int32_t *d_tb = nullptr, *d_tab = nullptr;
+    JW_CUDA(cudaMalloc((void**)&d_tb, tb.size() * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&d_tab, tab.size() * sizeof(int32_t)));
+    JW_CUDA(cudaMemcpyAsync(d_tb, tb.data(), tb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->has_missing)
+        jw_k_gram<true><<<(unsigned)tb.size(), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->d_means,
+            h->d_colsum, h->d_starts, h->d_gram_off, d_tb, d_tab, h->d_gram);
+    else
+        jw_k_gram<false><<<(unsigned)tb.size(), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->d_means,
+            h->d_colsum, h->d_starts, h->d_gram_off, d_tb, d_tab, h->d_gram);
+    JW_LAUNCH_CHECK(h);
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_tb); cudaFree(d_tab);
+    int rc = jw_fused_prepare(h);
+    if (rc) return rc;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// state movement
+// ------------------------------------------------------------------------------------------
+extern "C" int jwas_put_ycorr(jwas_handle* h, const float* y) {
+    JW_REQUIRE(h && y, "jwas_put_ycorr: null argument");
+    JW_CUDA(cudaSetDevice(h->device));
+    JW_CUDA(cudaMemcpyAsync(h->d_ycorr, y, (size_t)h->t * h->n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    h->next_maxabs = -1.0f;
+    return 0;
+}
+extern "C" int jwas_get_ycorr(jwas_handle* h, float* y) {
+    JW_REQUIRE(h && y, "jwas_get_ycorr: null argument");
+    JW_CUDA(cudaSetDevice(h->device));
+    JW_CUDA(cudaMemcpyAsync(y, h->d_ycorr, (size_t)h->t * h->n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int jwas_put_state(jwas_handle* h, const float* alpha, const float* beta, const int32_t* delta) {
+    JW_REQUIRE(h, "null handle");
+    JW_CUDA(cudaSetDevice(h->device));
+    size_t tp = (size_t)h->t * h->p;
+    if (alpha) JW_CUDA(cudaMemcpyAsync(h->d_alpha, alpha, tp * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (beta) JW_CUDA(cudaMemcpyAsync(h->d_beta, beta, tp * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (delta) JW_CUDA(cudaMemcpyAsync(h->d_delta, delta, tp * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int jwas_get_state(jwas_handle* h, float* alpha, float* beta, int32_t* delta) {
+    JW_REQUIRE(h, "null handle");
+    JW_CUDA(cudaSetDevice(h->device));
+    size_t tp = (size_t)h->t * h->p;
+    if (alpha) JW_CUDA(cudaMemcpyAsync(alpha, h->d_alpha, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (beta) JW_CUDA(cudaMemcpyAsync(beta, h->d_beta, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (delta) JW_CUDA(cudaMemcpyAsync(delta, h->d_delta, tp * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int jwas_ycorr_sub_malpha(jwas_handle* h) {
+    JW_REQUIRE(h, "null handle");
+    JW_CUDA(cudaSetDevice(h->device));
+    for (int k = 0; k < h->t; ++k) {
+        jw_k_mul_alpha<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(
+            h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_alpha + (size_t)k * h->p, -1.0f,
+            h->d_ycorr + (size_t)k * h->n, 1);
+        JW_LAUNCH_CHECK(h);
+    }
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    h->next_maxabs = -1.0f;
+    return 0;
+}
+extern "C" int jwas_mul_alpha(jwas_handle* h, int trait, float* out) {
+    JW_REQUIRE(h && out, "jwas_mul_alpha: null argument");
+    JW_REQUIRE(trait >= 0 && trait < h->t, "jwas_mul_alpha: trait out of range");
+    JW_CUDA(cudaSetDevice(h->device));
+    float* d_out = (float*)h->d_yq;   // scratch of n floats (re-quantised by the next sweep anyway)
+    jw_k_mul_alpha<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(
+        h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_alpha + (size_t)trait * h->p, 1.0f, d_out, 0);
+    JW_LAUNCH_CHECK(h);
+    JW_CUDA(cudaMemcpyAsync(out, d_out, h->n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// canonical chunked sum of a[i]*b[i] -> *d_out (device)
+static int canonical_dot(jwas_handle* h, const float* a, const float* b, int64_t n, double* d_out) {
+    int64_t nchunks = ceil_div(n, JW_CHUNK);
+    if (ensure_cap(&h->d_partials, &h->cap_partials, (size_t)nchunks)) return 10;
+    jw_k_chunk_prod<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(a, b, n, h->d_partials);
+    JW_LAUNCH_CHECK(h);
+    jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, d_out);
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int jwas_shift_ycorr(jwas_handle* h, int trait, float shift, double* sum, double* sumsq) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(trait >= 0 && trait < h->t, "jwas_shift_ycorr: trait out of range");
+    JW_CUDA(cudaSetDevice(h->device));
+    float* y = h->d_ycorr + (size_t)trait * h->n;
+    if (shift != 0.0f) {
+        jw_k_shift<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(y, h->n, shift);
+        JW_LAUNCH_CHECK(h);
+        h->next_maxabs = -1.0f;
+    }
+    // sum(y) = canonical dot with a vector of ones is avoided: use y*y and y*1 via two passes
+    double host[2] = {0, 0};
+    if (sumsq) { if (canonical_dot(h, y, y, h->n, h->d_stats)) return 10; }
+    if (sum) {
+        // ones vector: reuse d_dalpha region? keep it simple and exact: chunked sum kernel on (y, 1)
+        float* ones = (float*)h->d_yq;
+        JW_CUDA(cudaMemsetAsync(ones, 0, h->n * sizeof(float), h->stream));
+        jw_k_shift<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(ones, h->n, 1.0f);
+        JW_LAUNCH_CHECK(h);
+        // canonical_dot overwrites d_partials; run after sumsq finished (same stream -> ordered)
+        int64_t nchunks = ceil_div(h->n, JW_CHUNK);
+        jw_k_chunk_prod<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(y, ones, h->n, h->d_partials);
+        JW_LAUNCH_CHECK(h);
+        jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, h->d_stats + 1);
+        JW_LAUNCH_CHECK(h);
+    }
+    JW_CUDA(cudaMemcpyAsync(host, h->d_stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    if (sumsq) *sumsq = host[0];
+    if (sum) *sum = host[1];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// sweep driver
+// ------------------------------------------------------------------------------------------
+struct sweep_cfg {
+    int method = 0, schedule = 0, full_reps = 1;
+    double vare = 1.0, sigmaSq = 0.0;
+    int nclasses = 0, per_marker_pi = 0, per_marker_G = 0;
+    double gamma[JW_MAX_CLASSES] = {0};
+    double Rinv[16] = {0}, Ginv[16] = {0};
+    uint64_t seed = 0; uint32_t iter = 0;
+    const double* u = nullptr; const double* z = nullptr;  // device pointers
+};
+
+template <int METHOD, int T>
+static void launch_chain(jwas_handle* h, const jw_chain_args& A, int nblk, int threads) {
+    jw_k_chain<METHOD, T><<<nblk, threads, 0, h->stream>>>(A);
+}
+static int dispatch_chain(jwas_handle* h, const jw_chain_args& A, int nblk, int threads) {
+    int t = h->t;
+    if (A.method == 0 && t == 1) launch_chain<0, 1>(h, A, nblk, threads);
+    else if (A.method == 1 && t == 1) launch_chain<1, 1>(h, A, nblk, threads);
+    else if (A.method == 2 && t == 2) launch_chain<2, 2>(h, A, nblk, threads);
+    else if (A.method == 2 && t == 3) launch_chain<2, 3>(h, A, nblk, threads);
+    else if (A.method == 2 && t == 4) launch_chain<2, 4>(h, A, nblk, threads);
+    else { jw_set_error("unsupported (method, traits) combination"); return 2; }
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+static int prof_begin(jwas_handle* h) {
+    if (!h->opt_profile) return 0;
+    cudaEvent_t a, b;
+    JW_CUDA(cudaEventCreate(&a)); JW_CUDA(cudaEventCreate(&b));
+    h->prof_events.push_back(a); h->prof_events.push_back(b);
+    JW_CUDA(cudaEventRecord(a, h->stream));
+    return 0;
+}
+static int prof_end(jwas_handle* h) {
+    if (!h->opt_profile) return 0;
+    JW_CUDA(cudaEventRecord(h->prof_events.back(), h->stream));
+    return 0;
+}
+static void prof_collect(jwas_handle* h) {
+    h->prof_ms = 0.0; h->prof_launches = (int64_t)h->prof_events.size() / 2;
+    for (size_t i = 0; i + 1 < h->prof_events.size(); i += 2) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]);
+        h->prof_ms += ms;
+        cudaEventDestroy(h->prof_events[i]); cudaEventDestroy(h->prof_events[i + 1]);
+    }
+    h->prof_events.clear();
+}
+static int dispatch_dot(jwas_handle* h, int64_t j0, int64_t nj) {
+    if (prof_begin(h)) return 10;
+    dim3 grid((unsigned)ceil_div(nj, 8), (unsigned)ceil_div(ceil_div(h->n, 16), JW_DOT_SLAB_WORDS));
+    long long* mq = h->d_mq;
+#define JW_DOT(T_, M_) jw_k_block_dot<T_, M_><<<grid, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, j0, nj, h->d_yq, h->d_dq, mq)
+    bool ms = h->has_missing != 0;
+    switch (h->t) {
+        case 1: if (ms) JW_DOT(1, true); else JW_DOT(1, false); break;
+        case 2: if (ms) JW_DOT(2, true); else JW_DOT(2, false); break;
+        case 3: if (ms) JW_DOT(3, true); else JW_DOT(3, false); break;
+        default: if (ms) JW_DOT(4, true); else JW_DOT(4, false); break;
+    }
+#undef JW_DOT
+    JW_LAUNCH_CHECK(h);
+    if (prof_end(h)) return 10;
+    return 0;
+}
+static int dispatch_apply(jwas_handle* h) {
+    unsigned g = (unsigned)ceil_div(h->n, 256);
+#define JW_APPLY(T_) jw_k_apply<T_><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_ycorr)
+    switch (h->t) { case 1: JW_APPLY(1); break; case 2: JW_APPLY(2); break; case 3: JW_APPLY(3); break; default: JW_APPLY(4); }
+#undef JW_APPLY
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+
+static int collect_stats(jwas_handle* h, const sweep_cfg& c, int S, jwas_sweep_stats* st) {
+    const int t = h->t;
+    memset(st, 0, sizeof(*st));
+    // d_stats layout: [0..15] ycorr_ss, [16..31] alpha_ss, [32..47] beta_ss, [48] bayesr ssq
+    for (int a = 0; a < t; ++a)
+        for (int b = a; b < t; ++b) {
+            if (canonical_dot(h, h->d_ycorr + (size_t)a * h->n, h->d_ycorr + (size_t)b * h->n, h->n, h->d_stats + a * t + b)) return 10;
+            if (canonical_dot(h, h->d_alpha + (size_t)a * h->p, h->d_alpha + (size_t)b * h->p, h->p, h->d_stats + 16 + a * t + b)) return 10;
+            if (c.method != 1)
+                if (canonical_dot(h, h->d_beta + (size_t)a * h->p, h->d_beta + (size_t)b * h->p, h->p, h->d_stats + 32 + a * t + b)) return 10;
+        }
+    if (c.method == 1) {
+        int64_t nchunks = ceil_div(h->p, JW_CHUNK);
+        if (ensure_cap(&h->d_partials, &h->cap_partials, (size_t)nchunks)) return 10;
+        jw_k_chunk_bayesr<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(h->d_alpha, h->d_delta, h->p,
+            c.gamma[1], c.gamma[2], c.gamma[3], c.gamma[4], c.gamma[5], c.gamma[6], c.gamma[7], h->d_partials);
+        JW_LAUNCH_CHECK(h);
+        jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, h->d_stats + 48);
+        JW_LAUNCH_CHECK(h);
+    }
+    JW_CUDA(cudaMemsetAsync(h->d_counters + 4, 0, 24 * sizeof(unsigned long long), h->stream));
+    jw_k_counts<<<(unsigned)ceil_div(h->p, 256), 256, 0, h->stream>>>(h->d_alpha, h->d_delta, h->p, t, c.method, h->d_counters + 4);
+    JW_LAUNCH_CHECK(h);
+    JW_CUDA(cudaMemsetAsync(h->d_maxabs, 0, sizeof(float), h->stream));
+    jw_k_maxabs<<<64, 256, 0, h->stream>>>(h->d_ycorr, (int64_t)t * h->n, (unsigned*)h->d_maxabs);
+    JW_LAUNCH_CHECK(h);
+
+    double hs[49]; unsigned long long hc[28]; int32_t hf[4]; float hm;
+    JW_CUDA(cudaMemcpyAsync(hs, h->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(hc, h->d_counters, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(hf, h->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(&hm, h->d_maxabs, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaEventRecord(h->ev1, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_sweep_ms = ms;
+    prof_collect(h);
+    for (int a = 0; a < t; ++a)
+        for (int b = a; b < t; ++b) {
+            st->ycorr_ss[a * t + b] = st->ycorr_ss[b * t + a] = hs[a * t + b];
+            st->alpha_ss[a * t + b] = st->alpha_ss[b * t + a] = hs[16 + a * t + b];
+            st->beta_ss[a * t + b] = st->beta_ss[b * t + a] = hs[32 + a * t + b];
+        }
+    st->bayesr_ssq = hs[48];
+    st->n_active = (int64_t)hc[0]; st->n_rounds = (int64_t)hc[1];
+    for (int k = 0; k < t; ++k) { st->nnz_alpha[k] = (double)hc[4 + k]; st->sum_delta[k] = (double)hc[8 + k]; }
+    for (int q = 0; q < 16; ++q) st->class_counts[q] = (double)hc[12 + q];
+    st->ycorr_maxabs = hm; st->scale_exp = S; st->overflow = hf[0];
+    h->next_maxabs = hm;
+    if (hf[0]) { jw_set_error("ycorr fixed-point overflow: |ycorr| grew more than 4x inside one sweep"); return 3; }
+    return 0;
+}
+
+static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
+    JW_REQUIRE(h->nblocks > 0, "jwas_set_blocks must be called before a sweep");
+    JW_REQUIRE(st != nullptr, "stats is NULL");
+    const int t = h->t;
+    const int64_t n = h->n, p = h->p;
+    JW_CUDA(cudaEventRecord(h->ev0, h->stream));
+
+    // fixed-point scale from max|ycorr| (carried over from the previous sweep when untouched)
+    float maxabs = h->next_maxabs;
+    if (maxabs < 0.0f) {
+        JW_CUDA(cudaMemsetAsync(h->d_maxabs, 0, sizeof(float), h->stream));
+        jw_k_maxabs<<<64, 256, 0, h->stream>>>(h->d_ycorr, (int64_t)t * n, (unsigned*)h->d_maxabs);
+        JW_LAUNCH_CHECK(h);
+        JW_CUDA(cudaMemcpyAsync(&maxabs, h->d_maxabs, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        JW_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    const int S = jw_choose_scale_exp(maxabs);
+    const float scale = jw_pow2f(S);
+    const double invscale = (double)jw_pow2f(-S);
+
+    JW_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t), h->stream));
+    JW_CUDA(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+
+    jw_chain_args A;
+    memset(&A, 0, sizeof(A));
+    A.n = n; A.p = p; A.t = t; A.method = c.method; A.nclasses = c.nclasses;
+    A.nreps_mode = (c.schedule == JWAS_SCHED_EXACT) ? 0 : c.full_reps;
+    A.per_marker_pi = c.per_marker_pi; A.per_marker_G = c.per_marker_G;
+    A.starts = h->d_starts; A.gram_off = h->d_gram_off; A.gram = h->d_gram;
+    A.means = h->d_means; A.xpx = h->d_xpx;
+    A.dq = h->d_dq; A.mq = h->has_missing ? h->d_mq : nullptr; A.sq = h->d_sq;
+    A.invscale = invscale;
+    A.alpha = h->d_alpha; A.beta = h->d_beta; A.delta = h->d_delta; A.dalpha = h->d_dalpha;
+    A.vare = c.vare; A.sigmaSq = c.sigmaSq;
+    A.ve = h->d_ve; A.pi = h->d_pi; A.bigPi = h->d_pi; A.Gmat = h->d_ve;
+    memcpy(A.gamma, c.gamma, sizeof(A.gamma));
+    memcpy(A.Rinv, c.Rinv, sizeof(A.Rinv)); memcpy(A.Ginv, c.Ginv, sizeof(A.Ginv));
+    A.seed = c.seed; A.iter = c.iter; A.u = c.u; A.z = c.z;
+    A.act_idx = h->d_act_idx; A.act_cnt = h->d_act_cnt; A.counters = h->d_counters;
+    const int threads = (int)std::max<int64_t>(32, ceil_div(h->maxb, 32) * 32);
+
+    if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT) {
+        int rc = jw_fused_sweep(h, A, scale);
+        if (rc) return rc;
+        return collect_stats(h, c, S, st);
+    }
+
+    JW_CUDA(cudaMemsetAsync(h->d_dq, 0, (size_t)t * p * sizeof(long long), h->stream));
+    if (h->has_missing) JW_CUDA(cudaMemsetAsync(h->d_mq, 0, (size_t)t * p * sizeof(long long), h->stream));
+    dim3 qgrid((unsigned)std::min<int64_t>(ceil_div(n, 256), 1024), (unsigned)t);
+
+    if (c.schedule == JWAS_SCHED_INDEPENDENT) {
+        // all blocks read the entry snapshot (BayesABC.jl:205); one GEMV over all of M
+        JW_CUDA(cudaMemsetAsync(h->d_sq, 0, JW_MAX_TRAITS * sizeof(long long), h->stream));
+        jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags);
+        JW_LAUNCH_CHECK(h);
+        if (dispatch_dot(h, 0, p)) return 11;
+        A.block0 = 0; A.write_active_list = 0;
+        if (dispatch_chain(h, A, (int)h->nblocks, threads)) return 11;
+        jw_k_compact_active<<<1, 1024, 0, h->stream>>>(h->d_dalpha, p, t, h->d_act_idx, h->d_act_cnt);
+        JW_LAUNCH_CHECK(h);
+        if (dispatch_apply(h)) return 11;
+    } else {
+        for (int64_t ib = 0; ib < h->nblocks; ++ib) {
+            JW_CUDA(cudaMemsetAsync(h->d_sq, 0, JW_MAX_TRAITS * sizeof(long long), h->stream));
+            jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags);
+            JW_LAUNCH_CHECK(h);
+            if (dispatch_dot(h, h->starts[ib], h->starts[ib + 1] - h->starts[ib])) return 11;
+            A.block0 = (int)ib; A.write_active_list = 1;
+            if (dispatch_chain(h, A, 1, threads)) return 11;
+            if (dispatch_apply(h)) return 11;
+        }
+    }
+    return collect_stats(h, c, S, st);
+}
+
+static int upload_doubles(jwas_handle* h, double** dptr, size_t* cap, const double* src, size_t count) {
+    if (ensure_cap(dptr, cap, count)) return 10;
+    JW_CUDA(cudaMemcpyAsync(*dptr, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+static int fill_doubles(jwas_handle* h, double** dptr, size_t* cap, double v, size_t count) {
+    if (ensure_cap(dptr, cap, count)) return 10;
+    jw_k_fill_double<<<(unsigned)ceil_div((int64_t)count, 256), 256, 0, h->stream>>>(*dptr, (int64_t)count, v);
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+static int upload_draws(jwas_handle* h, sweep_cfg& c, const double* u, const double* z, int schedule, int full_reps) {
+    c.u = nullptr; c.z = nullptr;
+    if (!u && !z) return 0;
+    JW_REQUIRE(u && z, "replay draws: u and z must both be given");
+    size_t reps = (schedule == JWAS_SCHED_EXACT || !full_reps) ? 1 : (size_t)h->maxb;
+    size_t count = reps * h->t * h->p;
+    if (upload_doubles(h, &h->d_u, &h->cap_u, u, count)) return 10;
+    if (upload_doubles(h, &h->d_z, &h->cap_z, z, count)) return 10;
+    c.u = h->d_u; c.z = h->d_z;
+    return 0;
+}
+
+extern "C" int jwas_sweep_bayesabc(jwas_handle* h, int schedule, double vare, const double* var_effects,
+                                   const double* pi, uint64_t seed, uint32_t iter, const double* u,
+                                   const double* z, jwas_sweep_stats* stats) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t == 1, "jwas_sweep_bayesabc: single-trait handle required");
+    JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
+    JW_REQUIRE(vare > 0.0, "residual variance must be positive");
+    JW_CUDA(cudaSetDevice(h->device));
+    if (var_effects) { if (upload_doubles(h, &h->d_ve, &h->cap_ve, var_effects, (size_t)h->p)) return 10; }
+    else JW_REQUIRE(h->d_ve && h->cap_ve >= (size_t)h->p, "var_effects is NULL and no device-resident vector exists");
+    if (pi) { if (upload_doubles(h, &h->d_pi, &h->cap_pi, pi, (size_t)h->p)) return 10; }
+    else JW_REQUIRE(h->d_pi && h->cap_pi >= (size_t)h->p, "pi is NULL and no device-resident vector exists");
+    sweep_cfg c; c.method = 0; c.schedule = schedule; c.full_reps = 1; c.vare = vare; c.seed = seed; c.iter = iter;
+    if (upload_draws(h, c, u, z, schedule, 1)) return 10;
+    return run_sweep(h, c, stats);
+}
+
+extern "C" int jwas_sweep_bayesc(jwas_handle* h, int schedule, double vare, double var_effect, double pi,
+                                 uint64_t seed, uint32_t iter, jwas_sweep_stats* stats) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t == 1, "jwas_sweep_bayesc: single-trait handle required");
+    JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
+    JW_REQUIRE(vare > 0.0 && var_effect > 0.0, "variances must be positive");
+    JW_REQUIRE(pi >= 0.0 && pi <= 1.0, "pi must lie in [0,1]");
+    JW_CUDA(cudaSetDevice(h->device));
+    if (fill_doubles(h, &h->d_ve, &h->cap_ve, var_effect, (size_t)h->p)) return 10;
+    if (fill_doubles(h, &h->d_pi, &h->cap_pi, pi, (size_t)h->p)) return 10;
+    sweep_cfg c; c.method = 0; c.schedule = schedule; c.full_reps = 1; c.vare = vare; c.seed = seed; c.iter = iter;
+    return run_sweep(h, c, stats);
+}
+
+extern "C" int jwas_sweep_bayesr(jwas_handle* h, int schedule, int full_reps, double vare, double sigma_sq,
+                                 const double* pi, int per_marker_pi, const double* gamma, int nclasses,
+                                 uint64_t seed, uint32_t iter, const double* u, const double* z,
+                                 jwas_sweep_stats* stats) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t == 1, "jwas_sweep_bayesr: single-trait handle required");
+    JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
+    JW_REQUIRE(nclasses >= 2 && nclasses <= JW_MAX_CLASSES, "BayesR needs 2..8 mixture classes");
+    JW_REQUIRE(pi && gamma, "BayesR pi/gamma missing");
+    JW_REQUIRE(sigma_sq > 0.0, "BayesR sigmaSq must be positive.");
+    JW_REQUIRE(vare > 0.0, "residual variance must be positive");
+    if (!per_marker_pi) {
+        double s = 0.0;
+        for (int k = 0; k < nclasses; ++k) { JW_REQUIRE(pi[k] >= 0.0, "BayesR pi entries must be nonnegative."); s += pi[k]; }
+        JW_REQUIRE(std::fabs(s - 1.0) <= 1e-8, "BayesR pi must sum to 1.");
+    }
+    JW_CUDA(cudaSetDevice(h->device));
+    size_t npi = per_marker_pi ? (size_t)h->p * nclasses : (size_t)nclasses;
+    if (upload_doubles(h, &h->d_pi, &h->cap_pi, pi, npi)) return 10;
+    sweep_cfg c; c.method = 1; c.schedule = schedule; c.full_reps = full_reps ? 1 : 0; c.vare = vare;
+    c.sigmaSq = sigma_sq; c.nclasses = nclasses; c.per_marker_pi = per_marker_pi;
+    for (int k = 0; k < nclasses; ++k) c.gamma[k] = gamma[k];
+    c.seed = seed; c.iter = iter;
+    if (upload_draws(h, c, u, z, schedule, c.full_reps)) return 10;
+    return run_sweep(h, c, stats);
+}
+
+extern "C" int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, const double* G, int per_marker_G,
+                              const double* big_pi, int per_marker_pi, uint64_t seed, uint32_t iter,
+                              const double* u, const double* z, jwas_sweep_stats* stats) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t >= 2, "jwas_sweep_mt1: multi-trait handle required");
+    JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
+    JW_REQUIRE(R && G && big_pi, "jwas_sweep_mt1: R, G and big_pi are required");
+    JW_CUDA(cudaSetDevice(h->device));
+    const int t = h->t;
+    sweep_cfg c; c.method = 2; c.schedule = schedule; c.full_reps = 1; c.seed = seed; c.iter = iter;
+    c.per_marker_G = per_marker_G; c.per_marker_pi = per_marker_pi;
+    jw_inv_spd_fixed(R, t, c.Rinv);
+    if (per_marker_G) { if (upload_doubles(h, &h->d_ve, &h->cap_ve, G, (size_t)h->p * t * t)) return 10; }
+    else jw_inv_spd_fixed(G, t, c.Ginv);
+    size_t npi = (size_t)(per_marker_pi ? h->p : 1) << t;
+    if (upload_doubles(h, &h->d_pi, &h->cap_pi, big_pi, npi)) return 10;
+    if (upload_draws(h, c, u, z, schedule, 1)) return 10;
+    return run_sweep(h, c, stats);
+}
+
+extern "C" int jwas_sample_bayesb_variances(jwas_handle* h, double df, double scale, uint64_t seed,
+                                            uint32_t iter, double* out) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t == 1, "single-trait handle required");
+    JW_CUDA(cudaSetDevice(h->device));
+    if (ensure_cap(&h->d_ve, &h->cap_ve, (size_t)h->p)) return 10;
+    jw_k_bayesb_var<<<(unsigned)ceil_div(h->p, 256), 256, 0, h->stream>>>(h->d_beta, h->p, df, scale, seed, iter, h->d_ve);
+    JW_LAUNCH_CHECK(h);
+    if (out) JW_CUDA(cudaMemcpyAsync(out, h->d_ve, h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int jwas_accumulate(jwas_handle* h, double nsamples, int bayesr) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(nsamples >= 1.0, "nsamples must be >= 1");
+    JW_CUDA(cudaSetDevice(h->device));
+    int64_t tp = (int64_t)h->t * h->p;
+    jw_k_accumulate<<<(unsigned)ceil_div(tp, 256), 256, 0, h->stream>>>(h->d_alpha, h->d_delta, tp, nsamples, bayesr,
+                                                                      h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta);
+    JW_LAUNCH_CHECK(h);
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int jwas_get_means(jwas_handle* h, float* ma, float* ma2, float* md) {
+    JW_REQUIRE(h, "null handle");
+    JW_CUDA(cudaSetDevice(h->device));
+    size_t tp = (size_t)h->t * h->p;
+    if (ma) JW_CUDA(cudaMemcpyAsync(ma, h->d_mean_alpha, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (ma2) JW_CUDA(cudaMemcpyAsync(ma2, h->d_mean_alpha2, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (md) JW_CUDA(cudaMemcpyAsync(md, h->d_mean_delta, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int64_t jwas_kernel_launches(jwas_handle* h) { return h ? h->launches : 0; }
+extern "C" double jwas_last_sweep_ms(jwas_handle* h) { return h ? h->last_sweep_ms : 0.0; }
+extern "C" double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches) {
+    if (!h) return 0.0;
+    if (launches) *launches = h->prof_launches;
+    return h->prof_ms;
+}
+extern "C" void* jwas_stream(jwas_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
+    JW_REQUIRE(h && key, "jwas_set_option: null argument");
+    if (!strcmp(key, "profile")) { h->opt_profile = value; return 0; }
+    if (!strcmp(key, "engine")) { JW_REQUIRE(value == 0 || value == 1, "engine must be 0 or 1"); h->opt_engine = value; return 0; }
+    jw_set_error(std::string("unknown option: ") + key);
+    return 2;
+}

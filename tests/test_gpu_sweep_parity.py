@@ -1,0 +1,295 @@
+"""GPU parity: the CUDA sweep (through the C ABI) against the CPU oracle's contract-arithmetic
+sweep on the same seeded inputs.  Bar: inclusion indicators, effects and ycorr BIT-EXACT
+(north_star asks for indicators bit-exact and effects within 1e-5 relative; the arithmetic
+contract gives equality, so that is what is asserted)."""
+import numpy as np
+import pytest
+
+from helpers import Problem, uniform_starts, canonical_sum_prod
+
+pytestmark = pytest.mark.gpu
+
+GAMMA = np.array([0.0, 0.01, 0.1, 1.0])          # JWAS.jl:12 BAYESR_GAMMA
+PI_R = np.array([0.95, 0.03, 0.015, 0.005])      # tools4genotypes.jl:373-375
+
+
+@pytest.fixture(scope="module")
+def jw():
+    import jwas_b200
+    assert jwas_b200.device_count() > 0, "no CUDA device: the gpu-marked tests need a B200"
+    return jwas_b200
+
+
+def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=False, replay=False, engine=0,
+                 seed=11):
+    n, p = prob.n, prob.p
+    g = jw.GpuSweeper(prob.packed, n, 1)
+    g.set_blocks(starts)
+    g.set_option("engine", engine)
+    gm, gx = g.marker_stats()
+    np.testing.assert_array_equal(gm, prob.means)
+    np.testing.assert_array_equal(gx, prob.xpx)
+    yc, al, be, de = prob.fresh_state()
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    rng = np.random.default_rng(seed)
+    vare = prob.vary * 0.5
+    ve = np.full(p, prob.vary * 0.5 / (0.1 * prob.xpx.mean() / n * p))
+    if bayesb:
+        ve = ve * rng.uniform(0.5, 2.0, size=p)
+    piv = np.full(p, pi)
+    nreps_mode = 0 if schedule == jw.SCHED_EXACT else 1
+    maxb = int(np.diff(starts).max())
+    for it in range(1, nsweeps + 1):
+        u = z = None
+        if replay:
+            reps = maxb if nreps_mode else 1
+            u = rng.random(reps * p); z = rng.standard_normal(reps * p)
+        rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
+                                      method=oracle.METHOD_ABC, nreps_mode=nreps_mode,
+                                      independent=(schedule == jw.SCHED_INDEPENDENT), vare=vare,
+                                      varEffects=ve, pi=piv, seed=seed, it=it, u=u, z=z)
+        assert rc == 0
+        st = g.sweep_bayesabc(schedule, vare, ve, piv, seed, it, u, z)
+        ga, gb, gd = g.get_state()
+        gy = g.get_ycorr()
+        assert st.scale_exp == S
+        np.testing.assert_array_equal(gd, de, err_msg=f"delta differs at sweep {it}")
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32), err_msg=f"alpha differs at sweep {it}")
+        np.testing.assert_array_equal(gb.view(np.uint32), be.view(np.uint32), err_msg=f"beta differs at sweep {it}")
+        np.testing.assert_array_equal(gy.view(np.uint32), yc.view(np.uint32), err_msg=f"ycorr differs at sweep {it}")
+        assert st.sum_delta[0] == de.sum()
+        assert st.nnz_alpha[0] == np.count_nonzero(al)
+        assert st.alpha_ss[0] == canonical_sum_prod(al, al)
+        assert st.ycorr_ss[0] == canonical_sum_prod(yc, yc)
+        assert st.ycorr_maxabs == np.abs(yc).max()
+    assert de.sum() > 0, "degenerate test: nothing ever entered the model"
+    g.close()
+    return st
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.03])
+@pytest.mark.parametrize("n,p,b", [(500, 2000, 256), (501, 333, 64), (67, 50, 1), (1030, 700, 700)])
+def test_bayesc_exact_schedule(jw, oracle, n, p, b, missing):
+    prob = Problem(oracle, n, p, seed=n + p, missing=missing)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=4)
+
+
+def test_bayesb_per_marker_variances_and_replayed_draws(jw, oracle):
+    prob = Problem(oracle, 300, 400, seed=5)
+    run_pair_abc(jw, oracle, prob, uniform_starts(400, 128), jw.SCHED_EXACT, nsweeps=3, bayesb=True, replay=True)
+
+
+def test_bayesa_pi_zero(jw, oracle):
+    # BayesA is BayesB with pi = 0 (input_data_validation.jl:33-36): every marker is included
+    prob = Problem(oracle, 200, 60, seed=8)
+    st = run_pair_abc(jw, oracle, prob, uniform_starts(60, 16), jw.SCHED_EXACT, nsweeps=2, pi=0.0)
+    assert st.sum_delta[0] == 60
+
+
+@pytest.mark.parametrize("schedule_name", ["block", "independent"])
+@pytest.mark.parametrize("missing", [0.0, 0.02])
+def test_bayesc_block_schedules(jw, oracle, schedule_name, missing):
+    # BayesABC_block! nreps = block size (BayesABC.jl:153); explicit ragged starts
+    prob = Problem(oracle, 400, 157, seed=21, missing=missing)
+    starts = np.array([0, 20, 21, 60, 100, 157], dtype=np.int64)
+    sched = jw.SCHED_BLOCK if schedule_name == "block" else jw.SCHED_INDEPENDENT
+    run_pair_abc(jw, oracle, prob, starts, sched, nsweeps=3, replay=(schedule_name == "block"))
+
+
+def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3):
+    n, p = prob.n, prob.p
+    g = jw.GpuSweeper(prob.packed, n, 1)
+    g.set_blocks(starts)
+    yc, al, be, de = prob.fresh_state()
+    de[:] = 1
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    vare = prob.vary * 0.5
+    sigma = prob.vary * 0.5 / (prob.xpx.mean() / n * p * float(GAMMA @ PI_R))
+    nreps_mode = 0 if (schedule == jw.SCHED_EXACT or not full_reps) else 1
+    for it in range(1, nsweeps + 1):
+        rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, None, de,
+                                      method=oracle.METHOD_R, nreps_mode=nreps_mode,
+                                      independent=(schedule == jw.SCHED_INDEPENDENT), vare=vare,
+                                      sigmaSq=sigma, pi=PI_R, gamma=GAMMA, seed=seed, it=it)
+        assert rc == 0
+        st = g.sweep_bayesr(schedule, full_reps, vare, sigma, PI_R, GAMMA, seed, it)
+        ga, _, gd = g.get_state()
+        gy = g.get_ycorr()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(gy.view(np.uint32), yc.view(np.uint32))
+        counts = np.bincount(de, minlength=5)[1:5]
+        assert [st.class_counts[k] for k in range(4)] == counts.tolist()
+        ssq, nnz = oracle.bayesr_sigma_sufficient_statistics(al, de, GAMMA)
+        assert st.sum_delta[0] == nnz
+        assert st.bayesr_ssq == pytest.approx(ssq, rel=1e-12)
+    assert (de > 1).sum() > 0
+    g.close()
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.03])
+def test_bayesr_exact(jw, oracle, missing):
+    prob = Problem(oracle, 500, 1000, seed=31, missing=missing)
+    run_pair_r(jw, oracle, prob, uniform_starts(1000, 256), jw.SCHED_EXACT, 1, nsweeps=4)
+
+
+@pytest.mark.parametrize("schedule_name,full_reps", [("block", 1), ("block", 0), ("independent", 1)])
+def test_bayesr_block_schedules(jw, oracle, schedule_name, full_reps):
+    # bayesr_block_nreps burn-in gate (BayesR.jl:22-25): full_reps=0 during burn-in
+    prob = Problem(oracle, 300, 90, seed=33)
+    sched = jw.SCHED_BLOCK if schedule_name == "block" else jw.SCHED_INDEPENDENT
+    run_pair_r(jw, oracle, prob, uniform_starts(90, 17), sched, full_reps, nsweeps=3)
+
+
+def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9):
+    n, p, t = prob.n, prob.p, prob.t
+    g = jw.GpuSweeper(prob.packed, n, t)
+    g.set_blocks(starts)
+    yc, al, be, de = prob.fresh_state()
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    R = np.array([[1.0, 0.3], [0.3, 1.2]]) * prob.vary * 0.5
+    G = np.array([[1.0, 0.4], [0.4, 0.8]]) * prob.vary * 0.5 / (0.2 * prob.xpx.mean() / n * p)
+    bigPi = np.array([0.7, 0.1, 0.1, 0.1])
+    nreps_mode = 0 if schedule == jw.SCHED_EXACT else 1
+    for it in range(1, nsweeps + 1):
+        rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
+                                      method=oracle.METHOD_MT1, nreps_mode=nreps_mode,
+                                      independent=(schedule == jw.SCHED_INDEPENDENT), R=R, G=G, bigPi=bigPi,
+                                      seed=seed, it=it)
+        assert rc == 0
+        st = g.sweep_mt1(schedule, R, G, bigPi, seed, it)
+        ga, gb, gd = g.get_state()
+        gy = g.get_ycorr()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(gb.view(np.uint32), be.view(np.uint32))
+        np.testing.assert_array_equal(gy.view(np.uint32), yc.view(np.uint32))
+        states = de[:p] + 2 * de[p:]
+        assert [st.class_counts[k] for k in range(4)] == np.bincount(states, minlength=4).tolist()
+        assert st.beta_ss[1] == canonical_sum_prod(be[:p], be[p:])
+        assert st.ycorr_ss[1] == canonical_sum_prod(yc[:n], yc[n:])
+    assert de.sum() > 0
+    g.close()
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.03])
+def test_mt_sampler1_exact(jw, oracle, missing):
+    prob = Problem(oracle, 403, 600, seed=41, missing=missing, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(600, 200), jw.SCHED_EXACT, nsweeps=3)
+
+
+@pytest.mark.parametrize("schedule_name", ["block", "independent"])
+def test_mt_sampler1_block_schedules(jw, oracle, schedule_name):
+    prob = Problem(oracle, 200, 70, seed=43, ntraits=2)
+    sched = jw.SCHED_BLOCK if schedule_name == "block" else jw.SCHED_INDEPENDENT
+    run_pair_mt(jw, oracle, prob, uniform_starts(70, 16), sched, nsweeps=2)
+
+
+def test_ycorr_lifecycle_and_accumulators(jw, oracle):
+    """ycorr init (MCMC_BayesianAlphabet.jl:131-147), intercept shift (:207-220), getEBV product
+    (output.jl:302) and the running posterior means (output.jl:568-577)."""
+    prob = Problem(oracle, 333, 210, seed=51, missing=0.02)
+    n, p = prob.n, prob.p
+    g = jw.GpuSweeper(prob.packed, n, 1)
+    g.set_blocks(uniform_starts(p, 64))
+    rng = np.random.default_rng(1)
+    alpha = np.where(rng.random(p) < 0.2, rng.normal(size=p), 0.0).astype(np.float32)
+    y = prob.ycorr0.copy()
+    g.put_ycorr(y); g.put_state(alpha, np.zeros(p, np.float32), (alpha != 0).astype(np.int32))
+    ebv = g.mul_alpha(0)
+    np.testing.assert_allclose(ebv, oracle.mul_alpha(prob.packed, n, prob.means, alpha), rtol=1e-5, atol=1e-5)
+    g.ycorr_sub_malpha()
+    np.testing.assert_allclose(g.get_ycorr(), y - ebv, rtol=1e-5, atol=1e-5)
+    s, ss = g.shift_ycorr(0, 0.25)
+    yy = g.get_ycorr()
+    assert ss == canonical_sum_prod(yy, yy)
+    assert s == canonical_sum_prod(yy, np.ones_like(yy))
+    # accumulators
+    ma = np.zeros(p, np.float32); ma2 = np.zeros(p, np.float32); md = np.zeros(p, np.float32)
+    for k in range(1, 4):
+        a = (alpha * k).astype(np.float32); d = (rng.random(p) < 0.5).astype(np.int32)
+        g.put_state(a, None, d)
+        g.accumulate(k)
+        ma = (ma.astype(np.float64) + (a.astype(np.float64) - ma) / k).astype(np.float32)
+        ma2 = (ma2.astype(np.float64) + (a.astype(np.float64) ** 2 - ma2) / k).astype(np.float32)
+        md = (md.astype(np.float64) + (d - md.astype(np.float64)) / k).astype(np.float32)
+    gma, gma2, gmd = g.get_means()
+    np.testing.assert_array_equal(gma, ma); np.testing.assert_array_equal(gma2, ma2); np.testing.assert_array_equal(gmd, md)
+    g.close()
+
+
+def test_error_behaviour(jw, oracle):
+    """error("...") -> ErrorException in the reference; non-zero rc + message here."""
+    prob = Problem(oracle, 40, 10, seed=61)
+    g = jw.GpuSweeper(prob.packed, 40, 1)
+    with pytest.raises(jw.JwasError, match="jwas_set_blocks must be called"):
+        g.sweep_bayesc(jw.SCHED_EXACT, 1.0, 1.0, 0.9, 1, 1)
+    for bad in ([1, 5, 10], [0, 5, 5, 10], [0, 7, 3, 10], [0, 5, 12]):   # test_misc_coverage.jl:195-208
+        with pytest.raises(jw.JwasError, match="fast_blocks"):
+            g.set_blocks(np.array(bad, dtype=np.int64))
+    g.set_blocks(np.array([0, 5, 10], dtype=np.int64))
+    with pytest.raises(jw.JwasError, match="BayesR pi must sum to 1"):
+        g.sweep_bayesr(jw.SCHED_EXACT, 1, 1.0, 1.0, np.array([0.5, 0.2, 0.2, 0.2]), GAMMA, 1, 1)
+    with pytest.raises(jw.JwasError, match="sigmaSq must be positive"):
+        g.sweep_bayesr(jw.SCHED_EXACT, 1, 1.0, 0.0, PI_R, GAMMA, 1, 1)
+    g.close()
+    with pytest.raises(jw.JwasError, match="Genotype data is empty"):
+        jw.GpuSweeper(np.zeros((0, 1), np.uint8), 0, 1)
+
+
+def test_full_size_invariants(jw, oracle):
+    """At a size the oracle cannot run in seconds, check size-independent properties: after K
+    sweeps ycorr + M*alpha reproduces the input (linearity of the fused updates), counts and
+    sums agree with the state that comes back, and the same seed reproduces the same bits."""
+    rng = np.random.default_rng(7)
+    n, p = 20000, 30000
+    f = rng.uniform(0.05, 0.5, size=p)
+    packed = np.zeros((p, (n + 3) // 4), np.uint8)
+    for k in range(4):
+        c = (rng.random((p, (n + 3) // 4)) < f[:, None]).astype(np.uint8) + (rng.random((p, (n + 3) // 4)) < f[:, None]).astype(np.uint8)
+        packed |= c << (2 * k)
+    y = rng.normal(size=n).astype(np.float32)
+    outs = []
+    for rep in range(2):
+        g = jw.GpuSweeper(packed, n, 1)
+        g.set_blocks(uniform_starts(p, 512))
+        g.put_ycorr(y)
+        for it in range(1, 4):
+            st = g.sweep_bayesc(jw.SCHED_EXACT, 0.5, 1e-4, 0.98, 2026, it)
+        a, b, d = g.get_state(); yc = g.get_ycorr()
+        assert st.sum_delta[0] == d.sum() and st.nnz_alpha[0] == np.count_nonzero(a)
+        assert np.array_equal(d != 0, a != 0)
+        recon = yc + g.mul_alpha(0)
+        np.testing.assert_allclose(recon, y, atol=5e-4)
+        outs.append((a.copy(), d.copy(), yc.copy()))
+        g.close()
+    for x, y2 in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(x, y2)
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.05])
+def test_gram_blocks_match_oracle(jw, oracle, missing):
+    # GibbsMats XpRinvX (tools4genotypes.jl:263): every block, bit for bit
+    prob = Problem(oracle, 517, 300, seed=71, missing=missing)
+    g = jw.GpuSweeper(prob.packed, 517, 1)
+    starts = np.array([0, 1, 70, 199, 300], dtype=np.int64)
+    g.set_blocks(starts)
+    for ib in range(4):
+        G = g.get_gram(ib)
+        ref = oracle.gram_block(prob.packed, 517, prob.means, int(starts[ib]), int(starts[ib + 1] - starts[ib]))
+        np.testing.assert_array_equal(G.view(np.uint32), ref.view(np.uint32))
+    g.close()
+
+
+def test_synthetic_generator_roundtrip(jw, oracle):
+    g = jw.GpuSweeper.synthetic(1001, 257, 1, seed=5, missing_rate=0.01)
+    packed = g.get_packed()
+    means, xpx = oracle.marker_stats(packed, 1001)
+    gm, gx = g.marker_stats()
+    np.testing.assert_array_equal(gm, means); np.testing.assert_array_equal(gx, xpx)
+    af = means / 2
+    assert 0.02 < af.min() and af.max() < 0.56
+    codes = np.array([[(packed[j, i >> 2] >> ((i & 3) << 1)) & 3 for j in range(257)] for i in range(1001)])
+    assert 0.003 < (codes == 3).mean() < 0.03
+    assert (packed[:, -1] >> 2).max() == 0      # padding individuals are code 0 (1001 = 4*250 + 1)
+    g.close()
