@@ -85,7 +85,7 @@ jw_k_gram(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n,
         for (int e = threadIdx.x; e < JW_GT * JW_GK; e += 256) {
             int r = e / JW_GK, c = e % JW_GK;
             int64_t w = w0 + c;
-            uint32_t va = 0, vb = 0;
+            uint32_t va = 0xffffffffu, vb = 0xffffffffu;   // out of range = missing: counts nothing
             if (w < nwords) {
                 if (a0 + r < b) va = __ldg(reinterpret_cast<const uint32_t*>(packed + (s + a0 + r) * stride_d) + w);
                 if (c0 + r < b) vb = __ldg(reinterpret_cast<const uint32_t*>(packed + (s + c0 + r) * stride_d) + w);

@@ -56,7 +56,6 @@ jw_k_block_dot(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, 
 #pragma unroll
             for (int k = 0; k < T; ++k) {
                 const int4* yp = reinterpret_cast<const int4*>(yq + k * n + i0);
-                int part = 0, mpart = 0;
                 bool al = ((k * n + i0) & 3) == 0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -66,7 +65,6 @@ jw_k_block_dot(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, 
                     uint32_t c0 = (v >> (8 * g)) & 3u, c1 = (v >> (8 * g + 2)) & 3u,
                              c2 = (v >> (8 * g + 4)) & 3u, c3 = (v >> (8 * g + 6)) & 3u;
                     if (MISSING) {
-                        mpart = 0;
                         long long m = 0;
                         if (c0 == 3u) { m += q.x; c0 = 0; }
                         if (c1 == 3u) { m += q.y; c1 = 0; }
@@ -78,7 +76,6 @@ jw_k_block_dot(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, 
                     long long s4 = (long long)((int)c0 * q.x) + (long long)((int)c1 * q.y)
                                  + (long long)((int)c2 * q.z) + (long long)((int)c3 * q.w);
                     acc[k] += s4;
-                    (void)part; (void)mpart;
                 }
             }
         } else {
@@ -339,7 +336,7 @@ jw_k_chain(jw_chain_args A) {
             if (lane == 0) s_wmin[warp] = wmin;
             __syncthreads();
             if (warp == 0) {
-                int v = s_wmin[lane];
+                int v = (lane < (int)(blockDim.x >> 5)) ? s_wmin[lane] : 0x7fffffff;
                 v = __reduce_min_sync(0xffffffffu, v);
                 if (lane == 0) s_first = v;
             }
@@ -391,7 +388,7 @@ jw_k_chain(jw_chain_args A) {
         __syncthreads();
         if (m == 0) {
             int acc = 0;
-            for (int w = 0; w < 32; ++w) { int c = s_cnt[w]; s_cnt[w] = acc; acc += c; }
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { int c = s_cnt[w]; s_cnt[w] = acc; acc += c; }
             s_cnt[32] = acc;
         }
         __syncthreads();
