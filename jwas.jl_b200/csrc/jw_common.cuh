@@ -89,6 +89,7 @@ struct jwas_handle {
     std::vector<cudaEvent_t> prof_events;
     double prof_ms = 0.0; int64_t prof_launches = 0;
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
+    void* fused = nullptr;         // jw_fused_state (engine 1)
     float next_maxabs = -1.0f;     // carried from the previous sweep's stats when ycorr untouched
 };
 

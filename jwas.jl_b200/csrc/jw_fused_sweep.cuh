@@ -1,11 +1,461 @@
-// jw_fused_sweep.cuh -- persistent fused sweep ("engine 1"); placeholder until the
-// persistent kernel lands: engine 0 (multi-kernel) is the only engine.
+// jw_fused_sweep.cuh -- "engine 1": the whole marker sweep as ONE persistent cooperative kernel.
+//
+// Every CTA owns a slice of individuals (rows of M) for the whole sweep.  Per block of markers:
+//   1. apply the previous block's delta-alpha to the slice of ycorr (fused axpy, BayesABC.jl:48/184),
+//      re-quantise it and rebuild a shared-memory lookup table: for each group of 4 individuals
+//      (= one packed byte) the 256 possible partial dot products  sum_k value(code_k) * yq_k;
+//   2. stream the block's packed genotypes (re-tiled so that a warp reads 512 contiguous bytes:
+//      lane = byte-group, 16 markers per 128-bit load) and turn every byte into ONE table lookup
+//      + ONE integer add -- 4 genotypes per lookup instead of 3+ instructions per genotype;
+//   3. reduce across lanes and add the exact int64 partial rhs into global memory with
+//      red.add.u64 (integer atomics commute: any CTA order gives the same bits);
+//   4. CTA 0 waits for all slices (release/acquire counter), runs the in-block Gibbs chain
+//      (jw_chain_block, shared with engine 0) and publishes the block's ordered active list.
+// No host round trip, no kernel boundary, ycorr never leaves L2 for the duration of the sweep.
+// Spin loops carry a time-out that raises a sticky abort flag instead of hanging the device.
 #pragma once
 #include "jw_common.cuh"
 #include "jw_sweep_kernels.cuh"
-static int jw_fused_prepare(jwas_handle*) { return 0; }
-static void jw_fused_free(jwas_handle*) {}
-static int jw_fused_sweep(jwas_handle*, const jw_chain_args&, float) {
-    jw_set_error("engine 1 (persistent fused sweep) is not built into this library");
-    return 2;
+#include <cooperative_groups.h>
+
+#define JW_FUSED_THREADS 1024
+#define JW_FUSED_MAX_GS 96          // 3 lookups per lane and marker keep the int32 partial < 2^31
+
+struct jw_fused_state {
+    uint8_t* d_tiled = nullptr;
+    int64_t* d_chunk_off = nullptr;  // nblocks+1, in 16-marker chunks
+    int32_t* d_chunk_block = nullptr;
+    int* d_arrive = nullptr;         // nblocks
+    int* d_done = nullptr;           // 1
+    long long* d_sq_acc = nullptr;   // nblocks * T
+    int32_t* d_act_cnt_blk = nullptr;// nblocks
+    int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1;
+    int64_t total_chunks = 0;
+    size_t smem = 0;
+    bool ready = false;
+};
+
+struct jw_fused_args {
+    jw_chain_args C;
+    const uint8_t* tiled;
+    const int64_t* chunk_off;
+    const uint8_t* packed; int64_t stride_d;
+    int Gs, TS, n_vs, nblocks;
+    float* ycorr; float scale;
+    int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
+    int32_t* flags;              // [0] overflow, [2] abort
+    long long* dq; long long* mq;
+};
+
+// ---- re-tiling: marker-major .jgb2 image -> [block][row slice][16-marker chunk][byte group][16] ----
+__global__ void __launch_bounds__(256)
+jw_k_tile(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t nbytes,
+          const int64_t* __restrict__ starts, const int64_t* __restrict__ chunk_off,
+          const int32_t* __restrict__ chunk_block, int64_t total_chunks, int Gs, int n_vs,
+          uint8_t* __restrict__ tiled) {
+    int64_t unit = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (gc, vs, g), g fastest
+    int64_t total = total_chunks * n_vs * Gs;
+    if (unit >= total) return;
+    int g = (int)(unit % Gs);
+    int64_t r = unit / Gs;
+    int vs = (int)(r % n_vs);
+    int64_t gc = r / n_vs;
+    int k = chunk_block[gc];
+    int64_t mc = gc - chunk_off[k];
+    int64_t nchunks = chunk_off[k + 1] - chunk_off[k];
+    int64_t s = starts[k], e = starts[k + 1];
+    int64_t byteidx = (int64_t)vs * Gs + g;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (byteidx < nbytes) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            int64_t j = s + mc * 16 + q;
+            if (j < e) w[q >> 2] |= (uint32_t)packed[j * stride_d + byteidx] << (8 * (q & 3));
+        }
+    }
+    size_t off = ((size_t)(chunk_off[k] * n_vs + (int64_t)vs * nchunks) * Gs + (size_t)(mc * Gs + g)) * 16;
+    *reinterpret_cast<uint4*>(tiled + off) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ int jw_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void jw_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long jw_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// thread-0 spin until *p >= target; false on time-out/abort
+__device__ __forceinline__ bool jw_spin_ge(const int* p, int target, int32_t* flags) {
+    unsigned long long t0 = jw_globaltimer();
+    unsigned it = 0;
+    while (jw_ld_acquire(p) < target) {
+        if ((++it & 1023u) == 0) {
+            if (jw_ld_acquire(&flags[2]) != 0) return false;
+            if (jw_globaltimer() - t0 > 20000000000ull) { atomicExch(&flags[2], 1); return false; }
+        }
+    }
+    return true;
+}
+
+// value a code contributes: component 0 = additive value (0,1,2,0); MISS component = indicator of 3
+__device__ __forceinline__ int jw_tabval(unsigned c, int y, bool miss_comp) {
+    if (miss_comp) return c == 3u ? y : 0;
+    return c == 3u ? 0 : (int)c * y;
+}
+
+template <int METHOD, int T, int W>
+__global__ void __launch_bounds__(JW_FUSED_THREADS, 1)
+jw_k_fused(jw_fused_args F) {
+    extern __shared__ __align__(16) int jw_smem[];
+    constexpr bool MISS = (T == 1 && W == 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = JW_FUSED_THREADS / 32;
+    const int Gs = F.Gs, TS = F.TS, R = Gs * 4;
+    int* tab = jw_smem;                    // [256][TS][W]
+    int* yqs = tab + 256 * TS * W;         // [T][R]
+    __shared__ long long s_red[32 * JW_MAX_TRAITS];
+    __shared__ int s_ok;
+    const int64_t n = F.C.n, p = F.C.p;
+    const bool single = F.n_vs <= (int)gridDim.x;
+    long long sq_keep[T];                  // thread 0: this CTA's sum of yq over its slice(s)
+#pragma unroll
+    for (int kk = 0; kk < T; ++kk) sq_keep[kk] = 0;
+
+    for (int k = 0; k < F.nblocks; ++k) {
+        int prev_cnt = 0;
+        if (k > 0) {
+            if (tid == 0) s_ok = jw_spin_ge(F.done, k, F.flags) ? 1 : 0;
+            __syncthreads();
+            if (!s_ok) return;
+            prev_cnt = __ldcg(&F.act_cnt_blk[k - 1]);
+        }
+        const int64_t s = F.C.starts[k];
+        const int b = (int)(F.C.starts[k + 1] - s);
+        const int nchunks = (b + 15) >> 4;
+        const int32_t* prev_idx = F.act_idx_all + (k > 0 ? F.C.starts[k - 1] : 0);
+        const bool rebuild = (k == 0) || prev_cnt > 0 || !single;
+        long long sq_blk[T];
+#pragma unroll
+        for (int kk = 0; kk < T; ++kk) sq_blk[kk] = 0;
+
+        for (int vs = blockIdx.x; vs < F.n_vs; vs += gridDim.x) {
+            const int64_t row0 = (int64_t)vs * R;
+            if (rebuild) {
+                // ---- (1) fused axpy of the previous block + fixed-point image of the slice ----
+                long long qs[T];
+#pragma unroll
+                for (int kk = 0; kk < T; ++kk) qs[kk] = 0;
+                if (tid < R) {
+                    const int64_t row = row0 + tid;
+                    const bool rv = row < n;
+                    float v[T];
+#pragma unroll
+                    for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
+                    if (rv && prev_cnt > 0) {
+                        const int sh = (int)(row & 3) << 1;
+                        const int64_t byte = row >> 2;
+                        for (int a = 0; a < prev_cnt; ++a) {
+                            const int64_t j = __ldcg(prev_idx + a);
+                            const unsigned code = (F.packed[j * F.stride_d + byte] >> sh) & 3u;
+                            const float mu = F.C.means[j];
+                            const float xv = (code == 3u ? mu : (float)code) - mu;
+#pragma unroll
+                            for (int kk = 0; kk < T; ++kk) {
+                                const float d = __ldcg(&F.C.dalpha[kk * p + j]);
+                                if (d != 0.0f) v[kk] = fmaf(d, xv, v[kk]);
+                            }
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < T; ++kk) F.ycorr[kk * n + row] = v[kk];
+                    }
+                    int ovf = 0;
+#pragma unroll
+                    for (int kk = 0; kk < T; ++kk) {
+                        const int q = rv ? jw_quantize(v[kk], F.scale, &ovf) : 0;
+                        yqs[kk * R + tid] = q;
+                        qs[kk] = q;
+                    }
+                    if (ovf) atomicOr(&F.flags[0], 1);
+                }
+#pragma unroll
+                for (int kk = 0; kk < T; ++kk) {
+                    long long v = qs[kk];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) s_red[warp * JW_MAX_TRAITS + kk] = v;
+                }
+                __syncthreads();
+                if (tid == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < T; ++kk) {
+                        long long v = 0;
+                        for (int w = 0; w < nwarps; ++w) v += s_red[w * JW_MAX_TRAITS + kk];
+                        if (single) sq_keep[kk] = v; else sq_blk[kk] += v;
+                    }
+                }
+                // ---- (2) lookup tables: entry e of group g = sum over its 4 individuals ----
+                for (int item = tid; item < Gs * 16; item += JW_FUSED_THREADS) {
+                    const int g = item % Gs, ehi = item / Gs;
+                    const unsigned c2 = ehi & 3, c3 = ehi >> 2;
+#pragma unroll
+                    for (int comp = 0; comp < W; ++comp) {
+                        const int tr = MISS ? 0 : comp;
+                        const bool mc_ = MISS && comp == 1;
+                        const int y0 = yqs[tr * R + 4 * g], y1 = yqs[tr * R + 4 * g + 1],
+                                  y2 = yqs[tr * R + 4 * g + 2], y3 = yqs[tr * R + 4 * g + 3];
+                        const int B = jw_tabval(c2, y2, mc_) + jw_tabval(c3, y3, mc_);
+#pragma unroll
+                        for (int elo = 0; elo < 16; ++elo) {
+                            const int val = jw_tabval(elo & 3, y0, mc_) + jw_tabval(elo >> 2, y1, mc_) + B;
+                            tab[((ehi * 16 + elo) * TS + g) * W + comp] = val;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // ---- (3) stream the block's genotypes: one lookup per byte (4 individuals) ----
+            const uint8_t* tile = F.tiled +
+                ((size_t)(F.chunk_off[k] * F.n_vs + (int64_t)vs * nchunks) * Gs) * 16;
+            for (int mc = warp; mc < nchunks; mc += nwarps) {
+                int acc[16][W];
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+#pragma unroll
+                    for (int comp = 0; comp < W; ++comp) acc[q][comp] = 0;
+                for (int g = lane; g < Gs; g += 32) {
+                    const uint4 d = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
+                    const int* tg = tab + g * W;
+                    const uint32_t wds[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const uint32_t byte = (wds[q >> 2] >> (8 * (q & 3))) & 0xffu;
+                        if (W == 1) {
+                            acc[q][0] += tg[byte * TS];
+                        } else {
+                            const int2 e2 = *reinterpret_cast<const int2*>(tg + byte * TS * 2);
+                            acc[q][0] += e2.x; acc[q][W - 1] += e2.y;
+                        }
+                    }
+                }
+                // transposed butterfly: 16 markers x 32 lanes -> marker (lane>>1)&15 on every lane
+#pragma unroll
+                for (int comp = 0; comp < W; ++comp) {
+                    long long vals[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) vals[q] = acc[q][comp];
+#pragma unroll
+                    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+                        const bool up = (lane & mask) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const long long keep = up ? vals[i + half] : vals[i];
+                            const long long send = up ? vals[i] : vals[i + half];
+                            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                        }
+                    }
+                    const long long tot = vals[0] + __shfl_xor_sync(0xffffffffu, vals[0], 1);
+                    const int q = (lane >> 1) & 15;
+                    const int jj = mc * 16 + q;
+                    if ((lane & 1) == 0 && jj < b && tot != 0) {
+                        long long* dst = (MISS && comp == 1) ? &F.mq[s + jj]
+                                                             : &F.dq[(int64_t)(MISS ? 0 : comp) * p + s + jj];
+                        atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)tot);
+                    }
+                }
+            }
+            if (!single) __syncthreads();       // the next slice overwrites the tables
+        }
+        // ---- (4) publish this CTA's contribution, then CTA 0 runs the chain ----
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int kk = 0; kk < T; ++kk) {
+                const long long v = single ? sq_keep[kk] : sq_blk[kk];
+                if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&F.sq_acc[k * T + kk]), (unsigned long long)v);
+            }
+            __threadfence();
+            atomicAdd(&F.arrive[k], 1);
+        }
+        if (blockIdx.x == 0) {
+            if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], (int)gridDim.x, F.flags) ? 1 : 0;
+            __syncthreads();
+            if (!s_ok) return;
+            jw_chain_args A = F.C;
+            A.sq = F.sq_acc + k * T;
+            A.act_idx = F.act_idx_all + s;
+            A.act_cnt = F.act_cnt_blk + k;
+            A.write_active_list = 1;
+            jw_chain_block<METHOD, T>(A, k);
+            __syncthreads();
+            if (tid == 0) { __threadfence(); jw_st_release(F.done, k + 1); }
+        }
+    }
+}
+
+// final axpy of the last block (the in-kernel apply always lags one block behind)
+template <int T>
+__global__ void __launch_bounds__(256)
+jw_k_apply_last(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
+                const float* __restrict__ means, const float* __restrict__ dalpha,
+                const int32_t* __restrict__ act_idx, const int32_t* __restrict__ act_cnt,
+                float* __restrict__ y) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = *act_cnt;
+    if (i >= n || cnt == 0) return;
+    float v[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) v[k] = y[k * n + i];
+    const int sh = (int)(i & 3) << 1;
+    const int64_t byte = i >> 2;
+    for (int a = 0; a < cnt; ++a) {
+        int64_t j = act_idx[a];
+        unsigned code = (packed[j * stride_d + byte] >> sh) & 3u;
+        float mu = means[j];
+        float xv = (code == 3u ? mu : (float)code) - mu;
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            float d = dalpha[k * p + j];
+            if (d != 0.0f) v[k] = fmaf(d, xv, v[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) y[k * n + i] = v[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static void jw_fused_free(jwas_handle* h) {
+    jw_fused_state* f = (jw_fused_state*)h->fused;
+    if (!f) return;
+    void* ptrs[] = {f->d_tiled, f->d_chunk_off, f->d_chunk_block, f->d_arrive, f->d_done, f->d_sq_acc, f->d_act_cnt_blk};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete f;
+    h->fused = nullptr;
+}
+
+static bool jw_fused_supported(const jwas_handle* h) {
+    if (h->t == 1) return true;
+    if (h->t == 2 && !h->has_missing) return true;
+    return false;
+}
+
+static int jw_fused_prepare(jwas_handle* h) {
+    jw_fused_free(h);
+    if (!jw_fused_supported(h)) return 0;
+    jw_fused_state* f = new jw_fused_state();
+    h->fused = f;
+    const int64_t nbytes = (h->n + 3) / 4;
+    f->W = (h->t == 2 || h->has_missing) ? 2 : 1;
+    int64_t gs = (nbytes + h->sm_count - 1) / h->sm_count;
+    if (gs > JW_FUSED_MAX_GS) gs = JW_FUSED_MAX_GS;
+    if (gs < 1) gs = 1;
+    f->Gs = (int)gs;
+    f->TS = (int)((gs + 31) / 32 * 32);
+    f->n_vs = (int)((nbytes + gs - 1) / gs);
+    f->n_cta = std::min<int>(h->sm_count, f->n_vs);
+    f->smem = (size_t)256 * f->TS * f->W * 4 + (size_t)h->t * f->Gs * 4 * 4;
+    std::vector<int64_t> coff(h->nblocks + 1, 0);
+    std::vector<int32_t> cblk;
+    for (int64_t k = 0; k < h->nblocks; ++k) {
+        int64_t nc = (h->starts[k + 1] - h->starts[k] + 15) / 16;
+        coff[k + 1] = coff[k] + nc;
+        for (int64_t c = 0; c < nc; ++c) cblk.push_back((int32_t)k);
+    }
+    f->total_chunks = coff[h->nblocks];
+    size_t tiled_bytes = (size_t)f->total_chunks * f->n_vs * f->Gs * 16;
+    JW_CUDA(cudaMalloc((void**)&f->d_tiled, tiled_bytes));
+    JW_CUDA(cudaMalloc((void**)&f->d_chunk_off, coff.size() * sizeof(int64_t)));
+    JW_CUDA(cudaMalloc((void**)&f->d_chunk_block, cblk.size() * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&f->d_arrive, h->nblocks * sizeof(int)));
+    JW_CUDA(cudaMalloc((void**)&f->d_done, sizeof(int)));
+    JW_CUDA(cudaMalloc((void**)&f->d_sq_acc, (size_t)h->nblocks * h->t * sizeof(long long)));
+    JW_CUDA(cudaMalloc((void**)&f->d_act_cnt_blk, h->nblocks * sizeof(int32_t)));
+    JW_CUDA(cudaMemcpyAsync(f->d_chunk_off, coff.data(), coff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(f->d_chunk_block, cblk.data(), cblk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int64_t units = f->total_chunks * f->n_vs * f->Gs;
+    jw_k_tile<<<(unsigned)((units + 255) / 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, nbytes, h->d_starts,
+        f->d_chunk_off, f->d_chunk_block, f->total_chunks, f->Gs, f->n_vs, f->d_tiled);
+    h->launches += 1;
+    JW_CUDA(cudaGetLastError());
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    f->ready = true;
+    return 0;
+}
+
+template <int METHOD, int T, int W>
+static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
+    auto kern = jw_k_fused<METHOD, T, W>;
+    JW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
+    int occ = 0;
+    JW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JW_FUSED_THREADS, f->smem));
+    JW_REQUIRE(occ >= 1, "fused sweep kernel does not fit on an SM");
+    void* args[] = {(void*)&F};
+    JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(f->n_cta), dim3(JW_FUSED_THREADS), args, f->smem, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
+    jw_fused_state* f = (jw_fused_state*)h->fused;
+    JW_REQUIRE(f && f->ready, "engine 1 (persistent fused sweep) does not support this trait/missing combination");
+    const int t = h->t;
+    JW_CUDA(cudaMemsetAsync(h->d_dq, 0, (size_t)t * h->p * sizeof(long long), h->stream));
+    if (h->has_missing) JW_CUDA(cudaMemsetAsync(h->d_mq, 0, (size_t)t * h->p * sizeof(long long), h->stream));
+    JW_CUDA(cudaMemsetAsync(f->d_arrive, 0, h->nblocks * sizeof(int), h->stream));
+    JW_CUDA(cudaMemsetAsync(f->d_done, 0, sizeof(int), h->stream));
+    JW_CUDA(cudaMemsetAsync(f->d_sq_acc, 0, (size_t)h->nblocks * t * sizeof(long long), h->stream));
+    JW_CUDA(cudaMemsetAsync(f->d_act_cnt_blk, 0, h->nblocks * sizeof(int32_t), h->stream));
+    JW_CUDA(cudaMemsetAsync(h->d_flags + 2, 0, sizeof(int32_t), h->stream));
+    jw_fused_args F;
+    F.C = A;
+    F.tiled = f->d_tiled; F.chunk_off = f->d_chunk_off;
+    F.packed = h->d_packed; F.stride_d = h->stride_d;
+    F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks;
+    F.ycorr = h->d_ycorr; F.scale = scale;
+    F.arrive = f->d_arrive; F.done = f->d_done; F.sq_acc = f->d_sq_acc;
+    F.act_cnt_blk = f->d_act_cnt_blk; F.act_idx_all = h->d_act_idx;
+    F.flags = h->d_flags; F.dq = h->d_dq; F.mq = h->d_mq;
+    if (h->opt_profile) {
+        cudaEvent_t a, b;
+        JW_CUDA(cudaEventCreate(&a)); JW_CUDA(cudaEventCreate(&b));
+        h->prof_events.push_back(a); h->prof_events.push_back(b);
+        JW_CUDA(cudaEventRecord(a, h->stream));
+    }
+    int rc = 2;
+    const bool ms = h->has_missing != 0;
+    if (t == 1 && !ms) {
+        if (A.method == 0) rc = jw_fused_launch<0, 1, 1>(h, f, F);
+        else if (A.method == 1) rc = jw_fused_launch<1, 1, 1>(h, f, F);
+    } else if (t == 1 && ms) {
+        if (A.method == 0) rc = jw_fused_launch<0, 1, 2>(h, f, F);
+        else if (A.method == 1) rc = jw_fused_launch<1, 1, 2>(h, f, F);
+    } else if (t == 2 && !ms && A.method == 2) {
+        rc = jw_fused_launch<2, 2, 2>(h, f, F);
+    }
+    if (rc == 2) jw_set_error("engine 1: unsupported (method, traits, missing) combination");
+    if (rc) return rc;
+    if (h->opt_profile) JW_CUDA(cudaEventRecord(h->prof_events.back(), h->stream));
+    // the last block's axpy
+    const int64_t last = h->nblocks - 1;
+    unsigned g = (unsigned)((h->n + 255) / 256);
+    if (t == 1)
+        jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+            h->d_act_idx + h->starts[last], f->d_act_cnt_blk + last, h->d_ycorr);
+    else
+        jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+            h->d_act_idx + h->starts[last], f->d_act_cnt_blk + last, h->d_ycorr);
+    h->launches += 1;
+    JW_CUDA(cudaGetLastError());
+    // abort flag -> error
+    int32_t hf[4];
+    JW_CUDA(cudaMemcpyAsync(hf, h->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    if (hf[2]) { jw_set_error("engine 1: inter-CTA wait timed out (sweep aborted)"); return 12; }
+    return 0;
 }

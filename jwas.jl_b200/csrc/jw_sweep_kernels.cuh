@@ -169,14 +169,12 @@ __device__ __forceinline__ int jw_categorical(const double* probs, int k, double
 }
 
 template <int METHOD, int T>
-__global__ void __launch_bounds__(JW_MAX_BLOCK)
-jw_k_chain(jw_chain_args A) {
+__device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int ib) {
     __shared__ int s_wmin[32];
     __shared__ int s_first;
     __shared__ float s_d[JW_MAX_TRAITS];
     __shared__ int s_cnt[33];
 
-    const int ib = A.block0 + blockIdx.x;
     const int64_t s = A.starts[ib];
     const int b = (int)(A.starts[ib + 1] - s);
     const int m = threadIdx.x;
@@ -193,9 +191,10 @@ jw_k_chain(jw_chain_args A) {
     int d_cur[T];
 #pragma unroll
     for (int k = 0; k < T; ++k) {
-        long long dq = A.dq[k * p + j], mq = A.mq ? A.mq[k * p + j] : 0ll;
+        // .cg loads: these words were produced by other CTAs' atomics in the fused engine
+        long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
         double mu = (double)A.means[j];
-        r[k] = ((double)dq - mu * (double)(A.sq[k] - mq)) * A.invscale;
+        r[k] = ((double)dq - mu * (double)(__ldcg(&A.sq[k]) - mq)) * A.invscale;
         a_entry[k] = a_cur[k] = A.alpha[k * p + j];
         b_cur[k] = (METHOD == 1) ? 0.0f : A.beta[k * p + j];
         d_cur[k] = A.delta[k * p + j];
@@ -399,6 +398,12 @@ jw_k_chain(jw_chain_args A) {
         if (my_active) atomicAdd(&A.counters[0], my_active);
         if (my_rounds) atomicAdd(&A.counters[1], my_rounds);
     }
+}
+
+template <int METHOD, int T>
+__global__ void __launch_bounds__(JW_MAX_BLOCK)
+jw_k_chain(jw_chain_args A) {
+    jw_chain_block<METHOD, T>(A, A.block0 + (int)blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------

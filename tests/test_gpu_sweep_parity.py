@@ -96,10 +96,11 @@ def test_bayesc_block_schedules(jw, oracle, schedule_name, missing):
     run_pair_abc(jw, oracle, prob, starts, sched, nsweeps=3, replay=(schedule_name == "block"))
 
 
-def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3):
+def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
+    g.set_option("engine", engine)
     yc, al, be, de = prob.fresh_state()
     de[:] = 1
     g.put_ycorr(yc); g.put_state(al, be, de)
@@ -141,10 +142,11 @@ def test_bayesr_block_schedules(jw, oracle, schedule_name, full_reps):
     run_pair_r(jw, oracle, prob, uniform_starts(90, 17), sched, full_reps, nsweeps=3)
 
 
-def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9):
+def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0):
     n, p, t = prob.n, prob.p, prob.t
     g = jw.GpuSweeper(prob.packed, n, t)
     g.set_blocks(starts)
+    g.set_option("engine", engine)
     yc, al, be, de = prob.fresh_state()
     g.put_ycorr(yc); g.put_state(al, be, de)
     R = np.array([[1.0, 0.3], [0.3, 1.2]]) * prob.vary * 0.5
@@ -293,3 +295,32 @@ def test_synthetic_generator_roundtrip(jw, oracle):
     assert 0.003 < (codes == 3).mean() < 0.03
     assert (packed[:, -1] >> 2).max() == 0      # padding individuals are code 0 (1001 = 4*250 + 1)
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# engine 1: the persistent fused kernel must give the same bits as the oracle (and engine 0)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("missing", [0.0, 0.03])
+@pytest.mark.parametrize("n,p,b", [(500, 2000, 256), (501, 333, 64), (67, 50, 1), (1030, 700, 700),
+                                   (60013, 150, 64)])
+def test_fused_bayesc_exact(jw, oracle, n, p, b, missing):
+    # (60013, ...) needs more row slices than SMs: exercises the multi-slice path
+    prob = Problem(oracle, n, p, seed=n + p + 1, missing=missing)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1)
+
+
+def test_fused_bayesc_block_schedule(jw, oracle):
+    prob = Problem(oracle, 400, 157, seed=22, missing=0.02)
+    starts = np.array([0, 20, 21, 60, 100, 157], dtype=np.int64)
+    run_pair_abc(jw, oracle, prob, starts, jw.SCHED_BLOCK, nsweeps=2, engine=1)
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.03])
+def test_fused_bayesr(jw, oracle, missing):
+    prob = Problem(oracle, 700, 900, seed=35, missing=missing)
+    run_pair_r(jw, oracle, prob, uniform_starts(900, 256), jw.SCHED_EXACT, 1, nsweeps=3, engine=1)
+
+
+def test_fused_mt_sampler1(jw, oracle):
+    prob = Problem(oracle, 803, 500, seed=45, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(500, 128), jw.SCHED_EXACT, nsweeps=3, engine=1)
