@@ -183,7 +183,10 @@ class GpuSweeper:
     def ycorr_sub_malpha(self):
         _check(lib().jwas_ycorr_sub_malpha(self._h))
 
-    def shift_ycorr(self, trait, shift):
+    def shift_ycorr(self, trait, shift, want=True):
+        if not want:
+            _check(lib().jwas_shift_ycorr(self._h, trait, float(shift), None, None))
+            return None
         s, ss = C.c_double(), C.c_double()
         _check(lib().jwas_shift_ycorr(self._h, trait, float(shift), C.byref(s), C.byref(ss)))
         return s.value, ss.value

@@ -511,6 +511,16 @@ jw_k_chunk_prod(const float* __restrict__ a, const float* __restrict__ b, int64_
     for (int64_t i = beg; i < end; ++i) s += (double)a[i] * (double)b[i];
     partials[c] = s;
 }
+__global__ void __launch_bounds__(128)
+jw_k_chunk_sum(const float* __restrict__ a, int64_t n, double* __restrict__ partials) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t beg = c * JW_CHUNK;
+    if (beg >= n) return;
+    int64_t end = min(beg + JW_CHUNK, n);
+    double s = 0.0;
+    for (int64_t i = beg; i < end; ++i) s += (double)a[i];
+    partials[c] = s;
+}
 __global__ void jw_k_chunk_final(const double* __restrict__ partials, int64_t nchunks, double* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = 0.0;

@@ -340,6 +340,16 @@ static int canonical_dot(jwas_handle* h, const float* a, const float* b, int64_t
     return 0;
 }
 
+static int canonical_sum(jwas_handle* h, const float* a, int64_t n, double* d_out) {
+    int64_t nchunks = ceil_div(n, JW_CHUNK);
+    if (ensure_cap(&h->d_partials, &h->cap_partials, (size_t)nchunks)) return 10;
+    jw_k_chunk_sum<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(a, n, h->d_partials);
+    JW_LAUNCH_CHECK(h);
+    jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, d_out);
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+
 extern "C" int jwas_shift_ycorr(jwas_handle* h, int trait, float shift, double* sum, double* sumsq) {
     JW_REQUIRE(h, "null handle");
     JW_REQUIRE(trait >= 0 && trait < h->t, "jwas_shift_ycorr: trait out of range");
@@ -350,22 +360,10 @@ extern "C" int jwas_shift_ycorr(jwas_handle* h, int trait, float shift, double* 
         JW_LAUNCH_CHECK(h);
         h->next_maxabs = -1.0f;
     }
-    // sum(y) = canonical dot with a vector of ones is avoided: use y*y and y*1 via two passes
     double host[2] = {0, 0};
+    if (!sum && !sumsq) { JW_CUDA(cudaStreamSynchronize(h->stream)); return 0; }
     if (sumsq) { if (canonical_dot(h, y, y, h->n, h->d_stats)) return 10; }
-    if (sum) {
-        // ones vector: reuse d_dalpha region? keep it simple and exact: chunked sum kernel on (y, 1)
-        float* ones = (float*)h->d_yq;
-        JW_CUDA(cudaMemsetAsync(ones, 0, h->n * sizeof(float), h->stream));
-        jw_k_shift<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(ones, h->n, 1.0f);
-        JW_LAUNCH_CHECK(h);
-        // canonical_dot overwrites d_partials; run after sumsq finished (same stream -> ordered)
-        int64_t nchunks = ceil_div(h->n, JW_CHUNK);
-        jw_k_chunk_prod<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(y, ones, h->n, h->d_partials);
-        JW_LAUNCH_CHECK(h);
-        jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, h->d_stats + 1);
-        JW_LAUNCH_CHECK(h);
-    }
+    if (sum) { if (canonical_sum(h, y, h->n, h->d_stats + 1)) return 10; }
     JW_CUDA(cudaMemcpyAsync(host, h->d_stats, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaStreamSynchronize(h->stream));
     if (sumsq) *sumsq = host[0];
@@ -461,6 +459,8 @@ static int collect_stats(jwas_handle* h, const sweep_cfg& c, int S, jwas_sweep_s
             if (c.method != 1)
                 if (canonical_dot(h, h->d_beta + (size_t)a * h->p, h->d_beta + (size_t)b * h->p, h->p, h->d_stats + 32 + a * t + b)) return 10;
         }
+    for (int a = 0; a < t; ++a)
+        if (canonical_sum(h, h->d_ycorr + (size_t)a * h->n, h->n, h->d_stats + 49 + a)) return 10;
     if (c.method == 1) {
         int64_t nchunks = ceil_div(h->p, JW_CHUNK);
         if (ensure_cap(&h->d_partials, &h->cap_partials, (size_t)nchunks)) return 10;
@@ -477,7 +477,7 @@ static int collect_stats(jwas_handle* h, const sweep_cfg& c, int S, jwas_sweep_s
     jw_k_maxabs<<<64, 256, 0, h->stream>>>(h->d_ycorr, (int64_t)t * h->n, (unsigned*)h->d_maxabs);
     JW_LAUNCH_CHECK(h);
 
-    double hs[49]; unsigned long long hc[28]; int32_t hf[4]; float hm;
+    double hs[53]; unsigned long long hc[28]; int32_t hf[4]; float hm;
     JW_CUDA(cudaMemcpyAsync(hs, h->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaMemcpyAsync(hc, h->d_counters, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaMemcpyAsync(hf, h->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
@@ -495,6 +495,7 @@ static int collect_stats(jwas_handle* h, const sweep_cfg& c, int S, jwas_sweep_s
             st->beta_ss[a * t + b] = st->beta_ss[b * t + a] = hs[32 + a * t + b];
         }
     st->bayesr_ssq = hs[48];
+    for (int a = 0; a < t; ++a) st->ycorr_sum[a] = hs[49 + a];
     st->n_active = (int64_t)hc[0]; st->n_rounds = (int64_t)hc[1];
     for (int k = 0; k < t; ++k) { st->nnz_alpha[k] = (double)hc[4 + k]; st->sum_delta[k] = (double)hc[8 + k]; }
     for (int q = 0; q < 16; ++q) st->class_counts[q] = (double)hc[12 + q];

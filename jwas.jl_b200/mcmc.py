@@ -1,0 +1,208 @@
+"""Chain driver for the marker-effects path: the part of MCMC_BayesianAlphabet
+(MCMC/MCMC_BayesianAlphabet.jl:184-421) that surrounds the sweep -- intercept update,
+pi / sigma^2_alpha / sigma^2_e draws and posterior accumulation -- written against an abstract
+sweep backend so that tests can drive the identical host logic with the CPU oracle.
+
+The product only ever instantiates GpuBackend (below); nothing here imports the oracle.
+"""
+import math
+
+import numpy as np
+
+from ._lib import GpuSweeper, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT
+
+BAYESR_GAMMA = np.array([0.0, 0.01, 0.1, 1.0])      # JWAS.jl:12
+
+
+class HostRng:
+    """Host-side draws for the O(1) hyper-parameter updates (the reference uses Distributions.jl:
+    Chisq, Beta, Dirichlet, InverseWishart -- variance_components.jl, Pi.jl)."""
+
+    def __init__(self, seed):
+        self.g = np.random.Generator(np.random.Philox(seed))
+
+    def chisq(self, df):
+        return float(self.g.chisquare(df))
+
+    def beta(self, a, b):
+        return float(self.g.beta(a, b))
+
+    def dirichlet(self, a):
+        return self.g.dirichlet(np.asarray(a, dtype=np.float64))
+
+    def normal(self):
+        return float(self.g.standard_normal())
+
+    def inverse_wishart(self, df, scale):
+        """InverseWishart(df, scale) via Bartlett; scale is the sum-of-squares matrix."""
+        scale = np.asarray(scale, dtype=np.float64)
+        t = scale.shape[0]
+        L = np.linalg.cholesky(np.linalg.inv(scale))
+        A = np.zeros((t, t))
+        for i in range(t):
+            A[i, i] = math.sqrt(self.g.chisquare(df - i))
+            for j in range(i):
+                A[i, j] = self.g.standard_normal()
+        LA = L @ A
+        return np.linalg.inv(LA @ LA.T)
+
+
+class GpuBackend:
+    """Sweep backend = the CUDA library.  Holds M, ycorr, alpha/beta/delta on the device."""
+
+    name = "b200"
+
+    def __init__(self, sweeper: GpuSweeper):
+        self.s = sweeper
+
+    # ycorr lifecycle
+    def put_ycorr(self, y):
+        self.s.put_ycorr(y)
+
+    def get_ycorr(self):
+        return self.s.get_ycorr()
+
+    def shift_ycorr(self, trait, shift):
+        self.s.shift_ycorr(trait, shift, want=False)
+
+    def ycorr_sum(self, trait):
+        return self.s.shift_ycorr(trait, 0.0)[0]
+
+    def put_state(self, alpha, beta, delta):
+        self.s.put_state(alpha, beta, delta)
+
+    def get_state(self):
+        return self.s.get_state()
+
+    def sub_malpha(self):
+        self.s.ycorr_sub_malpha()
+
+    # sweeps return a dict of the reductions the hyper-parameter draws need
+    @staticmethod
+    def _stats(st, t):
+        return {
+            "ycorr_ss": np.array(st.ycorr_ss[:t * t]).reshape(t, t),
+            "alpha_ss": np.array(st.alpha_ss[:t * t]).reshape(t, t),
+            "beta_ss": np.array(st.beta_ss[:t * t]).reshape(t, t),
+            "ycorr_sum": np.array(st.ycorr_sum[:t]),
+            "nnz_alpha": np.array(st.nnz_alpha[:t]), "sum_delta": np.array(st.sum_delta[:t]),
+            "class_counts": np.array(st.class_counts[:16]), "bayesr_ssq": st.bayesr_ssq,
+            "n_active": st.n_active, "n_rounds": st.n_rounds,
+        }
+
+    def sweep_bayesc(self, schedule, vare, var_effect, pi, seed, it):
+        return self._stats(self.s.sweep_bayesc(schedule, vare, var_effect, pi, seed, it), 1)
+
+    def sweep_bayesabc(self, schedule, vare, var_effects, pi, seed, it):
+        return self._stats(self.s.sweep_bayesabc(schedule, vare, var_effects, pi, seed, it), 1)
+
+    def sweep_bayesr(self, schedule, full_reps, vare, sigma_sq, pi, gamma, seed, it):
+        return self._stats(self.s.sweep_bayesr(schedule, full_reps, vare, sigma_sq, pi, gamma, seed, it), 1)
+
+    def sweep_mt1(self, schedule, R, G, big_pi, seed, it):
+        return self._stats(self.s.sweep_mt1(schedule, R, G, big_pi, seed, it), self.s.t)
+
+    def sample_bayesb_variances(self, df, scale, seed, it):
+        self.s.sample_bayesb_variances(df, scale, seed, it)
+
+    def accumulate(self, nsamples, bayesr=False):
+        self.s.accumulate(nsamples, bayesr)
+
+    def get_means(self):
+        return self.s.get_means()
+
+
+def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin, output_samples_frequency,
+              seed, vare, var_effect, pi, df_effect, scale_effect, df_res, scale_res,
+              estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
+              R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
+              mu0=None, iter0=0):
+    """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
+
+    Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
+      [1] intercept Gibbs (:207-220, solver.jl:143-151)  [2] marker sweep (:224-290)
+      [3] pi (:294-317, Pi.jl)  [4] marker variance (:321-326, variance_components.jl:151-189)
+      [5] residual variance (:355-371)  [6] posterior means every saved iteration (:399-413).
+    Float32 re-casts of the variances follow :323-325, :368-370.
+    """
+    rng = HostRng([seed, iter0])
+    t = ntraits
+    mu = np.zeros(t) if mu0 is None else np.array(mu0, dtype=np.float64)
+    out = {"mu_mean": np.zeros(t), "vare_mean": 0.0, "vara_mean": 0.0, "pi_mean": 0.0, "nsamples": 0,
+           "trace": []}
+    if method == "BayesR":
+        pi = np.array(pi, dtype=np.float64)
+        out["pi_mean"] = np.zeros_like(pi)
+    if t > 1:
+        R = np.array(R, dtype=np.float64); G = np.array(G, dtype=np.float64)
+        big_pi = np.array(big_pi, dtype=np.float64)
+        out["vare_mean"] = np.zeros((t, t)); out["vara_mean"] = np.zeros((t, t)); out["pi_mean"] = np.zeros_like(big_pi)
+    nsamples = 0
+    ysum = None
+    for it in range(iter0 + 1, iter0 + chain_length + 1):
+        # [1] intercept: ycorr += mu; mu ~ N(mean(ycorr), vare/n); ycorr -= mu
+        if sample_intercept:
+            for k in range(t):
+                s = ysum[k] if ysum is not None else backend.ycorr_sum(k)
+                vk = vare if t == 1 else R[k, k]
+                mu_hat = mu[k] + s / n
+                new_mu = mu_hat + rng.normal() * math.sqrt(vk / n)
+                backend.shift_ycorr(k, np.float32(mu[k] - new_mu))
+                mu[k] = new_mu
+        # [2] marker effects
+        if method in ("BayesC", "BayesB", "BayesA"):
+            if t == 1:
+                if method == "BayesC":
+                    st = backend.sweep_bayesc(schedule, vare, var_effect, pi, seed, it)
+                else:
+                    st = backend.sweep_bayesabc(schedule, vare, None, None, seed, it)
+            else:
+                st = backend.sweep_mt1(schedule, R, G, big_pi, seed, it)
+        elif method == "BayesR":
+            full = 1 if it > burnin else 0          # bayesr_block_nreps, BayesR.jl:22-25
+            st = backend.sweep_bayesr(schedule, full, vare, var_effect, pi, BAYESR_GAMMA, seed, it)
+        else:
+            raise ValueError(method)
+        # [3] pi
+        if estimate_pi:
+            if t == 1 and method == "BayesR":
+                pi = rng.dirichlet(st["class_counts"][:len(pi)] + 1.0)          # Pi.jl:11-17
+            elif t == 1:
+                k_in = st["sum_delta"][0]
+                pi = rng.beta(p - k_in + 1, k_in + 1)                            # Pi.jl:7-9
+            else:
+                big_pi = rng.dirichlet(st["class_counts"][:1 << t] + 1.0)        # Pi.jl:20-42
+        # [4] marker effect variance
+        if estimate_variance:
+            if t == 1 and method == "BayesC":
+                k_in = st["sum_delta"][0]
+                var_effect = float(np.float32((st["alpha_ss"][0, 0] + df_effect * scale_effect)
+                                              / rng.chisq(k_in + df_effect)))   # variance_components.jl:160-162
+            elif t == 1 and method == "BayesR":
+                var_effect = float(np.float32((st["bayesr_ssq"] + df_effect * scale_effect)
+                                              / rng.chisq(st["sum_delta"][0] + df_effect)))  # :166-168
+            elif t == 1:
+                backend.sample_bayesb_variances(df_effect, scale_effect, seed, it)  # :169-172
+            else:
+                G = rng.inverse_wishart(df_effect + p, scale_G + st["beta_ss"]).astype(np.float32).astype(np.float64)
+        # [5] residual variance
+        if estimate_vare:
+            if t == 1:
+                vare = float(np.float32((st["ycorr_ss"][0, 0] + df_res * scale_res) / rng.chisq(n + df_res)))
+            else:
+                R = rng.inverse_wishart(df_res + n, scale_R + st["ycorr_ss"]).astype(np.float32).astype(np.float64)
+        ysum = st["ycorr_sum"]
+        out["trace"].append((it, float(st["sum_delta"][0]), st["n_active"], st["n_rounds"]))
+        # [6] posterior means
+        if it > burnin and (it - burnin) % output_samples_frequency == 0:
+            nsamples += 1
+            backend.accumulate(nsamples, bayesr=(method == "BayesR"))
+            out["mu_mean"] += (mu - out["mu_mean"]) / nsamples
+            out["vare_mean"] = out["vare_mean"] + ((vare if t == 1 else R) - out["vare_mean"]) / nsamples
+            if method != "BayesB" and method != "BayesA":
+                out["vara_mean"] = out["vara_mean"] + ((var_effect if t == 1 else G) - out["vara_mean"]) / nsamples
+            if estimate_pi:
+                out["pi_mean"] = out["pi_mean"] + ((pi if t == 1 else big_pi) - out["pi_mean"]) / nsamples
+    out.update(nsamples=nsamples, mu=mu, vare=vare if t == 1 else R, var_effect=var_effect if t == 1 else G,
+               pi=pi if t == 1 else big_pi)
+    return out
