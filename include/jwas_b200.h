@@ -142,6 +142,9 @@ double jwas_last_sweep_ms(jwas_handle* h);
 /* device time (ms, CUDA events on the handle's stream) and launch count of the dominant
  * genotype-streaming kernel(s) of the last sweep; needs jwas_set_option(h,"profile",1) */
 double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches);
+/* engine 1 phase timers of the last sweep, nanoseconds: out[0..4] = CTA 0 {wait previous chain,
+ * axpy+quantise+tables, stream, wait for all slices, chain}; out[8..12] = CTA 1, same phases */
+int jwas_get_phase_ns(jwas_handle* h, uint64_t* out16);
 /* raw CUDA stream of the handle (cudaStream_t) so callers can time on it */
 void* jwas_stream(jwas_handle* h);
 

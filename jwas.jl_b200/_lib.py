@@ -45,6 +45,7 @@ def lib():
         "jwas_get_packed": [vp, vp, i64],
         "jwas_get_gram": [vp, i64, vp],
         "jwas_last_stream_kernel_ms": [vp, C.POINTER(i64)],
+        "jwas_get_phase_ns": [vp, vp],
         "jwas_destroy": [vp],
         "jwas_device_count": [],
         "jwas_get_marker_stats": [vp, vp, vp],
@@ -241,6 +242,11 @@ class GpuSweeper:
         ma = np.empty(tp, np.float32); ma2 = np.empty(tp, np.float32); md = np.empty(tp, np.float32)
         _check(lib().jwas_get_means(self._h, _p(ma), _p(ma2), _p(md)))
         return ma, ma2, md
+
+    def phase_ns(self):
+        out = np.zeros(16, np.uint64)
+        _check(lib().jwas_get_phase_ns(self._h, _p(out)))
+        return out
 
     # -- introspection
     @property

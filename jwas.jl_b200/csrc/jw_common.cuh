@@ -57,6 +57,8 @@ struct jwas_handle {
     // hyper-parameter vectors resident on the device
     double* d_ve = nullptr;        // p (or p*t*t for per-marker G)
     double* d_pi = nullptr;        // p  (BayesR per-marker: p*nclasses; MT per-marker: p*2^t)
+    double* d_prep = nullptr;      // 6*p chain constants (BayesABC, repetition 0)
+    float* d_prep_beta0 = nullptr; // p
     double* d_u = nullptr;         // replay tables (allocated on demand)
     double* d_z = nullptr;
     size_t cap_ve = 0, cap_pi = 0, cap_u = 0, cap_z = 0;

@@ -85,6 +85,11 @@ __device__ __forceinline__ int jw_ld_acquire(const int* p) {
 __device__ __forceinline__ void jw_st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+// asynchronous HBM -> L2 prefetch of a contiguous region (TMA bulk prefetch, no SM involvement
+// after issue); bytes must be a multiple of 16
+__device__ __forceinline__ void jw_prefetch_l2(const void* ptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(ptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned long long jw_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -109,6 +114,17 @@ __device__ __forceinline__ int jw_tabval(unsigned c, int y, bool miss_comp) {
     return c == 3u ? 0 : (int)c * y;
 }
 
+// Lookup-table layout.  Entry e of byte-group g (g = gb*32 + l) lives at byte offset
+//   e*256 + sub(gb) + l*4*W (+4 for the second component):
+// every table row is 256 bytes, so (byte << 8) | lane_offset is ONE byte-permute of the packed word,
+// and the 32 lanes of a warp always hit 32 different banks (conflict-free by construction).
+//   W=1: sub = {0, 128, 65536}   (128 KB)        W=2: sub = {0, 65536, 131072}   (192 KB)
+template <int W>
+__host__ __device__ __forceinline__ constexpr int jw_tab_sub(int gb) {
+    return W == 1 ? (gb == 0 ? 0 : (gb == 1 ? 128 : 65536)) : gb * 65536;
+}
+#define JW_TAB_BYTES(W_) ((W_) == 1 ? 2 * 65536 : 3 * 65536)
+
 template <int METHOD, int T, int W>
 __global__ void __launch_bounds__(JW_FUSED_THREADS, 1)
 jw_k_fused(jw_fused_args F) {
@@ -117,12 +133,19 @@ jw_k_fused(jw_fused_args F) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = JW_FUSED_THREADS / 32;
     const int Gs = F.Gs, TS = F.TS, R = Gs * 4;
-    int* tab = jw_smem;                    // [256][TS][W]
-    int* yqs = tab + 256 * TS * W;         // [T][R]
+    unsigned char* tab = reinterpret_cast<unsigned char*>(jw_smem);
+    int* yqs = jw_smem + JW_TAB_BYTES(W) / 4;    // [T][R]
+    (void)TS;
     __shared__ long long s_red[32 * JW_MAX_TRAITS];
     __shared__ int s_ok;
     const int64_t n = F.C.n, p = F.C.p;
     const bool single = F.n_vs <= (int)gridDim.x;
+    // phase timers (ns): [0] wait for previous chain, [1] axpy+quantise+tables, [2] stream,
+    // [3] wait for all slices, [4] chain; CTA 0 -> counters[32..36], CTA 1 -> counters[40..44]
+    unsigned long long ph[5] = {0, 0, 0, 0, 0};
+    const bool timed = (tid == 0) && (blockIdx.x <= 1) && (F.C.counters != nullptr);
+    unsigned long long tm = timed ? jw_globaltimer() : 0;
+#define JW_PHASE(i) do { if (timed) { unsigned long long now__ = jw_globaltimer(); ph[i] += now__ - tm; tm = now__; } } while (0)
     long long sq_keep[T];                  // thread 0: this CTA's sum of yq over its slice(s)
 #pragma unroll
     for (int kk = 0; kk < T; ++kk) sq_keep[kk] = 0;
@@ -135,6 +158,7 @@ jw_k_fused(jw_fused_args F) {
             if (!s_ok) return;
             prev_cnt = __ldcg(&F.act_cnt_blk[k - 1]);
         }
+        JW_PHASE(0);
         const int64_t s = F.C.starts[k];
         const int b = (int)(F.C.starts[k + 1] - s);
         const int nchunks = (b + 15) >> 4;
@@ -212,12 +236,15 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
                         for (int elo = 0; elo < 16; ++elo) {
                             const int val = jw_tabval(elo & 3, y0, mc_) + jw_tabval(elo >> 2, y1, mc_) + B;
-                            tab[((ehi * 16 + elo) * TS + g) * W + comp] = val;
+                            const int gb = g >> 5, l = g & 31;
+                            const int sub = gb == 0 ? jw_tab_sub<W>(0) : (gb == 1 ? jw_tab_sub<W>(1) : jw_tab_sub<W>(2));
+                            *reinterpret_cast<int*>(tab + (ehi * 16 + elo) * 256 + sub + l * 4 * W + comp * 4) = val;
                         }
                     }
                 }
                 __syncthreads();
             }
+            JW_PHASE(1);
             // ---- (3) stream the block's genotypes: one lookup per byte (4 individuals) ----
             const uint8_t* tile = F.tiled +
                 ((size_t)(F.chunk_off[k] * F.n_vs + (int64_t)vs * nchunks) * Gs) * 16;
@@ -227,18 +254,31 @@ jw_k_fused(jw_fused_args F) {
                 for (int q = 0; q < 16; ++q)
 #pragma unroll
                     for (int comp = 0; comp < W; ++comp) acc[q][comp] = 0;
-                for (int g = lane; g < Gs; g += 32) {
-                    const uint4 d = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
-                    const int* tg = tab + g * W;
-                    const uint32_t wds[4] = {d.x, d.y, d.z, d.w};
+                // all of this chunk's 128-bit loads are issued before the first lookup
+                uint4 dv[JW_FUSED_MAX_GS / 32];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const uint32_t byte = (wds[q >> 2] >> (8 * (q & 3))) & 0xffu;
-                        if (W == 1) {
-                            acc[q][0] += tg[byte * TS];
-                        } else {
-                            const int2 e2 = *reinterpret_cast<const int2*>(tg + byte * TS * 2);
-                            acc[q][0] += e2.x; acc[q][W - 1] += e2.y;
+                for (int gb = 0; gb < JW_FUSED_MAX_GS / 32; ++gb) {
+                    const int g = gb * 32 + lane;
+                    dv[gb] = make_uint4(0, 0, 0, 0);
+                    if (g < Gs) dv[gb] = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
+                }
+#pragma unroll
+                for (int gb = 0; gb < JW_FUSED_MAX_GS / 32; ++gb) {
+                    const int g = gb * 32 + lane;
+                    if (g < Gs) {
+                        const unsigned char* tg = tab + jw_tab_sub<W>(gb);
+                        const uint32_t laneoff = (uint32_t)lane * 4u * W;
+                        const uint32_t wds[4] = {dv[gb].x, dv[gb].y, dv[gb].z, dv[gb].w};
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            // byte1 = packed byte q, byte0 = lane offset: (byte << 8) | laneoff
+                            const uint32_t off = __byte_perm(wds[q >> 2], laneoff, 0x6504u | ((q & 3) << 4));
+                            if (W == 1) {
+                                acc[q][0] += *reinterpret_cast<const int*>(tg + off);
+                            } else {
+                                const int2 e2 = *reinterpret_cast<const int2*>(tg + off);
+                                acc[q][0] += e2.x; acc[q][W - 1] += e2.y;
+                            }
                         }
                     }
                 }
@@ -281,20 +321,42 @@ jw_k_fused(jw_fused_args F) {
             __threadfence();
             atomicAdd(&F.arrive[k], 1);
         }
+        if (warp == 1 && k + 1 < F.nblocks) {
+            // while the chain runs: pull the next block's tile(s) of this CTA into L2
+            const int nb1 = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
+            const int nch1 = (nb1 + 15) >> 4;
+            for (int vs = blockIdx.x; vs < F.n_vs; vs += gridDim.x) {
+                const uint8_t* t1 = F.tiled + ((size_t)(F.chunk_off[k + 1] * F.n_vs + (int64_t)vs * nch1) * Gs) * 16;
+                const unsigned total = (unsigned)nch1 * Gs * 16;
+                const unsigned per = ((total / 32) + 15) & ~15u;
+                const unsigned off = per * lane;
+                if (off < total) jw_prefetch_l2(t1 + off, min(per, total - off));
+            }
+        }
+        JW_PHASE(2);
         if (blockIdx.x == 0) {
-            if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], (int)gridDim.x, F.flags) ? 1 : 0;
-            __syncthreads();
-            if (!s_ok) return;
             jw_chain_args A = F.C;
             A.sq = F.sq_acc + k * T;
             A.act_idx = F.act_idx_all + s;
             A.act_cnt = F.act_cnt_blk + k;
             A.write_active_list = 1;
-            jw_chain_block<METHOD, T>(A, k);
+            auto wait_all = [&]() -> bool {
+                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], (int)gridDim.x, F.flags) ? 1 : 0;
+                __syncthreads();
+                JW_PHASE(3);
+                return s_ok != 0;
+            };
+            if (!jw_chain_block<METHOD, T>(A, k, wait_all)) return;
             __syncthreads();
             if (tid == 0) { __threadfence(); jw_st_release(F.done, k + 1); }
+            JW_PHASE(4);
         }
     }
+    if (timed) {
+        const int base = blockIdx.x == 0 ? 32 : 40;
+        for (int i = 0; i < 5; ++i) F.C.counters[base + i] = ph[i];
+    }
+#undef JW_PHASE
 }
 
 // final axpy of the last block (the in-kernel apply always lags one block behind)
@@ -359,7 +421,7 @@ static int jw_fused_prepare(jwas_handle* h) {
     f->TS = (int)((gs + 31) / 32 * 32);
     f->n_vs = (int)((nbytes + gs - 1) / gs);
     f->n_cta = std::min<int>(h->sm_count, f->n_vs);
-    f->smem = (size_t)256 * f->TS * f->W * 4 + (size_t)h->t * f->Gs * 4 * 4;
+    f->smem = (size_t)(f->W == 1 ? 2 : 3) * 65536 + (size_t)h->t * f->Gs * 4 * 4;
     std::vector<int64_t> coff(h->nblocks + 1, 0);
     std::vector<int32_t> cblk;
     for (int64_t k = 0; k < h->nblocks; ++k) {

@@ -132,6 +132,10 @@ struct jw_chain_args {
     const double* bigPi;
     uint64_t seed; uint32_t iter;
     const double* u; const double* z;
+    // BayesABC draw-independent terms precomputed for repetition 0 by jw_k_prep_abc (all SMs)
+    // instead of inside the one chain CTA: [0]u [1]z*sqrt(invLhs) [2]invLhs [3]log(lhs)+log(ve)
+    // [4]log(1-pi) [5]log(pi), each p doubles; prep_beta0 = float(z*sqrt(ve)).  NULL = inline.
+    const double* prep; const float* prep_beta0;
     int32_t* act_idx; int32_t* act_cnt;     // ordered active list of this launch (single-block mode)
     int write_active_list;
     unsigned long long* counters;
@@ -168,11 +172,35 @@ __device__ __forceinline__ int jw_categorical(const double* probs, int k, double
     return i;
 }
 
-template <int METHOD, int T>
-__device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int ib) {
-    __shared__ int s_wmin[32];
-    __shared__ int s_first;
-    __shared__ float s_d[JW_MAX_TRAITS];
+__global__ void __launch_bounds__(256)
+jw_k_prep_abc(jw_chain_args A, double* __restrict__ prep, float* __restrict__ beta0) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = A.p;
+    if (j >= p) return;
+    const double x = (double)A.xpx[j];
+    const double invVarRes = 1.0 / A.vare;
+    const double ve = A.ve[j], pi = A.pi[j];
+    const double lhs = x * invVarRes + 1.0 / ve;
+    const double invLhs = 1.0 / lhs;
+    const double u = jw_get_u(A, j, 0, 0), z = jw_get_z(A, j, 0, 0);
+    prep[j] = u;
+    prep[p + j] = z * jw_sqrt(invLhs);
+    prep[2 * p + j] = invLhs;
+    prep[3 * p + j] = jw_log(lhs) + jw_log(ve);
+    prep[4 * p + j] = jw_log(1.0 - pi);
+    prep[5 * p + j] = jw_log(pi);
+    beta0[j] = (float)(z * jw_sqrt(ve));
+}
+
+struct jw_no_wait { __device__ __forceinline__ bool operator()() const { return true; } };
+
+// wait_fn() is called after everything that does not depend on the block rhs has been loaded
+// (state, constants, Gram-row prefetches): the fused engine spins there for the other CTAs'
+// partial sums, so those global-memory latencies hide behind the wait.  Returns false on abort.
+template <int METHOD, int T, class WaitFn>
+__device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int ib, WaitFn wait_fn) {
+    __shared__ int s_wmin[2][32];
+    __shared__ float s_dc[JW_MAX_TRAITS][JW_MAX_BLOCK];   // candidate delta-alpha of every active marker
     __shared__ int s_cnt[33];
 
     const int64_t s = A.starts[ib];
@@ -181,20 +209,18 @@ __device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int
     const bool valid = m < b;
     const int64_t j = s + (valid ? m : 0);
     const int lane = m & 31, warp = m >> 5;
+    const int nw = (int)(blockDim.x >> 5);
     const int64_t p = A.p;
     const float* G = A.gram + A.gram_off[ib];
     const double x = (double)A.xpx[j];
 
-    // rhs of this marker for every trait, state at block entry
+    // state at block entry
     double r[T];
     float a_entry[T], a_cur[T], b_cur[T];
     int d_cur[T];
+    const double mu = (double)A.means[j];
 #pragma unroll
     for (int k = 0; k < T; ++k) {
-        // .cg loads: these words were produced by other CTAs' atomics in the fused engine
-        long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
-        double mu = (double)A.means[j];
-        r[k] = ((double)dq - mu * (double)(__ldcg(&A.sq[k]) - mq)) * A.invscale;
         a_entry[k] = a_cur[k] = A.alpha[k * p + j];
         b_cur[k] = (METHOD == 1) ? 0.0f : A.beta[k * p + j];
         d_cur[k] = A.delta[k * p + j];
@@ -207,24 +233,65 @@ __device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int
     const double invVarRes = (METHOD == 2) ? 0.0 : 1.0 / A.vare;
 
     // draw-independent constants
-    double c_lhs = 0, c_invLhs = 0, c_L = 0, c_lpc = 0, c_lp0 = 0, c_ve = 1;
+    double c_invLhs = 0, c_L = 0, c_lpc = 0, c_lp0 = 0, c_ve = 1;
+    const bool use_prep = (METHOD == 0) && (A.prep != nullptr);
+    double u0 = 0.0, zs1_0 = 0.0; float beta0_0 = 0.0f;
     if (METHOD == 0) {
-        c_ve = A.ve[j];
-        double pi = A.pi[j];
-        c_lhs = x * invVarRes + 1.0 / c_ve;
-        c_invLhs = 1.0 / c_lhs;
-        c_L = jw_log(c_lhs) + jw_log(c_ve);
-        c_lpc = jw_log(1.0 - pi);
-        c_lp0 = jw_log(pi);
+        if (use_prep) {
+            c_invLhs = A.prep[2 * p + j]; c_L = A.prep[3 * p + j];
+            c_lpc = A.prep[4 * p + j]; c_lp0 = A.prep[5 * p + j];
+            u0 = A.prep[j]; zs1_0 = A.prep[p + j]; beta0_0 = A.prep_beta0[j];
+        } else {
+            c_ve = A.ve[j];
+            double pi = A.pi[j];
+            double c_lhs = x * invVarRes + 1.0 / c_ve;
+            c_invLhs = 1.0 / c_lhs;
+            c_L = jw_log(c_lhs) + jw_log(c_ve);
+            c_lpc = jw_log(1.0 - pi);
+            c_lp0 = jw_log(pi);
+        }
+    }
+    // markers that already carry an effect are certain to need their Gram row: start pulling it
+    // towards L2 now (one bulk prefetch per row)
+    if (valid) {
+        bool nz = false;
+#pragma unroll
+        for (int k = 0; k < T; ++k) nz = nz || (a_cur[k] != 0.0f);
+        if (nz) {
+            const float* row = G + (int64_t)m * b;
+            const unsigned long long a0 = (unsigned long long)row & ~15ull;
+            const unsigned bytes = (unsigned)((((unsigned long long)(row + b) + 15ull) & ~15ull) - a0);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+        }
+    }
+
+    if (!wait_fn()) return false;
+
+    // rhs of this marker for every trait
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        // .cg loads: these words were produced by other CTAs' atomics in the fused engine
+        long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
+        r[k] = ((double)dq - mu * (double)(__ldcg(&A.sq[k]) - mq)) * A.invscale;
     }
 
     const int nreps = A.nreps_mode ? b : 1;
     unsigned long long my_active = 0, my_rounds = 0;
+    int parity = 0;
 
     for (int rep = 0; rep < nreps; ++rep) {
         double u[T], z[T];
+        double zs1 = 0.0; float beta0 = 0.0f;        // METHOD 0: z*sqrt(invLhs), float(z*sqrt(ve))
+        if (METHOD == 0 && use_prep && rep == 0) {
+            u[0] = u0; zs1 = zs1_0; beta0 = beta0_0; z[0] = 0.0;
+        } else {
 #pragma unroll
-        for (int k = 0; k < T; ++k) { u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep); }
+            for (int k = 0; k < T; ++k) { u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep); }
+            if (METHOD == 0) {
+                if (use_prep) c_ve = A.ve[j];
+                zs1 = z[0] * jw_sqrt(c_invLhs); beta0 = (float)(z[0] * jw_sqrt(c_ve));
+            }
+        }
         int pos = 0;
         while (true) {
             // ---- evaluate this marker against the current rhs ----
@@ -240,11 +307,11 @@ __device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int
                     double prob1 = 1.0 / (1.0 + jw_exp(c_lp0 - logDelta1));
                     if (u[0] < prob1) {
                         newD[0] = 1;
-                        newA[0] = (float)(gHat + z[0] * jw_sqrt(c_invLhs));
+                        newA[0] = (float)(gHat + zs1);
                         newB[0] = newA[0];
                     } else {
                         newD[0] = 0;
-                        newB[0] = (float)(z[0] * jw_sqrt(c_ve));
+                        newB[0] = beta0;
                         newA[0] = 0.0f;
                     }
                     active = (a_cur[0] - newA[0]) != 0.0f;
@@ -328,43 +395,40 @@ __device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int
                         if ((a_cur[k] - newA[k]) != 0.0f) active = true;
                     }
                 }
+                if (active) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k) s_dc[k][m] = a_cur[k] - newA[k];
+                }
             }
-            // ---- first active marker among the pending ones ----
+            // ---- first active marker among the pending ones: ONE barrier per round ----
             int key = (pending && active) ? m : 0x7fffffff;
             int wmin = __reduce_min_sync(0xffffffffu, key);
-            if (lane == 0) s_wmin[warp] = wmin;
+            if (lane == 0) s_wmin[parity][warp] = wmin;
             __syncthreads();
-            if (warp == 0) {
-                int v = (lane < (int)(blockDim.x >> 5)) ? s_wmin[lane] : 0x7fffffff;
-                v = __reduce_min_sync(0xffffffffu, v);
-                if (lane == 0) s_first = v;
-            }
-            __syncthreads();
-            const int first = s_first;
+            int v = (lane < nw) ? s_wmin[parity][lane] : 0x7fffffff;
+            const int first = __reduce_min_sync(0xffffffffu, v);
+            parity ^= 1;
             my_rounds += (m == 0);
             // ---- commit everything up to and including `first` ----
             if (pending && m <= first) {
 #pragma unroll
-                for (int k = 0; k < T; ++k) {
-                    if (m == first) s_d[k] = a_cur[k] - newA[k];
-                    a_cur[k] = newA[k]; b_cur[k] = newB[k]; d_cur[k] = newD[k];
-                }
+                for (int k = 0; k < T; ++k) { a_cur[k] = newA[k]; b_cur[k] = newB[k]; d_cur[k] = newD[k]; }
                 if (m == first) my_active += 1;
             }
             if (first == 0x7fffffff) break;
-            __syncthreads();
             // ---- apply the committed marker's Gram row to the rhs ----
             if (valid && (A.nreps_mode || m > first)) {
                 float g = G[(int64_t)first * b + m];
 #pragma unroll
                 for (int k = 0; k < T; ++k) {
-                    float d = s_d[k];
+                    float d = s_dc[k][first];
                     if (d != 0.0f) r[k] += (double)d * (double)g;
                 }
             }
             pos = first + 1;
             if (pos >= b) break;
         }
+        __syncthreads();      // s_dc / s_wmin are reused by the next repetition
     }
 
     // ---- block exit: publish state and the net delta-alpha of every marker ----
@@ -398,12 +462,13 @@ __device__ __forceinline__ void jw_chain_block(const jw_chain_args& A, const int
         if (my_active) atomicAdd(&A.counters[0], my_active);
         if (my_rounds) atomicAdd(&A.counters[1], my_rounds);
     }
+    return true;
 }
 
 template <int METHOD, int T>
 __global__ void __launch_bounds__(JW_MAX_BLOCK)
 jw_k_chain(jw_chain_args A) {
-    jw_chain_block<METHOD, T>(A, A.block0 + (int)blockIdx.x);
+    jw_chain_block<METHOD, T>(A, A.block0 + (int)blockIdx.x, jw_no_wait());
 }
 
 // ------------------------------------------------------------------------------------------

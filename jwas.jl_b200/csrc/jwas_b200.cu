@@ -87,7 +87,7 @@ static int create_common(int64_t n, int64_t p, int t, int device, jwas_handle** 
     JW_CUDA(cudaMalloc((void**)&h->d_act_idx, p * sizeof(int32_t)));
     JW_CUDA(cudaMalloc((void**)&h->d_act_cnt, sizeof(int32_t)));
     JW_CUDA(cudaMalloc((void**)&h->d_flags, 4 * sizeof(int32_t)));
-    JW_CUDA(cudaMalloc((void**)&h->d_counters, 32 * sizeof(unsigned long long)));
+    JW_CUDA(cudaMalloc((void**)&h->d_counters, 64 * sizeof(unsigned long long)));
     JW_CUDA(cudaMalloc((void**)&h->d_maxabs, sizeof(float)));
     JW_CUDA(cudaMalloc((void**)&h->d_stats, 64 * sizeof(double)));
     for (void* z : {(void*)h->d_ycorr, (void*)h->d_yq}) JW_CUDA(cudaMemsetAsync(z, 0, tn * 4, h->stream));
@@ -191,7 +191,7 @@ extern "C" int jwas_destroy(jwas_handle* h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_ycorr, h->d_alpha,
                     h->d_beta, h->d_delta, h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta, h->d_ve,
-                    h->d_pi, h->d_u, h->d_z, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
+                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -545,6 +545,16 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     A.seed = c.seed; A.iter = c.iter; A.u = c.u; A.z = c.z;
     A.act_idx = h->d_act_idx; A.act_cnt = h->d_act_cnt; A.counters = h->d_counters;
     const int threads = (int)std::max<int64_t>(32, ceil_div(h->maxb, 32) * 32);
+    if (c.method == 0) {
+        // draw-independent chain terms for every marker, computed by the whole GPU up front
+        if (!h->d_prep) {
+            JW_CUDA(cudaMalloc((void**)&h->d_prep, (size_t)6 * p * sizeof(double)));
+            JW_CUDA(cudaMalloc((void**)&h->d_prep_beta0, (size_t)p * sizeof(float)));
+        }
+        jw_k_prep_abc<<<(unsigned)ceil_div(p, 256), 256, 0, h->stream>>>(A, h->d_prep, h->d_prep_beta0);
+        JW_LAUNCH_CHECK(h);
+        A.prep = h->d_prep; A.prep_beta0 = h->d_prep_beta0;
+    }
 
     if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT) {
         int rc = jw_fused_sweep(h, A, scale);
@@ -723,6 +733,13 @@ extern "C" double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches) 
     if (!h) return 0.0;
     if (launches) *launches = h->prof_launches;
     return h->prof_ms;
+}
+extern "C" int jwas_get_phase_ns(jwas_handle* h, uint64_t* out16) {
+    JW_REQUIRE(h && out16, "jwas_get_phase_ns: null argument");
+    JW_CUDA(cudaSetDevice(h->device));
+    JW_CUDA(cudaMemcpyAsync(out16, h->d_counters + 32, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 extern "C" void* jwas_stream(jwas_handle* h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
