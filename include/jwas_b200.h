@@ -122,6 +122,11 @@ int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, const double* 
                    uint64_t seed, uint32_t iter, const double* u, const double* z,
                    jwas_sweep_stats* stats);
 
+/* device-resident hyper-parameter vectors used when a sweep is called with NULL pointers:
+ * which = 0 -> var_effects[j] = value for all j (BayesB start, MCMC_BayesianAlphabet.jl:67-69);
+ * which = 1 -> pi[j] = value (bayesabc_pi_vector, BayesABC.jl:17-23) */
+int jwas_fill_hyper(jwas_handle* h, int which, double value);
+
 /* BayesB per-marker variance update on device (variance_components.jl:169-172):
  * var_j = (beta_j^2 + df*scale) / chisq(df+1), chi-square from the native stream. */
 int jwas_sample_bayesb_variances(jwas_handle* h, double df, double scale, uint64_t seed,

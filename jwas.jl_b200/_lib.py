@@ -60,6 +60,7 @@ def lib():
         "jwas_sweep_bayesr": [vp, i32, i32, dbl, dbl, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_mt1": [vp, i32, vp, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sample_bayesb_variances": [vp, dbl, dbl, u64, u32, vp],
+        "jwas_fill_hyper": [vp, i32, dbl],
         "jwas_accumulate": [vp, dbl, i32],
         "jwas_get_means": [vp, vp, vp, vp],
         "jwas_kernel_launches": [vp],
@@ -232,6 +233,9 @@ class GpuSweeper:
         out = np.empty(self.p, np.float64) if want else None
         _check(lib().jwas_sample_bayesb_variances(self._h, float(df), float(scale), int(seed), int(it), _p(out)))
         return out
+
+    def fill_hyper(self, which, value):
+        _check(lib().jwas_fill_hyper(self._h, {"var_effects": 0, "pi": 1}[which], float(value)))
 
     # -- posterior accumulators
     def accumulate(self, nsamples, bayesr=False):

@@ -1,0 +1,545 @@
+"""Host-side mirror of the reference interface for the marker-effects path.
+
+Same names, argument meaning and error behaviour as JWAS.jl for the calls a user makes around the
+marker sweep:  get_genotypes -> build_model -> (set_covariate/set_random) -> runMCMC, with the
+Genotypes / MME / MCMCinfo / Variance types (types.jl:56-64, 98-165, 225-248, 264-346).  The
+backend seam is the one the reference itself uses for `storage=:stream`
+(readgenotypes.jl:228-295, MCMC_BayesianAlphabet.jl:53-65, 243-251): `storage="gpu"` keeps the
+genotypes 2-bit packed in HBM behind a libjwasb200 handle and every sweep runs there.
+
+Only what the sweep needs is implemented: `y = intercept + <genotypes>` models (single- or
+multi-trait), BayesA/B/C, BayesR, multi-trait BayesC sampler I.  Everything else the reference
+offers (pedigree, covariates, random terms, SEM, RRM, categorical traits, annotations, GBLUP,
+BayesL, RR-BLUP) is outside this backend's scope and raises JwasError with a message saying so.
+"""
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import mcmc
+from ._lib import GpuSweeper, JwasError, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT
+
+try:  # pandas is what a DataFrame is here
+    import pandas as pd
+except Exception:  # pragma: no cover
+    pd = None
+
+DEFAULT_PANEL = 1024          # look-ahead panel of the exact schedule (GPU-internal)
+
+
+def error(msg):
+    raise JwasError(msg)
+
+
+# ------------------------------------------------------------------------------------ types
+@dataclass
+class Variance:                      # types.jl:56-64
+    val: object = False
+    df: float = 4.0
+    scale: object = False
+    estimate_variance: bool = True
+    estimate_scale: bool = False
+    constraint: bool = False
+
+
+@dataclass
+class Genotypes:                     # types.jl:98-165 (fields this path uses)
+    name: str = ""
+    obsID: list = field(default_factory=list)
+    markerID: list = field(default_factory=list)
+    nObs: int = 0
+    nMarkers: int = 0
+    alleleFreq: np.ndarray = None
+    sum2pq: float = 0.0
+    centered: bool = True
+    packed: np.ndarray = None        # marker-major 2-bit image (.jgb2 layout), host copy until runMCMC
+    marker_means: np.ndarray = None
+    method: str = "BayesC"
+    estimatePi: bool = True
+    π: object = 0.0
+    genetic_variance: Variance = field(default_factory=Variance)
+    G: Variance = field(default_factory=Variance)
+    ntraits: int = 1
+    α: list = None
+    β: list = None
+    δ: list = None
+    meanAlpha: list = None
+    meanAlpha2: list = None
+    meanDelta: list = None
+    mean_pi: object = None
+    multi_trait_sampler: str = "I"
+    storage_mode: str = "gpu"
+    stream_backend: object = None    # GpuSweeper once the chain starts
+    starting_value: object = False
+
+
+@dataclass
+class MCMCinfo:                      # types.jl:225-248
+    chain_length: int = 100
+    burnin: int = 0
+    output_samples_frequency: int = 1
+    seed: object = False
+    fast_blocks: object = False
+    independent_blocks: bool = False
+    outputEBV: bool = True
+    double_precision: bool = False
+    output_folder: str = "results"
+    printout_model_info: bool = False
+
+
+@dataclass
+class MME:                           # types.jl:264-346 (fields this path uses)
+    model_equations: str = ""
+    lhsVec: list = field(default_factory=list)
+    nModels: int = 1
+    M: list = field(default_factory=list)
+    R: Variance = field(default_factory=Variance)
+    MCMCinfo: MCMCinfo = None
+    obsID: list = None
+    sol: np.ndarray = None
+    output: dict = None
+
+
+# ------------------------------------------------------------------------------------ codec / QC
+def _pack_codes(codes):
+    """(n, p) codes 0/1/2 with 3 = missing -> (p, cld(n,4)) uint8, LSB first
+    (streaming_genotypes.jl:622-627)."""
+    n, p = codes.shape
+    stride = (n + 3) // 4
+    padded = np.zeros((stride * 4, p), dtype=np.uint8)
+    padded[:n] = codes
+    q = padded.reshape(stride, 4, p)
+    packed = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+    return np.ascontiguousarray(packed.T)
+
+
+def _unpack_codes(packed, n):
+    p, stride = packed.shape
+    out = np.empty((stride * 4, p), dtype=np.uint8)
+    for k in range(4):
+        out[k::4] = ((packed >> (2 * k)) & 3).T
+    return out[:n]
+
+
+def _codes_from_matrix(X, missing_value):
+    X = np.asarray(X)
+    miss = (X == missing_value) | ~np.isfinite(X.astype(np.float64))
+    Xr = np.where(miss, 0, X)
+    if not np.all((Xr == 0) | (Xr == 1) | (Xr == 2)):
+        error(f"Only 0/1/2 genotypes (and missing_value={missing_value}) are supported in storage=:gpu.")
+    codes = Xr.astype(np.uint8)
+    codes[miss] = 3
+    return codes
+
+
+def _column_stats(codes):
+    """Means over observed calls and allele frequencies (readgenotypes.jl:372-385,
+    streaming_genotypes.jl:560-585), Float32 like the reference."""
+    valid = codes != 3
+    nn = valid.sum(axis=0)
+    if np.any(nn == 0):
+        error("Marker %d has only missing values." % int(np.argmin(nn) + 1))
+    s = np.where(valid, codes, 0).sum(axis=0, dtype=np.int64)
+    means = (s.astype(np.float32) / nn.astype(np.float32)).astype(np.float32)
+    return means, nn, s
+
+
+def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_is_marker_variance=False,
+                  df=4.0, estimate_variance=True, estimate_scale=False, constraint=False, separator=",",
+                  header=True, double_precision=False, quality_control=True, MAF=0.01, missing_value=9.0,
+                  center=True, starting_value=False, annotations=False, multi_trait_sampler="I",
+                  storage="gpu", name="geno", obsID=None, markerID=None):
+    """readgenotypes.jl:213-448 for the GPU backend.
+
+    `file`: (n, p) array of 0/1/2 (missing_value for missing), a DataFrame whose first column holds
+    IDs, a CSV path, or the prefix of a packed `.jgb2` backend written by
+    prepare_streaming_genotypes (same files the reference's storage=:stream reads)."""
+    if multi_trait_sampler not in ("auto", "I", "II"):
+        error("multi_trait_sampler must be one of :auto, :I, or :II.")
+    if storage not in ("gpu",):
+        error("storage must be :gpu in this backend (:dense and :stream live in JWAS.jl).")
+    if method not in ("BayesA", "BayesB", "BayesC", "BayesR"):
+        error(f"method {method} is outside the GPU marker-sweep path (BayesA/B/C and BayesR only).")
+    if annotations is not False:
+        error("annotations are outside the GPU marker-sweep path.")
+    if double_precision:
+        error("double_precision=true is not supported with storage=:gpu.")
+    if not center:
+        error("storage=:gpu requires center=true.")
+    if estimate_scale:
+        error("estimate_scale=true is not supported with storage=:gpu.")
+    if method == "BayesR" and not isinstance(Pi, (list, tuple, np.ndarray)) and Pi != 0.0:
+        error("BayesR Pi must have length 4.")
+
+    if isinstance(file, str) and (os.path.exists(file + ".meta") or file.endswith((".jgb2", ".meta"))):
+        be = load_streaming_backend(file)
+        codes = _unpack_codes(be["packed"], be["nObs"])
+        obs, mk = be["obsID"], be["markerID"]
+        quality_control = False            # QC happened when the backend was prepared
+    else:
+        if isinstance(file, str):
+            if pd is None:
+                error("pandas is required to read genotype files.")
+            dfm = pd.read_csv(file, sep=separator, header=0 if header else None)
+            obs = [str(x) for x in dfm.iloc[:, 0]]
+            mk = [str(c) for c in dfm.columns[1:]] if header else [f"m{j + 1}" for j in range(dfm.shape[1] - 1)]
+            X = dfm.iloc[:, 1:].to_numpy()
+        elif pd is not None and isinstance(file, pd.DataFrame):
+            obs = [str(x) for x in file.iloc[:, 0]]
+            mk = [str(c) for c in file.columns[1:]]
+            X = file.iloc[:, 1:].to_numpy()
+        else:
+            X = np.asarray(file)
+            if X.ndim != 2:
+                error("genotypes must be a matrix.")
+            obs = [str(x) for x in obsID] if obsID is not None else [str(i + 1) for i in range(X.shape[0])]
+            mk = [str(x) for x in markerID] if markerID is not None else [f"m{j + 1}" for j in range(X.shape[1])]
+        if X.size == 0:
+            error("Genotype data is empty.")
+        codes = _codes_from_matrix(X, missing_value)
+
+    means, nn, s = _column_stats(codes)
+    af = (means / np.float32(2.0)).astype(np.float32)
+    if quality_control:                     # readgenotypes.jl:388-399: MAF filter + fixed loci
+        valid = codes != 3
+        cm = np.where(valid, codes, 0).astype(np.float64)
+        ss = (cm ** 2).sum(axis=0) - (s.astype(np.float64) ** 2) / nn
+        keep = (af > MAF) & (af < 1 - MAF) & (ss > 0)
+        if not keep.any():
+            error("No markers remain after streaming genotype quality control.")
+        codes = codes[:, keep]; means = means[keep]; af = af[keep]
+        mk = [m for m, k in zip(mk, keep) if k]
+    n, p = codes.shape
+    g = Genotypes(name=name, obsID=obs, markerID=mk, nObs=n, nMarkers=p, alleleFreq=af,
+                  sum2pq=float((2.0 * af.astype(np.float64) * (1 - af.astype(np.float64))).sum()),
+                  centered=True, packed=_pack_codes(codes), marker_means=means, method=method,
+                  estimatePi=bool(estimatePi), multi_trait_sampler=multi_trait_sampler,
+                  starting_value=starting_value)
+    g.π = Pi if not isinstance(Pi, (list, tuple)) else np.array(Pi, dtype=np.float64)
+    g.G = Variance(val=G if G_is_marker_variance else False, df=df, estimate_variance=estimate_variance,
+                   estimate_scale=estimate_scale, constraint=constraint)
+    g.genetic_variance = Variance(val=False if G_is_marker_variance else G, df=df)
+    if method == "BayesA":                 # input_data_validation.jl:33-36
+        g.method = "BayesB"; g.π = 0.0; g.estimatePi = False
+    return g
+
+
+# ------------------------------------------------------------------------------------ .jgb2 backend files
+def prepare_streaming_genotypes(file, *, output_prefix=None, separator=",", header=True, quality_control=True,
+                                MAF=0.01, missing_value=9.0, center=True):
+    """Writes the reference's packed backend files (streaming_genotypes.jl:819-877, dense path
+    :520-660): <prefix>.jgb2 + .meta and the Float32/Int32/text side-cars, readable by JWAS.jl's
+    storage=:stream and by get_genotypes(prefix) here."""
+    g = get_genotypes(file, 1.0, separator=separator, header=header, quality_control=quality_control, MAF=MAF,
+                      missing_value=missing_value, center=center)
+    prefix = os.path.abspath(output_prefix or (os.path.splitext(file)[0] + "_stream"))
+    paths = {k: prefix + ext for k, ext in (("data_path", ".jgb2"), ("obs_path", ".obsid.txt"),
+                                            ("marker_path", ".markerid.txt"), ("selected_path", ".selected.i32"),
+                                            ("mean_path", ".mean.f32"), ("xp_path", ".xpRinvx.f32"),
+                                            ("afreq_path", ".afreq.f32"))}
+    g.packed.tofile(paths["data_path"])
+    open(paths["obs_path"], "w").write("".join(x + "\n" for x in g.obsID))
+    open(paths["marker_path"], "w").write("".join(x + "\n" for x in g.markerID))
+    np.arange(1, g.nMarkers + 1, dtype=np.int32).tofile(paths["selected_path"])
+    g.marker_means.astype(np.float32).tofile(paths["mean_path"])
+    codes = _unpack_codes(g.packed, g.nObs)
+    valid = codes != 3
+    x = np.where(valid, codes.astype(np.float32) - g.marker_means[None, :], np.float32(0))
+    (x.astype(np.float64) ** 2).sum(axis=0).astype(np.float32).tofile(paths["xp_path"])
+    g.alleleFreq.astype(np.float32).tofile(paths["afreq_path"])
+    with open(prefix + ".meta", "w") as io:
+        for k, v in [("version", "1")] + list(paths.items()) + [("nObs", g.nObs), ("nMarkers", g.nMarkers),
+                                                               ("nMarkersAll", g.nMarkers),
+                                                               ("stride_bytes", (g.nObs + 3) // 4),
+                                                               ("centered", 1), ("sum2pq", repr(g.sum2pq))]:
+            io.write(f"{k}\t{v}\n")
+    return prefix
+
+
+def load_streaming_backend(path):
+    """streaming_genotypes.jl:884-971 (manifest: tab-separated key/value lines, :77-95)."""
+    prefix = os.path.abspath(path)
+    for ext in (".meta", ".jgb2"):
+        if prefix.endswith(ext):
+            prefix = prefix[:-len(ext)]
+    meta_path = prefix + ".meta"
+    if not os.path.isfile(meta_path):
+        error(f"Streaming manifest is not found: {meta_path}")
+    meta = {}
+    for line in open(meta_path):
+        parts = line.rstrip("\n").split("\t", 1)
+        if len(parts) == 2:
+            meta[parts[0]] = parts[1]
+    n, p, stride = int(meta["nObs"]), int(meta["nMarkers"]), int(meta["stride_bytes"])
+    if os.path.getsize(meta["data_path"]) != p * stride:
+        error(f"Packed genotype file size does not match metadata for {meta['data_path']}")
+    packed = np.fromfile(meta["data_path"], dtype=np.uint8).reshape(p, stride)
+    obs = [l.rstrip("\n") for l in open(meta["obs_path"])]
+    mk = [l.rstrip("\n") for l in open(meta["marker_path"])]
+    if len(obs) != n:
+        error(f"Number of IDs in {meta['obs_path']} does not match nObs in manifest.")
+    if len(mk) != p:
+        error(f"Number of markers in {meta['marker_path']} does not match nMarkers in manifest.")
+    return {"packed": packed, "nObs": n, "nMarkers": p, "obsID": obs, "markerID": mk,
+            "centered": int(meta["centered"]) == 1}
+
+
+# ------------------------------------------------------------------------------------ model
+def build_model(model_equations, R=False, *, df=4.0, genotypes=None, estimate_variance=True, constraint=False):
+    """build_MME.jl:42-156 for `trait = intercept + <genotype term>` equations (one per line or ';')."""
+    if not isinstance(model_equations, str) or not model_equations.strip():
+        error("Model equations are wrong.")
+    eqs = [e.strip() for e in model_equations.replace(";", "\n").split("\n") if e.strip()]
+    lhs, geno_names = [], None
+    for e in eqs:
+        if "=" not in e:
+            error("Model equations are wrong.")
+        l, r = [x.strip() for x in e.split("=", 1)]
+        terms = [t.strip() for t in r.split("+")]
+        if "intercept" not in terms:
+            error("storage=:gpu models must contain an intercept.")
+        others = [t for t in terms if t != "intercept"]
+        if geno_names is None:
+            geno_names = others
+        elif others != geno_names:
+            error("every equation must contain the same genotype term with storage=:gpu.")
+        lhs.append(l)
+    if genotypes is None:
+        import inspect
+        fr = inspect.currentframe().f_back
+        genotypes = {k: v for k, v in {**fr.f_globals, **fr.f_locals}.items() if isinstance(v, Genotypes)}
+    M = []
+    for nm in geno_names or []:
+        if nm not in genotypes:
+            error(f"{nm} is not a genotype term known to this backend: covariates, factors, pedigree and "
+                  "random terms are outside the GPU marker-sweep path.")
+        gi = genotypes[nm]; gi.name = nm; gi.ntraits = len(lhs)
+        M.append(gi)
+    if len(M) != 1:
+        error("exactly one genotype term is supported with storage=:gpu.")
+    return MME(model_equations=model_equations, lhsVec=lhs, nModels=len(lhs), M=M,
+               R=Variance(val=R, df=df, estimate_variance=estimate_variance, constraint=constraint))
+
+
+def set_covariate(*a, **k):
+    error("set_covariate: covariates are outside the GPU marker-sweep path.")
+
+
+def set_random(*a, **k):
+    error("set_random: random / pedigree terms are outside the GPU marker-sweep path.")
+
+
+def validate_fast_block_starts(block_starts, nmarkers):     # JWAS.jl:73-79 (1-based starts)
+    bs = list(block_starts)
+    if len(bs) == 0:
+        error("fast_blocks block start vector cannot be empty.")
+    if bs[0] != 1:
+        error("fast_blocks block starts must begin with 1.")
+    if not all(1 <= b <= nmarkers for b in bs):
+        error("fast_blocks block starts must be within 1:nMarkers.")
+    if not all(b2 > b1 for b1, b2 in zip(bs, bs[1:])):
+        error("fast_blocks block starts must be sorted and unique.")
+
+
+def resolve_fast_blocks(fast_blocks, chain_length, n_obs, n_markers):
+    """JWAS.jl:293-316.  Returns (0-based boundaries or None, chain_length)."""
+    if fast_blocks is False or fast_blocks is None:
+        return None, chain_length
+    if fast_blocks is True:
+        bsize = int(math.floor(math.sqrt(n_obs)))
+    elif isinstance(fast_blocks, (int, float, np.integer, np.floating)):
+        bsize = int(math.floor(fast_blocks))
+    elif isinstance(fast_blocks, (list, tuple, np.ndarray)) and all(float(b).is_integer() for b in fast_blocks):
+        validate_fast_block_starts([int(b) for b in fast_blocks], n_markers)
+        st = [int(b) - 1 for b in fast_blocks] + [n_markers]
+        return np.array(st, dtype=np.int64), chain_length          # explicit starts keep chain_length
+    else:
+        error("fast_blocks must be false, true, a positive number, or a vector of block start positions.")
+    if bsize < 1:
+        error("fast_blocks block size must be at least 1.")
+    starts1 = list(range(1, n_markers + 1, bsize))
+    if len(starts1) <= 1:
+        error("fast_blocks block size must create at least two block starts.")
+    chain_length = int(math.floor(chain_length / (starts1[1] - starts1[0])))   # number of outer loops
+    return np.array([s - 1 for s in starts1] + [n_markers], dtype=np.int64), chain_length
+
+
+def _frame(rows, cols):
+    return pd.DataFrame(rows, columns=cols) if pd is not None else {"columns": cols, "rows": rows}
+
+
+def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=None, seed=False,
+            fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
+            double_precision=False, heterogeneous_residuals=False, output_folder="results", device=0,
+            panel=DEFAULT_PANEL, engine=1, _backend_factory=None, **ignored):
+    """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
+    Returns the reference's output dictionary keys for this path: "location parameters",
+    "residual variance", "marker effects <name>", "pi_<name>", "EBV_<trait>"."""
+    if heterogeneous_residuals:
+        error("heterogeneous_residuals=true is not supported with storage=:gpu (unit weights only).")
+    if double_precision:
+        error("double_precision=true is not supported with storage=:gpu.")
+    if independent_blocks and fast_blocks is False:
+        error("independent_blocks=true requires fast_blocks != false.")
+    if burnin >= chain_length:
+        error("burnin must be smaller than chain_length.")
+    Mi = model.M[0]
+    t = model.nModels
+    if t > 1 and Mi.method != "BayesC":
+        error("multi-trait analysis with storage=:gpu supports BayesC (sampler I) only.")
+    if t > 1 and Mi.multi_trait_sampler not in ("I", "auto"):
+        error("multi_trait_sampler=:II is not supported with storage=:gpu.")
+    if t > 4:
+        error("at most 4 traits are supported with storage=:gpu.")
+    # ---- phenotypes aligned to the genotype IDs (JWAS.jl:381-402)
+    ids = [str(x) for x in (df.iloc[:, 0] if pd is not None and isinstance(df, pd.DataFrame) else df["ID"])]
+    pos = {k: i for i, k in enumerate(Mi.obsID)}
+    missing_ids = [i for i in ids if i not in pos]
+    if missing_ids:
+        error("phenotyped individuals without genotypes are not supported with storage=:gpu.")
+    rows = np.array([pos[i] for i in ids])
+    Y = np.array([np.asarray(df[tr], dtype=np.float64) for tr in model.lhsVec])
+    if not np.all(np.isfinite(Y)):
+        error("missing phenotypes are not supported with storage=:gpu.")
+    n = len(ids); p = Mi.nMarkers
+    packed = Mi.packed
+    if n != Mi.nObs or not np.array_equal(rows, np.arange(n)):
+        packed = _pack_codes(_unpack_codes(Mi.packed, Mi.nObs)[rows])
+
+    starts, chain_length = resolve_fast_blocks(fast_blocks, chain_length, n, p)
+    if output_samples_frequency is None:
+        output_samples_frequency = chain_length // 1000 if chain_length > 1000 else 1
+    seed_v = 0 if seed is False else int(seed)
+    model.MCMCinfo = MCMCinfo(chain_length=chain_length, burnin=burnin, output_samples_frequency=output_samples_frequency,
+                              seed=seed, fast_blocks=(False if starts is None else [int(s) + 1 for s in starts[:-1]]),
+                              independent_blocks=independent_blocks, outputEBV=outputEBV, output_folder=output_folder)
+    schedule = SCHED_EXACT if starts is None else (SCHED_INDEPENDENT if independent_blocks else SCHED_BLOCK)
+    if starts is None:
+        starts = np.array(list(range(0, p, min(panel, 1024))) + [p], dtype=np.int64)
+
+    # ---- default priors (input_data_validation.jl:296-350) and marker hyper-parameters
+    #      (tools4genotypes.jl:353-424)
+    vary = Y.var(axis=1, ddof=1)
+    if t == 1:
+        varg = vary[0] * 0.5
+        if model.R.val is False:
+            model.R.val = float(np.float32(vary[0] * 0.5))
+        model.R.scale = model.R.val * (model.R.df - 2) / model.R.df
+        if Mi.method == "BayesR":
+            pi = np.array([0.95, 0.03, 0.015, 0.005]) if np.isscalar(Mi.π) and Mi.π == 0.0 else np.array(Mi.π, float)
+            if len(pi) != 4:
+                error("BayesR Pi must have length 4.")
+            denom = Mi.sum2pq * float(mcmc.BAYESR_GAMMA @ pi)
+        else:
+            pi = float(Mi.π)
+            denom = (1 - pi) * Mi.sum2pq
+        if Mi.G.val is False:
+            gv = Mi.genetic_variance.val if Mi.genetic_variance.val is not False else varg
+            Mi.G.val = float(np.float32(gv / denom))
+        if not Mi.G.val > 0:
+            error("Marker effects variance is negative!")
+        Mi.G.scale = Mi.G.val * (Mi.G.df - 2) / Mi.G.df
+        Mi.π = pi
+    else:
+        if model.R.val is False:
+            model.R.val = np.diag(vary * 0.5)
+        model.R.val = np.array(model.R.val, dtype=np.float64)
+        model.R.scale = model.R.val * (model.R.df - t - 1)
+        if isinstance(Mi.π, dict):
+            big = np.zeros(1 << t)
+            for key, v in Mi.π.items():
+                big[sum(int(round(k)) << i for i, k in enumerate(key))] = v
+        elif np.isscalar(Mi.π) and Mi.π == 0.0:
+            big = np.zeros(1 << t); big[-1] = 1.0      # "all markers have effects on all traits"
+        else:
+            big = np.array(Mi.π, dtype=np.float64)
+        if abs(big.sum() - 1.0) > 1e-8:
+            error("Summation of probabilities of Pi is not equal to one.")
+        if Mi.G.val is False:
+            gv = np.array(Mi.genetic_variance.val, float) if Mi.genetic_variance.val is not False else np.diag(vary * 0.5)
+            denom = np.zeros((t, t))
+            for i in range(t):
+                for j in range(t):
+                    denom[i, j] = Mi.sum2pq * sum(big[s] for s in range(1 << t) if (s >> i) & 1 and (s >> j) & 1)
+            if np.any(denom <= 0):
+                error("Marker effects covariance matrix is not postive definite! Please modify the argument: Pi.")
+            Mi.G.val = gv / denom
+        Mi.G.val = np.array(Mi.G.val, dtype=np.float64)
+        if np.any(np.linalg.eigvalsh(Mi.G.val) <= 0):
+            error("Marker effects covariance matrix is not postive definite! Please modify the argument: Pi.")
+        Mi.G.scale = Mi.G.val * (Mi.G.df - t - 1)
+        Mi.π = big
+
+    # ---- device-resident backend: GibbsMats (MCMC_BayesianAlphabet.jl:58) + ycorr (:131-147)
+    if _backend_factory is not None:
+        backend = _backend_factory(packed, n, t, starts)
+    else:
+        sw = GpuSweeper(packed, n, t, device=device)
+        sw.set_blocks(starts)
+        sw.set_option("engine", engine)
+        backend = mcmc.GpuBackend(sw)
+        Mi.stream_backend = sw
+    mu0 = Y.mean(axis=1)
+    alpha0 = np.zeros(t * p, np.float32)
+    if Mi.starting_value is not False:
+        alpha0 = np.asarray(Mi.starting_value, dtype=np.float32).reshape(-1).copy()
+    delta0 = np.ones(t * p, np.int32)
+    backend.put_state(alpha0, alpha0.copy(), delta0)       # beta = copy(alpha), delta = ones (:89-90,119)
+    backend.put_ycorr((Y - mu0[:, None]).astype(np.float32).reshape(-1))
+    if np.any(alpha0 != 0):
+        backend.sub_malpha()
+
+    out = mcmc.run_chain(backend, n=n, p=p, ntraits=t, method=Mi.method, schedule=schedule,
+                         chain_length=chain_length, burnin=burnin, output_samples_frequency=output_samples_frequency,
+                         seed=seed_v, vare=model.R.val if t == 1 else None, var_effect=Mi.G.val if t == 1 else None,
+                         pi=Mi.π if t == 1 else None, df_effect=Mi.G.df, scale_effect=Mi.G.scale if t == 1 else None,
+                         df_res=model.R.df, scale_res=model.R.scale if t == 1 else None,
+                         estimate_pi=Mi.estimatePi, estimate_variance=Mi.G.estimate_variance,
+                         estimate_vare=model.R.estimate_variance,
+                         R=model.R.val if t > 1 else None, G=Mi.G.val if t > 1 else None,
+                         big_pi=Mi.π if t > 1 else None, scale_G=Mi.G.scale if t > 1 else None,
+                         scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV)
+
+    # ---- output dictionary (output.jl:108-212)
+    ma, ma2, md = backend.get_means()
+    Mi.meanAlpha = [ma[k * p:(k + 1) * p] for k in range(t)]
+    Mi.meanAlpha2 = [ma2[k * p:(k + 1) * p] for k in range(t)]
+    Mi.meanDelta = [md[k * p:(k + 1) * p] for k in range(t)]
+    al, be, de = backend.get_state()
+    Mi.α = [al[k * p:(k + 1) * p] for k in range(t)]
+    Mi.β = [be[k * p:(k + 1) * p] for k in range(t)]
+    Mi.δ = [de[k * p:(k + 1) * p] for k in range(t)]
+    output = {}
+    output["location parameters"] = _frame(
+        [[tr, "intercept", "intercept", out["mu_mean"][k], math.sqrt(abs(out["mu_mean2"][k] - out["mu_mean"][k] ** 2))]
+         for k, tr in enumerate(model.lhsVec)], ["Trait", "Effect", "Level", "Estimate", "SD"])
+    vm = np.atleast_2d(out["vare_mean"]); vm2 = np.atleast_2d(out["vare_mean2"])
+    output["residual variance"] = _frame(
+        [[f"{model.lhsVec[i]}_{model.lhsVec[j]}", vm[i, j], math.sqrt(abs(vm2[i, j] - vm[i, j] ** 2))]
+         for i in range(t) for j in range(t)], ["Covariance", "Estimate", "SD"])
+    rows_me = []
+    for k, tr in enumerate(model.lhsVec):
+        sd = np.sqrt(np.abs(Mi.meanAlpha2[k].astype(np.float64) - Mi.meanAlpha[k].astype(np.float64) ** 2))
+        rows_me += [[tr, mid, float(e), float(s_), float(d)] for mid, e, s_, d in
+                    zip(Mi.markerID, Mi.meanAlpha[k], sd, Mi.meanDelta[k])]
+    output["marker effects " + Mi.name] = _frame(rows_me, ["Trait", "Marker_ID", "Estimate", "SD", "Model_Frequency"])
+    if Mi.estimatePi:
+        pm = np.atleast_1d(out["pi_mean"]); pm2 = np.atleast_1d(out["pi_mean2"])
+        if t == 1 and Mi.method != "BayesR":
+            labels = ["π"]
+        elif t == 1:
+            labels = [f"class{c + 1}" for c in range(len(pm))]
+        else:
+            labels = [str([float((s >> i) & 1) for i in range(t)]) for s in range(1 << t)]
+        output["pi_" + Mi.name] = _frame([[l, pm[i], math.sqrt(abs(pm2[i] - pm[i] ** 2))] for i, l in enumerate(labels)],
+                                         ["π", "Estimate", "SD"])
+        Mi.mean_pi = out["pi_mean"]
+    if outputEBV and out.get("ebv_mean") is not None:
+        for k, tr in enumerate(model.lhsVec):
+            em, ev = out["ebv_mean"][k], out["ebv_var"][k]
+            output["EBV_" + tr] = _frame([[i, float(a), float(v)] for i, a, v in zip(ids, em, ev)], ["ID", "EBV", "PEV"])
+    model.output = output
+    model.sol = out["mu"]
+    return output

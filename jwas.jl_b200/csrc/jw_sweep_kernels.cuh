@@ -663,7 +663,7 @@ jw_k_accumulate(const float* __restrict__ alpha, const int32_t* __restrict__ del
 
 // BayesB: var_j = (beta_j^2 + df*scale)/chisq(df+1) (variance_components.jl:60-66, 169-172).
 // chisq(k) = 2*Gamma(k/2) by Marsaglia-Tsang with draws from the native stream
-// (slot 254/255 of the marker's counter space, attempt number in `rep`).
+// (pseudo-traits 126/127 of the marker's counter space, attempt number in `rep`).
 __global__ void __launch_bounds__(256)
 jw_k_bayesb_var(const float* __restrict__ beta, int64_t p, double df, double scale,
                 uint64_t seed, uint32_t iter, double* __restrict__ ve) {

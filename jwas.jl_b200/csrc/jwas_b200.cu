@@ -692,6 +692,16 @@ extern "C" int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, con
     return run_sweep(h, c, stats);
 }
 
+extern "C" int jwas_fill_hyper(jwas_handle* h, int which, double value) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(which == 0 || which == 1, "jwas_fill_hyper: which must be 0 (var_effects) or 1 (pi)");
+    JW_CUDA(cudaSetDevice(h->device));
+    if (which == 0) { JW_REQUIRE(value > 0.0, "variances must be positive"); if (fill_doubles(h, &h->d_ve, &h->cap_ve, value, (size_t)h->p)) return 10; }
+    else { JW_REQUIRE(value >= 0.0 && value <= 1.0, "pi must lie in [0,1]"); if (fill_doubles(h, &h->d_pi, &h->cap_pi, value, (size_t)h->p)) return 10; }
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int jwas_sample_bayesb_variances(jwas_handle* h, double df, double scale, uint64_t seed,
                                             uint32_t iter, double* out) {
     JW_REQUIRE(h, "null handle");

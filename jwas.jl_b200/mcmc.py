@@ -105,6 +105,12 @@ class GpuBackend:
     def sample_bayesb_variances(self, df, scale, seed, it):
         self.s.sample_bayesb_variances(df, scale, seed, it)
 
+    def fill_hyper(self, which, value):
+        self.s.fill_hyper(which, value)
+
+    def mul_alpha(self, trait):
+        return self.s.mul_alpha(trait)
+
     def accumulate(self, nsamples, bayesr=False):
         self.s.accumulate(nsamples, bayesr)
 
@@ -116,7 +122,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               seed, vare, var_effect, pi, df_effect, scale_effect, df_res, scale_res,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
-              mu0=None, iter0=0):
+              mu0=None, iter0=0, want_ebv=False):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -128,15 +134,20 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
     rng = HostRng([seed, iter0])
     t = ntraits
     mu = np.zeros(t) if mu0 is None else np.array(mu0, dtype=np.float64)
-    out = {"mu_mean": np.zeros(t), "vare_mean": 0.0, "vara_mean": 0.0, "pi_mean": 0.0, "nsamples": 0,
-           "trace": []}
+    out = {"mu_mean": np.zeros(t), "mu_mean2": np.zeros(t), "vare_mean": 0.0, "vare_mean2": 0.0,
+           "vara_mean": 0.0, "vara_mean2": 0.0, "pi_mean": 0.0, "pi_mean2": 0.0, "nsamples": 0, "trace": [],
+           "ebv_mean": None, "ebv_var": None}
     if method == "BayesR":
         pi = np.array(pi, dtype=np.float64)
-        out["pi_mean"] = np.zeros_like(pi)
+        out["pi_mean"] = np.zeros_like(pi); out["pi_mean2"] = np.zeros_like(pi)
     if t > 1:
         R = np.array(R, dtype=np.float64); G = np.array(G, dtype=np.float64)
         big_pi = np.array(big_pi, dtype=np.float64)
-        out["vare_mean"] = np.zeros((t, t)); out["vara_mean"] = np.zeros((t, t)); out["pi_mean"] = np.zeros_like(big_pi)
+        for key in ("vare_mean", "vare_mean2", "vara_mean", "vara_mean2"):
+            out[key] = np.zeros((t, t))
+        out["pi_mean"] = np.zeros_like(big_pi); out["pi_mean2"] = np.zeros_like(big_pi)
+    ebv_m = ebv_s = None
+    first_bayesb = True
     nsamples = 0
     ysum = None
     for it in range(iter0 + 1, iter0 + chain_length + 1):
@@ -155,6 +166,12 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                 if method == "BayesC":
                     st = backend.sweep_bayesc(schedule, vare, var_effect, pi, seed, it)
                 else:
+                    # BayesB/BayesA: G.val is a per-marker vector kept on the device
+                    # (MCMC_BayesianAlphabet.jl:67-69); pi is refreshed when it is re-sampled
+                    if first_bayesb:
+                        backend.fill_hyper("var_effects", var_effect)
+                        first_bayesb = False
+                    backend.fill_hyper("pi", pi)
                     st = backend.sweep_bayesabc(schedule, vare, None, None, seed, it)
             else:
                 st = backend.sweep_mt1(schedule, R, G, big_pi, seed, it)
@@ -198,11 +215,28 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
             nsamples += 1
             backend.accumulate(nsamples, bayesr=(method == "BayesR"))
             out["mu_mean"] += (mu - out["mu_mean"]) / nsamples
-            out["vare_mean"] = out["vare_mean"] + ((vare if t == 1 else R) - out["vare_mean"]) / nsamples
+            out["mu_mean2"] += (mu ** 2 - out["mu_mean2"]) / nsamples
+            ve_now = vare if t == 1 else R
+            out["vare_mean"] = out["vare_mean"] + (ve_now - out["vare_mean"]) / nsamples
+            out["vare_mean2"] = out["vare_mean2"] + (ve_now ** 2 - out["vare_mean2"]) / nsamples
             if method != "BayesB" and method != "BayesA":
-                out["vara_mean"] = out["vara_mean"] + ((var_effect if t == 1 else G) - out["vara_mean"]) / nsamples
+                va_now = var_effect if t == 1 else G
+                out["vara_mean"] = out["vara_mean"] + (va_now - out["vara_mean"]) / nsamples
+                out["vara_mean2"] = out["vara_mean2"] + (va_now ** 2 - out["vara_mean2"]) / nsamples
             if estimate_pi:
-                out["pi_mean"] = out["pi_mean"] + ((pi if t == 1 else big_pi) - out["pi_mean"]) / nsamples
+                pi_now = pi if t == 1 else big_pi
+                out["pi_mean"] = out["pi_mean"] + (pi_now - out["pi_mean"]) / nsamples
+                out["pi_mean2"] = out["pi_mean2"] + (pi_now ** 2 - out["pi_mean2"]) / nsamples
+            if want_ebv:                    # getEBV per saved sample (output.jl:281-306, 489-495)
+                e = np.array([backend.mul_alpha(k) for k in range(t)], dtype=np.float64)
+                if ebv_m is None:
+                    ebv_m = np.zeros_like(e); ebv_s = np.zeros_like(e)
+                d = e - ebv_m
+                ebv_m += d / nsamples
+                ebv_s += d * (e - ebv_m)
+    if ebv_m is not None:
+        out["ebv_mean"] = ebv_m
+        out["ebv_var"] = ebv_s / max(nsamples - 1, 1)
     out.update(nsamples=nsamples, mu=mu, vare=vare if t == 1 else R, var_effect=var_effect if t == 1 else G,
                pi=pi if t == 1 else big_pi)
     return out

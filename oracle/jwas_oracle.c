@@ -504,6 +504,40 @@ void jwo_bayesr_sigma_sufficient_statistics(const float* alpha, const int32_t* d
 }
 
 /* ======================================================================== */
+/* contract-arithmetic hyper-parameter helpers                              */
+/* ======================================================================== */
+
+/* BayesB per-marker variance (variance_components.jl:60-66, 169-172):
+ *   var_j = (beta_j^2 + df*scale) / chisq(df + 1),  chisq(k) = 2*Gamma(k/2) by Marsaglia-Tsang
+ * with draws from the native stream (pseudo-traits 126/127 of the marker's counter space, attempt
+ * number in the repetition field).  Twin of jw_k_bayesb_var. */
+void jwo_bayesb_variances(const float* beta, int64_t p, double df, double scale,
+                          uint64_t seed, uint32_t iter, double* ve) {
+    for (int64_t j = 0; j < p; ++j) {
+        double shape = 0.5 * (df + 1.0);
+        double boost = 1.0;
+        if (shape < 1.0) {
+            double uu = jw_draw_uniform(seed, (uint32_t)j, iter, 126u, 0u);
+            boost = jw_exp(jw_log(uu) / shape);
+            shape += 1.0;
+        }
+        double d = shape - 1.0 / 3.0, c = 1.0 / jw_sqrt(9.0 * d);
+        double g = d;
+        for (uint32_t att = 0; att < 64u; ++att) {
+            double zz = jw_draw_normal(seed, (uint32_t)j, iter, 127u, att);
+            double uu = jw_draw_uniform(seed, (uint32_t)j, iter, 127u, att);
+            double v = 1.0 + c * zz;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            if (jw_log(uu) < 0.5 * zz * zz + d - d * v + d * jw_log(v)) { g = d * v; break; }
+        }
+        double chisq = 2.0 * g * boost;
+        double b = (double)beta[j];
+        ve[j] = (b * b + df * scale) / chisq;
+    }
+}
+
+/* ======================================================================== */
 /* contract-arithmetic sweep                                                */
 /* ======================================================================== */
 

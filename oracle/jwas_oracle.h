@@ -94,6 +94,10 @@ int jwo_validate_block_starts(const int64_t* starts, int64_t nstarts, int64_t nm
 void jwo_bayesr_sigma_sufficient_statistics(const float* alpha, const int32_t* delta,
                                             const double* gamma, int64_t p, double* ssq, int64_t* nnz);
 
+/* BayesB per-marker variances under the contract stream (variance_components.jl:169-172) */
+void jwo_bayesb_variances(const float* beta, int64_t p, double df, double scale,
+                          uint64_t seed, uint32_t iter, double* ve);
+
 /* ---- contract-arithmetic sweep (what the CUDA path must reproduce bit for bit) ---- */
 #define JWO_METHOD_ABC 0   /* BayesA/B/C */
 #define JWO_METHOD_R   1   /* BayesR     */

@@ -194,6 +194,14 @@ def bayesr_sigma_sufficient_statistics(alpha, delta, gamma):
     return ssq.value, nnz.value
 
 
+def bayesb_variances(beta, df, scale, seed, it):
+    b = _f32(beta)
+    ve = np.empty(len(b), np.float64)
+    lib().jwo_bayesb_variances(_p(b), C.c_int64(len(b)), C.c_double(df), C.c_double(scale), C.c_uint64(seed),
+                               C.c_uint32(it), _p(ve))
+    return ve
+
+
 def max_threads():
     return lib().jwo_max_threads()
 

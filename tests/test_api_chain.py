@@ -1,0 +1,184 @@
+"""Host-side logic of the reference-facing API (get_genotypes / build_model / runMCMC) driven over
+the CPU oracle backend: schedules, priors, outputs, error behaviour.  Mirrors the reference's own
+smoke / reproducibility / schedule / constraint tests."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import jwas_b200 as jw
+from helpers import make_codes, make_phenotype
+from oracle_backend import factory
+from oracle import pyoracle as orc
+
+
+def make_data(n=120, p=90, seed=3, ntraits=1, missing=0.0):
+    codes = make_codes(n, p, seed, missing=missing).astype(float)
+    packed = orc.pack_codes(np.where(codes == 9, 9, codes).astype(int))
+    means, _ = orc.marker_stats(packed, n)
+    X = orc.dense_centered(packed, n, means)
+    Y = make_phenotype(X, seed, ntraits=ntraits)
+    ids = [f"a{i + 1}" for i in range(n)]
+    ph = pd.DataFrame({"ID": ids, **{f"y{k + 1}": Y[k] for k in range(ntraits)}})
+    return codes, ids, ph
+
+
+def test_bayesc_run_outputs_and_reproducibility():
+    codes, ids, ph = make_data()
+    outs = []
+    for _ in range(2):
+        geno = jw.get_genotypes(codes, 1.0, method="BayesC", Pi=0.9, obsID=ids, quality_control=False)
+        model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+        out = jw.runMCMC(model, ph, chain_length=30, burnin=10, seed=2026, _backend_factory=factory)
+        outs.append(out)
+    out = outs[0]
+    # runtests.jl:265-283: keys, ranges
+    for key in ("location parameters", "residual variance", "marker effects geno", "pi_geno", "EBV_y1"):
+        assert key in out
+    me = out["marker effects geno"]
+    assert list(me.columns) == ["Trait", "Marker_ID", "Estimate", "SD", "Model_Frequency"]
+    assert len(me) == 90 and me["Model_Frequency"].between(0, 1).all()
+    assert 0 < out["pi_geno"]["Estimate"][0] < 1
+    assert len(out["EBV_y1"]) == 120
+    # runtests.jl:302-320: same seed -> identical results
+    np.testing.assert_array_equal(outs[0]["marker effects geno"]["Estimate"], outs[1]["marker effects geno"]["Estimate"])
+    assert outs[0]["residual variance"]["Estimate"][0] == outs[1]["residual variance"]["Estimate"][0]
+    assert model.MCMCinfo.chain_length == 30
+
+
+@pytest.mark.parametrize("method", ["BayesA", "BayesB", "BayesR"])
+def test_other_methods_run(method):
+    codes, ids, ph = make_data(seed=5)
+    geno = jw.get_genotypes(codes, 1.0, method=method, obsID=ids, Pi=(0.0 if method != "BayesB" else 0.8))
+    model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+    out = jw.runMCMC(model, ph, chain_length=12, burnin=2, seed=1, outputEBV=False, _backend_factory=factory)
+    me = out["marker effects geno"]
+    assert me["Model_Frequency"].between(0, 1).all()
+    if method == "BayesR":           # test_bayesr.jl:339-342
+        assert out["pi_geno"]["Estimate"].sum() == pytest.approx(1.0)
+        assert len(out["pi_geno"]) == 4
+    if method == "BayesA":           # every marker stays in the model
+        assert (me["Model_Frequency"] == 1).all()
+
+
+def test_multitrait_bayesc_run():
+    codes, ids, ph = make_data(ntraits=2, seed=7)
+    geno = jw.get_genotypes(codes, np.array([[1.0, 0.5], [0.5, 1.0]]), method="BayesC", obsID=ids)
+    model = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.array([[1.0, 0.5], [0.5, 1.0]]),
+                           genotypes={"geno": geno})
+    out = jw.runMCMC(model, ph, chain_length=12, burnin=2, seed=123, _backend_factory=factory)
+    assert len(out["residual variance"]) == 4          # test_multitrait_mcmc.jl:120
+    assert len(out["marker effects geno"]) == 2 * geno.nMarkers
+    assert out["pi_geno"]["Estimate"].sum() == pytest.approx(1.0)
+    assert "EBV_y1" in out and "EBV_y2" in out
+
+
+def test_fast_blocks_schedule_semantics():
+    # JWAS.jl:293-316; test_misc_coverage.jl:116-209
+    codes, ids, ph = make_data(n=50, p=40, seed=9)
+
+    def run(**kw):
+        geno = jw.get_genotypes(codes, 1.0, method="BayesC", obsID=ids, quality_control=False)
+        model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+        out = jw.runMCMC(model, ph, seed=123, outputEBV=False, _backend_factory=factory, **kw)
+        return model, out
+
+    m, _ = run(chain_length=21, fast_blocks=True)                 # block = floor(sqrt(50)) = 7
+    assert m.MCMCinfo.fast_blocks == list(range(1, 41, 7)) and m.MCMCinfo.chain_length == 3
+    m, _ = run(chain_length=6, fast_blocks=[1, 3, 5], independent_blocks=True)
+    assert m.MCMCinfo.fast_blocks == [1, 3, 5] and m.MCMCinfo.chain_length == 6
+    assert m.MCMCinfo.independent_blocks is True
+    with pytest.raises(jw.JwasError, match="independent_blocks=true requires fast_blocks"):
+        run(chain_length=6, independent_blocks=True)
+    for bad in ([2, 4], [1, 3, 3], [3, 1], [1, 100]):
+        with pytest.raises(jw.JwasError, match="fast_blocks"):
+            run(chain_length=6, fast_blocks=bad)
+    with pytest.raises(jw.JwasError, match="at least two block starts"):
+        run(chain_length=6, fast_blocks=1000)
+
+
+def test_constraint_errors():
+    # input_data_validation.jl:45-66, 81-111 style guards for what this backend does not cover
+    codes, ids, ph = make_data(n=30, p=20)
+    with pytest.raises(jw.JwasError, match="outside the GPU marker-sweep path"):
+        jw.get_genotypes(codes, 1.0, method="RR-BLUP")
+    with pytest.raises(jw.JwasError, match="Only 0/1/2 genotypes"):
+        jw.get_genotypes(codes + 0.5, 1.0)
+    with pytest.raises(jw.JwasError, match="outside the GPU marker-sweep path"):
+        jw.set_random(None, "x")
+    geno = jw.get_genotypes(codes, 1.0, obsID=ids, quality_control=False)
+    with pytest.raises(jw.JwasError, match="not a genotype term"):
+        jw.build_model("y1 = intercept + x1 + geno", 1.0, genotypes={"geno": geno})
+    model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+    with pytest.raises(jw.JwasError, match="heterogeneous_residuals"):
+        jw.runMCMC(model, ph, heterogeneous_residuals=True, _backend_factory=factory)
+    ph2 = ph.copy(); ph2.loc[0, "ID"] = "zzz"
+    with pytest.raises(jw.JwasError, match="without genotypes"):
+        jw.runMCMC(model, ph2, _backend_factory=factory)
+
+
+def test_quality_control_and_phenotype_subset():
+    codes, ids, ph = make_data(n=60, p=30, seed=11)
+    codes[:, 3] = 1.0                       # fixed locus -> removed (readgenotypes.jl:388-399)
+    codes[:, 7] = 0.0; codes[0, 7] = 1.0    # MAF = 1/120 < 0.01 -> removed
+    geno = jw.get_genotypes(codes, 1.0, obsID=ids)
+    assert geno.nMarkers == 28 and "m4" not in geno.markerID and "m8" not in geno.markerID
+    model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+    sub = ph.iloc[::-1].iloc[:40].reset_index(drop=True)     # subset + reorder: genotypes follow phenotypes
+    out = jw.runMCMC(model, sub, chain_length=5, seed=1, _backend_factory=factory)
+    assert list(out["EBV_y1"]["ID"]) == list(sub["ID"])
+
+
+def test_jgb2_backend_files_roundtrip(tmp_path):
+    """prepare_streaming_genotypes / load_streaming_backend write and read the reference's packed
+    backend files (streaming_genotypes.jl:77-95, 636-654, 884-971): same manifest keys, .jgb2 bit
+    layout and Float32 side-cars."""
+    codes = np.array([[0, 1, 2, 0], [1, 0, 1, 2], [2, 9, 0, 1], [0, 2, 1, 0], [1, 1, 2, 2], [2, 0, 0, 1]], float)
+    csv = tmp_path / "geno_missing.csv"
+    pd.DataFrame(np.column_stack([[f"a{i}" for i in range(1, 7)], codes.astype(int)]),
+                 columns=["ID", "m1", "m2", "m3", "m4"]).to_csv(csv, index=False)
+    prefix = jw.prepare_streaming_genotypes(str(csv), quality_control=True)
+    assert os.path.isfile(prefix + ".jgb2") and os.path.isfile(prefix + ".meta")
+    meta = dict(l.rstrip("\n").split("\t", 1) for l in open(prefix + ".meta"))
+    for key in ("version", "data_path", "obs_path", "marker_path", "selected_path", "mean_path", "xp_path",
+                "afreq_path", "nObs", "nMarkers", "nMarkersAll", "stride_bytes", "centered", "sum2pq"):
+        assert key in meta
+    raw = np.fromfile(prefix + ".jgb2", dtype=np.uint8).reshape(4, 2)
+    assert raw[1].tolist() == [0xB1, 0x01]                    # test_streaming_codec.jl fixture, m2 with missing
+    g = jw.get_genotypes(prefix, 1.0, method="BayesC")
+    assert g.nObs == 6 and g.nMarkers == 4 and g.obsID == [f"a{i}" for i in range(1, 7)]
+    means = np.fromfile(meta["mean_path"], dtype=np.float32)
+    xp = np.fromfile(meta["xp_path"], dtype=np.float32)
+    for j in range(4):                                        # decode == dense, xpRinvx == dot(decoded, decoded)
+        d = orc.decode_marker(g.packed, 6, j, float(means[j]))
+        assert float(d @ d) == pytest.approx(float(xp[j]), abs=1e-5)
+    assert means[1] == pytest.approx(0.8)
+
+
+def test_contract_arithmetic_tracks_reference_arithmetic():
+    """The contract sweep (fixed-point dots, binary64 scalars) and the faithful Float32 restatement of
+    BayesABC! agree to Float32 rounding on a sweep with shared draws (same pattern as the reference's
+    dense-vs-stream check, test_streaming_codec.jl:53-105, atol 1e-4)."""
+    n, p = 300, 200
+    codes = make_codes(n, p, 13)
+    packed = orc.pack_codes(codes)
+    means, xpx = orc.marker_stats(packed, n)
+    X = orc.dense_centered(packed, n, means)
+    y = make_phenotype(X, 13)[0]
+    yc = (y - y.mean()).astype(np.float32)
+    rng = np.random.default_rng(0)
+    ve = np.full(p, 0.02); pi = np.full(p, 0.8)
+    y1, a1, b1, d1 = yc.copy(), np.zeros(p, np.float32), np.zeros(p, np.float32), np.zeros(p, np.float32)
+    y2, a2, b2, d2 = yc.copy(), np.zeros(p, np.float32), np.zeros(p, np.float32), np.zeros(p, np.int32)
+    y3, a3, b3, d3 = yc.copy(), np.zeros(p, np.float32), np.zeros(p, np.float32), np.zeros(p, np.float32)
+    for it in range(3):
+        u = rng.random(p); z = rng.standard_normal(p)
+        orc.bayesabc_ref(X, xpx, y1, a1, b1, d1, 1.0, ve, pi, u, z)
+        orc.sweep_contract(packed, n, means, xpx, [0, 64, 128, p], y2, a2, b2, d2, vare=1.0, varEffects=ve, pi=pi, u=u, z=z)
+        orc.bayesabc_streaming_ref(packed, n, means, xpx, y3, a3, b3, d3, 1.0, ve, pi, u, z)
+        np.testing.assert_array_equal(d1.astype(np.int32), d2)
+        np.testing.assert_allclose(a2, a1, atol=1e-4)
+        np.testing.assert_allclose(y2, y1, atol=1e-3)
+        np.testing.assert_allclose(a3, a1, atol=1e-4)       # dense == stream (reference's own check)
+    assert d2.sum() > 5
