@@ -790,3 +790,23 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
     free(yq); free(xbuf);
     return a->overflow ? 2 : 0;
 }
+
+/* ======================================================================== */
+/* contract primitives exposed for tests/test_contract.py                   */
+/* ======================================================================== */
+double jwo_c_log(double x) { return jw_log(x); }
+double jwo_c_exp(double x) { return jw_exp(x); }
+double jwo_c_cos2pi(double v) { return jw_cos2pi(v); }
+double jwo_c_normal(double u1, double u2) { return jw_normal(u1, u2); }
+void jwo_c_philox(const uint32_t* c, const uint32_t* k, uint32_t* out) {
+    jw_u32x4 r = jw_philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+}
+void jwo_c_draws(uint64_t seed, uint32_t iter, uint32_t trait, uint32_t rep, int64_t p, double* u, double* z) {
+    for (int64_t j = 0; j < p; ++j) {
+        u[j] = jw_draw_uniform(seed, (uint32_t)j, iter, trait, rep);
+        z[j] = jw_draw_normal(seed, (uint32_t)j, iter, trait, rep);
+    }
+}
+int32_t jwo_c_quantize(float y, float scale, int* ovf) { return jw_quantize(y, scale, ovf); }
+int jwo_c_scale_exp(float maxabs) { return jw_choose_scale_exp(maxabs); }

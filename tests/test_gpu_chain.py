@@ -52,7 +52,7 @@ def test_block_schedules_chain(kw):
 def test_multitrait_chain_matches_oracle_chain():
     codes, ids, ph = make_data(n=250, p=300, seed=25, ntraits=2)
     G = np.array([[1.0, 0.5], [0.5, 1.0]]); R = np.array([[1.0, 0.3], [0.3, 1.0]])
-    Pi = {(0.0, 0.0): 0.7, (1.0, 0.0): 0.1, (0.0, 1.0): 0.1, (1.0, 1.0): 0.1}
+    Pi = {(0.0, 0.0): 0.35, (1.0, 0.0): 0.20, (0.0, 1.0): 0.15, (1.0, 1.0): 0.30}
     g, o = both(codes, ids, ph, "y1 = intercept + geno\ny2 = intercept + geno", G, R, "BayesC", Pi,
                 chain_length=15, burnin=3)
     assert_same(g, o)
