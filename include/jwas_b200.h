@@ -139,6 +139,17 @@ int jwas_get_means(jwas_handle* h, float* mean_alpha, float* mean_alpha2, float*
 /* Gram block of block `ib` (b*b floats, row-major) -- XpRinvX[ib] of GibbsMats */
 int jwas_get_gram(jwas_handle* h, int64_t ib, float* out);
 
+/* ---- multi-GPU: individuals (rows of M) shard across the GPUs of one node, one process per GPU.
+ * Every rank holds the whole packed matrix and the replicated sampler state; rank r streams only
+ * rows [begin,end) of every column.  Per marker block the exact int64 partial rhs are summed with
+ * one NCCL all-reduce, every rank runs the identical chain (same draws -> same bits) and applies the
+ * axpy to its own rows; the ycorr shards are re-assembled at the end of the sweep.  Results are
+ * bit-identical for any number of ranks.  rank 0 calls jwas_nccl_unique_id and the host language
+ * broadcasts the 128 bytes (torch.distributed, MPI, a file ...). */
+int jwas_nccl_unique_id(uint8_t* out128);
+int jwas_init_sharding(jwas_handle* h, int rank, int world, const uint8_t* unique_id128);
+int jwas_get_row_range(jwas_handle* h, int64_t* begin, int64_t* end);
+
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 int64_t jwas_kernel_launches(jwas_handle* h);     /* kernels launched by this handle so far */
 int jwas_set_option(jwas_handle* h, const char* key, int64_t value);

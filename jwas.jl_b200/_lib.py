@@ -46,6 +46,9 @@ def lib():
         "jwas_get_gram": [vp, i64, vp],
         "jwas_last_stream_kernel_ms": [vp, C.POINTER(i64)],
         "jwas_get_phase_ns": [vp, vp],
+        "jwas_nccl_unique_id": [vp],
+        "jwas_init_sharding": [vp, i32, i32, vp],
+        "jwas_get_row_range": [vp, C.POINTER(i64), C.POINTER(i64)],
         "jwas_destroy": [vp],
         "jwas_device_count": [],
         "jwas_get_marker_stats": [vp, vp, vp],
@@ -93,6 +96,12 @@ def _p(a):
 
 def _arr(a, dt):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def nccl_unique_id():
+    out = np.zeros(128, np.uint8)
+    _check(lib().jwas_nccl_unique_id(_p(out)))
+    return out.tobytes()
 
 
 def device_count():
@@ -246,6 +255,15 @@ class GpuSweeper:
         ma = np.empty(tp, np.float32); ma2 = np.empty(tp, np.float32); md = np.empty(tp, np.float32)
         _check(lib().jwas_get_means(self._h, _p(ma), _p(ma2), _p(md)))
         return ma, ma2, md
+
+    def init_sharding(self, rank, world, unique_id=None):
+        uid = None if unique_id is None else np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        _check(lib().jwas_init_sharding(self._h, int(rank), int(world), _p(uid)))
+
+    def row_range(self):
+        b, e = C.c_int64(), C.c_int64()
+        _check(lib().jwas_get_row_range(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
 
     def phase_ns(self):
         out = np.zeros(16, np.uint64)

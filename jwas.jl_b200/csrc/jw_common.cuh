@@ -91,6 +91,11 @@ struct jwas_handle {
     std::vector<cudaEvent_t> prof_events;
     double prof_ms = 0.0; int64_t prof_launches = 0;
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
+    // row-sharded multi-GPU sweep: this rank streams rows [row_begin, row_end) of every column
+    int64_t row_begin = 0, row_end = 0;
+    int world = 1, rank = 0;
+    void* nccl_comm = nullptr;
+    std::vector<int64_t> shard_bounds;   // world+1 row boundaries (multiples of 16 except the last)
     void* fused = nullptr;         // jw_fused_state (engine 1)
     float next_maxabs = -1.0f;     // carried from the previous sweep's stats when ycorr untouched
 };

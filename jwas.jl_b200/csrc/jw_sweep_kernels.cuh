@@ -14,12 +14,14 @@
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 jw_k_quantize(const float* __restrict__ y, int64_t n, int t, float scale,
-              int32_t* __restrict__ yq, long long* __restrict__ sq, int32_t* __restrict__ flags) {
+              int32_t* __restrict__ yq, long long* __restrict__ sq, int32_t* __restrict__ flags,
+              int64_t r0, int64_t r1) {
     int k = blockIdx.y;
     long long acc = 0;
     int ovf = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int32_t q = jw_quantize(y[k * n + i], scale, &ovf);
+        // rows owned by other ranks contribute nothing to this rank's partial sums
+        int32_t q = (i >= r0 && i < r1) ? jw_quantize(y[k * n + i], scale, &ovf) : 0;
         yq[k * n + i] = q;
         acc += q;
     }
@@ -37,15 +39,14 @@ template <int T, bool MISSING>
 __global__ void __launch_bounds__(256)
 jw_k_block_dot(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
                int64_t j0, int64_t nj, const int32_t* __restrict__ yq,
-               long long* __restrict__ dq, long long* __restrict__ mq) {
+               long long* __restrict__ dq, long long* __restrict__ mq, int64_t w0, int64_t w1) {
     int64_t jj = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (jj >= nj) return;
     int64_t j = j0 + jj;
     int lane = threadIdx.x & 31;
     const uint32_t* col = reinterpret_cast<const uint32_t*>(packed + j * stride_d);
-    int64_t nwords = (n + 15) >> 4;
-    int64_t wbeg = (int64_t)blockIdx.y * JW_DOT_SLAB_WORDS;
-    int64_t wend = min(wbeg + JW_DOT_SLAB_WORDS, nwords);
+    int64_t wbeg = w0 + (int64_t)blockIdx.y * JW_DOT_SLAB_WORDS;
+    int64_t wend = min(wbeg + JW_DOT_SLAB_WORDS, w1);
     long long acc[T], macc[T];
 #pragma unroll
     for (int k = 0; k < T; ++k) { acc[k] = 0; macc[k] = 0; }
@@ -514,10 +515,10 @@ __global__ void __launch_bounds__(256)
 jw_k_apply(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
            const float* __restrict__ means, const float* __restrict__ dalpha,
            const int32_t* __restrict__ act_idx, const int32_t* __restrict__ act_cnt,
-           float* __restrict__ y) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+           float* __restrict__ y, int64_t r0, int64_t r1) {
+    int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = *act_cnt;
-    if (i >= n || cnt == 0) return;
+    if (i >= r1 || cnt == 0) return;
     float v[T];
 #pragma unroll
     for (int k = 0; k < T; ++k) v[k] = y[k * n + i];

@@ -9,6 +9,7 @@
 #include "jw_setup_kernels.cuh"
 #include "jw_sweep_kernels.cuh"
 #include "jw_fused_sweep.cuh"
+#include "jw_nccl.cuh"
 
 static thread_local std::string g_err;
 void jw_set_error(const std::string& s) { g_err = s; }
@@ -58,6 +59,7 @@ static int create_common(int64_t n, int64_t p, int t, int device, jwas_handle** 
     jwas_handle* h = new jwas_handle();
     h->device = device; h->n = n; h->p = p; h->t = t; h->stride = (n + 3) / 4;
     h->stride_d = ceil_div((n + 3) / 4, 16) * 16;
+    h->row_begin = 0; h->row_end = n;
     cudaDeviceProp prop;
     JW_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
@@ -195,6 +197,7 @@ extern "C" int jwas_destroy(jwas_handle* h) {
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (h->nccl_comm && jw_nccl()) jw_nccl()->CommDestroy(h->nccl_comm);
     jw_fused_free(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -424,9 +427,10 @@ static void prof_collect(jwas_handle* h) {
 }
 static int dispatch_dot(jwas_handle* h, int64_t j0, int64_t nj) {
     if (prof_begin(h)) return 10;
-    dim3 grid((unsigned)ceil_div(nj, 8), (unsigned)ceil_div(ceil_div(h->n, 16), JW_DOT_SLAB_WORDS));
+    const int64_t w0 = h->row_begin >> 4, w1 = ceil_div(h->row_end, 16);
+    dim3 grid((unsigned)ceil_div(nj, 8), (unsigned)std::max<int64_t>(1, ceil_div(w1 - w0, JW_DOT_SLAB_WORDS)));
     long long* mq = h->d_mq;
-#define JW_DOT(T_, M_) jw_k_block_dot<T_, M_><<<grid, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, j0, nj, h->d_yq, h->d_dq, mq)
+#define JW_DOT(T_, M_) jw_k_block_dot<T_, M_><<<grid, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, j0, nj, h->d_yq, h->d_dq, mq, w0, w1)
     bool ms = h->has_missing != 0;
     switch (h->t) {
         case 1: if (ms) JW_DOT(1, true); else JW_DOT(1, false); break;
@@ -440,8 +444,8 @@ static int dispatch_dot(jwas_handle* h, int64_t j0, int64_t nj) {
     return 0;
 }
 static int dispatch_apply(jwas_handle* h) {
-    unsigned g = (unsigned)ceil_div(h->n, 256);
-#define JW_APPLY(T_) jw_k_apply<T_><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_ycorr)
+    unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(h->row_end - h->row_begin, 256));
+#define JW_APPLY(T_) jw_k_apply<T_><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_ycorr, h->row_begin, h->row_end)
     switch (h->t) { case 1: JW_APPLY(1); break; case 2: JW_APPLY(2); break; case 3: JW_APPLY(3); break; default: JW_APPLY(4); }
 #undef JW_APPLY
     JW_LAUNCH_CHECK(h);
@@ -505,6 +509,42 @@ static int collect_stats(jwas_handle* h, const sweep_cfg& c, int S, jwas_sweep_s
     return 0;
 }
 
+// multi-GPU: exact int64 partial rhs of markers [j0, j0+nj) summed over ranks (C1 of SURVEY 2a)
+static int reduce_block_rhs(jwas_handle* h, int64_t j0, int64_t nj) {
+    if (h->world == 1) return 0;
+    jw_nccl_api* N = jw_nccl();
+    JW_REQUIRE(N && h->nccl_comm, "multi-GPU sweep without an initialised NCCL communicator");
+    JW_NCCL(N->GroupStart());
+    for (int k = 0; k < h->t; ++k) {
+        long long* dq = h->d_dq + (size_t)k * h->p + j0;
+        JW_NCCL(N->AllReduce(dq, dq, (size_t)nj, JW_NCCL_INT64, JW_NCCL_SUM, h->nccl_comm, h->stream));
+        if (h->has_missing) {
+            long long* mq = h->d_mq + (size_t)k * h->p + j0;
+            JW_NCCL(N->AllReduce(mq, mq, (size_t)nj, JW_NCCL_INT64, JW_NCCL_SUM, h->nccl_comm, h->stream));
+        }
+    }
+    JW_NCCL(N->AllReduce(h->d_sq, h->d_sq, (size_t)h->t, JW_NCCL_INT64, JW_NCCL_SUM, h->nccl_comm, h->stream));
+    JW_NCCL(N->GroupEnd());
+    return 0;
+}
+// multi-GPU: every rank updated only its own rows of ycorr; make the vector whole again
+static int gather_ycorr(jwas_handle* h) {
+    if (h->world == 1) return 0;
+    jw_nccl_api* N = jw_nccl();
+    JW_REQUIRE(N && h->nccl_comm, "multi-GPU sweep without an initialised NCCL communicator");
+    JW_NCCL(N->GroupStart());
+    for (int r = 0; r < h->world; ++r) {
+        int64_t b0 = h->shard_bounds[r], b1 = h->shard_bounds[r + 1];
+        if (b1 <= b0) continue;
+        for (int k = 0; k < h->t; ++k) {
+            float* ptr = h->d_ycorr + (size_t)k * h->n + b0;
+            JW_NCCL(N->Broadcast(ptr, ptr, (size_t)(b1 - b0), JW_NCCL_FLOAT32, r, h->nccl_comm, h->stream));
+        }
+    }
+    JW_NCCL(N->GroupEnd());
+    return 0;
+}
+
 static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     JW_REQUIRE(h->nblocks > 0, "jwas_set_blocks must be called before a sweep");
     JW_REQUIRE(st != nullptr, "stats is NULL");
@@ -556,7 +596,7 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
         A.prep = h->d_prep; A.prep_beta0 = h->d_prep_beta0;
     }
 
-    if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT) {
+    if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT && h->world == 1) {
         int rc = jw_fused_sweep(h, A, scale);
         if (rc) return rc;
         return collect_stats(h, c, S, st);
@@ -569,9 +609,10 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     if (c.schedule == JWAS_SCHED_INDEPENDENT) {
         // all blocks read the entry snapshot (BayesABC.jl:205); one GEMV over all of M
         JW_CUDA(cudaMemsetAsync(h->d_sq, 0, JW_MAX_TRAITS * sizeof(long long), h->stream));
-        jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags);
+        jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags, h->row_begin, h->row_end);
         JW_LAUNCH_CHECK(h);
         if (dispatch_dot(h, 0, p)) return 11;
+        if (reduce_block_rhs(h, 0, p)) return 13;
         A.block0 = 0; A.write_active_list = 0;
         if (dispatch_chain(h, A, (int)h->nblocks, threads)) return 11;
         jw_k_compact_active<<<1, 1024, 0, h->stream>>>(h->d_dalpha, p, t, h->d_act_idx, h->d_act_cnt);
@@ -580,14 +621,16 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     } else {
         for (int64_t ib = 0; ib < h->nblocks; ++ib) {
             JW_CUDA(cudaMemsetAsync(h->d_sq, 0, JW_MAX_TRAITS * sizeof(long long), h->stream));
-            jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags);
+            jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags, h->row_begin, h->row_end);
             JW_LAUNCH_CHECK(h);
             if (dispatch_dot(h, h->starts[ib], h->starts[ib + 1] - h->starts[ib])) return 11;
+            if (reduce_block_rhs(h, h->starts[ib], h->starts[ib + 1] - h->starts[ib])) return 13;
             A.block0 = (int)ib; A.write_active_list = 1;
             if (dispatch_chain(h, A, 1, threads)) return 11;
             if (dispatch_apply(h)) return 11;
         }
     }
+    if (gather_ycorr(h)) return 13;
     return collect_stats(h, c, S, st);
 }
 
@@ -734,6 +777,45 @@ extern "C" int jwas_get_means(jwas_handle* h, float* ma, float* ma2, float* md) 
     if (ma2) JW_CUDA(cudaMemcpyAsync(ma2, h->d_mean_alpha2, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (md) JW_CUDA(cudaMemcpyAsync(md, h->d_mean_delta, tp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int jwas_nccl_unique_id(uint8_t* out128) {
+    JW_REQUIRE(out128, "jwas_nccl_unique_id: null argument");
+    jw_nccl_api* N = jw_nccl();
+    JW_REQUIRE(N, "libnccl.so.2 could not be loaded");
+    jw_nccl_id id;
+    JW_NCCL(N->GetUniqueId(&id));
+    memcpy(out128, id.internal, JW_NCCL_UNIQUE_ID_BYTES);
+    return 0;
+}
+extern "C" int jwas_init_sharding(jwas_handle* h, int rank, int world, const uint8_t* unique_id128) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(world >= 1 && rank >= 0 && rank < world, "jwas_init_sharding: bad rank/world");
+    JW_CUDA(cudaSetDevice(h->device));
+    // row shards: equal numbers of 16-individual words per rank, the remainder to the first ranks
+    const int64_t nwords = ceil_div(h->n, 16);
+    h->shard_bounds.assign(world + 1, 0);
+    for (int r = 0; r < world; ++r) {
+        int64_t w = nwords / world + (r < nwords % world ? 1 : 0);
+        h->shard_bounds[r + 1] = std::min<int64_t>(h->n, h->shard_bounds[r] + w * 16);
+    }
+    h->shard_bounds[world] = h->n;
+    h->rank = rank; h->world = world;
+    h->row_begin = h->shard_bounds[rank]; h->row_end = h->shard_bounds[rank + 1];
+    if (world > 1) {
+        JW_REQUIRE(unique_id128, "jwas_init_sharding: unique id required for world > 1");
+        jw_nccl_api* N = jw_nccl();
+        JW_REQUIRE(N, "libnccl.so.2 could not be loaded");
+        jw_nccl_id id;
+        memcpy(id.internal, unique_id128, JW_NCCL_UNIQUE_ID_BYTES);
+        JW_NCCL(N->CommInitRank(&h->nccl_comm, world, id, rank));
+    }
+    return 0;
+}
+extern "C" int jwas_get_row_range(jwas_handle* h, int64_t* begin, int64_t* end) {
+    JW_REQUIRE(h && begin && end, "null argument");
+    *begin = h->row_begin; *end = h->row_end;
     return 0;
 }
 

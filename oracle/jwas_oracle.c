@@ -630,6 +630,7 @@ static void inv_spd_fixed(const double* A, int t, double* Ai) {
 int jwo_sweep_contract(jwo_sweep_args* a) {
     const int64_t n = a->n, p = a->p;
     const int t = a->ntraits;
+    const int64_t r0 = a->row_end > 0 ? a->row_begin : 0, r1 = a->row_end > 0 ? a->row_end : n;
     if (t < 1 || t > 8) return 1;
     if (a->method == JWO_METHOD_MT1 && t < 2) return 1;
 
@@ -662,7 +663,7 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
             for (int k = 0; k < t; ++k) {
                 sq[k] = 0;
                 for (int64_t i = 0; i < n; ++i) {
-                    int32_t q = jw_quantize(a->ycorr[k * n + i], scale, &a->overflow);
+                    int32_t q = (i >= r0 && i < r1) ? jw_quantize(a->ycorr[k * n + i], scale, &a->overflow) : 0;
                     yq[k * n + i] = q; sq[k] += q;
                 }
             }
@@ -673,19 +674,29 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
         float* G = (float*)malloc(sizeof(float) * (size_t)(b * b));
         float* aold = (float*)malloc(sizeof(float) * (size_t)(b * t));
         jwo_gram_block(a->packed, n, a->stride, a->means, s, b, G);
+        int64_t* dqv = (int64_t*)calloc((size_t)(2 * b * t + t), sizeof(int64_t));
+        int64_t* mqv = dqv + b * t;
+        int64_t* sqv = mqv + b * t;
         for (int64_t jj = 0; jj < b; ++jj) {
             const uint8_t* col = a->packed + (s + jj) * a->stride;
             for (int k = 0; k < t; ++k) {
                 int64_t dq = 0, mq = 0;
-                for (int64_t i = 0; i < n; ++i) {
+                for (int64_t i = r0; i < r1; ++i) {
                     unsigned c = jw_code(col, i);
                     if (c == 3u) mq += yq[k * n + i]; else dq += (int64_t)c * yq[k * n + i];
                 }
-                double mu = (double)a->means[s + jj];
-                r[k * b + jj] = ((double)dq - mu * (double)(sq[k] - mq)) * invscale;
-                aold[k * b + jj] = a->alpha[k * p + s + jj];
+                dqv[k * b + jj] = dq; mqv[k * b + jj] = mq;
             }
         }
+        for (int k = 0; k < t; ++k) sqv[k] = sq[k];
+        if (a->allreduce) a->allreduce(a->ctx, dqv, 2 * b * t + t);     /* C1: per-block rhs all-reduce */
+        for (int64_t jj = 0; jj < b; ++jj)
+            for (int k = 0; k < t; ++k) {
+                double mu = (double)a->means[s + jj];
+                r[k * b + jj] = ((double)dqv[k * b + jj] - mu * (double)(sqv[k] - mqv[k * b + jj])) * invscale;
+                aold[k * b + jj] = a->alpha[k * p + s + jj];
+            }
+        free(dqv);
         /* (3) in-block chain (BayesABC.jl:153-178, BayesR.jl:146-184, MTBayesABC.jl:276-327) */
         int nreps = a->nreps_mode ? (int)b : 1;
         for (int rep = 0; rep < nreps; ++rep) {
@@ -770,7 +781,7 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
                 if (d != 0.0f) {
                     jwo_decode_marker(a->packed + (s + jj) * a->stride, n, a->means[s + jj], 1, xbuf);
                     float* y = a->ycorr + k * n;
-                    for (int64_t i = 0; i < n; ++i) y[i] = fmaf(d, xbuf[i], y[i]);
+                    for (int64_t i = r0; i < r1; ++i) y[i] = fmaf(d, xbuf[i], y[i]);
                 }
             }
         free(r); free(G); free(aold);
@@ -782,7 +793,7 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
                 if (d != 0.0f) {
                     jwo_decode_marker(a->packed + j * a->stride, n, a->means[j], 1, xbuf);
                     float* y = a->ycorr + k * n;
-                    for (int64_t i = 0; i < n; ++i) y[i] = fmaf(d, xbuf[i], y[i]);
+                    for (int64_t i = r0; i < r1; ++i) y[i] = fmaf(d, xbuf[i], y[i]);
                 }
             }
         free(dall);

@@ -133,6 +133,11 @@ typedef struct {
     /* outputs */
     int overflow;                /* sticky: fixed-point clamp was hit */
     int scale_exp;               /* S used */
+    /* row-sharded emulation (multi-GPU host logic on CPU): this "rank" owns rows [row_begin,row_end)
+     * (row_end == 0 -> all rows); allreduce sums an int64 buffer in place over the ranks */
+    int64_t row_begin, row_end;
+    void (*allreduce)(void* ctx, int64_t* buf, int64_t count);
+    void* ctx;
 } jwo_sweep_args;
 
 int jwo_sweep_contract(jwo_sweep_args* a);

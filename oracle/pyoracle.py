@@ -37,7 +37,12 @@ class _SweepArgs(C.Structure):
         ("seed", C.c_uint64), ("iter", C.c_uint32),
         ("u", C.c_void_p), ("z", C.c_void_p),
         ("overflow", C.c_int), ("scale_exp", C.c_int),
+        ("row_begin", C.c_int64), ("row_end", C.c_int64),
+        ("allreduce", C.c_void_p), ("ctx", C.c_void_p),
     ]
+
+
+ALLREDUCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_int64), C.c_int64)
 
 
 _lib = None
@@ -209,7 +214,8 @@ def max_threads():
 # ---------------------------------------------------------------- contract sweep
 def sweep_contract(packed, n, means, xpx, starts, ycorr, alpha, beta, delta, *, method=METHOD_ABC,
                    nreps_mode=0, independent=False, vare=1.0, varEffects=None, pi=None,
-                   sigmaSq=0.0, gamma=None, R=None, G=None, bigPi=None, seed=0, it=1, u=None, z=None):
+                   sigmaSq=0.0, gamma=None, R=None, G=None, bigPi=None, seed=0, it=1, u=None, z=None,
+                   row_range=None, allreduce=None):
     """State arrays are modified in place: ycorr (t*n,) f32, alpha/beta (t*p,) f32, delta (t*p,) i32.
     starts: 0-based block boundaries of length nblocks+1."""
     p, stride = packed.shape
@@ -251,5 +257,13 @@ def sweep_contract(packed, n, means, xpx, starts, ycorr, alpha, beta, delta, *, 
             a.per_marker_pi = int(bp.ndim == 2)
     a.seed = int(seed); a.iter = int(it)
     a.u = hold(u, np.float64); a.z = hold(z, np.float64)
+    if row_range is not None:
+        a.row_begin, a.row_end = int(row_range[0]), int(row_range[1])
+    if allreduce is not None:
+        def _cb(ctx, buf, count):
+            arr = np.ctypeslib.as_array(buf, shape=(count,))
+            allreduce(arr)
+        cb = ALLREDUCE_CB(_cb); keep.append(cb)
+        a.allreduce = C.cast(cb, C.c_void_p)
     rc = lib().jwo_sweep_contract(C.byref(a))
     return rc, a.scale_exp

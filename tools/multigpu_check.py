@@ -1,0 +1,60 @@
+"""torchrun --nproc-per-node N tools/multigpu_check.py : the row-sharded NCCL sweep on N GPUs must give
+the same bits as the single-GPU sweep (engine 0 and engine 1) for BayesC (with missing data), BayesR
+and 2-trait BayesC."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.distributed as dist
+import jwas_b200
+from jwas_b200 import multigpu
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+rank, world = multigpu.init_process_group("nccl")
+n, p = 30011, 3000
+GAMMA = np.array([0.0, 0.01, 0.1, 1.0]); PI_R = np.array([0.95, 0.03, 0.015, 0.005])
+
+
+def run(t, method, sharded, engine, miss):
+    g = jwas_b200.GpuSweeper.synthetic(n, p, t, seed=11, missing_rate=miss, device=local)
+    g.set_blocks(np.array(list(range(0, p, 512)) + [p], dtype=np.int64))
+    g.set_option("engine", engine)
+    if sharded:
+        multigpu.attach(g, rank, world)
+    y = np.random.default_rng(3).standard_normal(t * n).astype(np.float32)
+    g.put_ycorr(y)
+    if method == "R":
+        g.put_state(None, None, np.ones(p, np.int32))
+    for it in (1, 2, 3):
+        if method == "C":
+            g.sweep_bayesc(jwas_b200.SCHED_EXACT, 1.0, 2e-3, 0.99, 5, it)
+        elif method == "R":
+            g.sweep_bayesr(jwas_b200.SCHED_EXACT, 1, 1.0, 5e-3, PI_R, GAMMA, 5, it)
+        elif method == "I":
+            g.sweep_bayesc(jwas_b200.SCHED_INDEPENDENT, 1.0, 2e-3, 0.99, 5, it)
+        else:
+            g.sweep_mt1(jwas_b200.SCHED_EXACT, np.array([[1.0, 0.3], [0.3, 1.0]]), np.array([[2e-3, 5e-4], [5e-4, 2e-3]]),
+                        np.array([0.97, 0.01, 0.01, 0.01]), 5, it)
+    a, b, d = g.get_state(); yc = g.get_ycorr()
+    g.close()
+    return a, b, d, yc
+
+
+ok = True
+for t, method, miss in ((1, "C", 0.01), (1, "R", 0.0), (2, "M", 0.0), (1, "I", 0.0)):
+    ref = run(t, method, False, 0, miss)
+    fused = run(t, method, False, 1, miss) if method != "I" else ref
+    sh = run(t, method, True, 0, miss)
+    same = all(np.array_equal(x, y) for x, y in zip(ref, sh)) and all(np.array_equal(x, y) for x, y in zip(ref, fused))
+    nz = int(np.count_nonzero(ref[0]))
+    print(f"rank {rank}/{world} method {method} t={t}: sharded==single==fused: {same} (nonzero effects {nz})", flush=True)
+    ok = ok and same and nz > 0
+res = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(res, op=dist.ReduceOp.MIN)
+dist.barrier()
+dist.destroy_process_group()
+if rank == 0:
+    print("MULTIGPU_CHECK", "PASS" if int(res.item()) == 1 else "FAIL")
+sys.exit(0 if int(res.item()) == 1 else 1)
