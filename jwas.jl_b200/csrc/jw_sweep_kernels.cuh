@@ -134,7 +134,7 @@ struct jw_chain_args {
     uint64_t seed; uint32_t iter;
     const double* u; const double* z;
     // BayesABC draw-independent terms precomputed for repetition 0 by jw_k_prep_abc (all SMs)
-    // instead of inside the one chain CTA: [0]u [1]z*sqrt(invLhs) [2]invLhs [3]log(lhs)+log(ve)
+    // instead of inside the one chain CTA: [0]log(1/u-1) [1]z*sqrt(invLhs) [2]invLhs [3]log(lhs)+log(ve)
     // [4]log(1-pi) [5]log(pi), each p doubles; prep_beta0 = float(z*sqrt(ve)).  NULL = inline.
     const double* prep; const float* prep_beta0;
     int32_t* act_idx; int32_t* act_cnt;     // ordered active list of this launch (single-block mode)
@@ -184,7 +184,7 @@ jw_k_prep_abc(jw_chain_args A, double* __restrict__ prep, float* __restrict__ be
     const double lhs = x * invVarRes + 1.0 / ve;
     const double invLhs = 1.0 / lhs;
     const double u = jw_get_u(A, j, 0, 0), z = jw_get_z(A, j, 0, 0);
-    prep[j] = u;
+    prep[j] = jw_logit_threshold(u);
     prep[p + j] = z * jw_sqrt(invLhs);
     prep[2 * p + j] = invLhs;
     prep[3 * p + j] = jw_log(lhs) + jw_log(ve);
@@ -254,11 +254,13 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
     }
     // markers that already carry an effect are certain to need their Gram row: start pulling it
     // towards L2 now (one bulk prefetch per row)
+    bool row_requested = false;
     if (valid) {
         bool nz = false;
 #pragma unroll
         for (int k = 0; k < T; ++k) nz = nz || (a_cur[k] != 0.0f);
         if (nz) {
+            row_requested = true;
             const float* row = G + (int64_t)m * b;
             const unsigned long long a0 = (unsigned long long)row & ~15ull;
             const unsigned bytes = (unsigned)((((unsigned long long)(row + b) + 15ull) & ~15ull) - a0);
@@ -287,7 +289,10 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
             u[0] = u0; zs1 = zs1_0; beta0 = beta0_0; z[0] = 0.0;
         } else {
 #pragma unroll
-            for (int k = 0; k < T; ++k) { u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep); }
+            for (int k = 0; k < T; ++k) {
+                u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep);
+                if (METHOD != 1) u[k] = jw_logit_threshold(u[k]);
+            }
             if (METHOD == 0) {
                 if (use_prep) c_ve = A.ve[j];
                 zs1 = z[0] * jw_sqrt(c_invLhs); beta0 = (float)(z[0] * jw_sqrt(c_ve));
@@ -305,8 +310,7 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                     double rhs = (r[0] + x * aold) * invVarRes;
                     double gHat = rhs * c_invLhs;
                     double logDelta1 = -0.5 * (c_L - gHat * rhs) + c_lpc;
-                    double prob1 = 1.0 / (1.0 + jw_exp(c_lp0 - logDelta1));
-                    if (u[0] < prob1) {
+                    if (c_lp0 - logDelta1 < u[0]) {           // u[] holds the log-odds threshold of the draw
                         newD[0] = 1;
                         newA[0] = (float)(gHat + zs1);
                         newB[0] = newA[0];
@@ -382,8 +386,7 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                         }
                         double logDelta0 = -0.5 * (jw_log(Ginv11) - gHat0 * gHat0 * Ginv11) + jw_log(Pi[s0]);
                         double logDelta1 = -0.5 * (jw_log(C11) - gHat1 * gHat1 * C11) + jw_log(Pi[s1]);
-                        double prob1 = 1.0 / (1.0 + jw_exp(logDelta0 - logDelta1));
-                        if (u[k] < prob1) {
+                        if (logDelta0 - logDelta1 < u[k]) {
                             dd[k] = 1;
                             newA[k] = (float)(gHat1 + z[k] * jw_sqrt(invLhs1));
                             bb[k] = (double)newA[k];
@@ -399,6 +402,14 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                 if (active) {
 #pragma unroll
                     for (int k = 0; k < T; ++k) s_dc[k][m] = a_cur[k] - newA[k];
+                    if (!row_requested) {
+                        // first time this marker looks active: start pulling its Gram row towards L2
+                        row_requested = true;
+                        const float* row = G + (int64_t)m * b;
+                        const unsigned long long a0 = (unsigned long long)row & ~15ull;
+                        const unsigned bytes = (unsigned)((((unsigned long long)(row + b) + 15ull) & ~15ull) - a0);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+                    }
                 }
             }
             // ---- first active marker among the pending ones: ONE barrier per round ----

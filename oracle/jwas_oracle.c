@@ -560,9 +560,8 @@ static float abc_step_contract(double r, float xpx, float* alpha, float* beta, i
     double gHat = rhs * invLhs;
     double logDelta1 = -0.5 * (jw_log(lhs) + jw_log(varEffect) - gHat * rhs) + jw_log(1.0 - pi);
     double logDelta0 = jw_log(pi);
-    double prob1 = 1.0 / (1.0 + jw_exp(logDelta0 - logDelta1));
     float oldA = *alpha, newA;
-    if (u < prob1) {
+    if (logDelta0 - logDelta1 < jw_logit_threshold(u)) {      /* rand() < probDelta1, log-odds form */
         *delta = 1;
         newA = (float)(gHat + z * jw_sqrt(invLhs));
         *beta = newA;
@@ -749,10 +748,9 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
                         }
                         double logDelta0 = -0.5 * (jw_log(Ginv11) - gHat0 * gHat0 * Ginv11) + jw_log(Pi[s0]);
                         double logDelta1 = -0.5 * (jw_log(C11) - gHat1 * gHat1 * C11) + jw_log(Pi[s1]);
-                        double prob1 = 1.0 / (1.0 + jw_exp(logDelta0 - logDelta1));
                         double uu = draw_u(a, j, k, rep), zz = draw_z(a, j, k, rep);
                         float oldA = a->alpha[k * p + j], newA;
-                        if (uu < prob1) {
+                        if (logDelta0 - logDelta1 < jw_logit_threshold(uu)) {
                             dd[k] = 1;
                             newA = (float)(gHat1 + zz * jw_sqrt(invLhs1));
                             bb[k] = (double)newA;
