@@ -8,7 +8,8 @@
 #include "../../include/jwas_contract.h"
 
 #define JW_MAX_TRAITS 4
-#define JW_MAX_BLOCK 1024      // one chain thread per marker of a block
+#define JW_MAX_BLOCK 1024      // chain threads per CTA (one marker each per sub-block)
+#define JW_MAX_PANEL 4096      // largest block of the exact schedule (walked in sub-blocks)
 #define JW_MAX_CLASSES 8
 
 void jw_set_error(const std::string& s);

@@ -29,7 +29,7 @@ struct jw_fused_state {
     int* d_done = nullptr;           // 1
     long long* d_sq_acc = nullptr;   // nblocks * T
     int32_t* d_act_cnt_blk = nullptr;// nblocks
-    int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1;
+    int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1, list_cap = 0;
     int64_t total_chunks = 0;
     size_t smem = 0;
     bool ready = false;
@@ -40,7 +40,7 @@ struct jw_fused_args {
     const uint8_t* tiled;
     const int64_t* chunk_off;
     const uint8_t* packed; int64_t stride_d;
-    int Gs, TS, n_vs, nblocks;
+    int Gs, TS, n_vs, nblocks, list_cap;
     float* ycorr; float scale;
     int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
     int32_t* flags;              // [0] overflow, [2] abort
@@ -346,7 +346,8 @@ jw_k_fused(jw_fused_args F) {
                 JW_PHASE(3);
                 return s_ok != 0;
             };
-            if (!jw_chain_block<METHOD, T>(A, k, wait_all)) return;
+            unsigned char* chain_smem = reinterpret_cast<unsigned char*>(yqs + ((T * R + 3) & ~3));
+            if (!jw_chain_block<METHOD, T>(A, k, wait_all, chain_smem, F.list_cap)) return;
             __syncthreads();
             if (tid == 0) { __threadfence(); jw_st_release(F.done, k + 1); }
             JW_PHASE(4);
@@ -421,7 +422,10 @@ static int jw_fused_prepare(jwas_handle* h) {
     f->TS = (int)((gs + 31) / 32 * 32);
     f->n_vs = (int)((nbytes + gs - 1) / gs);
     f->n_cta = std::min<int>(h->sm_count, f->n_vs);
-    f->smem = (size_t)(f->W == 1 ? 2 : 3) * 65536 + (size_t)h->t * f->Gs * 4 * 4;
+    f->list_cap = h->maxb > JW_MAX_BLOCK ? (int)h->maxb : 0;
+    f->smem = (size_t)(f->W == 1 ? 2 : 3) * 65536 + (((size_t)h->t * f->Gs * 4 + 3) & ~(size_t)3) * 4
+              + jw_chain_smem_bytes(h->t, f->list_cap);
+    if (f->smem > 227 * 1024) { delete f; h->fused = nullptr; return 0; }   // engine 0 only for this shape
     std::vector<int64_t> coff(h->nblocks + 1, 0);
     std::vector<int32_t> cblk;
     for (int64_t k = 0; k < h->nblocks; ++k) {
@@ -478,7 +482,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.C = A;
     F.tiled = f->d_tiled; F.chunk_off = f->d_chunk_off;
     F.packed = h->d_packed; F.stride_d = h->stride_d;
-    F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks;
+    F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks; F.list_cap = f->list_cap;
     F.ycorr = h->d_ycorr; F.scale = scale;
     F.arrive = f->d_arrive; F.done = f->d_done; F.sq_acc = f->d_sq_acc;
     F.act_cnt_blk = f->d_act_cnt_blk; F.act_idx_all = h->d_act_idx;

@@ -198,21 +198,48 @@ struct jw_no_wait { __device__ __forceinline__ bool operator()() const { return 
 // wait_fn() is called after everything that does not depend on the block rhs has been loaded
 // (state, constants, Gram-row prefetches): the fused engine spins there for the other CTAs'
 // partial sums, so those global-memory latencies hide behind the wait.  Returns false on abort.
+// Shared memory of the chain (dynamic, carved from a caller-supplied base):
+//   wmin[2][32] | cnt[33] | dc[T][1024] | list_idx[cap] | list_d[T][cap]
+// The commit list exists only for panels larger than one thread-block of markers (cap = panel size).
+#define JW_CHAIN_SB 1024
+__host__ __device__ inline size_t jw_chain_smem_bytes(int T, int list_cap) {
+    return 256 + 256 + (size_t)T * JW_CHAIN_SB * 4 + (size_t)list_cap * 4 * (1 + T);
+}
+
+// wait_fn() is called after everything that does not depend on the block rhs has been loaded
+// (state, constants, Gram-row prefetches): the fused engine spins there for the other CTAs'
+// partial sums, so those global-memory latencies hide behind the wait.  Returns false on abort.
+//
+// Panels larger than the thread block are walked in sub-blocks of blockDim.x markers; every commit is
+// appended to a list so that a later sub-block starts from  base rhs + sum_commits d*G[commit][j]
+// (added in commit order: the same sums, in the same order, as the one-thread-per-marker chain).
 template <int METHOD, int T, class WaitFn>
-__device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int ib, WaitFn wait_fn) {
-    __shared__ int s_wmin[2][32];
-    __shared__ float s_dc[JW_MAX_TRAITS][JW_MAX_BLOCK];   // candidate delta-alpha of every active marker
-    __shared__ int s_cnt[33];
+__device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int ib, WaitFn wait_fn,
+                                               unsigned char* smem_base, const int list_cap) {
+    int (*s_wmin)[32] = reinterpret_cast<int (*)[32]>(smem_base);
+    int* s_cnt = reinterpret_cast<int*>(smem_base + 256);
+    float* s_dc = reinterpret_cast<float*>(smem_base + 512);                  // [T][JW_CHAIN_SB]
+    int* s_lidx = reinterpret_cast<int*>(smem_base + 512 + T * JW_CHAIN_SB * 4);
+    float* s_ld = reinterpret_cast<float*>(s_lidx + list_cap);                // [T][list_cap]
 
     const int64_t s = A.starts[ib];
     const int b = (int)(A.starts[ib + 1] - s);
-    const int m = threadIdx.x;
-    const bool valid = m < b;
-    const int64_t j = s + (valid ? m : 0);
-    const int lane = m & 31, warp = m >> 5;
+    const int SB = (int)blockDim.x;
+    const int nsub = (b + SB - 1) / SB;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int nw = (int)(blockDim.x >> 5);
     const int64_t p = A.p;
     const float* G = A.gram + A.gram_off[ib];
+    unsigned long long my_active = 0, my_rounds = 0;
+    int parity = 0;
+    int ncommit = 0;          // commits recorded for later sub-blocks (uniform across the CTA)
+    int act_total = 0;        // markers with a net delta so far (ordered active list)
+
+  for (int sb = 0; sb < nsub; ++sb) {
+    const int m = sb * SB + tid;           // marker position inside the panel
+    const bool valid = m < b;
+    const int64_t j = s + (valid ? m : 0);
     const double x = (double)A.xpx[j];
 
     // state at block entry
@@ -268,7 +295,7 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         }
     }
 
-    if (!wait_fn()) return false;
+    if (sb == 0) { if (!wait_fn()) return false; }
 
     // rhs of this marker for every trait
 #pragma unroll
@@ -277,10 +304,18 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
         r[k] = ((double)dq - mu * (double)(__ldcg(&A.sq[k]) - mq)) * A.invscale;
     }
+    if (sb > 0 && valid) {
+        for (int e = 0; e < ncommit; ++e) {
+            const float g = G[(int64_t)s_lidx[e] * b + m];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const float d = s_ld[k * list_cap + e];
+                if (d != 0.0f) r[k] += (double)d * (double)g;
+            }
+        }
+    }
 
     const int nreps = A.nreps_mode ? b : 1;
-    unsigned long long my_active = 0, my_rounds = 0;
-    int parity = 0;
 
     for (int rep = 0; rep < nreps; ++rep) {
         double u[T], z[T];
@@ -298,10 +333,10 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                 zs1 = z[0] * jw_sqrt(c_invLhs); beta0 = (float)(z[0] * jw_sqrt(c_ve));
             }
         }
-        int pos = 0;
+        int pos = 0;                   // position inside the sub-block
         while (true) {
             // ---- evaluate this marker against the current rhs ----
-            bool pending = valid && m >= pos;
+            bool pending = valid && tid >= pos;
             float newA[T], newB[T]; int newD[T];
             bool active = false;
             if (pending) {
@@ -401,7 +436,7 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                 }
                 if (active) {
 #pragma unroll
-                    for (int k = 0; k < T; ++k) s_dc[k][m] = a_cur[k] - newA[k];
+                    for (int k = 0; k < T; ++k) s_dc[k * JW_CHAIN_SB + tid] = a_cur[k] - newA[k];
                     if (!row_requested) {
                         // first time this marker looks active: start pulling its Gram row towards L2
                         row_requested = true;
@@ -413,32 +448,41 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                 }
             }
             // ---- first active marker among the pending ones: ONE barrier per round ----
-            int key = (pending && active) ? m : 0x7fffffff;
+            int key = (pending && active) ? tid : 0x7fffffff;
             int wmin = __reduce_min_sync(0xffffffffu, key);
             if (lane == 0) s_wmin[parity][warp] = wmin;
             __syncthreads();
             int v = (lane < nw) ? s_wmin[parity][lane] : 0x7fffffff;
             const int first = __reduce_min_sync(0xffffffffu, v);
             parity ^= 1;
-            my_rounds += (m == 0);
+            my_rounds += (tid == 0);
             // ---- commit everything up to and including `first` ----
-            if (pending && m <= first) {
+            if (pending && tid <= first) {
 #pragma unroll
                 for (int k = 0; k < T; ++k) { a_cur[k] = newA[k]; b_cur[k] = newB[k]; d_cur[k] = newD[k]; }
-                if (m == first) my_active += 1;
+                if (tid == first) my_active += 1;
             }
             if (first == 0x7fffffff) break;
             // ---- apply the committed marker's Gram row to the rhs ----
-            if (valid && (A.nreps_mode || m > first)) {
-                float g = G[(int64_t)first * b + m];
+            const int fg = sb * SB + first;        // committed marker's position inside the panel
+            if (valid && (A.nreps_mode || tid > first)) {
+                float g = G[(int64_t)fg * b + m];
 #pragma unroll
                 for (int k = 0; k < T; ++k) {
-                    float d = s_dc[k][first];
+                    float d = s_dc[k * JW_CHAIN_SB + first];
                     if (d != 0.0f) r[k] += (double)d * (double)g;
                 }
             }
+            if (sb + 1 < nsub) {                   // later sub-blocks replay this commit
+                if (tid == 0) {
+                    s_lidx[ncommit] = fg;
+#pragma unroll
+                    for (int k = 0; k < T; ++k) s_ld[k * list_cap + ncommit] = s_dc[k * JW_CHAIN_SB + first];
+                }
+                ncommit += 1;
+            }
             pos = first + 1;
-            if (pos >= b) break;
+            if (pos >= SB || sb * SB + pos >= b) break;
         }
         __syncthreads();      // s_dc / s_wmin are reused by the next repetition
     }
@@ -457,19 +501,22 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         }
     }
     if (A.write_active_list) {
-        // ordered compaction of this block's markers with any non-zero delta
+        // ordered compaction of this sub-block's markers with any non-zero delta
         unsigned bal = __ballot_sync(0xffffffffu, any);
         if (lane == 0) s_cnt[warp] = __popc(bal);
         __syncthreads();
-        if (m == 0) {
+        if (tid == 0) {
             int acc = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { int c = s_cnt[w]; s_cnt[w] = acc; acc += c; }
+            for (int w = 0; w < nw; ++w) { int c = s_cnt[w]; s_cnt[w] = acc; acc += c; }
             s_cnt[32] = acc;
         }
         __syncthreads();
-        if (any) A.act_idx[s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
-        if (m == 0) *A.act_cnt = s_cnt[32];
+        if (any) A.act_idx[act_total + s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
+        act_total += s_cnt[32];
     }
+    __syncthreads();          // shared scratch is reused by the next sub-block
+  }   // sub-blocks
+    if (A.write_active_list && tid == 0) *A.act_cnt = act_total;
     if (A.counters) {
         if (my_active) atomicAdd(&A.counters[0], my_active);
         if (my_rounds) atomicAdd(&A.counters[1], my_rounds);
@@ -479,8 +526,9 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
 
 template <int METHOD, int T>
 __global__ void __launch_bounds__(JW_MAX_BLOCK)
-jw_k_chain(jw_chain_args A) {
-    jw_chain_block<METHOD, T>(A, A.block0 + (int)blockIdx.x, jw_no_wait());
+jw_k_chain(jw_chain_args A, int list_cap) {
+    extern __shared__ __align__(16) unsigned char jw_chain_dyn[];
+    jw_chain_block<METHOD, T>(A, A.block0 + (int)blockIdx.x, jw_no_wait(), jw_chain_dyn, list_cap);
 }
 
 // ------------------------------------------------------------------------------------------

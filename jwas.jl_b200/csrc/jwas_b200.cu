@@ -229,7 +229,7 @@ extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nb
         int64_t b = starts[i + 1] - starts[i];
         JW_REQUIRE(b > 0, "fast_blocks block starts must be sorted and unique.");
         JW_REQUIRE(starts[i] >= 0 && starts[i] < h->p, "fast_blocks block starts must be within 1:nMarkers.");
-        JW_REQUIRE(b <= JW_MAX_BLOCK, "fast_blocks: block size above 1024 is not supported by the GPU backend.");
+        JW_REQUIRE(b <= JW_MAX_PANEL, "fast_blocks: block size above 4096 is not supported by the GPU backend.");
         off[i] = total; total += b * b; maxb = std::max(maxb, b);
     }
     JW_CUDA(cudaSetDevice(h->device));
@@ -389,7 +389,11 @@ struct sweep_cfg {
 
 template <int METHOD, int T>
 static void launch_chain(jwas_handle* h, const jw_chain_args& A, int nblk, int threads) {
-    jw_k_chain<METHOD, T><<<nblk, threads, 0, h->stream>>>(A);
+    const int list_cap = h->maxb > JW_MAX_BLOCK ? (int)h->maxb : 0;
+    const size_t smem = jw_chain_smem_bytes(T, list_cap);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(jw_k_chain<METHOD, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    jw_k_chain<METHOD, T><<<nblk, threads, smem, h->stream>>>(A, list_cap);
 }
 static int dispatch_chain(jwas_handle* h, const jw_chain_args& A, int nblk, int threads) {
     int t = h->t;
@@ -584,7 +588,9 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     memcpy(A.Rinv, c.Rinv, sizeof(A.Rinv)); memcpy(A.Ginv, c.Ginv, sizeof(A.Ginv));
     A.seed = c.seed; A.iter = c.iter; A.u = c.u; A.z = c.z;
     A.act_idx = h->d_act_idx; A.act_cnt = h->d_act_cnt; A.counters = h->d_counters;
-    const int threads = (int)std::max<int64_t>(32, ceil_div(h->maxb, 32) * 32);
+    const int threads = (int)std::min<int64_t>(JW_MAX_BLOCK, std::max<int64_t>(32, ceil_div(h->maxb, 32) * 32));
+    JW_REQUIRE(c.schedule == JWAS_SCHED_EXACT || h->maxb <= JW_MAX_BLOCK,
+               "fast_blocks: block size above 1024 is supported by the exact schedule only.");
     if (c.method == 0) {
         // draw-independent chain terms for every marker, computed by the whole GPU up front
         if (!h->d_prep) {

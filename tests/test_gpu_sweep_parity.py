@@ -324,3 +324,21 @@ def test_fused_bayesr(jw, oracle, missing):
 def test_fused_mt_sampler1(jw, oracle):
     prob = Problem(oracle, 803, 500, seed=45, ntraits=2)
     run_pair_mt(jw, oracle, prob, uniform_starts(500, 128), jw.SCHED_EXACT, nsweeps=3, engine=1)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+def test_large_panels_walked_in_subblocks(jw, oracle, engine):
+    """Panels above 1024 markers (exact schedule only): the chain walks them in sub-blocks and replays the
+    commits of earlier sub-blocks from a list -- same bits as the one-marker-per-thread chain/oracle."""
+    prob = Problem(oracle, 160, 3100, seed=91, missing=0.0)
+    run_pair_abc(jw, oracle, prob, uniform_starts(3100, 1500), jw.SCHED_EXACT, nsweeps=3, engine=engine, pi=0.97)
+
+
+def test_large_panels_rejected_for_block_schedules(jw, oracle):
+    prob = Problem(oracle, 64, 1300, seed=92)
+    g = jw.GpuSweeper(prob.packed, 64, 1)
+    g.set_blocks(np.array([0, 1300], dtype=np.int64))
+    g.put_ycorr(prob.ycorr0)
+    with pytest.raises(jw.JwasError, match="exact schedule only"):
+        g.sweep_bayesc(jw.SCHED_BLOCK, 1.0, 0.01, 0.9, 1, 1)
+    g.close()
