@@ -121,7 +121,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--p", type=int, default=0)
-    ap.add_argument("--panel", type=int, default=1024, help="look-ahead panel (markers per block)")
+    ap.add_argument("--panel", type=int, default=4096, help="look-ahead panel (markers per block)")
     ap.add_argument("--burnin", type=int, default=40, help="untimed chain iterations before warm-up")
     ap.add_argument("--engine", type=int, default=1)
     ap.add_argument("--fixed-pi", action="store_true", help="keep pi=0.95 fixed (reference perf scripts: estimatePi=false)")

@@ -26,7 +26,7 @@ try:  # pandas is what a DataFrame is here
 except Exception:  # pragma: no cover
     pd = None
 
-DEFAULT_PANEL = 1024          # look-ahead panel of the exact schedule (GPU-internal)
+DEFAULT_PANEL = 4096          # look-ahead panel of the exact schedule (GPU-internal; 1024 with missing calls / multi-trait)
 
 
 def error(msg):
@@ -417,7 +417,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                               independent_blocks=independent_blocks, outputEBV=outputEBV, output_folder=output_folder)
     schedule = SCHED_EXACT if starts is None else (SCHED_INDEPENDENT if independent_blocks else SCHED_BLOCK)
     if starts is None:
-        starts = np.array(list(range(0, p, min(panel, 1024))) + [p], dtype=np.int64)
+        has_missing = bool(np.any((packed & (packed >> 1) & 0x55) != 0))
+        pmax = 4096 if (t == 1 and not has_missing) else 1024
+        starts = np.array(list(range(0, p, max(1, min(panel, pmax)))) + [p], dtype=np.int64)
 
     # ---- default priors (input_data_validation.jl:296-350) and marker hyper-parameters
     #      (tools4genotypes.jl:353-424)

@@ -285,11 +285,19 @@ jw_k_fused(jw_fused_args F) {
                 // transposed butterfly: 16 markers x 32 lanes -> marker (lane>>1)&15 on every lane
 #pragma unroll
                 for (int comp = 0; comp < W; ++comp) {
-                    long long vals[16];
+                    // round 1 on the 32-bit partials (half the shuffles, half the live registers)
+                    long long vals[8];
+                    {
+                        const bool up = (lane & 16) != 0;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) vals[q] = acc[q][comp];
+                        for (int i = 0; i < 8; ++i) {
+                            const int keep = up ? acc[i + 8][comp] : acc[i][comp];
+                            const int send = up ? acc[i][comp] : acc[i + 8][comp];
+                            vals[i] = (long long)keep + (long long)__shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+                    }
 #pragma unroll
-                    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+                    for (int half = 4, mask = 8; half >= 1; half >>= 1, mask >>= 1) {
                         const bool up = (lane & mask) != 0;
 #pragma unroll
                         for (int i = 0; i < half; ++i) {

@@ -236,6 +236,28 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
     int ncommit = 0;          // commits recorded for later sub-blocks (uniform across the CTA)
     int act_total = 0;        // markers with a net delta so far (ordered active list)
 
+    // pull the panel's chain inputs (state, statistics, precomputed terms) towards L2 in bulk: one
+    // lane per array, issued before anything waits
+    if (warp == 0) {
+        const void* base = nullptr; unsigned esz = 0;
+        switch (lane) {
+            case 0: base = A.alpha + s; esz = 4; break;
+            case 1: base = A.delta + s; esz = 4; break;
+            case 2: base = A.xpx + s; esz = 4; break;
+            case 3: base = A.means + s; esz = 4; break;
+            case 4: if (METHOD != 1) { base = A.beta + s; esz = 4; } break;
+            case 5: if (A.prep_beta0) { base = A.prep_beta0 + s; esz = 4; } break;
+            case 6: case 7: case 8: case 9: case 10: case 11:
+                if (A.prep) { base = A.prep + (int64_t)(lane - 6) * p + s; esz = 8; } break;
+            default: break;
+        }
+        if (base && nsub > 1) {
+            const unsigned long long a0 = (unsigned long long)base & ~15ull;
+            const unsigned bytes = (unsigned)((((unsigned long long)base + (unsigned long long)b * esz + 15ull) & ~15ull) - a0);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+        }
+    }
+
   for (int sb = 0; sb < nsub; ++sb) {
     const int m = sb * SB + tid;           // marker position inside the panel
     const bool valid = m < b;
