@@ -228,8 +228,16 @@ def main():
     peak, peak_src = measured_peaks()
     bytes_per_sweep = p * math.ceil(n / 4)
     ach = bytes_per_sweep / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
+    try:
+        if args.engine == 1 and (n, p) == (50000, 600000):
+            rd = {l.split(",")[0]: l.strip().split(",") for l in open(os.path.join(ROOT, "profiles", "r1_fused_kernel_ncu_summary.csv"))}
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            traffic = sum(float(rd[k][2]) * scale[rd[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": None,
+                "frac": (ach / peak) if ach else None, "traffic": traffic,
                 "kernel": "jw_k_fused (persistent sweep)" if args.engine == 1 else "jw_k_block_dot (summed over the sweep's launches)",
                 "kernel_ms_per_sweep": k_ms, "kernel_launches_per_sweep": k_launches,
                 "algorithmic_bytes_per_launch": bytes_per_sweep / max(k_launches, 1), "peak_source": peak_src,
