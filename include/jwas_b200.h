@@ -159,8 +159,9 @@ double jwas_last_sweep_ms(jwas_handle* h);
  * genotype-streaming kernel(s) of the last sweep; needs jwas_set_option(h,"profile",1) */
 double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches);
 /* engine 1 phase timers of the last sweep, nanoseconds: out[0..4] = CTA 0 {wait previous chain,
- * axpy+quantise+tables, stream, wait for all slices, chain}; out[8..12] = CTA 1, same phases */
-int jwas_get_phase_ns(jwas_handle* h, uint64_t* out16);
+ * axpy+quantise+tables, stream, wait for all slices, chain}; out[8..12] = CTA 1, same phases;
+ * out[16..20] = the dedicated chain CTA of the lagged schedule (option "lag" = 1) */
+int jwas_get_phase_ns(jwas_handle* h, uint64_t* out24);
 /* raw CUDA stream of the handle (cudaStream_t) so callers can time on it */
 void* jwas_stream(jwas_handle* h);
 

@@ -70,6 +70,9 @@ struct jwas_handle {
     int64_t* d_starts = nullptr;
     int64_t* d_gram_off = nullptr;
     float* d_gram = nullptr;
+    float* d_gramx = nullptr;      // cross-Gram X_{k-1}'X_k of consecutive blocks (lagged schedule), on demand
+    int64_t* d_gramx_off = nullptr;
+    std::vector<int64_t> gramx_off;
     int64_t nblocks = 0, maxb = 0;
 
     // sweep workspace
@@ -91,6 +94,7 @@ struct jwas_handle {
     int64_t opt_profile = 0;       // 1 = time the genotype-streaming kernel(s) with CUDA events
     std::vector<cudaEvent_t> prof_events;
     double prof_ms = 0.0; int64_t prof_launches = 0;
+    int64_t opt_lag = 0;           // 1 = lagged exact schedule (engine 1): chain k overlaps stream k+1
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
     // row-sharded multi-GPU sweep: this rank streams rows [row_begin, row_end) of every column
     int64_t row_begin = 0, row_end = 0;

@@ -40,7 +40,8 @@ struct jw_fused_args {
     const uint8_t* tiled;
     const int64_t* chunk_off;
     const uint8_t* packed; int64_t stride_d;
-    int Gs, TS, n_vs, nblocks, list_cap;
+    int Gs, TS, n_vs, nblocks, list_cap, lag;
+    const float* gramx; const int64_t* gramx_off;
     float* ycorr; float scale;
     int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
     int32_t* flags;              // [0] overflow, [2] abort
@@ -139,11 +140,17 @@ jw_k_fused(jw_fused_args F) {
     __shared__ long long s_red[32 * JW_MAX_TRAITS];
     __shared__ int s_ok;
     const int64_t n = F.C.n, p = F.C.p;
-    const bool single = F.n_vs <= (int)gridDim.x;
+    // lag = 1: the last CTA only runs chains, the others only stream, so that the chain of block k
+    // overlaps the streaming of block k+1 (which needs the updates of blocks <= k-1 only)
+    const int lag = F.lag;
+    const int n_stream = lag ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const bool is_chain_cta = lag ? (blockIdx.x == gridDim.x - 1) : (blockIdx.x == 0);
+    const bool is_stream_cta = lag ? (blockIdx.x < (unsigned)n_stream) : true;
+    const bool single = F.n_vs <= n_stream;
     // phase timers (ns): [0] wait for previous chain, [1] axpy+quantise+tables, [2] stream,
     // [3] wait for all slices, [4] chain; CTA 0 -> counters[32..36], CTA 1 -> counters[40..44]
     unsigned long long ph[5] = {0, 0, 0, 0, 0};
-    const bool timed = (tid == 0) && (blockIdx.x <= 1) && (F.C.counters != nullptr);
+    const bool timed = (tid == 0) && (blockIdx.x <= 1 || is_chain_cta) && (F.C.counters != nullptr);
     unsigned long long tm = timed ? jw_globaltimer() : 0;
 #define JW_PHASE(i) do { if (timed) { unsigned long long now__ = jw_globaltimer(); ph[i] += now__ - tm; tm = now__; } } while (0)
     long long sq_keep[T];                  // thread 0: this CTA's sum of yq over its slice(s)
@@ -151,24 +158,26 @@ jw_k_fused(jw_fused_args F) {
     for (int kk = 0; kk < T; ++kk) sq_keep[kk] = 0;
 
     for (int k = 0; k < F.nblocks; ++k) {
-        int prev_cnt = 0;
-        if (k > 0) {
-            if (tid == 0) s_ok = jw_spin_ge(F.done, k, F.flags) ? 1 : 0;
-            __syncthreads();
-            if (!s_ok) return;
-            prev_cnt = __ldcg(&F.act_cnt_blk[k - 1]);
-        }
-        JW_PHASE(0);
         const int64_t s = F.C.starts[k];
         const int b = (int)(F.C.starts[k + 1] - s);
+        if (is_stream_cta) {
+        int prev_cnt = 0;
+        const int ap = k - 1 - lag;              // block whose updates reach ycorr before this block streams
+        if (ap >= 0) {
+            if (tid == 0) s_ok = jw_spin_ge(F.done, ap + 1, F.flags) ? 1 : 0;
+            __syncthreads();
+            if (!s_ok) return;
+            prev_cnt = __ldcg(&F.act_cnt_blk[ap]);
+        }
+        JW_PHASE(0);
         const int nchunks = (b + 15) >> 4;
-        const int32_t* prev_idx = F.act_idx_all + (k > 0 ? F.C.starts[k - 1] : 0);
+        const int32_t* prev_idx = F.act_idx_all + (ap >= 0 ? F.C.starts[ap] : 0);
         const bool rebuild = (k == 0) || prev_cnt > 0 || !single;
         long long sq_blk[T];
 #pragma unroll
         for (int kk = 0; kk < T; ++kk) sq_blk[kk] = 0;
 
-        for (int vs = blockIdx.x; vs < F.n_vs; vs += gridDim.x) {
+        for (int vs = blockIdx.x; vs < F.n_vs; vs += n_stream) {
             const int64_t row0 = (int64_t)vs * R;
             if (rebuild) {
                 // ---- (1) fused axpy of the previous block + fixed-point image of the slice ----
@@ -333,7 +342,7 @@ jw_k_fused(jw_fused_args F) {
             // while the chain runs: pull the next block's tile(s) of this CTA into L2
             const int nb1 = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
             const int nch1 = (nb1 + 15) >> 4;
-            for (int vs = blockIdx.x; vs < F.n_vs; vs += gridDim.x) {
+            for (int vs = blockIdx.x; vs < F.n_vs; vs += n_stream) {
                 const uint8_t* t1 = F.tiled + ((size_t)(F.chunk_off[k + 1] * F.n_vs + (int64_t)vs * nch1) * Gs) * 16;
                 const unsigned total = (unsigned)nch1 * Gs * 16;
                 const unsigned per = ((total / 32) + 15) & ~15u;
@@ -342,14 +351,21 @@ jw_k_fused(jw_fused_args F) {
             }
         }
         JW_PHASE(2);
-        if (blockIdx.x == 0) {
+        }   // streaming role
+        if (is_chain_cta) {
             jw_chain_args A = F.C;
+            if (lag && k > 0) {
+                A.xgram = F.gramx + F.gramx_off[k];
+                A.xlist = F.act_idx_all + F.C.starts[k - 1];
+                A.xcount = F.act_cnt_blk + (k - 1);
+                A.xstart = F.C.starts[k - 1];
+            }
             A.sq = F.sq_acc + k * T;
             A.act_idx = F.act_idx_all + s;
             A.act_cnt = F.act_cnt_blk + k;
             A.write_active_list = 1;
             auto wait_all = [&]() -> bool {
-                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], (int)gridDim.x, F.flags) ? 1 : 0;
+                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
                 __syncthreads();
                 JW_PHASE(3);
                 return s_ok != 0;
@@ -362,7 +378,7 @@ jw_k_fused(jw_fused_args F) {
         }
     }
     if (timed) {
-        const int base = blockIdx.x == 0 ? 32 : 40;
+        const int base = (blockIdx.x == 0 && !(is_chain_cta && lag)) ? 32 : (is_chain_cta ? 48 : 40);
         for (int i = 0; i < 5; ++i) F.C.counters[base + i] = ph[i];
     }
 #undef JW_PHASE
@@ -423,7 +439,8 @@ static int jw_fused_prepare(jwas_handle* h) {
     h->fused = f;
     const int64_t nbytes = (h->n + 3) / 4;
     f->W = (h->t == 2 || h->has_missing) ? 2 : 1;
-    int64_t gs = (nbytes + h->sm_count - 1) / h->sm_count;
+    const int64_t streamers = std::max(1, h->sm_count - 1);   // one SM is kept for the chain (lag = 1)
+    int64_t gs = (nbytes + streamers - 1) / streamers;
     if (gs > JW_FUSED_MAX_GS) gs = JW_FUSED_MAX_GS;
     if (gs < 1) gs = 1;
     f->Gs = (int)gs;
@@ -470,7 +487,8 @@ static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) 
     JW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JW_FUSED_THREADS, f->smem));
     JW_REQUIRE(occ >= 1, "fused sweep kernel does not fit on an SM");
     void* args[] = {(void*)&F};
-    JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(f->n_cta), dim3(JW_FUSED_THREADS), args, f->smem, h->stream));
+    const int grid = F.lag ? std::min<int>(h->sm_count, f->n_vs + 1) : f->n_cta;
+    JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(JW_FUSED_THREADS), args, f->smem, h->stream));
     h->launches += 1;
     return 0;
 }
@@ -491,6 +509,9 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.tiled = f->d_tiled; F.chunk_off = f->d_chunk_off;
     F.packed = h->d_packed; F.stride_d = h->stride_d;
     F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks; F.list_cap = f->list_cap;
+    F.lag = (int)h->opt_lag;
+    JW_REQUIRE(!F.lag || (A.nreps_mode == 0 && h->d_gramx), "lag = 1 needs the exact schedule and the cross-Gram blocks");
+    F.gramx = h->d_gramx; F.gramx_off = h->d_gramx_off;
     F.ycorr = h->d_ycorr; F.scale = scale;
     F.arrive = f->d_arrive; F.done = f->d_done; F.sq_acc = f->d_sq_acc;
     F.act_cnt_blk = f->d_act_cnt_blk; F.act_idx_all = h->d_act_idx;
@@ -515,17 +536,18 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     if (rc == 2) jw_set_error("engine 1: unsupported (method, traits, missing) combination");
     if (rc) return rc;
     if (h->opt_profile) JW_CUDA(cudaEventRecord(h->prof_events.back(), h->stream));
-    // the last block's axpy
-    const int64_t last = h->nblocks - 1;
-    unsigned g = (unsigned)((h->n + 255) / 256);
-    if (t == 1)
-        jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
-            h->d_act_idx + h->starts[last], f->d_act_cnt_blk + last, h->d_ycorr);
-    else
-        jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
-            h->d_act_idx + h->starts[last], f->d_act_cnt_blk + last, h->d_ycorr);
-    h->launches += 1;
-    JW_CUDA(cudaGetLastError());
+    // the axpy of the last block (and of the one before it under the lagged schedule)
+    for (int64_t blk = std::max<int64_t>(0, h->nblocks - 1 - F.lag); blk < h->nblocks; ++blk) {
+        unsigned g = (unsigned)((h->n + 255) / 256);
+        if (t == 1)
+            jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr);
+        else
+            jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr);
+        h->launches += 1;
+        JW_CUDA(cudaGetLastError());
+    }
     // abort flag -> error
     int32_t hf[4];
     JW_CUDA(cudaMemcpyAsync(hf, h->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));

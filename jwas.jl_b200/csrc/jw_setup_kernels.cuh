@@ -61,15 +61,17 @@ template <bool MISSING>
 __global__ void __launch_bounds__(256)
 jw_k_gram(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n,
           const float* __restrict__ means, const int32_t* __restrict__ colsum,
-          const int64_t* __restrict__ starts, const int64_t* __restrict__ gram_off,
-          const int32_t* __restrict__ tile_block, const int32_t* __restrict__ tile_ab,
+          const int64_t* __restrict__ starts, const int64_t* __restrict__ tile_off,
+          const int32_t* __restrict__ tile_blocks, const int32_t* __restrict__ tile_ab,
           float* __restrict__ gram) {
     __shared__ uint32_t sA[JW_GT][JW_GK + 1];
     __shared__ uint32_t sB[JW_GT][JW_GK + 1];
-    const int ib = tile_block[blockIdx.x];
+    // rows come from marker block rb, columns from block cb (rb == cb: the block's own Gram;
+    // cb == rb + 1: the cross-Gram used by the lagged schedule)
+    const int rb = tile_blocks[2 * blockIdx.x], cb = tile_blocks[2 * blockIdx.x + 1];
     const int ta = tile_ab[2 * blockIdx.x], tb = tile_ab[2 * blockIdx.x + 1];
-    const int64_t s = starts[ib];
-    const int b = (int)(starts[ib + 1] - s);
+    const int64_t s = starts[rb], sc = starts[cb];
+    const int b = (int)(starts[rb + 1] - s), bc = (int)(starts[cb + 1] - sc);
     const int a0 = ta * JW_GT, c0 = tb * JW_GT;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // micro-tile coordinates
     const int64_t nwords = stride_d >> 2;
@@ -88,7 +90,7 @@ jw_k_gram(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n,
             uint32_t va = 0xffffffffu, vb = 0xffffffffu;   // out of range = missing: counts nothing
             if (w < nwords) {
                 if (a0 + r < b) va = __ldg(reinterpret_cast<const uint32_t*>(packed + (s + a0 + r) * stride_d) + w);
-                if (c0 + r < b) vb = __ldg(reinterpret_cast<const uint32_t*>(packed + (s + c0 + r) * stride_d) + w);
+                if (c0 + r < bc) vb = __ldg(reinterpret_cast<const uint32_t*>(packed + (sc + c0 + r) * stride_d) + w);
             }
             sA[r][c] = va; sB[r][c] = vb;
         }
@@ -127,12 +129,12 @@ jw_k_gram(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int a = a0 + ty * 4 + i, c = c0 + tx * 4 + k;
-            if (a < b && c < b) {
+            if (a < b && c < bc) {
                 long long sa, sb, nvv;
                 if (MISSING) { sa = Sa[i][k]; sb = Sb[i][k]; nvv = (long long)Nvv[i][k] - pad; }
-                else { sa = colsum[s + a]; sb = colsum[s + c]; nvv = n; }
-                gram[gram_off[ib] + (int64_t)a * b + c] =
-                    jw_gram_value(Nab[i][k], sa, sb, nvv, means[s + a], means[s + c]);
+                else { sa = colsum[s + a]; sb = colsum[sc + c]; nvv = n; }
+                gram[tile_off[blockIdx.x] + (int64_t)a * bc + c] =
+                    jw_gram_value(Nab[i][k], sa, sb, nvv, means[s + a], means[sc + c]);
             }
         }
 }

@@ -137,6 +137,9 @@ struct jw_chain_args {
     // instead of inside the one chain CTA: [0]log(1/u-1) [1]z*sqrt(invLhs) [2]invLhs [3]log(lhs)+log(ve)
     // [4]log(1-pi) [5]log(pi), each p doubles; prep_beta0 = float(z*sqrt(ve)).  NULL = inline.
     const double* prep; const float* prep_beta0;
+    // lagged schedule: the previous block's updates are not in ycorr yet; its ordered active list and
+    // the cross-Gram X_{k-1}'X_k (rows = previous block's markers) correct the rhs of this block
+    const float* xgram; const int32_t* xlist; const int32_t* xcount; int64_t xstart;
     int32_t* act_idx; int32_t* act_cnt;     // ordered active list of this launch (single-block mode)
     int write_active_list;
     unsigned long long* counters;
@@ -325,6 +328,18 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         // .cg loads: these words were produced by other CTAs' atomics in the fused engine
         long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
         r[k] = ((double)dq - mu * (double)(__ldcg(&A.sq[k]) - mq)) * A.invscale;
+    }
+    if (A.xgram != nullptr && valid) {
+        const int xc = __ldcg(A.xcount);
+        for (int e = 0; e < xc; ++e) {
+            const int64_t ja = __ldcg(A.xlist + e);
+            const float g = A.xgram[(ja - A.xstart) * b + m];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const float d = __ldcg(&A.dalpha[k * p + ja]);
+                if (d != 0.0f) r[k] += (double)d * (double)g;
+            }
+        }
     }
     if (sb > 0 && valid) {
         for (int e = 0; e < ncommit; ++e) {

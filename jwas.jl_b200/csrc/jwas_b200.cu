@@ -193,7 +193,7 @@ extern "C" int jwas_destroy(jwas_handle* h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_ycorr, h->d_alpha,
                     h->d_beta, h->d_delta, h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta, h->d_ve,
-                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
+                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_gramx, h->d_gramx_off, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -218,6 +218,50 @@ extern "C" int jwas_get_marker_stats(jwas_handle* h, float* means, float* xpx) {
 // ------------------------------------------------------------------------------------------
 // block partition + Gram blocks (JWAS.jl:73-79 validation; tools4genotypes.jl:259-269)
 // ------------------------------------------------------------------------------------------
+// Gram blocks (cross = false) or cross-Gram of consecutive blocks (cross = true): every 64x64 tile
+static int build_gram(jwas_handle* h, bool cross) {
+    const int64_t nb = h->nblocks;
+    std::vector<int32_t> tblk, tab; std::vector<int64_t> toff;
+    std::vector<int64_t> xoff(nb, 0);
+    int64_t total = 0;
+    for (int64_t i = cross ? 1 : 0; i < nb; ++i) {
+        const int64_t rb = cross ? i - 1 : i, cb = i;
+        const int64_t br = h->starts[rb + 1] - h->starts[rb], bc = h->starts[cb + 1] - h->starts[cb];
+        const int64_t off = cross ? total : h->gram_off[i];
+        if (cross) { xoff[i] = total; total += br * bc; }
+        const int nta = (int)ceil_div(br, JW_GT), ntb = (int)ceil_div(bc, JW_GT);
+        for (int a = 0; a < nta; ++a) for (int c = 0; c < ntb; ++c) {
+            tblk.push_back((int32_t)rb); tblk.push_back((int32_t)cb); tab.push_back(a); tab.push_back(c); toff.push_back(off);
+        }
+    }
+    float* out = h->d_gram;
+    if (cross) {
+        h->gramx_off = xoff;
+        JW_CUDA(cudaMalloc((void**)&h->d_gramx, std::max<size_t>(1, (size_t)total) * sizeof(float)));
+        JW_CUDA(cudaMalloc((void**)&h->d_gramx_off, nb * sizeof(int64_t)));
+        JW_CUDA(cudaMemcpyAsync(h->d_gramx_off, xoff.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        out = h->d_gramx;
+    }
+    if (toff.empty()) return 0;
+    int32_t *d_tb = nullptr, *d_tab = nullptr; int64_t* d_toff = nullptr;
+    JW_CUDA(cudaMalloc((void**)&d_tb, tblk.size() * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&d_tab, tab.size() * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&d_toff, toff.size() * sizeof(int64_t)));
+    JW_CUDA(cudaMemcpyAsync(d_tb, tblk.data(), tblk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(d_toff, toff.data(), toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->has_missing)
+        jw_k_gram<true><<<(unsigned)toff.size(), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->d_means,
+            h->d_colsum, h->d_starts, d_toff, d_tb, d_tab, out);
+    else
+        jw_k_gram<false><<<(unsigned)toff.size(), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->d_means,
+            h->d_colsum, h->d_starts, d_toff, d_tb, d_tab, out);
+    JW_LAUNCH_CHECK(h);
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_tb); cudaFree(d_tab); cudaFree(d_toff);
+    return 0;
+}
+
 extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nblocks) {
     JW_REQUIRE(h, "null handle");
     JW_REQUIRE(starts && nblocks > 0, "fast_blocks block start vector cannot be empty.");
@@ -242,26 +286,11 @@ extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nb
     JW_CUDA(cudaMalloc((void**)&h->d_gram, (size_t)total * sizeof(float)));
     JW_CUDA(cudaMemcpyAsync(h->d_starts, starts, (nblocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     JW_CUDA(cudaMemcpyAsync(h->d_gram_off, off.data(), nblocks * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    // tile list: every 64x64 tile of every block
-    std::vector<int32_t> tb, tab;
-    for (int64_t i = 0; i < nblocks; ++i) {
-        int nt = (int)ceil_div(starts[i + 1] - starts[i], JW_GT);
-        for (int a = 0; a < nt; ++a) for (int c = 0; c < nt; ++c) { tb.push_back((int32_t)i); tab.push_back(a); tab.push_back(c); }
-    }
-    int32_t *d_tb = nullptr, *d_tab = nullptr;
-    JW_CUDA(cudaMalloc((void**)&d_tb, tb.size() * sizeof(int32_t)));
-    JW_CUDA(cudaMalloc((void**)&d_tab, tab.size() * sizeof(int32_t)));
-    JW_CUDA(cudaMemcpyAsync(d_tb, tb.data(), tb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    JW_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    if (h->has_missing)
-        jw_k_gram<true><<<(unsigned)tb.size(), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->d_means,
-            h->d_colsum, h->d_starts, h->d_gram_off, d_tb, d_tab, h->d_gram);
-    else
-        jw_k_gram<false><<<(unsigned)tb.size(), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->d_means,
-            h->d_colsum, h->d_starts, h->d_gram_off, d_tb, d_tab, h->d_gram);
-    JW_LAUNCH_CHECK(h);
-    JW_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(d_tb); cudaFree(d_tab);
+    int rc0 = build_gram(h, false);
+    if (rc0) return rc0;
+    if (h->d_gramx) { cudaFree(h->d_gramx); h->d_gramx = nullptr; }
+    if (h->d_gramx_off) { cudaFree(h->d_gramx_off); h->d_gramx_off = nullptr; }
+    if (h->opt_lag) { rc0 = build_gram(h, true); if (rc0) return rc0; }
     int rc = jw_fused_prepare(h);
     if (rc) return rc;
     return 0;
@@ -832,10 +861,10 @@ extern "C" double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches) 
     if (launches) *launches = h->prof_launches;
     return h->prof_ms;
 }
-extern "C" int jwas_get_phase_ns(jwas_handle* h, uint64_t* out16) {
-    JW_REQUIRE(h && out16, "jwas_get_phase_ns: null argument");
+extern "C" int jwas_get_phase_ns(jwas_handle* h, uint64_t* out24) {
+    JW_REQUIRE(h && out24, "jwas_get_phase_ns: null argument");
     JW_CUDA(cudaSetDevice(h->device));
-    JW_CUDA(cudaMemcpyAsync(out16, h->d_counters + 32, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(out24, h->d_counters + 32, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -843,6 +872,13 @@ extern "C" void* jwas_stream(jwas_handle* h) { return h ? (void*)h->stream : nul
 extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
     JW_REQUIRE(h && key, "jwas_set_option: null argument");
     if (!strcmp(key, "profile")) { h->opt_profile = value; return 0; }
+    if (!strcmp(key, "lag")) {
+        JW_REQUIRE(value == 0 || value == 1, "lag must be 0 or 1");
+        JW_CUDA(cudaSetDevice(h->device));
+        h->opt_lag = value;
+        if (value == 1 && h->nblocks > 0 && !h->d_gramx) return build_gram(h, true);   // cross-Gram on demand
+        return 0;
+    }
     if (!strcmp(key, "engine")) { JW_REQUIRE(value == 0 || value == 1, "engine must be 0 or 1"); h->opt_engine = value; return 0; }
     jw_set_error(std::string("unknown option: ") + key);
     return 2;

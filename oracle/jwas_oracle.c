@@ -626,12 +626,30 @@ static void inv_spd_fixed(const double* A, int t, double* Ai) {
     for (int i = 0; i < t; ++i) for (int j = 0; j < t; ++j) Ai[i * t + j] = M[i][t + j];
 }
 
+/* ycorr[k] += X_b * d[k] for the markers [s, e) whose stored delta is non-zero, ascending marker order */
+static void apply_block_deltas(const jwo_sweep_args* a, const float* dstore, int64_t s, int64_t e,
+                               int64_t r0, int64_t r1, float* xbuf) {
+    const int64_t n = a->n, p = a->p;
+    for (int k = 0; k < a->ntraits; ++k)
+        for (int64_t j = s; j < e; ++j) {
+            float d = dstore[k * p + j];
+            if (d != 0.0f) {
+                jwo_decode_marker(a->packed + j * a->stride, n, a->means[j], 1, xbuf);
+                float* y = a->ycorr + k * n;
+                for (int64_t i = r0; i < r1; ++i) y[i] = fmaf(d, xbuf[i], y[i]);
+            }
+        }
+}
+
 int jwo_sweep_contract(jwo_sweep_args* a) {
     const int64_t n = a->n, p = a->p;
     const int t = a->ntraits;
     const int64_t r0 = a->row_end > 0 ? a->row_begin : 0, r1 = a->row_end > 0 ? a->row_end : n;
     if (t < 1 || t > 8) return 1;
     if (a->method == JWO_METHOD_MT1 && t < 2) return 1;
+    const int lag = a->lag;
+    if (lag != 0 && lag != 1) return 1;
+    if (lag == 1 && (a->independent || a->nreps_mode)) return 1;   /* exact schedule only */
 
     /* fixed-point scale from max|ycorr| over all traits (one S per sweep) */
     float maxabs = 0.0f;
@@ -644,7 +662,7 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
 
     int32_t* yq = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n * t));
     float* xbuf = (float*)malloc(sizeof(float) * (size_t)n);
-    float* dall = a->independent ? (float*)calloc((size_t)(p * t), sizeof(float)) : NULL;
+    float* dall = (a->independent || lag) ? (float*)calloc((size_t)(p * t), sizeof(float)) : NULL;
     int64_t sq[8];
     double Rinv[64], Ginv[64];
     if (a->method == JWO_METHOD_MT1) {
@@ -656,6 +674,8 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
     int have_q = 0;
     for (int64_t ib = 0; ib < a->nblocks; ++ib) {
         int64_t s = a->starts[ib], e = a->starts[ib + 1], b = e - s;
+        /* (0) lagged schedule: the updates of block ib-2 reach ycorr only now */
+        if (lag && ib >= 2) apply_block_deltas(a, dall, a->starts[ib - 2], a->starts[ib - 1], r0, r1, xbuf);
         /* (1) fixed-point image of ycorr.  Independent blocks all see the entry snapshot
          *     (BayesABC.jl:205, BayesR.jl:209, MTBayesABC.jl:350). */
         if (!a->independent || !have_q) {
@@ -696,6 +716,23 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
                 aold[k * b + jj] = a->alpha[k * p + s + jj];
             }
         free(dqv);
+        /* (2b) lagged schedule: block ib-1's updates are not in ycorr yet -- correct the rhs with the
+         *      cross-Gram rows of its non-zero deltas, in commit (= marker) order */
+        if (lag && ib >= 1) {
+            for (int64_t ja = a->starts[ib - 1]; ja < a->starts[ib]; ++ja) {
+                int any = 0;
+                for (int k = 0; k < t; ++k) any = any || (dall[k * p + ja] != 0.0f);
+                if (!any) continue;
+                for (int64_t jj = 0; jj < b; ++jj) {
+                    jwo_pair q = pair_counts(a->packed + ja * a->stride, a->packed + (s + jj) * a->stride, n);
+                    float g = gram_value(q, a->means[ja], a->means[s + jj]);
+                    for (int k = 0; k < t; ++k) {
+                        float d = dall[k * p + ja];
+                        if (d != 0.0f) r[k * b + jj] += (double)d * (double)g;
+                    }
+                }
+            }
+        }
         /* (3) in-block chain (BayesABC.jl:153-178, BayesR.jl:146-184, MTBayesABC.jl:276-327) */
         int nreps = a->nreps_mode ? (int)b : 1;
         for (int rep = 0; rep < nreps; ++rep) {
@@ -775,7 +812,7 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
         for (int k = 0; k < t; ++k)
             for (int64_t jj = 0; jj < b; ++jj) {
                 float d = aold[k * b + jj] - a->alpha[k * p + s + jj];
-                if (a->independent) { dall[k * p + s + jj] = d; continue; }
+                if (a->independent || lag) { dall[k * p + s + jj] = d; continue; }
                 if (d != 0.0f) {
                     jwo_decode_marker(a->packed + (s + jj) * a->stride, n, a->means[s + jj], 1, xbuf);
                     float* y = a->ycorr + k * n;
@@ -784,7 +821,11 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
             }
         free(r); free(G); free(aold);
     }
-    if (a->independent) {                       /* BayesABC.jl:251-253 */
+    if (lag) {                                  /* the last two blocks' updates */
+        if (a->nblocks >= 2) apply_block_deltas(a, dall, a->starts[a->nblocks - 2], a->starts[a->nblocks - 1], r0, r1, xbuf);
+        apply_block_deltas(a, dall, a->starts[a->nblocks - 1], a->starts[a->nblocks], r0, r1, xbuf);
+        free(dall);
+    } else if (a->independent) {                /* BayesABC.jl:251-253 */
         for (int k = 0; k < t; ++k)
             for (int64_t j = 0; j < p; ++j) {
                 float d = dall[k * p + j];

@@ -39,6 +39,7 @@ class _SweepArgs(C.Structure):
         ("overflow", C.c_int), ("scale_exp", C.c_int),
         ("row_begin", C.c_int64), ("row_end", C.c_int64),
         ("allreduce", C.c_void_p), ("ctx", C.c_void_p),
+        ("lag", C.c_int),
     ]
 
 
@@ -215,7 +216,7 @@ def max_threads():
 def sweep_contract(packed, n, means, xpx, starts, ycorr, alpha, beta, delta, *, method=METHOD_ABC,
                    nreps_mode=0, independent=False, vare=1.0, varEffects=None, pi=None,
                    sigmaSq=0.0, gamma=None, R=None, G=None, bigPi=None, seed=0, it=1, u=None, z=None,
-                   row_range=None, allreduce=None):
+                   row_range=None, allreduce=None, lag=0):
     """State arrays are modified in place: ycorr (t*n,) f32, alpha/beta (t*p,) f32, delta (t*p,) i32.
     starts: 0-based block boundaries of length nblocks+1."""
     p, stride = packed.shape
@@ -265,5 +266,6 @@ def sweep_contract(packed, n, means, xpx, starts, ycorr, alpha, beta, delta, *, 
             allreduce(arr)
         cb = ALLREDUCE_CB(_cb); keep.append(cb)
         a.allreduce = C.cast(cb, C.c_void_p)
+    a.lag = int(lag)
     rc = lib().jwo_sweep_contract(C.byref(a))
     return rc, a.scale_exp

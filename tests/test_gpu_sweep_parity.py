@@ -21,11 +21,12 @@ def jw():
 
 
 def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=False, replay=False, engine=0,
-                 seed=11):
+                 seed=11, lag=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
     g.set_option("engine", engine)
+    g.set_option("lag", lag)
     gm, gx = g.marker_stats()
     np.testing.assert_array_equal(gm, prob.means)
     np.testing.assert_array_equal(gx, prob.xpx)
@@ -47,7 +48,7 @@ def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=
         rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
                                       method=oracle.METHOD_ABC, nreps_mode=nreps_mode,
                                       independent=(schedule == jw.SCHED_INDEPENDENT), vare=vare,
-                                      varEffects=ve, pi=piv, seed=seed, it=it, u=u, z=z)
+                                      varEffects=ve, pi=piv, seed=seed, it=it, u=u, z=z, lag=lag)
         assert rc == 0
         st = g.sweep_bayesabc(schedule, vare, ve, piv, seed, it, u, z)
         ga, gb, gd = g.get_state()
@@ -342,3 +343,17 @@ def test_large_panels_rejected_for_block_schedules(jw, oracle):
     with pytest.raises(jw.JwasError, match="exact schedule only"):
         g.sweep_bayesc(jw.SCHED_BLOCK, 1.0, 0.01, 0.9, 1, 1)
     g.close()
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.03])
+@pytest.mark.parametrize("n,p,b", [(500, 2000, 256), (501, 333, 64), (67, 50, 1), (1030, 700, 700),
+                                   (60013, 150, 64), (160, 3100, 1500)])
+def test_fused_lagged_schedule(jw, oracle, n, p, b, missing):
+    """option lag=1: chain of block k overlaps the streaming of block k+1; the rhs of a block is computed
+    from ycorr without the previous block's updates and corrected with the cross-Gram -- bit-exact against
+    the oracle's lagged schedule."""
+    if b > 1024 and missing > 0:
+        pytest.skip("panels above 1024 with missing calls run on engine 0")
+    prob = Problem(oracle, n, p, seed=n + p + 7, missing=missing)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1,
+                 pi=(0.97 if b > 1024 else 0.9))
