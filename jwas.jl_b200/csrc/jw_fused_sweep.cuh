@@ -360,6 +360,10 @@ jw_k_fused(jw_fused_args F) {
                 A.xcount = F.act_cnt_blk + (k - 1);
                 A.xstart = F.C.starts[k - 1];
             }
+            if (lag && k + 1 < F.nblocks) {
+                A.xgram_next = F.gramx + F.gramx_off[k + 1];
+                A.b_next = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
+            }
             A.sq = F.sq_acc + k * T;
             A.act_idx = F.act_idx_all + s;
             A.act_cnt = F.act_cnt_blk + k;

@@ -140,6 +140,7 @@ struct jw_chain_args {
     // lagged schedule: the previous block's updates are not in ycorr yet; its ordered active list and
     // the cross-Gram X_{k-1}'X_k (rows = previous block's markers) correct the rhs of this block
     const float* xgram; const int32_t* xlist; const int32_t* xcount; int64_t xstart;
+    const float* xgram_next; int b_next;    // cross-Gram towards the next block: rows are prefetched at commit
     int32_t* act_idx; int32_t* act_cnt;     // ordered active list of this launch (single-block mode)
     int write_active_list;
     unsigned long long* counters;
@@ -331,13 +332,26 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
     }
     if (A.xgram != nullptr && valid) {
         const int xc = __ldcg(A.xcount);
-        for (int e = 0; e < xc; ++e) {
-            const int64_t ja = __ldcg(A.xlist + e);
-            const float g = A.xgram[(ja - A.xstart) * b + m];
+        // four entries' loads are in flight together; the additions stay in commit order
+        for (int e0 = 0; e0 < xc; e0 += 4) {
+            int64_t ja[4]; float g[4]; float dd[4][T];
 #pragma unroll
-            for (int k = 0; k < T; ++k) {
-                const float d = __ldcg(&A.dalpha[k * p + ja]);
-                if (d != 0.0f) r[k] += (double)d * (double)g;
+            for (int q = 0; q < 4; ++q) ja[q] = (e0 + q < xc) ? (int64_t)__ldcg(A.xlist + e0 + q) : -1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (ja[q] >= 0) {
+                    g[q] = A.xgram[(ja[q] - A.xstart) * b + m];
+#pragma unroll
+                    for (int k = 0; k < T; ++k) dd[q][k] = __ldcg(&A.dalpha[k * p + ja[q]]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (ja[q] >= 0) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k)
+                        if (dd[q][k] != 0.0f) r[k] += (double)dd[q][k] * (double)g[q];
+                }
             }
         }
     }
@@ -509,6 +523,13 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                     float d = s_dc[k * JW_CHAIN_SB + first];
                     if (d != 0.0f) r[k] += (double)d * (double)g;
                 }
+            }
+            if (A.xgram_next != nullptr && tid == 0) {
+                // the next block's chain will need this marker's cross-Gram row: start moving it to L2
+                const float* row = A.xgram_next + (int64_t)fg * A.b_next;
+                const unsigned long long a0 = (unsigned long long)row & ~15ull;
+                const unsigned bytes = (unsigned)((((unsigned long long)(row + A.b_next) + 15ull) & ~15ull) - a0);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
             }
             if (sb + 1 < nsub) {                   // later sub-blocks replay this commit
                 if (tid == 0) {

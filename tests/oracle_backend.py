@@ -22,6 +22,7 @@ class OracleBackend:
         self.alpha = np.zeros(tp, np.float32); self.beta = np.zeros(tp, np.float32); self.delta = np.zeros(tp, np.int32)
         self.ma = np.zeros(tp, np.float32); self.ma2 = np.zeros(tp, np.float32); self.md = np.zeros(tp, np.float32)
         self.ve = None; self.pi = None
+        self.lag = 0
 
     def put_ycorr(self, y):
         self.y[:] = np.asarray(y, np.float32).reshape(-1)
@@ -91,7 +92,8 @@ class OracleBackend:
         rc, _ = orc.sweep_contract(self.packed, self.n, self.means, self.xpx, self.starts, self.y, self.alpha,
                                    self.beta, self.delta, method=method,
                                    nreps_mode=0 if (schedule == SCHED_EXACT or not full_reps) else 1,
-                                   independent=(schedule == SCHED_INDEPENDENT), seed=seed, it=it, **kw)
+                                   independent=(schedule == SCHED_INDEPENDENT), seed=seed, it=it,
+                                   lag=(self.lag if schedule == SCHED_EXACT else 0), **kw)
         assert rc == 0, "oracle fixed-point overflow"
         return self._stats(method)
 

@@ -97,11 +97,12 @@ def test_bayesc_block_schedules(jw, oracle, schedule_name, missing):
     run_pair_abc(jw, oracle, prob, starts, sched, nsweeps=3, replay=(schedule_name == "block"))
 
 
-def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0):
+def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
     g.set_option("engine", engine)
+    g.set_option("lag", lag)
     yc, al, be, de = prob.fresh_state()
     de[:] = 1
     g.put_ycorr(yc); g.put_state(al, be, de)
@@ -112,7 +113,7 @@ def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, e
         rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, None, de,
                                       method=oracle.METHOD_R, nreps_mode=nreps_mode,
                                       independent=(schedule == jw.SCHED_INDEPENDENT), vare=vare,
-                                      sigmaSq=sigma, pi=PI_R, gamma=GAMMA, seed=seed, it=it)
+                                      sigmaSq=sigma, pi=PI_R, gamma=GAMMA, seed=seed, it=it, lag=lag)
         assert rc == 0
         st = g.sweep_bayesr(schedule, full_reps, vare, sigma, PI_R, GAMMA, seed, it)
         ga, _, gd = g.get_state()
@@ -143,11 +144,12 @@ def test_bayesr_block_schedules(jw, oracle, schedule_name, full_reps):
     run_pair_r(jw, oracle, prob, uniform_starts(90, 17), sched, full_reps, nsweeps=3)
 
 
-def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0):
+def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0):
     n, p, t = prob.n, prob.p, prob.t
     g = jw.GpuSweeper(prob.packed, n, t)
     g.set_blocks(starts)
     g.set_option("engine", engine)
+    g.set_option("lag", lag)
     yc, al, be, de = prob.fresh_state()
     g.put_ycorr(yc); g.put_state(al, be, de)
     R = np.array([[1.0, 0.3], [0.3, 1.2]]) * prob.vary * 0.5
@@ -158,7 +160,7 @@ def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0):
         rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
                                       method=oracle.METHOD_MT1, nreps_mode=nreps_mode,
                                       independent=(schedule == jw.SCHED_INDEPENDENT), R=R, G=G, bigPi=bigPi,
-                                      seed=seed, it=it)
+                                      seed=seed, it=it, lag=lag)
         assert rc == 0
         st = g.sweep_mt1(schedule, R, G, bigPi, seed, it)
         ga, gb, gd = g.get_state()
@@ -357,3 +359,10 @@ def test_fused_lagged_schedule(jw, oracle, n, p, b, missing):
     prob = Problem(oracle, n, p, seed=n + p + 7, missing=missing)
     run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1,
                  pi=(0.97 if b > 1024 else 0.9))
+
+
+def test_fused_lagged_bayesr_and_multitrait(jw, oracle):
+    prob = Problem(oracle, 700, 900, seed=36, missing=0.02)
+    run_pair_r(jw, oracle, prob, uniform_starts(900, 256), jw.SCHED_EXACT, 1, nsweeps=3, engine=1, lag=1)
+    prob = Problem(oracle, 803, 500, seed=46, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(500, 128), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1)
