@@ -160,8 +160,9 @@ double jwas_last_sweep_ms(jwas_handle* h);
 double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches);
 /* engine 1 phase timers of the last sweep, nanoseconds: out[0..4] = CTA 0 {wait previous chain,
  * axpy+quantise+tables, stream, wait for all slices, chain}; out[8..12] = CTA 1, same phases;
- * out[16..20] = the dedicated chain CTA of the lagged schedule (option "lag" = 1) */
-int jwas_get_phase_ns(jwas_handle* h, uint64_t* out24);
+ * out[16..20] = the dedicated chain CTA of the lagged schedule (option "lag" = 1);
+ * out[24..28] = inside the chain {preload issue, wait, rhs + corrections, rounds, epilogue} (32 values) */
+int jwas_get_phase_ns(jwas_handle* h, uint64_t* out32);
 /* raw CUDA stream of the handle (cudaStream_t) so callers can time on it */
 void* jwas_stream(jwas_handle* h);
 

@@ -266,7 +266,7 @@ class GpuSweeper:
         return b.value, e.value
 
     def phase_ns(self):
-        out = np.zeros(24, np.uint64)
+        out = np.zeros(32, np.uint64)
         _check(lib().jwas_get_phase_ns(self._h, _p(out)))
         return out
 

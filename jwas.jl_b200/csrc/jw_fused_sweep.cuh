@@ -29,7 +29,7 @@ struct jw_fused_state {
     int* d_done = nullptr;           // 1
     long long* d_sq_acc = nullptr;   // nblocks * T
     int32_t* d_act_cnt_blk = nullptr;// nblocks
-    int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1, list_cap = 0;
+    int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1, list_cap = 0, two_lists = 0;
     int64_t total_chunks = 0;
     size_t smem = 0;
     bool ready = false;
@@ -42,6 +42,7 @@ struct jw_fused_args {
     const uint8_t* packed; int64_t stride_d;
     int Gs, TS, n_vs, nblocks, list_cap, lag;
     const float* gramx; const int64_t* gramx_off;
+    int timers, two_lists;
     float* ycorr; float scale;
     int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
     int32_t* flags;              // [0] overflow, [2] abort
@@ -150,9 +151,10 @@ jw_k_fused(jw_fused_args F) {
     // phase timers (ns): [0] wait for previous chain, [1] axpy+quantise+tables, [2] stream,
     // [3] wait for all slices, [4] chain; CTA 0 -> counters[32..36], CTA 1 -> counters[40..44]
     unsigned long long ph[5] = {0, 0, 0, 0, 0};
-    const bool timed = (tid == 0) && (blockIdx.x <= 1 || is_chain_cta) && (F.C.counters != nullptr);
+    const bool timed = (tid == 0) && (blockIdx.x <= 1 || is_chain_cta) && (F.C.counters != nullptr) && F.timers;
     unsigned long long tm = timed ? jw_globaltimer() : 0;
 #define JW_PHASE(i) do { if (timed) { unsigned long long now__ = jw_globaltimer(); ph[i] += now__ - tm; tm = now__; } } while (0)
+    int prev_commits = 0;                  // chain CTA, lagged schedule: commits of the previous block (smem list)
     long long sq_keep[T];                  // thread 0: this CTA's sum of yq over its slice(s)
 #pragma unroll
     for (int kk = 0; kk < T; ++kk) sq_keep[kk] = 0;
@@ -353,21 +355,26 @@ jw_k_fused(jw_fused_args F) {
         JW_PHASE(2);
         }   // streaming role
         if (is_chain_cta) {
-            jw_chain_args A = F.C;
+            jw_chain_blk B;
+            B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
             if (lag && k > 0) {
-                A.xgram = F.gramx + F.gramx_off[k];
-                A.xlist = F.act_idx_all + F.C.starts[k - 1];
-                A.xcount = F.act_cnt_blk + (k - 1);
-                A.xstart = F.C.starts[k - 1];
+                B.xgram = F.gramx + F.gramx_off[k];
+                B.xlist = F.act_idx_all + F.C.starts[k - 1];
+                B.xcount = F.act_cnt_blk + (k - 1);
+                B.xstart = F.C.starts[k - 1];
             }
             if (lag && k + 1 < F.nblocks) {
-                A.xgram_next = F.gramx + F.gramx_off[k + 1];
-                A.b_next = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
+                B.xgram_next = F.gramx + F.gramx_off[k + 1];
+                B.b_next = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
             }
-            A.sq = F.sq_acc + k * T;
-            A.act_idx = F.act_idx_all + s;
-            A.act_cnt = F.act_cnt_blk + k;
-            A.write_active_list = 1;
+            B.s = s; B.b = b; B.gram_off = F.C.gram_off[k];
+            B.xcount_smem = (lag && F.two_lists) ? prev_commits : -1;
+            B.prefetch_s = 0; B.prefetch_b = 0;
+            if (k + 1 < F.nblocks) { B.prefetch_s = F.C.starts[k + 1]; B.prefetch_b = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]); }
+            B.sq = F.sq_acc + k * T;
+            B.act_idx = F.act_idx_all + s;
+            B.act_cnt = F.act_cnt_blk + k;
+            B.write_active_list = 1;
             auto wait_all = [&]() -> bool {
                 if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
                 __syncthreads();
@@ -375,7 +382,9 @@ jw_k_fused(jw_fused_args F) {
                 return s_ok != 0;
             };
             unsigned char* chain_smem = reinterpret_cast<unsigned char*>(yqs + ((T * R + 3) & ~3));
-            if (!jw_chain_block<METHOD, T>(A, k, wait_all, chain_smem, F.list_cap)) return;
+            const int nc = jw_chain_block<METHOD, T>(F.C, B, k, wait_all, chain_smem, F.list_cap);
+            if (nc < 0) return;
+            prev_commits = nc;
             __syncthreads();
             if (tid == 0) { __threadfence(); jw_st_release(F.done, k + 1); }
             JW_PHASE(4);
@@ -451,9 +460,12 @@ static int jw_fused_prepare(jwas_handle* h) {
     f->TS = (int)((gs + 31) / 32 * 32);
     f->n_vs = (int)((nbytes + gs - 1) / gs);
     f->n_cta = std::min<int>(h->sm_count, f->n_vs);
-    f->list_cap = h->maxb > JW_MAX_BLOCK ? (int)h->maxb : 0;
-    f->smem = (size_t)(f->W == 1 ? 2 : 3) * 65536 + (((size_t)h->t * f->Gs * 4 + 3) & ~(size_t)3) * 4
-              + jw_chain_smem_bytes(h->t, f->list_cap);
+    // commit lists: one for panels above 1024 markers; two (ping-pong, capacity = largest block) when they
+    // fit, so that the lagged schedule's cross-Gram correction reads the previous block's commits on chip
+    const size_t base_smem = (size_t)(f->W == 1 ? 2 : 3) * 65536 + (((size_t)h->t * f->Gs * 4 + 3) & ~(size_t)3) * 4;
+    f->two_lists = (base_smem + jw_chain_smem_bytes(h->t, (int)h->maxb, 2) <= 227 * 1024) ? 1 : 0;
+    f->list_cap = f->two_lists ? (int)h->maxb : (h->maxb > JW_MAX_BLOCK ? (int)h->maxb : 0);
+    f->smem = base_smem + jw_chain_smem_bytes(h->t, f->list_cap, f->two_lists ? 2 : 1);
     if (f->smem > 227 * 1024) { delete f; h->fused = nullptr; return 0; }   // engine 0 only for this shape
     std::vector<int64_t> coff(h->nblocks + 1, 0);
     std::vector<int32_t> cblk;
@@ -513,7 +525,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.tiled = f->d_tiled; F.chunk_off = f->d_chunk_off;
     F.packed = h->d_packed; F.stride_d = h->stride_d;
     F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks; F.list_cap = f->list_cap;
-    F.lag = (int)h->opt_lag;
+    F.lag = (int)h->opt_lag; F.timers = (int)h->opt_timers; F.two_lists = f->two_lists;
     JW_REQUIRE(!F.lag || (A.nreps_mode == 0 && h->d_gramx), "lag = 1 needs the exact schedule and the cross-Gram blocks");
     F.gramx = h->d_gramx; F.gramx_off = h->d_gramx_off;
     F.ycorr = h->d_ycorr; F.scale = scale;

@@ -144,6 +144,7 @@ struct jw_chain_args {
     int32_t* act_idx; int32_t* act_cnt;     // ordered active list of this launch (single-block mode)
     int write_active_list;
     unsigned long long* counters;
+    int timers;                    // 1 = accumulate phase timers (tools/phase_probe.py); off in production
 };
 
 __device__ __forceinline__ double jw_get_u(const jw_chain_args& A, int64_t j, int trait, int rep) {
@@ -199,6 +200,25 @@ jw_k_prep_abc(jw_chain_args A, double* __restrict__ prep, float* __restrict__ be
 
 struct jw_no_wait { __device__ __forceinline__ bool operator()() const { return true; } };
 
+// what changes from block to block (kept small so the big jw_chain_args can stay in parameter space)
+struct jw_chain_blk {
+    const long long* sq;
+    int32_t* act_idx; int32_t* act_cnt; int write_active_list;
+    const float* xgram; const int32_t* xlist; const int32_t* xcount; int64_t xstart;
+    const float* xgram_next; int b_next;
+    int64_t prefetch_s; int prefetch_b;     // next block's chain inputs to pull towards L2 (0 = none)
+    int64_t s; int b; int64_t gram_off;     // this block: first marker, size, Gram offset (b = 0: look them up)
+    // (c) previous block's commits kept in shared memory by the dedicated chain CTA (lagged schedule)
+    int xcount_smem;                        // >= 0: number of entries in the shared list; -1: use xlist/xcount
+};
+__device__ __forceinline__ jw_chain_blk jw_chain_blk_from(const jw_chain_args& A) {
+    jw_chain_blk B;
+    B.sq = A.sq; B.act_idx = A.act_idx; B.act_cnt = A.act_cnt; B.write_active_list = A.write_active_list;
+    B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
+    B.prefetch_s = 0; B.prefetch_b = 0; B.s = 0; B.b = 0; B.gram_off = 0; B.xcount_smem = -1;
+    return B;
+}
+
 // wait_fn() is called after everything that does not depend on the block rhs has been loaded
 // (state, constants, Gram-row prefetches): the fused engine spins there for the other CTAs'
 // partial sums, so those global-memory latencies hide behind the wait.  Returns false on abort.
@@ -206,8 +226,8 @@ struct jw_no_wait { __device__ __forceinline__ bool operator()() const { return 
 //   wmin[2][32] | cnt[33] | dc[T][1024] | list_idx[cap] | list_d[T][cap]
 // The commit list exists only for panels larger than one thread-block of markers (cap = panel size).
 #define JW_CHAIN_SB 1024
-__host__ __device__ inline size_t jw_chain_smem_bytes(int T, int list_cap) {
-    return 256 + 256 + (size_t)T * JW_CHAIN_SB * 4 + (size_t)list_cap * 4 * (1 + T);
+__host__ __device__ inline size_t jw_chain_smem_bytes(int T, int list_cap, int nlists = 1) {
+    return 256 + 256 + (size_t)T * JW_CHAIN_SB * 4 + (size_t)nlists * list_cap * 4 * (1 + T);
 }
 
 // wait_fn() is called after everything that does not depend on the block rhs has been loaded
@@ -218,47 +238,63 @@ __host__ __device__ inline size_t jw_chain_smem_bytes(int T, int list_cap) {
 // appended to a list so that a later sub-block starts from  base rhs + sum_commits d*G[commit][j]
 // (added in commit order: the same sums, in the same order, as the one-thread-per-marker chain).
 template <int METHOD, int T, class WaitFn>
-__device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int ib, WaitFn wait_fn,
-                                               unsigned char* smem_base, const int list_cap) {
+__device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_chain_blk& B, const int ib,
+                                              WaitFn wait_fn, unsigned char* smem_base, const int list_cap) {
     int (*s_wmin)[32] = reinterpret_cast<int (*)[32]>(smem_base);
     int* s_cnt = reinterpret_cast<int*>(smem_base + 256);
     float* s_dc = reinterpret_cast<float*>(smem_base + 512);                  // [T][JW_CHAIN_SB]
-    int* s_lidx = reinterpret_cast<int*>(smem_base + 512 + T * JW_CHAIN_SB * 4);
+    // commit list(s): [cap ints][T*cap floats] each.  With B.xcount_smem >= 0 (dedicated chain CTA of the
+    // lagged schedule) two lists alternate: this block writes list (ib & 1) and reads the previous
+    // block's commits from the other one -- the cross-Gram correction then needs no global list.
+    const bool two_lists = B.xcount_smem >= 0;
+    unsigned char* lbase = smem_base + 512 + T * JW_CHAIN_SB * 4;
+    const size_t lbytes = (size_t)list_cap * 4 * (1 + T);
+    int* s_lidx = reinterpret_cast<int*>(lbase + (two_lists ? (size_t)(ib & 1) * lbytes : 0));
     float* s_ld = reinterpret_cast<float*>(s_lidx + list_cap);                // [T][list_cap]
+    const int* s_pidx = reinterpret_cast<const int*>(lbase + (size_t)((ib & 1) ^ 1) * lbytes);
+    const float* s_pd = reinterpret_cast<const float*>(s_pidx + list_cap);
 
-    const int64_t s = A.starts[ib];
-    const int b = (int)(A.starts[ib + 1] - s);
+    const int64_t s = B.b > 0 ? B.s : A.starts[ib];
+    const int b = B.b > 0 ? B.b : (int)(A.starts[ib + 1] - s);
     const int SB = (int)blockDim.x;
     const int nsub = (b + SB - 1) / SB;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int nw = (int)(blockDim.x >> 5);
     const int64_t p = A.p;
-    const float* G = A.gram + A.gram_off[ib];
+    const float* G = A.gram + (B.b > 0 ? B.gram_off : A.gram_off[ib]);
     unsigned long long my_active = 0, my_rounds = 0;
+    unsigned long long ct[6] = {0, 0, 0, 0, 0, 0};
+    const bool ctimed = (threadIdx.x == 0) && (A.counters != nullptr) && A.timers;
+    unsigned long long ctm = 0;
+    if (ctimed) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ctm));
+#define JW_CT(i) do { if (ctimed) { unsigned long long n__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(n__)); ct[i] += n__ - ctm; ctm = n__; } } while (0)
     int parity = 0;
     int ncommit = 0;          // commits recorded for later sub-blocks (uniform across the CTA)
     int act_total = 0;        // markers with a net delta so far (ordered active list)
 
-    // pull the panel's chain inputs (state, statistics, precomputed terms) towards L2 in bulk: one
-    // lane per array, issued before anything waits
-    if (warp == 0) {
-        const void* base = nullptr; unsigned esz = 0;
-        switch (lane) {
-            case 0: base = A.alpha + s; esz = 4; break;
-            case 1: base = A.delta + s; esz = 4; break;
-            case 2: base = A.xpx + s; esz = 4; break;
-            case 3: base = A.means + s; esz = 4; break;
-            case 4: if (METHOD != 1) { base = A.beta + s; esz = 4; } break;
-            case 5: if (A.prep_beta0) { base = A.prep_beta0 + s; esz = 4; } break;
-            case 6: case 7: case 8: case 9: case 10: case 11:
-                if (A.prep) { base = A.prep + (int64_t)(lane - 6) * p + s; esz = 8; } break;
-            default: break;
-        }
-        if (base && nsub > 1) {
-            const unsigned long long a0 = (unsigned long long)base & ~15ull;
-            const unsigned bytes = (unsigned)((((unsigned long long)base + (unsigned long long)b * esz + 15ull) & ~15ull) - a0);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+    // pull the NEXT block's chain inputs (state, statistics, precomputed terms) towards L2 in bulk, one
+    // lane per array: they are needed one whole chain later, so the latency is off the critical path
+    if (warp == 0 && B.prefetch_b > 0) {
+        const int64_t ps = B.prefetch_s; const int pb = B.prefetch_b;
+        for (int kk = 0; kk < T; ++kk) {
+            const void* base = nullptr; unsigned esz = 0;
+            switch (lane) {
+                case 0: base = A.alpha + kk * p + ps; esz = 4; break;
+                case 1: base = A.delta + kk * p + ps; esz = 4; break;
+                case 2: if (kk == 0) { base = A.xpx + ps; esz = 4; } break;
+                case 3: if (kk == 0) { base = A.means + ps; esz = 4; } break;
+                case 4: if (METHOD != 1) { base = A.beta + kk * p + ps; esz = 4; } break;
+                case 5: if (A.prep_beta0 && kk == 0) { base = A.prep_beta0 + ps; esz = 4; } break;
+                case 6: case 7: case 8: case 9: case 10: case 11:
+                    if (A.prep && kk == 0) { base = A.prep + (int64_t)(lane - 6) * p + ps; esz = 8; } break;
+                default: break;
+            }
+            if (base) {
+                const unsigned long long a0 = (unsigned long long)base & ~15ull;
+                const unsigned bytes = (unsigned)((((unsigned long long)base + (unsigned long long)pb * esz + 15ull) & ~15ull) - a0);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+            }
         }
     }
 
@@ -321,26 +357,46 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         }
     }
 
-    if (sb == 0) { if (!wait_fn()) return false; }
+    JW_CT(0);
+    if (sb == 0) { if (!wait_fn()) return -1; }
+    JW_CT(1);
 
     // rhs of this marker for every trait
 #pragma unroll
     for (int k = 0; k < T; ++k) {
         // .cg loads: these words were produced by other CTAs' atomics in the fused engine
         long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
-        r[k] = ((double)dq - mu * (double)(__ldcg(&A.sq[k]) - mq)) * A.invscale;
+        r[k] = ((double)dq - mu * (double)(__ldcg(&B.sq[k]) - mq)) * A.invscale;
     }
-    if (A.xgram != nullptr && valid) {
-        const int xc = __ldcg(A.xcount);
+    if (B.xgram != nullptr && valid && two_lists) {
+        // previous block's commits from shared memory; four cross-Gram loads in flight, adds in order
+        const int xc = B.xcount_smem;
+        for (int e0 = 0; e0 < xc; e0 += 4) {
+            float g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[q] = (e0 + q < xc) ? B.xgram[(int64_t)s_pidx[e0 + q] * b + m] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (e0 + q < xc) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k) {
+                        const float d = s_pd[k * list_cap + e0 + q];
+                        if (d != 0.0f) r[k] += (double)d * (double)g[q];
+                    }
+                }
+            }
+        }
+    } else if (B.xgram != nullptr && valid) {
+        const int xc = __ldcg(B.xcount);
         // four entries' loads are in flight together; the additions stay in commit order
         for (int e0 = 0; e0 < xc; e0 += 4) {
             int64_t ja[4]; float g[4]; float dd[4][T];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ja[q] = (e0 + q < xc) ? (int64_t)__ldcg(A.xlist + e0 + q) : -1;
+            for (int q = 0; q < 4; ++q) ja[q] = (e0 + q < xc) ? (int64_t)__ldcg(B.xlist + e0 + q) : -1;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (ja[q] >= 0) {
-                    g[q] = A.xgram[(ja[q] - A.xstart) * b + m];
+                    g[q] = B.xgram[(ja[q] - B.xstart) * b + m];
 #pragma unroll
                     for (int k = 0; k < T; ++k) dd[q][k] = __ldcg(&A.dalpha[k * p + ja[q]]);
                 }
@@ -366,6 +422,7 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         }
     }
 
+    JW_CT(2);
     const int nreps = A.nreps_mode ? b : 1;
 
     for (int rep = 0; rep < nreps; ++rep) {
@@ -524,14 +581,14 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
                     if (d != 0.0f) r[k] += (double)d * (double)g;
                 }
             }
-            if (A.xgram_next != nullptr && tid == 0) {
+            if (B.xgram_next != nullptr && tid == 0) {
                 // the next block's chain will need this marker's cross-Gram row: start moving it to L2
-                const float* row = A.xgram_next + (int64_t)fg * A.b_next;
+                const float* row = B.xgram_next + (int64_t)fg * B.b_next;
                 const unsigned long long a0 = (unsigned long long)row & ~15ull;
-                const unsigned bytes = (unsigned)((((unsigned long long)(row + A.b_next) + 15ull) & ~15ull) - a0);
+                const unsigned bytes = (unsigned)((((unsigned long long)(row + B.b_next) + 15ull) & ~15ull) - a0);
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
             }
-            if (sb + 1 < nsub) {                   // later sub-blocks replay this commit
+            if (sb + 1 < nsub || two_lists) {      // later sub-blocks (and the next block) replay this commit
                 if (tid == 0) {
                     s_lidx[ncommit] = fg;
 #pragma unroll
@@ -545,6 +602,7 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
         __syncthreads();      // s_dc / s_wmin are reused by the next repetition
     }
 
+    JW_CT(3);
     // ---- block exit: publish state and the net delta-alpha of every marker ----
     bool any = false;
     if (valid) {
@@ -558,35 +616,41 @@ __device__ __forceinline__ bool jw_chain_block(const jw_chain_args& A, const int
             any = any || (d != 0.0f);
         }
     }
-    if (A.write_active_list) {
-        // ordered compaction of this sub-block's markers with any non-zero delta
-        unsigned bal = __ballot_sync(0xffffffffu, any);
-        if (lane == 0) s_cnt[warp] = __popc(bal);
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int w = 0; w < nw; ++w) { int c = s_cnt[w]; s_cnt[w] = acc; acc += c; }
-            s_cnt[32] = acc;
+    if (B.write_active_list) {
+        // ordered compaction of this sub-block's markers with any non-zero delta (nothing to do in the
+        // common case of a sub-block without updates)
+        if (__syncthreads_or(any ? 1 : 0)) {
+            unsigned bal = __ballot_sync(0xffffffffu, any);
+            if (lane == 0) s_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int c = (lane < nw) ? s_cnt[lane] : 0;          // every warp scans the 32 warp counts
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int warp_off = __shfl_sync(0xffffffffu, incl - c, warp);
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (any) B.act_idx[act_total + warp_off + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
+            act_total += total;
         }
-        __syncthreads();
-        if (any) A.act_idx[act_total + s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
-        act_total += s_cnt[32];
     }
     __syncthreads();          // shared scratch is reused by the next sub-block
+    JW_CT(4);
   }   // sub-blocks
-    if (A.write_active_list && tid == 0) *A.act_cnt = act_total;
+    if (B.write_active_list && tid == 0) *B.act_cnt = act_total;
+    if (ctimed) for (int i = 0; i < 5; ++i) atomicAdd(&A.counters[56 + i], ct[i]);
+#undef JW_CT
     if (A.counters) {
         if (my_active) atomicAdd(&A.counters[0], my_active);
         if (my_rounds) atomicAdd(&A.counters[1], my_rounds);
     }
-    return true;
+    return ncommit;
 }
 
 template <int METHOD, int T>
 __global__ void __launch_bounds__(JW_MAX_BLOCK)
 jw_k_chain(jw_chain_args A, int list_cap) {
     extern __shared__ __align__(16) unsigned char jw_chain_dyn[];
-    jw_chain_block<METHOD, T>(A, A.block0 + (int)blockIdx.x, jw_no_wait(), jw_chain_dyn, list_cap);
+    jw_chain_block<METHOD, T>(A, jw_chain_blk_from(A), A.block0 + (int)blockIdx.x, jw_no_wait(), jw_chain_dyn, list_cap);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -600,6 +600,7 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
 
     JW_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t), h->stream));
     JW_CUDA(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+    JW_CUDA(cudaMemsetAsync(h->d_counters + 56, 0, 8 * sizeof(unsigned long long), h->stream));
 
     jw_chain_args A;
     memset(&A, 0, sizeof(A));
@@ -616,7 +617,7 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     memcpy(A.gamma, c.gamma, sizeof(A.gamma));
     memcpy(A.Rinv, c.Rinv, sizeof(A.Rinv)); memcpy(A.Ginv, c.Ginv, sizeof(A.Ginv));
     A.seed = c.seed; A.iter = c.iter; A.u = c.u; A.z = c.z;
-    A.act_idx = h->d_act_idx; A.act_cnt = h->d_act_cnt; A.counters = h->d_counters;
+    A.act_idx = h->d_act_idx; A.act_cnt = h->d_act_cnt; A.counters = h->d_counters; A.timers = (int)h->opt_timers;
     const int threads = (int)std::min<int64_t>(JW_MAX_BLOCK, std::max<int64_t>(32, ceil_div(h->maxb, 32) * 32));
     JW_REQUIRE(c.schedule == JWAS_SCHED_EXACT || h->maxb <= JW_MAX_BLOCK,
                "fast_blocks: block size above 1024 is supported by the exact schedule only.");
@@ -864,7 +865,7 @@ extern "C" double jwas_last_stream_kernel_ms(jwas_handle* h, int64_t* launches) 
 extern "C" int jwas_get_phase_ns(jwas_handle* h, uint64_t* out24) {
     JW_REQUIRE(h && out24, "jwas_get_phase_ns: null argument");
     JW_CUDA(cudaSetDevice(h->device));
-    JW_CUDA(cudaMemcpyAsync(out24, h->d_counters + 32, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(out24, h->d_counters + 32, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -872,6 +873,7 @@ extern "C" void* jwas_stream(jwas_handle* h) { return h ? (void*)h->stream : nul
 extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
     JW_REQUIRE(h && key, "jwas_set_option: null argument");
     if (!strcmp(key, "profile")) { h->opt_profile = value; return 0; }
+    if (!strcmp(key, "timers")) { h->opt_timers = value; return 0; }
     if (!strcmp(key, "lag")) {
         JW_REQUIRE(value == 0 || value == 1, "lag must be 0 or 1");
         JW_CUDA(cudaSetDevice(h->device));

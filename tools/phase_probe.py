@@ -12,7 +12,7 @@ ap.add_argument("--pi", type=float, default=0.999); ap.add_argument("--ve", type
 a = ap.parse_args()
 g = jwas_b200.GpuSweeper.synthetic(a.n, a.p, 1, seed=2026)
 starts = np.array(list(range(0, a.p, a.panel)) + [a.p], dtype=np.int64)
-g.set_blocks(starts); g.set_option("engine", 1); g.set_option("lag", a.lag)
+g.set_blocks(starts); g.set_option("engine", 1); g.set_option("lag", a.lag); g.set_option("timers", 1)
 rng = np.random.default_rng(1)
 g.put_ycorr(rng.standard_normal(a.n).astype(np.float32))
 nb = len(starts) - 1
@@ -21,4 +21,4 @@ for it in range(1, a.sweeps + 1):
     ph = g.phase_ns().astype(np.float64) / nb
     print(f"sweep {it}: {g.last_sweep_ms:.2f} ms  model={int(st.sum_delta[0])} active={st.n_active} rounds={st.n_rounds} | "
           f"CTA0 ns/block: wait_prev={ph[0]:.0f} rebuild={ph[1]:.0f} stream={ph[2]:.0f} wait_all={ph[3]:.0f} chain={ph[4]:.0f} | "
-          f"CTA1: wait_prev={ph[8]:.0f} rebuild={ph[9]:.0f} stream={ph[10]:.0f} | chainCTA: wait_all={ph[19]:.0f} chain={ph[20]:.0f}")
+          f"CTA1: wait_prev={ph[8]:.0f} rebuild={ph[9]:.0f} stream={ph[10]:.0f} | chainCTA: wait_all={ph[19]:.0f} chain={ph[20]:.0f} | in-chain: preload={ph[24]:.0f} wait={ph[25]:.0f} rhs={ph[26]:.0f} rounds={ph[27]:.0f} epilogue={ph[28]:.0f}")
