@@ -768,11 +768,23 @@ jw_k_chunk_sum(const float* __restrict__ a, int64_t n, double* __restrict__ part
     for (int64_t i = beg; i < end; ++i) s += (double)a[i];
     partials[c] = s;
 }
-__global__ void jw_k_chunk_final(const double* __restrict__ partials, int64_t nchunks, double* out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int64_t c = 0; c < nchunks; ++c) s += partials[c];
-        *out = s;
+// chunk sums -> sums of 256 consecutive chunk sums (index order, one thread each) -> final sum of those
+// (index order, one thread).  Same three levels in tests/helpers.py:canonical_sum_prod.
+__global__ void __launch_bounds__(JW_CHUNK)
+jw_k_chunk_final(const double* __restrict__ partials, int64_t nchunks, double* out) {
+    __shared__ double s_g[JW_CHUNK];
+    const int64_t ngroups = (nchunks + JW_CHUNK - 1) / JW_CHUNK;      // <= 256 for up to 16.7M elements
+    double s = 0.0;
+    if (threadIdx.x < ngroups) {
+        const int64_t beg = (int64_t)threadIdx.x * JW_CHUNK, end = min(beg + JW_CHUNK, nchunks);
+        for (int64_t c = beg; c < end; ++c) s += partials[c];
+    }
+    s_g[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int64_t g = 0; g < ngroups; ++g) tot += s_g[g];
+        *out = tot;
     }
 }
 // BayesR: sum alpha^2 / gamma[delta] over delta > 1 (variance_components.jl:68-79)
@@ -792,22 +804,36 @@ jw_k_chunk_bayesr(const float* __restrict__ alpha, const int32_t* __restrict__ d
     }
     partials[c] = s;
 }
-// integer statistics: counts are exact under any order
+// integer statistics: counts are exact under any order.  Per-thread flags are reduced inside the block
+// (ballots + shared counters) so that each block issues one atomic per counter, not one per marker.
 __global__ void __launch_bounds__(256)
 jw_k_counts(const float* __restrict__ alpha, const int32_t* __restrict__ delta, int64_t p, int t,
             int method, unsigned long long* __restrict__ out /* [0..3] nnz, [4..7] sumdelta, [8..23] classes */) {
+    __shared__ unsigned int s_c[24];
+    if (threadIdx.x < 24) s_c[threadIdx.x] = 0;
+    __syncthreads();
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p) return;
-    int state = 0;
+    const bool in = j < p;
+    int state = 0, cls = -1;
     for (int k = 0; k < t; ++k) {
-        if (alpha[k * p + j] != 0.0f) atomicAdd(&out[k], 1ull);
-        int d = delta[k * p + j];
-        if (method == 1) { if (d > 1) atomicAdd(&out[4 + k], 1ull); }
-        else if (d != 0) atomicAdd(&out[4 + k], 1ull);
+        const bool nz = in && alpha[k * p + j] != 0.0f;
+        const int d = in ? delta[k * p + j] : 0;
+        const bool dl = in && (method == 1 ? d > 1 : d != 0);
+        unsigned b1 = __ballot_sync(0xffffffffu, nz), b2 = __ballot_sync(0xffffffffu, dl);
+        if ((threadIdx.x & 31) == 0) {
+            if (b1) atomicAdd(&s_c[k], __popc(b1));
+            if (b2) atomicAdd(&s_c[4 + k], __popc(b2));
+        }
         state |= (d != 0) << k;
+        if (k == 0) cls = d - 1;
     }
-    if (method == 1) atomicAdd(&out[8 + (delta[j] - 1)], 1ull);
-    else atomicAdd(&out[8 + state], 1ull);
+    const int bin = method == 1 ? cls : state;
+    for (int c = 0; c < 16; ++c) {
+        unsigned bb = __ballot_sync(0xffffffffu, in && bin == c);
+        if ((threadIdx.x & 31) == 0 && bb) atomicAdd(&s_c[8 + c], __popc(bb));
+    }
+    __syncthreads();
+    if (threadIdx.x < 24 && s_c[threadIdx.x]) atomicAdd(&out[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
 }
 // sum / max|.| of ycorr (order-free: integer-like max; the sum is informational)
 __global__ void __launch_bounds__(256)

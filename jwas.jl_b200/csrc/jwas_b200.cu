@@ -364,20 +364,22 @@ extern "C" int jwas_mul_alpha(jwas_handle* h, int trait, float* out) {
 // canonical chunked sum of a[i]*b[i] -> *d_out (device)
 static int canonical_dot(jwas_handle* h, const float* a, const float* b, int64_t n, double* d_out) {
     int64_t nchunks = ceil_div(n, JW_CHUNK);
+    JW_REQUIRE(nchunks <= (int64_t)JW_CHUNK * JW_CHUNK, "vector too long for the canonical reduction (16.7M elements)");
     if (ensure_cap(&h->d_partials, &h->cap_partials, (size_t)nchunks)) return 10;
     jw_k_chunk_prod<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(a, b, n, h->d_partials);
     JW_LAUNCH_CHECK(h);
-    jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, d_out);
+    jw_k_chunk_final<<<1, JW_CHUNK, 0, h->stream>>>(h->d_partials, nchunks, d_out);
     JW_LAUNCH_CHECK(h);
     return 0;
 }
 
 static int canonical_sum(jwas_handle* h, const float* a, int64_t n, double* d_out) {
     int64_t nchunks = ceil_div(n, JW_CHUNK);
+    JW_REQUIRE(nchunks <= (int64_t)JW_CHUNK * JW_CHUNK, "vector too long for the canonical reduction (16.7M elements)");
     if (ensure_cap(&h->d_partials, &h->cap_partials, (size_t)nchunks)) return 10;
     jw_k_chunk_sum<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(a, n, h->d_partials);
     JW_LAUNCH_CHECK(h);
-    jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, d_out);
+    jw_k_chunk_final<<<1, JW_CHUNK, 0, h->stream>>>(h->d_partials, nchunks, d_out);
     JW_LAUNCH_CHECK(h);
     return 0;
 }
@@ -504,7 +506,7 @@ static int collect_stats(jwas_handle* h, const sweep_cfg& c, int S, jwas_sweep_s
         jw_k_chunk_bayesr<<<(unsigned)ceil_div(nchunks, 128), 128, 0, h->stream>>>(h->d_alpha, h->d_delta, h->p,
             c.gamma[1], c.gamma[2], c.gamma[3], c.gamma[4], c.gamma[5], c.gamma[6], c.gamma[7], h->d_partials);
         JW_LAUNCH_CHECK(h);
-        jw_k_chunk_final<<<1, 32, 0, h->stream>>>(h->d_partials, nchunks, h->d_stats + 48);
+        jw_k_chunk_final<<<1, JW_CHUNK, 0, h->stream>>>(h->d_partials, nchunks, h->d_stats + 48);
         JW_LAUNCH_CHECK(h);
     }
     JW_CUDA(cudaMemsetAsync(h->d_counters + 4, 0, 24 * sizeof(unsigned long long), h->stream));

@@ -35,21 +35,27 @@ def uniform_starts(p, b):
 
 
 def canonical_sum_prod(a, b):
-    """Same order as jw_k_chunk_prod/jw_k_chunk_final: 256-element chunks summed in index order,
-    chunk sums added in order; binary64."""
+    """Same order as jw_k_chunk_prod/jw_k_chunk_final: 256-element chunks summed in index order, then
+    groups of 256 chunk sums summed in index order, then the group sums added in order; binary64."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-    prod = a * b
-    n = prod.size
-    pad = (-n) % 256
-    if pad:
-        prod = np.concatenate([prod, np.zeros(pad)])
-    chunks = prod.reshape(-1, 256)
-    part = np.zeros(chunks.shape[0])
-    for c in range(256):          # sequential over the chunk, vectorised over chunks
-        part = part + chunks[:, c]
+    v = a * b
+
+    def level(x):
+        pad = (-x.size) % 256
+        if pad:
+            x = np.concatenate([x, np.zeros(pad)])
+        rows = x.reshape(-1, 256)
+        acc = np.zeros(rows.shape[0])
+        for c in range(256):          # sequential within a chunk, vectorised over chunks
+            acc = acc + rows[:, c]
+        return acc
+
+    part = level(v)
+    groups = level(part)
+    assert groups.size <= 256
     total = 0.0
-    for v in part:
-        total = total + v
+    for g in groups:
+        total = total + g
     return float(total)
 
 
