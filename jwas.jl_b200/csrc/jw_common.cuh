@@ -11,6 +11,7 @@
 #define JW_MAX_BLOCK 1024      // chain threads per CTA (one marker each per sub-block)
 #define JW_MAX_PANEL 4096      // largest block of the exact schedule (walked in sub-blocks)
 #define JW_MAX_CLASSES 8
+#define JW_R_CLASSES 4          // BayesR mixture classes on the device (BAYESR_GAMMA, JWAS.jl:12)
 
 void jw_set_error(const std::string& s);
 
@@ -60,6 +61,10 @@ struct jwas_handle {
     double* d_pi = nullptr;        // p  (BayesR per-marker: p*nclasses; MT per-marker: p*2^t)
     double* d_prep = nullptr;      // 6*p chain constants (BayesABC, repetition 0)
     float* d_prep_beta0 = nullptr; // p
+    double* d_draws = nullptr;     // 2*t*p: draws of repetition 0 (BayesR / multi-trait)
+    size_t cap_draws = 0;
+    double* d_prep_rm = nullptr;   // BayesR / multi-trait rhs-independent terms
+    size_t cap_prep_rm = 0;
     double* d_u = nullptr;         // replay tables (allocated on demand)
     double* d_z = nullptr;
     size_t cap_ve = 0, cap_pi = 0, cap_u = 0, cap_z = 0;

@@ -137,6 +137,12 @@ struct jw_chain_args {
     // instead of inside the one chain CTA: [0]log(1/u-1) [1]z*sqrt(invLhs) [2]invLhs [3]log(lhs)+log(ve)
     // [4]log(1-pi) [5]log(pi), each p doubles; prep_beta0 = float(z*sqrt(ve)).  NULL = inline.
     const double* prep; const float* prep_beta0;
+    const double* draws_u; const double* draws_z;   // jw_k_prep_draws output (t*p each) or NULL
+    // BayesR / multi-trait: rhs-independent terms.  prep_rm (jw_k_prep_rm): BayesR [(c-1)*p+j] = invLhs_c,
+    // [(K-1+c-1)*p+j] = log(invLhs_c)-log(varEffect_c); multi-trait [k*p+j] = log(C11_k).  The logs of the
+    // global priors are evaluated once on the host with the same jw_log.
+    const double* prep_rm; int host_logs;
+    double lpi[JW_MAX_CLASSES]; double mt_lG[JW_MAX_TRAITS]; double mt_lPi[16];
     // lagged schedule: the previous block's updates are not in ycorr yet; its ordered active list and
     // the cross-Gram X_{k-1}'X_k (rows = previous block's markers) correct the rhs of this block
     const float* xgram; const int32_t* xlist; const int32_t* xcount; int64_t xstart;
@@ -176,6 +182,40 @@ __device__ __forceinline__ int jw_categorical(const double* probs, int k, double
     double cp = probs[0]; int i = 0;
     while (cp <= u && i < k - 1) { i += 1; cp += probs[i]; }
     return i;
+}
+
+// draws of repetition 0 for every (trait, marker), computed by the whole GPU instead of inside the one
+// chain CTA: du = log-odds threshold of the uniform (BayesR: the uniform itself), dz = standard normal
+__global__ void __launch_bounds__(256)
+jw_k_prep_draws(jw_chain_args A, double* __restrict__ du, double* __restrict__ dz) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= A.p * A.t) return;
+    const int k = (int)(idx / A.p); const int64_t j = idx % A.p;
+    double u = jw_get_u(A, j, k, 0);
+    du[idx] = (A.method == 1) ? u : jw_logit_threshold(u);
+    dz[idx] = jw_get_z(A, j, k, 0);
+}
+
+__global__ void __launch_bounds__(256)
+jw_k_prep_rm(jw_chain_args A, double* __restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = A.p;
+    if (j >= p) return;
+    const double x = (double)A.xpx[j];
+    if (A.method == 1) {
+        const double invVarRes = 1.0 / A.vare;
+        const int K1 = A.nclasses - 1;
+        for (int c = 1; c < A.nclasses; ++c) {
+            double varEffect = A.gamma[c] * A.sigmaSq;
+            double lhs = x * invVarRes + 1.0 / varEffect;
+            double invLhs = 1.0 / lhs;
+            out[(int64_t)(c - 1) * p + j] = invLhs;
+            out[(int64_t)(K1 + c - 1) * p + j] = jw_log(invLhs) - jw_log(varEffect);
+        }
+    } else {
+        for (int k = 0; k < A.t; ++k)
+            out[(int64_t)k * p + j] = jw_log(A.Ginv[k * A.t + k] + A.Rinv[k * A.t + k] * x);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -422,6 +462,53 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         }
     }
 
+    // BayesR: class terms that do not depend on the rhs (BayesR.jl:64-72)
+    // (exactly JW_R_CLASSES = 4 mixture classes, as BAYESR_GAMMA in JWAS.jl:12; loops fully unrolled so
+    //  the per-class terms live in registers)
+    double rc_invLhs[JW_R_CLASSES], rc_base[JW_R_CLASSES], rc_lpi[JW_R_CLASSES];
+    if (METHOD == 1) {
+        rc_invLhs[0] = 0.0; rc_base[0] = 0.0;
+        if (A.prep_rm != nullptr && A.host_logs) {
+            const int K1 = JW_R_CLASSES - 1;
+            rc_lpi[0] = A.lpi[0];
+#pragma unroll
+            for (int c = 1; c < JW_R_CLASSES; ++c) {
+                rc_invLhs[c] = A.prep_rm[(int64_t)(c - 1) * p + j];
+                rc_base[c] = A.prep_rm[(int64_t)(K1 + c - 1) * p + j];
+                rc_lpi[c] = A.lpi[c];
+            }
+        } else {
+            const double* pij = A.per_marker_pi ? A.pi + j * JW_R_CLASSES : A.pi;
+            rc_lpi[0] = jw_log(pij[0]);
+#pragma unroll
+            for (int c = 1; c < JW_R_CLASSES; ++c) {
+                double varEffect = A.gamma[c] * A.sigmaSq;
+                double lhs = x * invVarRes + 1.0 / varEffect;
+                rc_invLhs[c] = 1.0 / lhs;
+                rc_base[c] = jw_log(rc_invLhs[c]) - jw_log(varEffect);
+                rc_lpi[c] = jw_log(pij[c]);
+            }
+        }
+    }
+    // multi-trait sampler I: logs of the per-marker constants (MTBayesABC.jl:88-105)
+    double mt_lG[T], mt_lC[T], mt_lPi[1 << T];
+    if (METHOD == 2) {
+        if (A.prep_rm != nullptr && A.host_logs) {
+#pragma unroll
+            for (int k = 0; k < T; ++k) { mt_lG[k] = A.mt_lG[k]; mt_lC[k] = A.prep_rm[(int64_t)k * p + j]; }
+#pragma unroll
+            for (int q = 0; q < (1 << T); ++q) mt_lPi[q] = A.mt_lPi[q];
+        } else {
+            const double* Pi = A.per_marker_pi ? A.bigPi + j * (1 << T) : A.bigPi;
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                mt_lG[k] = jw_log(Ginv[k * T + k]);
+                mt_lC[k] = jw_log(Ginv[k * T + k] + A.Rinv[k * T + k] * x);
+            }
+#pragma unroll
+            for (int q = 0; q < (1 << T); ++q) mt_lPi[q] = jw_log(Pi[q]);
+        }
+    }
     JW_CT(2);
     const int nreps = A.nreps_mode ? b : 1;
 
@@ -433,8 +520,12 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         } else {
 #pragma unroll
             for (int k = 0; k < T; ++k) {
-                u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep);
-                if (METHOD != 1) u[k] = jw_logit_threshold(u[k]);
+                if (rep == 0 && A.draws_u != nullptr) {
+                    u[k] = A.draws_u[k * p + j]; z[k] = A.draws_z[k * p + j];
+                } else {
+                    u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep);
+                    if (METHOD != 1) u[k] = jw_logit_threshold(u[k]);
+                }
             }
             if (METHOD == 0) {
                 if (use_prep) c_ve = A.ve[j];
@@ -466,38 +557,39 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
                 } else if (METHOD == 1) {
                     double aold = (double)a_cur[0];
                     double rhs = (r[0] + x * aold) * invVarRes;
-                    const double* pij = A.per_marker_pi ? A.pi + j * A.nclasses : A.pi;
-                    double lp[JW_MAX_CLASSES], pr[JW_MAX_CLASSES];
-                    lp[0] = jw_log(pij[0]);
-                    for (int c = 1; c < A.nclasses; ++c) {
-                        double varEffect = A.gamma[c] * A.sigmaSq;
-                        double lhs = x * invVarRes + 1.0 / varEffect;
-                        double invLhs = 1.0 / lhs;
-                        double betaHat = invLhs * rhs;
-                        lp[c] = 0.5 * (jw_log(invLhs) - jw_log(varEffect) + betaHat * rhs) + jw_log(pij[c]);
+                    double lp[JW_R_CLASSES], ex[JW_R_CLASSES];
+                    lp[0] = rc_lpi[0];
+#pragma unroll
+                    for (int c = 1; c < JW_R_CLASSES; ++c) {
+                        double betaHat = rc_invLhs[c] * rhs;
+                        lp[c] = 0.5 * (rc_base[c] + betaHat * rhs) + rc_lpi[c];
                     }
                     double mx = lp[0];
-                    for (int c = 1; c < A.nclasses; ++c) if (lp[c] > mx) mx = lp[c];
+#pragma unroll
+                    for (int c = 1; c < JW_R_CLASSES; ++c) if (lp[c] > mx) mx = lp[c];
                     double se = 0.0;
-                    for (int c = 0; c < A.nclasses; ++c) se += jw_exp(lp[c] - mx);
-                    double log_norm = mx + jw_log(se);
-                    for (int c = 0; c < A.nclasses; ++c) pr[c] = jw_exp(lp[c] - log_norm);
-                    int cls = jw_categorical(pr, A.nclasses, u[0]);
+#pragma unroll
+                    for (int c = 0; c < JW_R_CLASSES; ++c) { ex[c] = jw_exp(lp[c] - mx); se += ex[c]; }
+                    // Categorical(exp(lp - logsumexp)) (BayesR.jl:74-79) drawn on the unnormalised weights:
+                    // first class whose cumulative weight exceeds u * sum
+                    const double target = u[0] * se;
+                    int cls = 0; double cp = ex[0];
+#pragma unroll
+                    for (int c = 1; c < JW_R_CLASSES; ++c) {
+                        if (cls == c - 1 && cp <= target) { cls = c; cp += ex[c]; }
+                    }
                     newD[0] = cls + 1;
                     newA[0] = 0.0f;
                     if (cls > 0) {
-                        double varEffect = A.gamma[cls] * A.sigmaSq;
-                        double lhs = x * invVarRes + 1.0 / varEffect;
-                        double invLhs = 1.0 / lhs;
-                        double betaHat = invLhs * rhs;
-                        newA[0] = (float)(betaHat + z[0] * jw_sqrt(invLhs));
+                        const double il = cls == 1 ? rc_invLhs[1] : (cls == 2 ? rc_invLhs[2] : rc_invLhs[3]);
+                        double betaHat = il * rhs;
+                        newA[0] = (float)(betaHat + z[0] * jw_sqrt(il));
                     }
                     newB[0] = 0.0f;
                     active = (a_cur[0] - newA[0]) != 0.0f;
                 } else {
                     // MTBayesABC.jl:78-125
                     double bb[T], olda[T], w[T]; int dd[T];
-                    const double* Pi = A.per_marker_pi ? A.bigPi + j * (1 << T) : A.bigPi;
 #pragma unroll
                     for (int k = 0; k < T; ++k) {
                         bb[k] = (double)b_cur[k]; olda[k] = (double)a_cur[k]; dd[k] = d_cur[k] != 0;
@@ -527,8 +619,8 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
                             int dqq = (q == k) ? 0 : dd[q];
                             s0 |= dqq << q; s1 |= ((q == k) ? 1 : dqq) << q;
                         }
-                        double logDelta0 = -0.5 * (jw_log(Ginv11) - gHat0 * gHat0 * Ginv11) + jw_log(Pi[s0]);
-                        double logDelta1 = -0.5 * (jw_log(C11) - gHat1 * gHat1 * C11) + jw_log(Pi[s1]);
+                        double logDelta0 = -0.5 * (mt_lG[k] - gHat0 * gHat0 * Ginv11) + mt_lPi[s0];
+                        double logDelta1 = -0.5 * (mt_lC[k] - gHat1 * gHat1 * C11) + mt_lPi[s1];
                         if (logDelta0 - logDelta1 < u[k]) {
                             dd[k] = 1;
                             newA[k] = (float)(gHat1 + z[k] * jw_sqrt(invLhs1));

@@ -193,7 +193,7 @@ extern "C" int jwas_destroy(jwas_handle* h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_ycorr, h->d_alpha,
                     h->d_beta, h->d_delta, h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta, h->d_ve,
-                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_gramx, h->d_gramx_off, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
+                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_draws, h->d_prep_rm, h->d_gramx, h->d_gramx_off, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -414,6 +414,7 @@ struct sweep_cfg {
     int nclasses = 0, per_marker_pi = 0, per_marker_G = 0;
     double gamma[JW_MAX_CLASSES] = {0};
     double Rinv[16] = {0}, Ginv[16] = {0};
+    double pi_host[16] = {0};     // global class / joint-state priors (BayesR, multi-trait)
     uint64_t seed = 0; uint32_t iter = 0;
     const double* u = nullptr; const double* z = nullptr;  // device pointers
 };
@@ -632,6 +633,26 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
         jw_k_prep_abc<<<(unsigned)ceil_div(p, 256), 256, 0, h->stream>>>(A, h->d_prep, h->d_prep_beta0);
         JW_LAUNCH_CHECK(h);
         A.prep = h->d_prep; A.prep_beta0 = h->d_prep_beta0;
+    } else {
+        // BayesR / multi-trait: the draws of repetition 0 (Philox, Box-Muller, log-odds thresholds)
+        if (ensure_cap(&h->d_draws, &h->cap_draws, (size_t)2 * t * p)) return 10;
+        jw_k_prep_draws<<<(unsigned)ceil_div((int64_t)t * p, 256), 256, 0, h->stream>>>(A, h->d_draws, h->d_draws + (size_t)t * p);
+        JW_LAUNCH_CHECK(h);
+        A.draws_u = h->d_draws; A.draws_z = h->d_draws + (size_t)t * p;
+        // rhs-independent terms per marker on all SMs; logs of the global priors once on the host
+        if (!c.per_marker_pi && !c.per_marker_G) {
+            const size_t cnt = (size_t)(c.method == 1 ? 2 * (c.nclasses - 1) : t) * p;
+            if (ensure_cap(&h->d_prep_rm, &h->cap_prep_rm, cnt)) return 10;
+            A.host_logs = 1;
+            if (c.method == 1) for (int k = 0; k < c.nclasses; ++k) A.lpi[k] = jw_log(c.pi_host[k]);
+            else {
+                for (int k = 0; k < t; ++k) A.mt_lG[k] = jw_log(c.Ginv[k * t + k]);
+                for (int q = 0; q < (1 << t); ++q) A.mt_lPi[q] = jw_log(c.pi_host[q]);
+            }
+            jw_k_prep_rm<<<(unsigned)ceil_div(p, 256), 256, 0, h->stream>>>(A, h->d_prep_rm);
+            JW_LAUNCH_CHECK(h);
+            A.prep_rm = h->d_prep_rm;
+        }
     }
 
     if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT && h->world == 1) {
@@ -733,7 +754,7 @@ extern "C" int jwas_sweep_bayesr(jwas_handle* h, int schedule, int full_reps, do
     JW_REQUIRE(h, "null handle");
     JW_REQUIRE(h->t == 1, "jwas_sweep_bayesr: single-trait handle required");
     JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
-    JW_REQUIRE(nclasses >= 2 && nclasses <= JW_MAX_CLASSES, "BayesR needs 2..8 mixture classes");
+    JW_REQUIRE(nclasses == JW_R_CLASSES, "BayesR Pi must have length 4.");
     JW_REQUIRE(pi && gamma, "BayesR pi/gamma missing");
     JW_REQUIRE(sigma_sq > 0.0, "BayesR sigmaSq must be positive.");
     JW_REQUIRE(vare > 0.0, "residual variance must be positive");
@@ -748,6 +769,7 @@ extern "C" int jwas_sweep_bayesr(jwas_handle* h, int schedule, int full_reps, do
     sweep_cfg c; c.method = 1; c.schedule = schedule; c.full_reps = full_reps ? 1 : 0; c.vare = vare;
     c.sigmaSq = sigma_sq; c.nclasses = nclasses; c.per_marker_pi = per_marker_pi;
     for (int k = 0; k < nclasses; ++k) c.gamma[k] = gamma[k];
+    if (!per_marker_pi) for (int k = 0; k < nclasses; ++k) c.pi_host[k] = pi[k];
     c.seed = seed; c.iter = iter;
     if (upload_draws(h, c, u, z, schedule, c.full_reps)) return 10;
     return run_sweep(h, c, stats);
@@ -767,6 +789,7 @@ extern "C" int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, con
     jw_inv_spd_fixed(R, t, c.Rinv);
     if (per_marker_G) { if (upload_doubles(h, &h->d_ve, &h->cap_ve, G, (size_t)h->p * t * t)) return 10; }
     else jw_inv_spd_fixed(G, t, c.Ginv);
+    if (!per_marker_pi) for (int q = 0; q < (1 << t); ++q) c.pi_host[q] = big_pi[q];
     size_t npi = (size_t)(per_marker_pi ? h->p : 1) << t;
     if (upload_doubles(h, &h->d_pi, &h->cap_pi, big_pi, npi)) return 10;
     if (upload_draws(h, c, u, z, schedule, 1)) return 10;

@@ -592,10 +592,13 @@ static float r_step_contract(double r, float xpx, float* alpha, int32_t* delta,
     double mx = lp[0];
     for (int k = 1; k < nclasses; ++k) if (lp[k] > mx) mx = lp[k];
     double se = 0.0;
-    for (int k = 0; k < nclasses; ++k) se += jw_exp(lp[k] - mx);
-    double log_norm = mx + jw_log(se);
-    for (int k = 0; k < nclasses; ++k) pr[k] = jw_exp(lp[k] - log_norm);
-    int cls = categorical_from_uniform(pr, nclasses, u);
+    for (int k = 0; k < nclasses; ++k) { pr[k] = jw_exp(lp[k] - mx); se += pr[k]; }
+    /* Categorical(exp(lp - logsumexp)) (BayesR.jl:74-79; Distributions.jl: first i with cumsum > u)
+     * drawn on the unnormalised weights e_k = exp(lp_k - max): first class whose cumulative weight
+     * exceeds u * sum(e) -- the same event without the second round of exps */
+    double target = u * se;
+    int cls = 0; double cp = pr[0];
+    while (cp <= target && cls < nclasses - 1) { cls += 1; cp += pr[cls]; }
     *delta = cls + 1;
     float oldA = *alpha, newA = 0.0f;
     if (cls > 0) {
