@@ -166,9 +166,9 @@ def main():
     t_setup = time.perf_counter()
     g = jwas_b200.GpuSweeper.synthetic(n, p, 1, seed=2026)
     starts = np.array(list(range(0, p, args.panel)) + [p], dtype=np.int64)
-    g.set_blocks(starts)
     g.set_option("engine", args.engine)
     g.set_option("lag", args.lag if args.engine == 1 else 0)
+    g.set_blocks(starts)
     means, xpx = g.marker_stats()
     # phenotype: y = sum_qtl x_j a_j + e, h2 = 0.5
     rng = np.random.default_rng(7)

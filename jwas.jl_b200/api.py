@@ -481,9 +481,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         backend.lag = use_lag
     else:
         sw = GpuSweeper(packed, n, t, device=device)
-        sw.set_blocks(starts)
         sw.set_option("engine", engine)
         sw.set_option("lag", use_lag)
+        sw.set_blocks(starts)
         backend = mcmc.GpuBackend(sw)
         Mi.stream_backend = sw
     mu0 = Y.mean(axis=1)

@@ -22,7 +22,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
            "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
-           "-o", SO, SRC]
+           "-o", SO, SRC, "-lcublas"]
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
     subprocess.check_call(cmd)

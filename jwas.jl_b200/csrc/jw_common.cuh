@@ -99,6 +99,7 @@ struct jwas_handle {
     int64_t opt_profile = 0;       // 1 = time the genotype-streaming kernel(s) with CUDA events
     std::vector<cudaEvent_t> prof_events;
     double prof_ms = 0.0; int64_t prof_launches = 0;
+    int64_t opt_gram_popc = 0;     // 1 = build Gram blocks with the popcount kernel (default: bf16 tensor-core GEMM)
     int64_t opt_timers = 0;        // 1 = in-kernel phase timers (tools/phase_probe.py)
     int64_t opt_lag = 0;           // 1 = lagged exact schedule (engine 1): chain k overlaps stream k+1
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel

@@ -138,3 +138,54 @@ jw_k_gram(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n,
             }
         }
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Gram blocks on the tensor cores.  X_b'X_b IS a GEMM in the reference (tools4genotypes.jl:263,
+// `Xblock' * Xblock` -> sgemm), so the plain library GEMM is the right tool: codes 0/1/2 and the
+// observed-mask 0/1 are exact in bf16, products are exact, and FP32 accumulation of integers below
+// 2^24 is exact in any order -- the integer pair counts come out bit-identical to the popcount
+// kernel above, which stays as the fall-back (n >= 2^22) and as the cross-check in the tests.
+// ------------------------------------------------------------------------------------------
+#include <cuda_bf16.h>
+
+// unpack the markers [s, s+b) into column-major bf16 matrices (lda = n_pad): C = code value (missing -> 0),
+// V = 1 where observed (only written when MISSING)
+template <bool MISSING>
+__global__ void __launch_bounds__(256)
+jw_k_unpack_bf16(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t n_pad,
+                 int64_t s, int b, __nv_bfloat16* __restrict__ C, __nv_bfloat16* __restrict__ V) {
+    const int64_t nbytes_pad = n_pad >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (marker, byte)
+    if (idx >= (int64_t)b * nbytes_pad) return;
+    const int m = (int)(idx / nbytes_pad); const int64_t byte = idx % nbytes_pad;
+    const unsigned v = (byte < stride_d) ? packed[(s + m) * stride_d + byte] : 0u;
+    __nv_bfloat16 c[4], o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = byte * 4 + k;
+        unsigned code = (v >> (2 * k)) & 3u;
+        const bool obs = (code != 3u) && (i < n);
+        c[k] = __float2bfloat16((obs ? (float)code : 0.0f));
+        o[k] = __float2bfloat16(obs ? 1.0f : 0.0f);
+    }
+    __nv_bfloat16* dst = C + (int64_t)m * n_pad + byte * 4;
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(c);
+    if (MISSING) *reinterpret_cast<uint2*>(V + (int64_t)m * n_pad + byte * 4) = *reinterpret_cast<uint2*>(o);
+}
+
+// exact integer counts (as floats) -> centred Float32 Gram values
+template <bool MISSING>
+__global__ void __launch_bounds__(256)
+jw_k_gram_finalize(const float* __restrict__ Nab, const float* __restrict__ Sa, const float* __restrict__ Sb,
+                   const float* __restrict__ Nvv, int64_t n, const float* __restrict__ means,
+                   const int32_t* __restrict__ colsum, int64_t s_r, int b_r, int64_t s_c, int b_c,
+                   float* __restrict__ out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)b_r * b_c) return;
+    const int a = (int)(idx / b_c), c = (int)(idx % b_c);
+    long long sa, sb, nvv;
+    if (MISSING) { sa = (long long)Sa[idx]; sb = (long long)Sb[idx]; nvv = (long long)Nvv[idx]; }
+    else { sa = colsum[s_r + a]; sb = colsum[s_c + c]; nvv = n; }
+    out[idx] = jw_gram_value((long long)Nab[idx], sa, sb, nvv, means[s_r + a], means[s_c + c]);
+}

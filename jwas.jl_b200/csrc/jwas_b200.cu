@@ -10,6 +10,7 @@
 #include "jw_sweep_kernels.cuh"
 #include "jw_fused_sweep.cuh"
 #include "jw_nccl.cuh"
+#include <cublas_v2.h>
 
 static thread_local std::string g_err;
 void jw_set_error(const std::string& s) { g_err = s; }
@@ -218,6 +219,82 @@ extern "C" int jwas_get_marker_stats(jwas_handle* h, float* means, float* xpx) {
 // ------------------------------------------------------------------------------------------
 // block partition + Gram blocks (JWAS.jl:73-79 validation; tools4genotypes.jl:259-269)
 // ------------------------------------------------------------------------------------------
+#define JW_CUBLAS(call)                                                                 \
+    do {                                                                                \
+        cublasStatus_t r__ = (call);                                                    \
+        if (r__ != CUBLAS_STATUS_SUCCESS) {                                             \
+            jw_set_error(std::string(#call) + ": cuBLAS status " + std::to_string((int)r__)); \
+            return 14;                                                                  \
+        }                                                                               \
+    } while (0)
+
+// Gram blocks (and the cross-Gram of consecutive blocks) as bf16 tensor-core GEMMs on unpacked
+// 0/1/2 codes; integer-exact (see jw_setup_kernels.cuh).  One pass over the blocks, the previous
+// block's unpacked panel is kept for the cross product.
+static int build_gram_gemm(jwas_handle* h, bool want_cross) {
+    const int64_t nb = h->nblocks, n = h->n;
+    const int64_t n_pad = ceil_div(n, 16) * 16;
+    const int64_t maxb = h->maxb;
+    const bool ms = h->has_missing != 0;
+    cublasHandle_t cb = nullptr;
+    JW_CUBLAS(cublasCreate(&cb));
+    JW_CUBLAS(cublasSetStream(cb, h->stream));
+    __nv_bfloat16 *C[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr};
+    float* cnt[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int q = 0; q < 2; ++q) {
+        JW_CUDA(cudaMalloc((void**)&C[q], (size_t)n_pad * maxb * sizeof(__nv_bfloat16)));
+        if (ms) JW_CUDA(cudaMalloc((void**)&V[q], (size_t)n_pad * maxb * sizeof(__nv_bfloat16)));
+    }
+    for (int q = 0; q < (ms ? 4 : 1); ++q) JW_CUDA(cudaMalloc((void**)&cnt[q], (size_t)maxb * maxb * sizeof(float)));
+    if (want_cross) {
+        std::vector<int64_t> xoff(nb, 0);
+        int64_t total = 0;
+        for (int64_t i = 1; i < nb; ++i) { xoff[i] = total; total += (h->starts[i] - h->starts[i - 1]) * (h->starts[i + 1] - h->starts[i]); }
+        h->gramx_off = xoff;
+        JW_CUDA(cudaMalloc((void**)&h->d_gramx, std::max<size_t>(1, (size_t)total) * sizeof(float)));
+        JW_CUDA(cudaMalloc((void**)&h->d_gramx_off, nb * sizeof(int64_t)));
+        JW_CUDA(cudaMemcpyAsync(h->d_gramx_off, xoff.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    const float one = 1.0f, zero = 0.0f;
+    auto gemm = [&](const __nv_bfloat16* A, int m, const __nv_bfloat16* B, int nn, float* out) -> cublasStatus_t {
+        // out (column-major m x nn, ld m) = A^T (m x n) * B (n x nn): out[c + a*m] = sum_i A[i,c] * B[i,a]
+        return cublasGemmEx(cb, CUBLAS_OP_T, CUBLAS_OP_N, m, nn, (int)n_pad, &one, A, CUDA_R_16BF, (int)n_pad,
+                            B, CUDA_R_16BF, (int)n_pad, &zero, out, CUDA_R_32F, m, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    };
+    for (int64_t k = 0; k < nb; ++k) {
+        const int cur = (int)(k & 1), prv = cur ^ 1;
+        const int64_t s = h->starts[k]; const int b = (int)(h->starts[k + 1] - s);
+        const int64_t units = (int64_t)b * (n_pad >> 2);
+        if (ms) jw_k_unpack_bf16<true><<<(unsigned)ceil_div(units, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, n_pad, s, b, C[cur], V[cur]);
+        else jw_k_unpack_bf16<false><<<(unsigned)ceil_div(units, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, n_pad, s, b, C[cur], nullptr);
+        JW_LAUNCH_CHECK(h);
+        for (int pass = 0; pass < (want_cross && k > 0 ? 2 : 1); ++pass) {
+            // pass 0: rows = cols = block k ; pass 1: rows = block k-1, cols = block k
+            const int r = pass == 0 ? cur : prv;
+            const int64_t s_r = pass == 0 ? s : h->starts[k - 1];
+            const int b_r = pass == 0 ? b : (int)(h->starts[k] - h->starts[k - 1]);
+            float* out = pass == 0 ? h->d_gram + h->gram_off[k] : h->d_gramx + h->gramx_off[k];
+            JW_CUBLAS(gemm(C[cur], b, C[r], b_r, cnt[0]));                       // Nab[a][c]
+            if (ms) {
+                JW_CUBLAS(gemm(V[cur], b, C[r], b_r, cnt[1]));                   // sum_i C_r[i,a] V_c[i,c]
+                JW_CUBLAS(gemm(C[cur], b, V[r], b_r, cnt[2]));                   // sum_i V_r[i,a] C_c[i,c]
+                JW_CUBLAS(gemm(V[cur], b, V[r], b_r, cnt[3]));
+                jw_k_gram_finalize<true><<<(unsigned)ceil_div((int64_t)b_r * b, 256), 256, 0, h->stream>>>(
+                    cnt[0], cnt[1], cnt[2], cnt[3], n, h->d_means, h->d_colsum, s_r, b_r, s, b, out);
+            } else {
+                jw_k_gram_finalize<false><<<(unsigned)ceil_div((int64_t)b_r * b, 256), 256, 0, h->stream>>>(
+                    cnt[0], nullptr, nullptr, nullptr, n, h->d_means, h->d_colsum, s_r, b_r, s, b, out);
+            }
+            JW_LAUNCH_CHECK(h);
+        }
+    }
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < 2; ++q) { cudaFree(C[q]); if (V[q]) cudaFree(V[q]); }
+    for (int q = 0; q < 4; ++q) if (cnt[q]) cudaFree(cnt[q]);
+    cublasDestroy(cb);
+    return 0;
+}
+
 // Gram blocks (cross = false) or cross-Gram of consecutive blocks (cross = true): every 64x64 tile
 static int build_gram(jwas_handle* h, bool cross) {
     const int64_t nb = h->nblocks;
@@ -286,11 +363,16 @@ extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nb
     JW_CUDA(cudaMalloc((void**)&h->d_gram, (size_t)total * sizeof(float)));
     JW_CUDA(cudaMemcpyAsync(h->d_starts, starts, (nblocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     JW_CUDA(cudaMemcpyAsync(h->d_gram_off, off.data(), nblocks * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    int rc0 = build_gram(h, false);
-    if (rc0) return rc0;
     if (h->d_gramx) { cudaFree(h->d_gramx); h->d_gramx = nullptr; }
     if (h->d_gramx_off) { cudaFree(h->d_gramx_off); h->d_gramx_off = nullptr; }
-    if (h->opt_lag) { rc0 = build_gram(h, true); if (rc0) return rc0; }
+    int rc0;
+    const bool use_gemm = !h->opt_gram_popc && h->n < ((int64_t)1 << 22);   // 4n < 2^24: FP32 sums exact
+    if (use_gemm) { rc0 = build_gram_gemm(h, h->opt_lag != 0); if (rc0) return rc0; }
+    else {
+        rc0 = build_gram(h, false);
+        if (rc0) return rc0;
+        if (h->opt_lag) { rc0 = build_gram(h, true); if (rc0) return rc0; }
+    }
     int rc = jw_fused_prepare(h);
     if (rc) return rc;
     return 0;
@@ -899,11 +981,15 @@ extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
     JW_REQUIRE(h && key, "jwas_set_option: null argument");
     if (!strcmp(key, "profile")) { h->opt_profile = value; return 0; }
     if (!strcmp(key, "timers")) { h->opt_timers = value; return 0; }
+    if (!strcmp(key, "gram_popcount")) { h->opt_gram_popc = value; return 0; }   // 1 = popcount kernel instead of the GEMM
     if (!strcmp(key, "lag")) {
         JW_REQUIRE(value == 0 || value == 1, "lag must be 0 or 1");
         JW_CUDA(cudaSetDevice(h->device));
         h->opt_lag = value;
-        if (value == 1 && h->nblocks > 0 && !h->d_gramx) return build_gram(h, true);   // cross-Gram on demand
+        if (value == 1 && h->nblocks > 0 && !h->d_gramx) {                             // cross-Gram on demand
+            if (!h->opt_gram_popc && h->n < ((int64_t)1 << 22)) return build_gram_gemm(h, true);
+            return build_gram(h, true);
+        }
         return 0;
     }
     if (!strcmp(key, "engine")) { JW_REQUIRE(value == 0 || value == 1, "engine must be 0 or 1"); h->opt_engine = value; return 0; }

@@ -366,3 +366,19 @@ def test_fused_lagged_bayesr_and_multitrait(jw, oracle):
     run_pair_r(jw, oracle, prob, uniform_starts(900, 256), jw.SCHED_EXACT, 1, nsweeps=3, engine=1, lag=1)
     prob = Problem(oracle, 803, 500, seed=46, ntraits=2)
     run_pair_mt(jw, oracle, prob, uniform_starts(500, 128), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1)
+
+
+def test_gram_gemm_equals_popcount_at_full_n(jw):
+    """The bf16 tensor-core GEMM and the popcount kernel must give the same Gram blocks bit for bit
+    (integer pair counts below 2^24 are exact in FP32), at the benchmark's n, with and without missing."""
+    for miss in (0.0, 0.01):
+        outs = []
+        for popc in (0, 1):
+            g = jw.GpuSweeper.synthetic(50000, 700, 1, seed=3, missing_rate=miss)
+            g.set_option("gram_popcount", popc)
+            g.set_option("lag", 1)
+            g.set_blocks(np.array([0, 300, 700], dtype=np.int64))
+            outs.append([g.get_gram(0), g.get_gram(1)])
+            g.close()
+        for a, b in zip(*outs):
+            np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
