@@ -149,6 +149,13 @@ int jwas_get_gram(jwas_handle* h, int64_t ib, float* out);
 int jwas_nccl_unique_id(uint8_t* out128);
 int jwas_init_sharding(jwas_handle* h, int rank, int world, const uint8_t* unique_id128);
 int jwas_get_row_range(jwas_handle* h, int64_t* begin, int64_t* end);
+/* Fused multi-GPU sweep (engine 1, lag 1): every rank exports its exchange buffer as a CUDA IPC handle
+ * (64 bytes), the host language all-gathers the handles, every rank imports them.  The persistent
+ * kernel then pushes each block's exact int64 partial rhs straight into the peers' memory over NVLink
+ * (one communication CTA per GPU) -- no NCCL call, no kernel boundary inside the sweep.  Without the
+ * import the sharded sweep falls back to engine 0 with one NCCL all-reduce per block. */
+int jwas_ipc_export(jwas_handle* h, uint8_t* out64);
+int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world * 64 bytes in rank order */);
 
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 int64_t jwas_kernel_launches(jwas_handle* h);     /* kernels launched by this handle so far */

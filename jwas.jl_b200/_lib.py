@@ -49,6 +49,8 @@ def lib():
         "jwas_nccl_unique_id": [vp],
         "jwas_init_sharding": [vp, i32, i32, vp],
         "jwas_get_row_range": [vp, C.POINTER(i64), C.POINTER(i64)],
+        "jwas_ipc_export": [vp, vp],
+        "jwas_ipc_import": [vp, vp],
         "jwas_destroy": [vp],
         "jwas_device_count": [],
         "jwas_get_marker_stats": [vp, vp, vp],
@@ -259,6 +261,15 @@ class GpuSweeper:
     def init_sharding(self, rank, world, unique_id=None):
         uid = None if unique_id is None else np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
         _check(lib().jwas_init_sharding(self._h, int(rank), int(world), _p(uid)))
+
+    def ipc_export(self):
+        out = np.zeros(64, np.uint8)
+        _check(lib().jwas_ipc_export(self._h, _p(out)))
+        return out.tobytes()
+
+    def ipc_import(self, handles):
+        buf = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        _check(lib().jwas_ipc_import(self._h, _p(buf)))
 
     def row_range(self):
         b, e = C.c_int64(), C.c_int64()

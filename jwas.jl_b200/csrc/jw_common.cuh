@@ -108,6 +108,11 @@ struct jwas_handle {
     int world = 1, rank = 0;
     void* nccl_comm = nullptr;
     std::vector<int64_t> shard_bounds;   // world+1 row boundaries (multiples of 16 except the last)
+    // fused multi-GPU exchange (IPC-mapped peer memory): one allocation = [flags 1 KB][4 rings x 8 ranks x slot]
+    unsigned char* d_xbuf = nullptr; size_t xbuf_bytes = 0; int64_t x_slot_words = 0; int x_slot_b = 0;
+    void* peer_bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    long long** d_peer_slots = nullptr; int** d_peer_flags = nullptr;
+    int ipc_ready = 0; int64_t sweep_seq = 0;
     void* fused = nullptr;         // jw_fused_state (engine 1)
     float next_maxabs = -1.0f;     // carried from the previous sweep's stats when ycorr untouched
 };

@@ -43,6 +43,14 @@ struct jw_fused_args {
     int Gs, TS, n_vs, nblocks, list_cap, lag;
     const float* gramx; const int64_t* gramx_off;
     int timers, two_lists;
+    // multi-GPU (rows sharded over `world` GPUs of one node, one process each): this rank streams the
+    // byte-group slices [vs0, vs1); a communication CTA pushes the block's exact int64 partial rhs into
+    // every peer's exchange slots over NVLink (IPC-mapped peer memory) and raises a flag there.
+    int world, rank, vs0, vs1;
+    long long* const* peer_slots;       // world pointers: each rank's slot buffer as seen from this GPU
+    int* const* peer_flags;             // world pointers: each rank's flag array [ring][world]
+    long long* my_slots; int* my_flags; // this rank's own buffers (local addresses)
+    int64_t slot_stride; int slot_b; int64_t ring_stride; int flag_base;
     float* ycorr; float scale;
     int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
     int32_t* flags;              // [0] overflow, [2] abort
@@ -144,10 +152,13 @@ jw_k_fused(jw_fused_args F) {
     // lag = 1: the last CTA only runs chains, the others only stream, so that the chain of block k
     // overlaps the streaming of block k+1 (which needs the updates of blocks <= k-1 only)
     const int lag = F.lag;
-    const int n_stream = lag ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const bool multi = F.world > 1;                      // needs lag = 1
+    const int n_stream = lag ? (int)gridDim.x - 1 - (multi ? 1 : 0) : (int)gridDim.x;
     const bool is_chain_cta = lag ? (blockIdx.x == gridDim.x - 1) : (blockIdx.x == 0);
+    const bool is_comm_cta = multi && (blockIdx.x == gridDim.x - 2);
     const bool is_stream_cta = lag ? (blockIdx.x < (unsigned)n_stream) : true;
-    const bool single = F.n_vs <= n_stream;
+    const int n_vs_local = F.vs1 - F.vs0;
+    const bool single = n_vs_local <= n_stream;
     // phase timers (ns): [0] wait for previous chain, [1] axpy+quantise+tables, [2] stream,
     // [3] wait for all slices, [4] chain; CTA 0 -> counters[32..36], CTA 1 -> counters[40..44]
     unsigned long long ph[5] = {0, 0, 0, 0, 0};
@@ -179,7 +190,7 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
         for (int kk = 0; kk < T; ++kk) sq_blk[kk] = 0;
 
-        for (int vs = blockIdx.x; vs < F.n_vs; vs += n_stream) {
+        for (int vs = F.vs0 + blockIdx.x; vs < F.vs1; vs += n_stream) {
             const int64_t row0 = (int64_t)vs * R;
             if (rebuild) {
                 // ---- (1) fused axpy of the previous block + fixed-point image of the slice ----
@@ -344,7 +355,7 @@ jw_k_fused(jw_fused_args F) {
             // while the chain runs: pull the next block's tile(s) of this CTA into L2
             const int nb1 = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
             const int nch1 = (nb1 + 15) >> 4;
-            for (int vs = blockIdx.x; vs < F.n_vs; vs += n_stream) {
+            for (int vs = F.vs0 + blockIdx.x; vs < F.vs1; vs += n_stream) {
                 const uint8_t* t1 = F.tiled + ((size_t)(F.chunk_off[k + 1] * F.n_vs + (int64_t)vs * nch1) * Gs) * 16;
                 const unsigned total = (unsigned)nch1 * Gs * 16;
                 const unsigned per = ((total / 32) + 15) & ~15u;
@@ -354,6 +365,31 @@ jw_k_fused(jw_fused_args F) {
         }
         JW_PHASE(2);
         }   // streaming role
+        if (is_comm_cta) {
+            // wait for this GPU's slices, then push the block's partial rhs to every rank (own included)
+            if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+            __syncthreads();
+            if (!s_ok) return;
+            const int ring = k & 3;
+            const int per = 2 * T * F.slot_b + T;                 // int64 words of one slot
+            for (int rk = 0; rk < F.world; ++rk) {
+                long long* dst = F.peer_slots[rk] + (int64_t)ring * F.ring_stride + (int64_t)F.rank * F.slot_stride;
+                for (int e = tid; e < per; e += JW_FUSED_THREADS) {
+                    long long v;
+                    if (e < T * F.slot_b) { const int kk = e / F.slot_b, mm = e % F.slot_b; v = mm < b ? __ldcg(&F.dq[(int64_t)kk * p + s + mm]) : 0; }
+                    else if (e < 2 * T * F.slot_b) { const int e2 = e - T * F.slot_b; const int kk = e2 / F.slot_b, mm = e2 % F.slot_b;
+                                                     v = (mm < b && F.C.mq) ? __ldcg(&F.mq[(int64_t)kk * p + s + mm]) : 0; }
+                    else v = __ldcg(&F.sq_acc[k * T + (e - 2 * T * F.slot_b)]);
+                    dst[e] = v;
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < F.world) {
+                int* fl = F.peer_flags[tid] + ring * F.world + F.rank;
+                asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(fl), "r"(F.flag_base + k + 1) : "memory");
+            }
+        }
         if (is_chain_cta) {
             jw_chain_blk B;
             B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
@@ -371,12 +407,33 @@ jw_k_fused(jw_fused_args F) {
             B.xcount_smem = (lag && F.two_lists) ? prev_commits : -1;
             B.prefetch_s = 0; B.prefetch_b = 0;
             if (k + 1 < F.nblocks) { B.prefetch_s = F.C.starts[k + 1]; B.prefetch_b = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]); }
+            B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0;
+            if (multi) {
+                B.xslots = F.my_slots + (int64_t)(k & 3) * F.ring_stride;
+                B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
+            }
             B.sq = F.sq_acc + k * T;
             B.act_idx = F.act_idx_all + s;
             B.act_cnt = F.act_cnt_blk + k;
             B.write_active_list = 1;
             auto wait_all = [&]() -> bool {
-                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+                if (multi) {
+                    // every rank's partial rhs of this block has landed in my slots
+                    if (tid == 0) s_ok = 1;
+                    __syncthreads();
+                    if (tid < F.world) {
+                        const int* fl = F.my_flags + (k & 3) * F.world + tid;
+                        unsigned long long t0 = jw_globaltimer(); unsigned it = 0; int v;
+                        while (true) {
+                            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                            if (v >= F.flag_base + k + 1) break;
+                            if ((++it & 1023u) == 0) {
+                                if (jw_ld_acquire(&F.flags[2]) != 0) { s_ok = 0; break; }
+                                if (jw_globaltimer() - t0 > 20000000000ull) { atomicExch(&F.flags[2], 1); s_ok = 0; break; }
+                            }
+                        }
+                    }
+                } else if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
                 __syncthreads();
                 JW_PHASE(3);
                 return s_ok != 0;
@@ -403,10 +460,10 @@ __global__ void __launch_bounds__(256)
 jw_k_apply_last(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
                 const float* __restrict__ means, const float* __restrict__ dalpha,
                 const int32_t* __restrict__ act_idx, const int32_t* __restrict__ act_cnt,
-                float* __restrict__ y) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                float* __restrict__ y, int64_t r0, int64_t r1) {
+    int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = *act_cnt;
-    if (i >= n || cnt == 0) return;
+    if (i >= r1 || cnt == 0) return;
     float v[T];
 #pragma unroll
     for (int k = 0; k < T; ++k) v[k] = y[k * n + i];
@@ -452,8 +509,10 @@ static int jw_fused_prepare(jwas_handle* h) {
     h->fused = f;
     const int64_t nbytes = (h->n + 3) / 4;
     f->W = (h->t == 2 || h->has_missing) ? 2 : 1;
-    const int64_t streamers = std::max(1, h->sm_count - 1);   // one SM is kept for the chain (lag = 1)
+    // one SM is kept for the chain (lag = 1); a second one for the NVLink push when rows are sharded
+    const int64_t streamers = (int64_t)h->world * std::max(1, h->sm_count - (h->world > 1 ? 2 : 1));
     int64_t gs = (nbytes + streamers - 1) / streamers;
+    if (h->world > 1) gs = (gs + 3) / 4 * 4;                 // shard boundaries on 16-individual words
     if (gs > JW_FUSED_MAX_GS) gs = JW_FUSED_MAX_GS;
     if (gs < 1) gs = 1;
     f->Gs = (int)gs;
@@ -492,6 +551,15 @@ static int jw_fused_prepare(jwas_handle* h) {
     JW_CUDA(cudaGetLastError());
     JW_CUDA(cudaStreamSynchronize(h->stream));
     f->ready = true;
+    if (h->world > 1) {
+        // contiguous byte-group slices per rank; individuals follow
+        const int64_t R = (int64_t)f->Gs * 4;
+        h->shard_bounds.assign(h->world + 1, 0);
+        for (int r = 0; r <= h->world; ++r)
+            h->shard_bounds[r] = std::min<int64_t>(h->n, ((int64_t)f->n_vs * r / h->world) * R);
+        h->shard_bounds[h->world] = h->n;
+        h->row_begin = h->shard_bounds[h->rank]; h->row_end = h->shard_bounds[h->rank + 1];
+    }
     return 0;
 }
 
@@ -503,7 +571,8 @@ static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) 
     JW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JW_FUSED_THREADS, f->smem));
     JW_REQUIRE(occ >= 1, "fused sweep kernel does not fit on an SM");
     void* args[] = {(void*)&F};
-    const int grid = F.lag ? std::min<int>(h->sm_count, f->n_vs + 1) : f->n_cta;
+    const int grid = F.world > 1 ? std::min<int>(h->sm_count, (F.vs1 - F.vs0) + 2)
+                                 : (F.lag ? std::min<int>(h->sm_count, f->n_vs + 1) : f->n_cta);
     JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(JW_FUSED_THREADS), args, f->smem, h->stream));
     h->launches += 1;
     return 0;
@@ -528,6 +597,19 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.lag = (int)h->opt_lag; F.timers = (int)h->opt_timers; F.two_lists = f->two_lists;
     JW_REQUIRE(!F.lag || (A.nreps_mode == 0 && h->d_gramx), "lag = 1 needs the exact schedule and the cross-Gram blocks");
     F.gramx = h->d_gramx; F.gramx_off = h->d_gramx_off;
+    F.world = h->world; F.rank = h->rank; F.vs0 = 0; F.vs1 = f->n_vs;
+    F.peer_slots = nullptr; F.peer_flags = nullptr; F.my_slots = nullptr; F.my_flags = nullptr;
+    F.slot_stride = 0; F.slot_b = 0; F.ring_stride = 0; F.flag_base = 0;
+    if (h->world > 1) {
+        JW_REQUIRE(h->ipc_ready && F.lag, "multi-GPU fused sweep needs lag = 1 and jwas_ipc_import");
+        JW_REQUIRE(h->maxb <= h->x_slot_b, "exchange slots are smaller than the largest block (call jwas_ipc_export after jwas_set_blocks)");
+        F.vs0 = (int)((int64_t)f->n_vs * h->rank / h->world); F.vs1 = (int)((int64_t)f->n_vs * (h->rank + 1) / h->world);
+        F.peer_slots = h->d_peer_slots; F.peer_flags = h->d_peer_flags;
+        F.my_flags = (int*)h->d_xbuf; F.my_slots = (long long*)(h->d_xbuf + 1024);
+        F.slot_b = h->x_slot_b; F.slot_stride = h->x_slot_words; F.ring_stride = 8 * h->x_slot_words;
+        F.flag_base = (int)(h->sweep_seq * (h->nblocks + 1));
+        h->sweep_seq += 1;
+    }
     F.ycorr = h->d_ycorr; F.scale = scale;
     F.arrive = f->d_arrive; F.done = f->d_done; F.sq_acc = f->d_sq_acc;
     F.act_cnt_blk = f->d_act_cnt_blk; F.act_idx_all = h->d_act_idx;
@@ -554,13 +636,13 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     if (h->opt_profile) JW_CUDA(cudaEventRecord(h->prof_events.back(), h->stream));
     // the axpy of the last block (and of the one before it under the lagged schedule)
     for (int64_t blk = std::max<int64_t>(0, h->nblocks - 1 - F.lag); blk < h->nblocks; ++blk) {
-        unsigned g = (unsigned)((h->n + 255) / 256);
+        unsigned g = (unsigned)std::max<int64_t>(1, (h->row_end - h->row_begin + 255) / 256);
         if (t == 1)
             jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
-                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr);
+                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr, h->row_begin, h->row_end);
         else
             jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
-                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr);
+                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr, h->row_begin, h->row_end);
         h->launches += 1;
         JW_CUDA(cudaGetLastError());
     }

@@ -250,12 +250,16 @@ struct jw_chain_blk {
     int64_t s; int b; int64_t gram_off;     // this block: first marker, size, Gram offset (b = 0: look them up)
     // (c) previous block's commits kept in shared memory by the dedicated chain CTA (lagged schedule)
     int xcount_smem;                        // >= 0: number of entries in the shared list; -1: use xlist/xcount
+    // multi-GPU fused sweep: the block's partial rhs of every rank, pushed over NVLink into this GPU's
+    // exchange slots: [rank][ dq: T*slot_b | mq: T*slot_b | sq: T ] (int64); NULL = single GPU
+    const long long* xslots; int xworld; int64_t slot_stride; int slot_b;
 };
 __device__ __forceinline__ jw_chain_blk jw_chain_blk_from(const jw_chain_args& A) {
     jw_chain_blk B;
     B.sq = A.sq; B.act_idx = A.act_idx; B.act_cnt = A.act_cnt; B.write_active_list = A.write_active_list;
     B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
     B.prefetch_s = 0; B.prefetch_b = 0; B.s = 0; B.b = 0; B.gram_off = 0; B.xcount_smem = -1;
+    B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0;
     return B;
 }
 
@@ -405,8 +409,21 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
 #pragma unroll
     for (int k = 0; k < T; ++k) {
         // .cg loads: these words were produced by other CTAs' atomics in the fused engine
-        long long dq = __ldcg(&A.dq[k * p + j]), mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
-        r[k] = ((double)dq - mu * (double)(__ldcg(&B.sq[k]) - mq)) * A.invscale;
+        long long dq, mq, sqk;
+        if (B.xslots != nullptr) {
+            // exact int64 sums over the ranks' partial rhs (any order gives the same bits)
+            dq = 0; mq = 0; sqk = 0;
+            for (int rk = 0; rk < B.xworld; ++rk) {
+                const long long* sl = B.xslots + (int64_t)rk * B.slot_stride;
+                dq += __ldcg(sl + (int64_t)k * B.slot_b + m);
+                if (A.mq) mq += __ldcg(sl + (int64_t)(T + k) * B.slot_b + m);
+                sqk += __ldcg(sl + (int64_t)2 * T * B.slot_b + k);
+            }
+        } else {
+            dq = __ldcg(&A.dq[k * p + j]); mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
+            sqk = __ldcg(&B.sq[k]);
+        }
+        r[k] = ((double)dq - mu * (double)(sqk - mq)) * A.invscale;
     }
     if (B.xgram != nullptr && valid && two_lists) {
         // previous block's commits from shared memory; four cross-Gram loads in flight, adds in order

@@ -198,6 +198,8 @@ extern "C" int jwas_destroy(jwas_handle* h) {
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
+    for (int r = 0; r < 8; ++r) if (h->peer_bufs[r]) cudaIpcCloseMemHandle(h->peer_bufs[r]);
+    for (void* q : {(void*)h->d_xbuf, (void*)h->d_peer_slots, (void*)h->d_peer_flags}) if (q) cudaFree(q);
     if (h->nccl_comm && jw_nccl()) jw_nccl()->CommDestroy(h->nccl_comm);
     jw_fused_free(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -737,9 +739,10 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
         }
     }
 
-    if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT && h->world == 1) {
+    if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT && (h->world == 1 || (h->ipc_ready && h->opt_lag))) {
         int rc = jw_fused_sweep(h, A, scale);
         if (rc) return rc;
+        if (gather_ycorr(h)) return 13;
         return collect_stats(h, c, S, st);
     }
 
@@ -953,7 +956,53 @@ extern "C" int jwas_init_sharding(jwas_handle* h, int rank, int world, const uin
         jw_nccl_id id;
         memcpy(id.internal, unique_id128, JW_NCCL_UNIQUE_ID_BYTES);
         JW_NCCL(N->CommInitRank(&h->nccl_comm, world, id, rank));
+        if (h->nblocks > 0) { int rc = jw_fused_prepare(h); if (rc) return rc; }   // slices re-cut for `world` GPUs
     }
+    return 0;
+}
+
+// ---- fused multi-GPU exchange buffers over CUDA IPC ------------------------------------------
+extern "C" int jwas_ipc_export(jwas_handle* h, uint8_t* out64) {
+    JW_REQUIRE(h && out64, "jwas_ipc_export: null argument");
+    JW_REQUIRE(h->nblocks > 0, "jwas_ipc_export: call jwas_set_blocks first");
+    JW_CUDA(cudaSetDevice(h->device));
+    if (!h->d_xbuf) {
+        h->x_slot_b = (int)h->maxb;
+        h->x_slot_words = (int64_t)2 * h->t * h->x_slot_b + h->t;
+        h->xbuf_bytes = 1024 + (size_t)4 * 8 * h->x_slot_words * sizeof(long long);
+        JW_CUDA(cudaMalloc((void**)&h->d_xbuf, h->xbuf_bytes));
+        JW_CUDA(cudaMemset(h->d_xbuf, 0, h->xbuf_bytes));
+    }
+    cudaIpcMemHandle_t hd;
+    JW_CUDA(cudaIpcGetMemHandle(&hd, h->d_xbuf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out64, &hd, 64);
+    return 0;
+}
+extern "C" int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world * 64 bytes, rank order */) {
+    JW_REQUIRE(h && handles, "jwas_ipc_import: null argument");
+    JW_REQUIRE(h->world > 1 && h->world <= 8, "jwas_ipc_import: call jwas_init_sharding first (2..8 ranks)");
+    JW_REQUIRE(h->d_xbuf, "jwas_ipc_import: call jwas_ipc_export first");
+    JW_CUDA(cudaSetDevice(h->device));
+    long long* slots[8]; int* flags[8];
+    for (int r = 0; r < h->world; ++r) {
+        void* base = h->d_xbuf;
+        if (r != h->rank) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, handles + (size_t)r * 64, 64);
+            JW_CUDA(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_bufs[r] = base;
+        }
+        flags[r] = (int*)base;
+        slots[r] = (long long*)((unsigned char*)base + 1024);
+    }
+    if (!h->d_peer_slots) {
+        JW_CUDA(cudaMalloc((void**)&h->d_peer_slots, 8 * sizeof(long long*)));
+        JW_CUDA(cudaMalloc((void**)&h->d_peer_flags, 8 * sizeof(int*)));
+    }
+    JW_CUDA(cudaMemcpy(h->d_peer_slots, slots, h->world * sizeof(long long*), cudaMemcpyHostToDevice));
+    JW_CUDA(cudaMemcpy(h->d_peer_flags, flags, h->world * sizeof(int*), cudaMemcpyHostToDevice));
+    h->ipc_ready = 1;
     return 0;
 }
 extern "C" int jwas_get_row_range(jwas_handle* h, int64_t* begin, int64_t* end) {

@@ -49,13 +49,26 @@ def broadcast_bytes(payload, nbytes, src=0):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach(sweeper, rank, world):
+def attach(sweeper, rank, world, fused=True):
     """Turn a GpuSweeper holding the full matrix into rank `rank` of a `world`-way row-sharded sweep."""
     from ._lib import nccl_unique_id
     uid = broadcast_bytes(nccl_unique_id() if rank == 0 else b"", 128, src=0) if world > 1 else None
     sweeper.init_sharding(rank, world, uid)
-    assert list(sweeper.row_range()) == shard_bounds(sweeper.n, world)[rank:rank + 2]
+    if world > 1 and fused:
+        # exchange buffers for the in-kernel NVLink reduction: all-gather the 64-byte IPC handles
+        handles = all_gather_bytes(sweeper.ipc_export(), 64)
+        sweeper.ipc_import(handles)
     return sweeper
+
+
+def all_gather_bytes(payload, nbytes):
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    outs = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, mine)
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
 
 
 def bench_main(args, cfg, config):
@@ -69,10 +82,12 @@ def bench_main(args, cfg, config):
     rank, world = init_process_group("nccl")
     n = args.n or cfg["n"]; p = args.p or cfg["p"]
     g = jwas_b200.GpuSweeper.synthetic(n, p, 1, seed=2026, device=local)      # identical on every rank
-    panel = max(args.panel, 4096)          # engine 0 pays a launch + an all-reduce per block: fewer, larger blocks
+    panel = args.panel
+    g.set_option("engine", args.engine)
+    g.set_option("lag", 1 if args.engine == 1 else 0)
     starts = np.array(list(range(0, p, panel)) + [p], dtype=np.int64)
     g.set_blocks(starts)
-    attach(g, rank, world)
+    attach(g, rank, world, fused=(args.engine == 1))
     means, _ = g.marker_stats()
     rng = np.random.default_rng(7)
     nq = max(1, p // 1000)
@@ -123,12 +138,15 @@ def bench_main(args, cfg, config):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "int64 dots / f64 scalars / f32 state", "data": "synthetic",
-                "config": dict(config, parallelism=f"rows sharded over {world} GPUs; one int64 NCCL all-reduce of the "
-                               "block rhs per marker block, chain replicated", engine=0, panel=panel,
+                "config": dict(config, parallelism=(f"rows sharded over {world} GPUs; persistent kernel pushes the int64 block rhs "
+                               "into peer memory over NVLink (IPC), chain replicated" if args.engine == 1 else
+                               f"rows sharded over {world} GPUs; one int64 NCCL all-reduce of the block rhs per marker block, "
+                               "chain replicated"), engine=args.engine, panel=panel,
                                markers_in_model=float(np.mean([t[1] for t in out["trace"]]))),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": src,
-                             "kernel": "jw_k_block_dot (per-GPU bytes, summed over the sweep's launches)",
+                             "kernel": ("jw_k_fused (per-GPU bytes)" if args.engine == 1 else
+                                        "jw_k_block_dot (per-GPU bytes, summed over the sweep's launches)"),
                              "kernel_ms_per_sweep": k_ms, "kernel_launches_per_sweep": k_launches},
                 "e2e": None, "gpu_launches": int(launches)}
         print(json.dumps(line))

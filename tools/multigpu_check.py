@@ -17,12 +17,13 @@ n, p = 30011, 3000
 GAMMA = np.array([0.0, 0.01, 0.1, 1.0]); PI_R = np.array([0.95, 0.03, 0.015, 0.005])
 
 
-def run(t, method, sharded, engine, miss):
+def run(t, method, sharded, engine, miss, lag=0):
     g = jwas_b200.GpuSweeper.synthetic(n, p, t, seed=11, missing_rate=miss, device=local)
-    g.set_blocks(np.array(list(range(0, p, 512)) + [p], dtype=np.int64))
     g.set_option("engine", engine)
+    g.set_option("lag", lag)
+    g.set_blocks(np.array(list(range(0, p, 512)) + [p], dtype=np.int64))
     if sharded:
-        multigpu.attach(g, rank, world)
+        multigpu.attach(g, rank, world, fused=(engine == 1))
     y = np.random.default_rng(3).standard_normal(t * n).astype(np.float32)
     g.put_ycorr(y)
     if method == "R":
@@ -48,6 +49,13 @@ for t, method, miss in ((1, "C", 0.01), (1, "R", 0.0), (2, "M", 0.0), (1, "I", 0
     fused = run(t, method, False, 1, miss) if method != "I" else ref
     sh = run(t, method, True, 0, miss)
     same = all(np.array_equal(x, y) for x, y in zip(ref, sh)) and all(np.array_equal(x, y) for x, y in zip(ref, fused))
+    if method != "I":
+        # fused persistent kernel with the in-kernel NVLink reduction (lagged schedule) vs one GPU
+        ref1 = run(t, method, False, 1, miss, lag=1)
+        sh1 = run(t, method, True, 1, miss, lag=1)
+        same1 = all(np.array_equal(x, y) for x, y in zip(ref1, sh1))
+        print(f"rank {rank}/{world} method {method} t={t}: fused multi-GPU (NVLink push) == fused single GPU: {same1}", flush=True)
+        same = same and same1
     nz = int(np.count_nonzero(ref[0]))
     print(f"rank {rank}/{world} method {method} t={t}: sharded==single==fused: {same} (nonzero effects {nz})", flush=True)
     ok = ok and same and nz > 0
