@@ -119,8 +119,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
-    ap.add_argument("--n", type=int, default=0)
-    ap.add_argument("--p", type=int, default=0)
+    ap.add_argument("--n", "--nobs", dest="n", type=int, default=0)          # --nobs/--nmarkers: safe under torchrun
+    ap.add_argument("--p", "--nmarkers", dest="p", type=int, default=0)
     ap.add_argument("--panel", type=int, default=2048, help="look-ahead panel (markers per block)")
     ap.add_argument("--burnin", type=int, default=40, help="untimed chain iterations before warm-up")
     ap.add_argument("--engine", type=int, default=1)
