@@ -127,6 +127,11 @@ int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, const double* 
  * which = 1 -> pi[j] = value (bayesabc_pi_vector, BayesABC.jl:17-23) */
 int jwas_fill_hyper(jwas_handle* h, int which, double value);
 
+/* _MTBayesABC_samplerII! (MTBayesABC.jl:129-210; block :439-537, independent :539-646): joint draw of the
+ * 2^t inclusion states, t = 2.  big_pi: 4 joint-state priors in the order 00,10,01,11. */
+int jwas_sweep_mt2(jwas_handle* h, int schedule, const double* R, const double* G, const double* big_pi,
+                   uint64_t seed, uint32_t iter, const double* u, const double* z, jwas_sweep_stats* stats);
+
 /* BayesB per-marker variance update on device (variance_components.jl:169-172):
  * var_j = (beta_j^2 + df*scale) / chisq(df+1), chi-square from the native stream. */
 int jwas_sample_bayesb_variances(jwas_handle* h, double df, double scale, uint64_t seed,

@@ -64,6 +64,7 @@ def lib():
         "jwas_sweep_bayesc": [vp, i32, dbl, dbl, dbl, u64, u32, C.POINTER(SweepStats)],
         "jwas_sweep_bayesr": [vp, i32, i32, dbl, dbl, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_mt1": [vp, i32, vp, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
+        "jwas_sweep_mt2": [vp, i32, vp, vp, vp, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sample_bayesb_variances": [vp, dbl, dbl, u64, u32, vp],
         "jwas_fill_hyper": [vp, i32, dbl],
         "jwas_accumulate": [vp, dbl, i32],
@@ -238,6 +239,14 @@ class GpuSweeper:
         uu, zz = _arr(u, np.float64), _arr(z, np.float64)
         _check(lib().jwas_sweep_mt1(self._h, schedule, _p(Rm), _p(Gm), int(Gm.ndim == 3), _p(bp),
                                     int(bp.ndim == 2), int(seed), int(it), _p(uu), _p(zz), C.byref(st)))
+        return st
+
+    def sweep_mt2(self, schedule, R, G, big_pi, seed, it, u=None, z=None):
+        st = SweepStats()
+        Rm, Gm, bp = _arr(R, np.float64), _arr(G, np.float64), _arr(big_pi, np.float64)
+        uu, zz = _arr(u, np.float64), _arr(z, np.float64)
+        _check(lib().jwas_sweep_mt2(self._h, schedule, _p(Rm), _p(Gm), _p(bp), int(seed), int(it), _p(uu), _p(zz),
+                                    C.byref(st)))
         return st
 
     def sample_bayesb_variances(self, df, scale, seed, it, want=False):

@@ -389,8 +389,11 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     t = model.nModels
     if t > 1 and Mi.method != "BayesC":
         error("multi-trait analysis with storage=:gpu supports BayesC (sampler I) only.")
-    if t > 1 and Mi.multi_trait_sampler not in ("I", "auto"):
-        error("multi_trait_sampler=:II is not supported with storage=:gpu.")
+    mt_sampler = "I"
+    if t > 1 and Mi.multi_trait_sampler == "II":
+        if t != 2:
+            error("multi_trait_sampler=:II is supported for exactly 2 traits with storage=:gpu.")
+        mt_sampler = "II"
     if t > 4:
         error("at most 4 traits are supported with storage=:gpu.")
     # ---- phenotypes aligned to the genotype IDs (JWAS.jl:381-402)
@@ -505,7 +508,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          estimate_vare=model.R.estimate_variance,
                          R=model.R.val if t > 1 else None, G=Mi.G.val if t > 1 else None,
                          big_pi=Mi.π if t > 1 else None, scale_G=Mi.G.scale if t > 1 else None,
-                         scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV)
+                         scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler)
 
     # ---- output dictionary (output.jl:108-212)
     ma, ma2, md = backend.get_means()

@@ -192,7 +192,7 @@ jw_k_prep_draws(jw_chain_args A, double* __restrict__ du, double* __restrict__ d
     if (idx >= A.p * A.t) return;
     const int k = (int)(idx / A.p); const int64_t j = idx % A.p;
     double u = jw_get_u(A, j, k, 0);
-    du[idx] = (A.method == 1) ? u : jw_logit_threshold(u);
+    du[idx] = (A.method == 1 || A.method == 3) ? u : jw_logit_threshold(u);
     dz[idx] = jw_get_z(A, j, k, 0);
 }
 
@@ -360,11 +360,11 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         d_cur[k] = A.delta[k * p + j];
     }
     double Ginv[T * T];
-    if (METHOD == 2) {
+    if (METHOD == 2 || METHOD == 3) {
         if (A.per_marker_G) jw_inv_spd_fixed(A.Gmat + j * T * T, T, Ginv);
         else for (int q = 0; q < T * T; ++q) Ginv[q] = A.Ginv[q];
     }
-    const double invVarRes = (METHOD == 2) ? 0.0 : 1.0 / A.vare;
+    const double invVarRes = (METHOD == 2 || METHOD == 3) ? 0.0 : 1.0 / A.vare;
 
     // draw-independent constants
     double c_invLhs = 0, c_L = 0, c_lpc = 0, c_lp0 = 0, c_ve = 1;
@@ -541,7 +541,7 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
                     u[k] = A.draws_u[k * p + j]; z[k] = A.draws_z[k * p + j];
                 } else {
                     u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep);
-                    if (METHOD != 1) u[k] = jw_logit_threshold(u[k]);
+                    if (METHOD != 1 && METHOD != 3) u[k] = jw_logit_threshold(u[k]);
                 }
             }
             if (METHOD == 0) {
@@ -604,6 +604,44 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
                     }
                     newB[0] = 0.0f;
                     active = (a_cur[0] - newA[0]) != 0.0f;
+                } else if (METHOD == 3) {
+                    // MTBayesABC.jl:163-208 (sampler II, joint states), T == 2; twin of the oracle's MT2 step
+                    const double w0 = r[0] + x * (double)a_cur[0];
+                    const double w1 = r[T - 1] + x * (double)a_cur[T - 1];
+                    const double z0 = z[0], z1 = z[T - 1], uu = u[0];
+                    double ld[4], bc0[4], bc1[4];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        const double d0 = (double)(st & 1), d1 = (double)((st >> 1) & 1);
+                        const double l00 = d0 * A.Rinv[0] * x + Ginv[0];
+                        const double l01 = (d0 * d1) * A.Rinv[1] * x + Ginv[1];
+                        const double l11 = d1 * A.Rinv[3] * x + Ginv[T * T - 1];
+                        const double rhs0 = d0 * (A.Rinv[0] * w0 + A.Rinv[2] * w1);
+                        const double rhs1 = d1 * (A.Rinv[1] * w0 + A.Rinv[3] * w1);
+                        const double det = l00 * l11 - l01 * l01;
+                        const double i00 = l11 / det, i11 = l00 / det, i01 = -l01 / det;
+                        const double g0 = i00 * rhs0 + i01 * rhs1, g1 = i01 * rhs0 + i11 * rhs1;
+                        ld[st] = -0.5 * (jw_log(det) - (rhs0 * g0 + rhs1 * g1)) + jw_log(A.bigPi[st]);
+                        const double L00 = jw_sqrt(i00), L10 = i01 / L00, L11 = jw_sqrt(i11 - L10 * L10);
+                        bc0[st] = g0 + L00 * z0;
+                        bc1[st] = g1 + L10 * z0 + L11 * z1;
+                    }
+                    double mx = ld[0];
+#pragma unroll
+                    for (int st = 1; st < 4; ++st) if (ld[st] > mx) mx = ld[st];
+                    double ex[4], se = 0.0;
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) { ex[st] = jw_exp(ld[st] - mx); se += ex[st]; }
+                    const double target = uu * se;
+                    int lab = 0; double cp = ex[0];
+#pragma unroll
+                    for (int c = 1; c < 4; ++c) { if (lab == c - 1 && cp <= target) { lab = c; cp += ex[c]; } }
+                    const float b0 = (float)(lab == 0 ? bc0[0] : lab == 1 ? bc0[1] : lab == 2 ? bc0[2] : bc0[3]);
+                    const float b1 = (float)(lab == 0 ? bc1[0] : lab == 1 ? bc1[1] : lab == 2 ? bc1[2] : bc1[3]);
+                    newB[0] = b0; newB[T - 1] = b1;
+                    newD[0] = lab & 1; newD[T - 1] = (lab >> 1) & 1;
+                    newA[0] = newD[0] ? b0 : 0.0f; newA[T - 1] = newD[T - 1] ? b1 : 0.0f;
+                    active = ((a_cur[0] - newA[0]) != 0.0f) || ((a_cur[T - 1] - newA[T - 1]) != 0.0f);
                 } else {
                     // MTBayesABC.jl:78-125
                     double bb[T], olda[T], w[T]; int dd[T];

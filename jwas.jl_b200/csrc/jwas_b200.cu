@@ -518,6 +518,7 @@ static int dispatch_chain(jwas_handle* h, const jw_chain_args& A, int nblk, int 
     else if (A.method == 2 && t == 2) launch_chain<2, 2>(h, A, nblk, threads);
     else if (A.method == 2 && t == 3) launch_chain<2, 3>(h, A, nblk, threads);
     else if (A.method == 2 && t == 4) launch_chain<2, 4>(h, A, nblk, threads);
+    else if (A.method == 3 && t == 2) launch_chain<3, 2>(h, A, nblk, threads);
     else { jw_set_error("unsupported (method, traits) combination"); return 2; }
     JW_LAUNCH_CHECK(h);
     return 0;
@@ -879,6 +880,24 @@ extern "C" int jwas_sweep_mt1(jwas_handle* h, int schedule, const double* R, con
     if (upload_doubles(h, &h->d_pi, &h->cap_pi, big_pi, npi)) return 10;
     if (upload_draws(h, c, u, z, schedule, 1)) return 10;
     return run_sweep(h, c, stats);
+}
+
+extern "C" int jwas_sweep_mt2(jwas_handle* h, int schedule, const double* R, const double* G, const double* big_pi,
+                              uint64_t seed, uint32_t iter, const double* u, const double* z, jwas_sweep_stats* stats) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t == 2, "jwas_sweep_mt2: sampler II is implemented for exactly 2 traits");
+    JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
+    JW_REQUIRE(R && G && big_pi, "jwas_sweep_mt2: R, G and big_pi are required");
+    JW_CUDA(cudaSetDevice(h->device));
+    sweep_cfg c; c.method = 3; c.schedule = schedule; c.full_reps = 1; c.seed = seed; c.iter = iter;
+    jw_inv_spd_fixed(R, 2, c.Rinv);
+    jw_inv_spd_fixed(G, 2, c.Ginv);
+    for (int q = 0; q < 4; ++q) c.pi_host[q] = big_pi[q];
+    c.per_marker_pi = 1;          // keeps the generic prep of sampler I out of the way (no hoisted logs here)
+    if (upload_doubles(h, &h->d_pi, &h->cap_pi, big_pi, 4)) return 10;
+    if (upload_draws(h, c, u, z, schedule, 1)) return 10;
+    int rc = run_sweep(h, c, stats);
+    return rc;
 }
 
 extern "C" int jwas_fill_hyper(jwas_handle* h, int which, double value) {

@@ -102,6 +102,9 @@ class GpuBackend:
     def sweep_mt1(self, schedule, R, G, big_pi, seed, it):
         return self._stats(self.s.sweep_mt1(schedule, R, G, big_pi, seed, it), self.s.t)
 
+    def sweep_mt2(self, schedule, R, G, big_pi, seed, it):
+        return self._stats(self.s.sweep_mt2(schedule, R, G, big_pi, seed, it), self.s.t)
+
     def sample_bayesb_variances(self, df, scale, seed, it):
         self.s.sample_bayesb_variances(df, scale, seed, it)
 
@@ -122,7 +125,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               seed, vare, var_effect, pi, df_effect, scale_effect, df_res, scale_res,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
-              mu0=None, iter0=0, want_ebv=False):
+              mu0=None, iter0=0, want_ebv=False, mt_sampler="I"):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -174,7 +177,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                     backend.fill_hyper("pi", pi)
                     st = backend.sweep_bayesabc(schedule, vare, None, None, seed, it)
             else:
-                st = backend.sweep_mt1(schedule, R, G, big_pi, seed, it)
+                st = (backend.sweep_mt2 if mt_sampler == "II" else backend.sweep_mt1)(schedule, R, G, big_pi, seed, it)
         elif method == "BayesR":
             full = 1 if it > burnin else 0          # bayesr_block_nreps, BayesR.jl:22-25
             st = backend.sweep_bayesr(schedule, full, vare, var_effect, pi, BAYESR_GAMMA, seed, it)

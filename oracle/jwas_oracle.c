@@ -650,6 +650,7 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
     const int64_t r0 = a->row_end > 0 ? a->row_begin : 0, r1 = a->row_end > 0 ? a->row_end : n;
     if (t < 1 || t > 8) return 1;
     if (a->method == JWO_METHOD_MT1 && t < 2) return 1;
+    if (a->method == JWO_METHOD_MT2 && t != 2) return 1;
     const int lag = a->lag;
     if (lag != 0 && lag != 1) return 1;
     if (lag == 1 && (a->independent || a->nreps_mode)) return 1;   /* exact schedule only */
@@ -668,11 +669,11 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
     float* dall = (a->independent || lag) ? (float*)calloc((size_t)(p * t), sizeof(float)) : NULL;
     int64_t sq[8];
     double Rinv[64], Ginv[64];
-    if (a->method == JWO_METHOD_MT1) {
+    if (a->method == JWO_METHOD_MT1 || a->method == JWO_METHOD_MT2) {
         inv_spd_fixed(a->Rmat, t, Rinv);
         if (!a->per_marker_G) inv_spd_fixed(a->Gmat, t, Ginv);
     }
-    double invVarRes = (a->method == JWO_METHOD_MT1) ? 0.0 : 1.0 / a->vare;
+    double invVarRes = (a->method == JWO_METHOD_MT1 || a->method == JWO_METHOD_MT2) ? 0.0 : 1.0 / a->vare;
 
     int have_q = 0;
     for (int64_t ib = 0; ib < a->nblocks; ++ib) {
@@ -754,6 +755,46 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
                                               draw_u(a, j, 0, rep), draw_z(a, j, 0, rep));
                     if (d != 0.0f)
                         for (int64_t m = 0; m < b; ++m) r[m] += (double)d * (double)G[jj * b + m];
+                } else if (a->method == JWO_METHOD_MT2) {
+                    /* MTBayesABC.jl:163-208 (sampler II, joint states), t = 2, binary64.
+                     * States in the order 00,10,01,11 (annotation_setup.jl:18); shared normals z0,z1;
+                     * the label is drawn on the unnormalised weights exp(logDelta - max). */
+                    double x = (double)a->xpx[j];
+                    double w0 = r[jj] + x * (double)a->alpha[j];
+                    double w1 = r[b + jj] + x * (double)a->alpha[p + j];
+                    double z0 = draw_z(a, j, 0, rep), z1 = draw_z(a, j, 1, rep), uu = draw_u(a, j, 0, rep);
+                    double ld[4], bc0[4], bc1[4];
+                    for (int st = 0; st < 4; ++st) {
+                        double d0 = (double)(st & 1), d1 = (double)((st >> 1) & 1);
+                        double l00 = d0 * Rinv[0] * x + Ginv[0];
+                        double l01 = (d0 * d1) * Rinv[1] * x + Ginv[1];
+                        double l11 = d1 * Rinv[3] * x + Ginv[3];
+                        double rhs0 = d0 * (Rinv[0] * w0 + Rinv[2] * w1);
+                        double rhs1 = d1 * (Rinv[1] * w0 + Rinv[3] * w1);
+                        double det = l00 * l11 - l01 * l01;
+                        double i00 = l11 / det, i11 = l00 / det, i01 = -l01 / det;
+                        double g0 = i00 * rhs0 + i01 * rhs1, g1 = i01 * rhs0 + i11 * rhs1;
+                        ld[st] = -0.5 * (jw_log(det) - (rhs0 * g0 + rhs1 * g1)) + jw_log(a->bigPi[st]);
+                        double L00 = jw_sqrt(i00), L10 = i01 / L00, L11 = jw_sqrt(i11 - L10 * L10);
+                        bc0[st] = g0 + L00 * z0;
+                        bc1[st] = g1 + L10 * z0 + L11 * z1;
+                    }
+                    double mx = ld[0];
+                    for (int st = 1; st < 4; ++st) if (ld[st] > mx) mx = ld[st];
+                    double ex[4], se = 0.0;
+                    for (int st = 0; st < 4; ++st) { ex[st] = jw_exp(ld[st] - mx); se += ex[st]; }
+                    double target = uu * se;
+                    int lab = 0; double cp = ex[0];
+                    while (cp <= target && lab < 3) { lab += 1; cp += ex[lab]; }
+                    float bsel[2] = { (float)bc0[lab], (float)bc1[lab] };
+                    for (int k = 0; k < 2; ++k) {
+                        int dk = (lab >> k) & 1;
+                        float oldA = a->alpha[k * p + j], newA = dk ? bsel[k] : 0.0f;
+                        a->alpha[k * p + j] = newA; a->beta[k * p + j] = bsel[k]; a->delta[k * p + j] = dk;
+                        float d = oldA - newA;
+                        if (d != 0.0f)
+                            for (int64_t m = 0; m < b; ++m) r[k * b + m] += (double)d * (double)G[jj * b + m];
+                    }
                 } else {
                     /* MTBayesABC.jl:78-125, binary64 */
                     double bb[8], olda[8], w[8]; int dd[8];

@@ -102,6 +102,7 @@ void jwo_bayesb_variances(const float* beta, int64_t p, double df, double scale,
 #define JWO_METHOD_ABC 0   /* BayesA/B/C */
 #define JWO_METHOD_R   1   /* BayesR     */
 #define JWO_METHOD_MT1 2   /* multi-trait BayesABC sampler I */
+#define JWO_METHOD_MT2 3   /* multi-trait BayesABC sampler II (joint 2^t states), t = 2 */
 
 typedef struct {
     /* genotypes */

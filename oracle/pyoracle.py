@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libjwas_oracle.so")
 
-METHOD_ABC, METHOD_R, METHOD_MT1 = 0, 1, 2
+METHOD_ABC, METHOD_R, METHOD_MT1, METHOD_MT2 = 0, 1, 2, 3
 
 
 def build(force=False):
@@ -254,7 +254,7 @@ def sweep_contract(packed, n, means, xpx, starts, ycorr, alpha, beta, delta, *, 
     if bigPi is not None:
         bp = np.ascontiguousarray(bigPi, dtype=np.float64); keep.append(bp)
         a.bigPi = _p(bp)
-        if method == METHOD_MT1:
+        if method in (METHOD_MT1, METHOD_MT2):
             a.per_marker_pi = int(bp.ndim == 2)
     a.seed = int(seed); a.iter = int(it)
     a.u = hold(u, np.float64); a.z = hold(z, np.float64)

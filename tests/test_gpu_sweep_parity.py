@@ -144,7 +144,7 @@ def test_bayesr_block_schedules(jw, oracle, schedule_name, full_reps):
     run_pair_r(jw, oracle, prob, uniform_starts(90, 17), sched, full_reps, nsweeps=3)
 
 
-def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0):
+def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0, sampler="I"):
     n, p, t = prob.n, prob.p, prob.t
     g = jw.GpuSweeper(prob.packed, n, t)
     g.set_blocks(starts)
@@ -158,11 +158,12 @@ def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, l
     nreps_mode = 0 if schedule == jw.SCHED_EXACT else 1
     for it in range(1, nsweeps + 1):
         rc, S = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
-                                      method=oracle.METHOD_MT1, nreps_mode=nreps_mode,
+                                      method=(oracle.METHOD_MT2 if sampler == "II" else oracle.METHOD_MT1),
+                                      nreps_mode=nreps_mode,
                                       independent=(schedule == jw.SCHED_INDEPENDENT), R=R, G=G, bigPi=bigPi,
                                       seed=seed, it=it, lag=lag)
         assert rc == 0
-        st = g.sweep_mt1(schedule, R, G, bigPi, seed, it)
+        st = (g.sweep_mt2 if sampler == "II" else g.sweep_mt1)(schedule, R, G, bigPi, seed, it)
         ga, gb, gd = g.get_state()
         gy = g.get_ycorr()
         np.testing.assert_array_equal(gd, de)
@@ -382,3 +383,15 @@ def test_gram_gemm_equals_popcount_at_full_n(jw):
             g.close()
         for a, b in zip(*outs):
             np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("engine,lag", [(0, 0), (1, 0), (1, 1)])
+def test_mt_sampler2_joint_states(jw, oracle, engine, lag):
+    # _MTBayesABC_samplerII! (MTBayesABC.jl:129-210): joint draw of the 4 inclusion states, 2 traits
+    prob = Problem(oracle, 403, 600, seed=47, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(600, 200), jw.SCHED_EXACT, nsweeps=3, engine=engine, lag=lag, sampler="II")
+
+
+def test_mt_sampler2_block_schedule(jw, oracle):
+    prob = Problem(oracle, 200, 70, seed=48, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(70, 16), jw.SCHED_BLOCK, nsweeps=2, sampler="II")

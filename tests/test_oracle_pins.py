@@ -186,8 +186,10 @@ def test_mt_sampler_targets_closed_form(oracle, mode):
     assert np.abs(emp - exact).max() < 0.02
 
 
-def test_mt_contract_sampler_targets_closed_form(oracle):
-    """Same closed form, through the contract-arithmetic sweep on a packed one-marker problem."""
+@pytest.mark.parametrize("method_name", ["MT1", "MT2"])
+def test_mt_contract_sampler_targets_closed_form(oracle, method_name):
+    """Same closed form, through the contract-arithmetic sweeps (sampler I and sampler II) on a packed
+    one-marker problem."""
     codes = np.array([[0], [1], [2], [1], [0], [2], [1]])
     n = 7
     packed = oracle.pack_codes(codes)
@@ -200,7 +202,8 @@ def test_mt_contract_sampler_targets_closed_form(oracle):
     counts = np.zeros(4)
     for it in range(1, 20001):
         rc, _ = oracle.sweep_contract(packed, n, means, xpx, [0, 1], ycorr, alpha, beta, delta,
-                                      method=oracle.METHOD_MT1, R=MT_R, G=MT_G, bigPi=MT_PI, seed=77, it=it)
+                                      method=getattr(oracle, "METHOD_" + method_name), R=MT_R, G=MT_G, bigPi=MT_PI,
+                                      seed=77, it=it)
         assert rc == 0
         if it > 3000:
             counts[delta[0] + 2 * delta[1]] += 1
