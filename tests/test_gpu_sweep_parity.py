@@ -395,3 +395,71 @@ def test_mt_sampler2_joint_states(jw, oracle, engine, lag):
 def test_mt_sampler2_block_schedule(jw, oracle):
     prob = Problem(oracle, 200, 70, seed=48, ntraits=2)
     run_pair_mt(jw, oracle, prob, uniform_starts(70, 16), jw.SCHED_BLOCK, nsweeps=2, sampler="II")
+
+
+@pytest.mark.parametrize("t", [3, 4])
+def test_mt_sampler1_three_and_four_traits(jw, oracle, t):
+    """Sampler I is written for any number of traits (MTBayesABC.jl:78-125); the device path covers t <= 4."""
+    n, p = 257, 180
+    prob = Problem(oracle, n, p, seed=60 + t, ntraits=t, missing=0.01)
+    g = jw.GpuSweeper(prob.packed, n, t)
+    starts = uniform_starts(p, 64)
+    g.set_blocks(starts)
+    yc, al, be, de = prob.fresh_state()
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    rng = np.random.default_rng(t)
+    A = rng.normal(size=(t, t)); R = (A @ A.T + t * np.eye(t)) * prob.vary * 0.2
+    B = rng.normal(size=(t, t)); G = (B @ B.T + t * np.eye(t)) * prob.vary * 0.02 / (prob.xpx.mean() / n * p)
+    bigPi = rng.dirichlet(np.ones(1 << t))
+    for it in (1, 2, 3):
+        rc, _ = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
+                                      method=oracle.METHOD_MT1, R=R, G=G, bigPi=bigPi, seed=4, it=it)
+        assert rc == 0
+        st = g.sweep_mt1(jw.SCHED_EXACT, R, G, bigPi, 4, it)
+        ga, gb, gd = g.get_state()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(g.get_ycorr().view(np.uint32), yc.view(np.uint32))
+        states = sum(de[k * p:(k + 1) * p] << k for k in range(t))
+        assert [st.class_counts[q] for q in range(1 << t)][:16] == np.bincount(states, minlength=1 << t).tolist()[:16]
+    assert de.sum() > 0
+    g.close()
+
+
+def test_tiny_problems(jw, oracle):
+    """n < 4 individuals, a single marker, blocks of one marker."""
+    for n, p in ((3, 5), (1, 1), (9, 1)):
+        codes = np.array([[(i + j) % 3 for j in range(p)] for i in range(n)])
+        if n == 1:
+            codes[:] = 1
+        packed = oracle.pack_codes(codes)
+        means, xpx = oracle.marker_stats(packed, n)
+        starts = uniform_starts(p, 1)
+        for engine in (0, 1):
+            g = jw.GpuSweeper(packed, n, 1)
+            g.set_blocks(starts); g.set_option("engine", engine)
+            yc = np.linspace(-1, 1, n).astype(np.float32) if n > 1 else np.array([0.5], np.float32)
+            al = np.zeros(p, np.float32); be = np.zeros(p, np.float32); de = np.zeros(p, np.int32)
+            g.put_ycorr(yc); g.put_state(al, be, de)
+            ve = np.full(p, 0.5); pi = np.full(p, 0.5)
+            rc, _ = oracle.sweep_contract(packed, n, means, xpx, starts, yc, al, be, de, vare=1.0, varEffects=ve, pi=pi, seed=2, it=1)
+            g.sweep_bayesabc(jw.SCHED_EXACT, 1.0, ve, pi, 2, 1)
+            ga, gb, gd = g.get_state()
+            np.testing.assert_array_equal(gd, de); np.testing.assert_array_equal(ga, al)
+            np.testing.assert_array_equal(g.get_ycorr(), yc)
+            g.close()
+
+
+def test_fixed_point_overflow_is_reported(jw, oracle):
+    """ycorr growing more than 4x inside one sweep hits the fixed-point clamp: the call fails loudly
+    (sticky flag), it never returns silently wrong numbers."""
+    prob = Problem(oracle, 64, 40, seed=77)
+    g = jw.GpuSweeper(prob.packed, 64, 1)
+    g.set_blocks(uniform_starts(40, 8))
+    y = (prob.ycorr0 * 1e-6).astype(np.float32)          # tiny residuals ...
+    g.put_ycorr(y)
+    alpha = np.zeros(40, np.float32); alpha[:4] = 50.0   # ... but huge effects that the first block removes
+    g.put_state(alpha, alpha.copy(), (alpha != 0).astype(np.int32))
+    with pytest.raises(jw.JwasError, match="fixed-point overflow"):
+        g.sweep_bayesc(jw.SCHED_EXACT, 1.0, 1e-12, 1.0 - 1e-12, 1, 1)
+    g.close()
