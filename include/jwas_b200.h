@@ -132,6 +132,11 @@ int jwas_fill_hyper(jwas_handle* h, int which, double value);
 int jwas_sweep_mt2(jwas_handle* h, int schedule, const double* R, const double* G, const double* big_pi,
                    uint64_t seed, uint32_t iter, const double* u, const double* z, jwas_sweep_stats* stats);
 
+/* megaBayesABC! (BayesABC.jl:1-7; constraint=true, MCMC_BayesianAlphabet.jl:233-234): one single-trait BayesABC
+ * step per trait with vare[k], var_effects[k], pi[k] (t entries each) -- the traits share one column read. */
+int jwas_sweep_mega(jwas_handle* h, int schedule, const double* vare, const double* var_effects, const double* pi,
+                    uint64_t seed, uint32_t iter, const double* u, const double* z, jwas_sweep_stats* stats);
+
 /* BayesB per-marker variance update on device (variance_components.jl:169-172):
  * var_j = (beta_j^2 + df*scale) / chisq(df+1), chi-square from the native stream. */
 int jwas_sample_bayesb_variances(jwas_handle* h, double df, double scale, uint64_t seed,

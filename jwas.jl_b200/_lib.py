@@ -65,6 +65,7 @@ def lib():
         "jwas_sweep_bayesr": [vp, i32, i32, dbl, dbl, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_mt1": [vp, i32, vp, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_mt2": [vp, i32, vp, vp, vp, u64, u32, vp, vp, C.POINTER(SweepStats)],
+        "jwas_sweep_mega": [vp, i32, vp, vp, vp, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sample_bayesb_variances": [vp, dbl, dbl, u64, u32, vp],
         "jwas_fill_hyper": [vp, i32, dbl],
         "jwas_accumulate": [vp, dbl, i32],
@@ -247,6 +248,14 @@ class GpuSweeper:
         uu, zz = _arr(u, np.float64), _arr(z, np.float64)
         _check(lib().jwas_sweep_mt2(self._h, schedule, _p(Rm), _p(Gm), _p(bp), int(seed), int(it), _p(uu), _p(zz),
                                     C.byref(st)))
+        return st
+
+    def sweep_mega(self, schedule, vare, var_effects, pi, seed, it, u=None, z=None):
+        st = SweepStats()
+        v, ve, pv = _arr(vare, np.float64), _arr(var_effects, np.float64), _arr(pi, np.float64)
+        uu, zz = _arr(u, np.float64), _arr(z, np.float64)
+        _check(lib().jwas_sweep_mega(self._h, schedule, _p(v), _p(ve), _p(pv), int(seed), int(it), _p(uu), _p(zz),
+                                     C.byref(st)))
         return st
 
     def sample_bayesb_variances(self, df, scale, seed, it, want=False):

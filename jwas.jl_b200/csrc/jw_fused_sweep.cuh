@@ -632,6 +632,8 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
         rc = jw_fused_launch<2, 2, 2>(h, f, F);
     } else if (t == 2 && !ms && A.method == 3) {
         rc = jw_fused_launch<3, 2, 2>(h, f, F);
+    } else if (t == 2 && !ms && A.method == 4) {
+        rc = jw_fused_launch<4, 2, 2>(h, f, F);
     }
     if (rc == 2) jw_set_error("engine 1: unsupported (method, traits, missing) combination");
     if (rc) return rc;

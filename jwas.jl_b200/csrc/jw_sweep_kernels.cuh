@@ -364,7 +364,7 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         if (A.per_marker_G) jw_inv_spd_fixed(A.Gmat + j * T * T, T, Ginv);
         else for (int q = 0; q < T * T; ++q) Ginv[q] = A.Ginv[q];
     }
-    const double invVarRes = (METHOD == 2 || METHOD == 3) ? 0.0 : 1.0 / A.vare;
+    const double invVarRes = (METHOD == 2 || METHOD == 3 || METHOD == 4) ? 0.0 : 1.0 / A.vare;
 
     // draw-independent constants
     double c_invLhs = 0, c_L = 0, c_lpc = 0, c_lp0 = 0, c_ve = 1;
@@ -604,6 +604,30 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
                     }
                     newB[0] = 0.0f;
                     active = (a_cur[0] - newA[0]) != 0.0f;
+                } else if (METHOD == 4) {
+                    // megaBayesABC! (BayesABC.jl:1-7): T independent BayesABC steps; trait k uses
+                    // vare = 1/Rinv[k] (diagonal stored), varEffect = Ginv[k] (variance itself), pi = lpi[k]
+#pragma unroll
+                    for (int k = 0; k < T; ++k) {
+                        const double ivr = A.Rinv[k], vek = A.Ginv[k], pik = A.lpi[k];
+                        const double aold = (double)a_cur[k];
+                        const double rhs = (r[k] + x * aold) * ivr;
+                        const double lhs = x * ivr + 1.0 / vek;
+                        const double invLhs = 1.0 / lhs;
+                        const double gHat = rhs * invLhs;
+                        const double logDelta1 = -0.5 * (jw_log(lhs) + jw_log(vek) - gHat * rhs) + jw_log(1.0 - pik);
+                        const double logDelta0 = jw_log(pik);
+                        if (logDelta0 - logDelta1 < u[k]) {
+                            newD[k] = 1;
+                            newA[k] = (float)(gHat + z[k] * jw_sqrt(invLhs));
+                            newB[k] = newA[k];
+                        } else {
+                            newD[k] = 0;
+                            newB[k] = (float)(z[k] * jw_sqrt(vek));
+                            newA[k] = 0.0f;
+                        }
+                        if ((a_cur[k] - newA[k]) != 0.0f) active = true;
+                    }
                 } else if (METHOD == 3) {
                     // MTBayesABC.jl:163-208 (sampler II, joint states), T == 2; twin of the oracle's MT2 step
                     const double w0 = r[0] + x * (double)a_cur[0];

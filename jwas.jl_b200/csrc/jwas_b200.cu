@@ -499,6 +499,7 @@ struct sweep_cfg {
     double gamma[JW_MAX_CLASSES] = {0};
     double Rinv[16] = {0}, Ginv[16] = {0};
     double pi_host[16] = {0};     // global class / joint-state priors (BayesR, multi-trait)
+    int mega = 0;
     uint64_t seed = 0; uint32_t iter = 0;
     const double* u = nullptr; const double* z = nullptr;  // device pointers
 };
@@ -519,6 +520,9 @@ static int dispatch_chain(jwas_handle* h, const jw_chain_args& A, int nblk, int 
     else if (A.method == 2 && t == 3) launch_chain<2, 3>(h, A, nblk, threads);
     else if (A.method == 2 && t == 4) launch_chain<2, 4>(h, A, nblk, threads);
     else if (A.method == 3 && t == 2) launch_chain<3, 2>(h, A, nblk, threads);
+    else if (A.method == 4 && t == 2) launch_chain<4, 2>(h, A, nblk, threads);
+    else if (A.method == 4 && t == 3) launch_chain<4, 3>(h, A, nblk, threads);
+    else if (A.method == 4 && t == 4) launch_chain<4, 4>(h, A, nblk, threads);
     else { jw_set_error("unsupported (method, traits) combination"); return 2; }
     JW_LAUNCH_CHECK(h);
     return 0;
@@ -705,6 +709,7 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     memcpy(A.gamma, c.gamma, sizeof(A.gamma));
     memcpy(A.Rinv, c.Rinv, sizeof(A.Rinv)); memcpy(A.Ginv, c.Ginv, sizeof(A.Ginv));
     A.seed = c.seed; A.iter = c.iter; A.u = c.u; A.z = c.z;
+    if (c.mega) for (int k = 0; k < t; ++k) A.lpi[k] = c.pi_host[k];     // mega: the per-trait pi itself
     A.act_idx = h->d_act_idx; A.act_cnt = h->d_act_cnt; A.counters = h->d_counters; A.timers = (int)h->opt_timers;
     const int threads = (int)std::min<int64_t>(JW_MAX_BLOCK, std::max<int64_t>(32, ceil_div(h->maxb, 32) * 32));
     JW_REQUIRE(c.schedule == JWAS_SCHED_EXACT || h->maxb <= JW_MAX_BLOCK,
@@ -898,6 +903,26 @@ extern "C" int jwas_sweep_mt2(jwas_handle* h, int schedule, const double* R, con
     if (upload_draws(h, c, u, z, schedule, 1)) return 10;
     int rc = run_sweep(h, c, stats);
     return rc;
+}
+
+extern "C" int jwas_sweep_mega(jwas_handle* h, int schedule, const double* vare, const double* var_effects,
+                               const double* pi, uint64_t seed, uint32_t iter, const double* u, const double* z,
+                               jwas_sweep_stats* stats) {
+    JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->t >= 2, "jwas_sweep_mega: multi-trait handle required");
+    JW_REQUIRE(schedule >= 0 && schedule <= 2, "unknown schedule");
+    JW_REQUIRE(vare && var_effects && pi, "jwas_sweep_mega: vare, var_effects and pi are required");
+    JW_CUDA(cudaSetDevice(h->device));
+    sweep_cfg c; c.method = 4; c.schedule = schedule; c.full_reps = 1; c.seed = seed; c.iter = iter;
+    for (int k = 0; k < h->t; ++k) {
+        JW_REQUIRE(vare[k] > 0.0 && var_effects[k] > 0.0, "variances must be positive");
+        JW_REQUIRE(pi[k] >= 0.0 && pi[k] <= 1.0, "pi must lie in [0,1]");
+        c.Rinv[k] = 1.0 / vare[k]; c.Ginv[k] = var_effects[k]; c.pi_host[k] = pi[k];
+    }
+    c.per_marker_pi = 1;          // no sampler-I prep
+    c.mega = 1;
+    if (upload_draws(h, c, u, z, schedule, 1)) return 10;
+    return run_sweep(h, c, stats);
 }
 
 extern "C" int jwas_fill_hyper(jwas_handle* h, int which, double value) {

@@ -755,6 +755,15 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
                                               draw_u(a, j, 0, rep), draw_z(a, j, 0, rep));
                     if (d != 0.0f)
                         for (int64_t m = 0; m < b; ++m) r[m] += (double)d * (double)G[jj * b + m];
+                } else if (a->method == JWO_METHOD_MEGA) {
+                    /* megaBayesABC! (BayesABC.jl:1-7): trait k uses vare[k,k], varEffects[k,k], pi[k] */
+                    for (int k = 0; k < t; ++k) {
+                        float d = abc_step_contract(r[k * b + jj], a->xpx[j], &a->alpha[k * p + j], &a->beta[k * p + j],
+                                                    &a->delta[k * p + j], 1.0 / a->Rmat[k * t + k], a->Gmat[k * t + k],
+                                                    a->bigPi[k], draw_u(a, j, k, rep), draw_z(a, j, k, rep));
+                        if (d != 0.0f)
+                            for (int64_t m = 0; m < b; ++m) r[k * b + m] += (double)d * (double)G[jj * b + m];
+                    }
                 } else if (a->method == JWO_METHOD_MT2) {
                     /* MTBayesABC.jl:163-208 (sampler II, joint states), t = 2, binary64.
                      * States in the order 00,10,01,11 (annotation_setup.jl:18); shared normals z0,z1;

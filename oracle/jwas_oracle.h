@@ -103,6 +103,8 @@ void jwo_bayesb_variances(const float* beta, int64_t p, double df, double scale,
 #define JWO_METHOD_R   1   /* BayesR     */
 #define JWO_METHOD_MT1 2   /* multi-trait BayesABC sampler I */
 #define JWO_METHOD_MT2 3   /* multi-trait BayesABC sampler II (joint 2^t states), t = 2 */
+#define JWO_METHOD_MEGA 4  /* megaBayesABC! (constraint=true): one single-trait BayesABC step per trait;
+                              vare, varEffects, pi come per trait through Rmat / Gmat diagonals and bigPi[k] */
 
 typedef struct {
     /* genotypes */

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libjwas_oracle.so")
 
-METHOD_ABC, METHOD_R, METHOD_MT1, METHOD_MT2 = 0, 1, 2, 3
+METHOD_ABC, METHOD_R, METHOD_MT1, METHOD_MT2, METHOD_MEGA = 0, 1, 2, 3, 4
 
 
 def build(force=False):

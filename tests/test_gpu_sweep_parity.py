@@ -463,3 +463,32 @@ def test_fixed_point_overflow_is_reported(jw, oracle):
     with pytest.raises(jw.JwasError, match="fixed-point overflow"):
         g.sweep_bayesc(jw.SCHED_EXACT, 1.0, 1e-12, 1.0 - 1e-12, 1, 1)
     g.close()
+
+
+@pytest.mark.parametrize("engine,lag,t", [(0, 0, 2), (1, 1, 2), (0, 0, 3)])
+def test_mega_bayesabc_independent_traits(jw, oracle, engine, lag, t):
+    """megaBayesABC! (BayesABC.jl:1-7, constraint=true): one single-trait step per trait, one column read."""
+    n, p = 300, 400
+    prob = Problem(oracle, n, p, seed=80 + t, ntraits=t)
+    g = jw.GpuSweeper(prob.packed, n, t)
+    g.set_option("engine", engine); g.set_option("lag", lag)
+    starts = uniform_starts(p, 128)
+    g.set_blocks(starts)
+    yc, al, be, de = prob.fresh_state()
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    vare = np.array([0.5, 0.7, 0.6, 0.9][:t]) * prob.vary
+    ve = np.array([1.0, 2.0, 0.5, 1.5][:t]) * prob.vary * 0.5 / (0.1 * prob.xpx.mean() / n * p)
+    pi = np.array([0.9, 0.8, 0.95, 0.85][:t])
+    for it in (1, 2, 3):
+        rc, _ = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
+                                      method=oracle.METHOD_MEGA, R=np.diag(vare), G=np.diag(ve), bigPi=pi, seed=6, it=it, lag=lag)
+        assert rc == 0
+        st = g.sweep_mega(jw.SCHED_EXACT, vare, ve, pi, 6, it)
+        ga, gb, gd = g.get_state()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(gb.view(np.uint32), be.view(np.uint32))
+        np.testing.assert_array_equal(g.get_ycorr().view(np.uint32), yc.view(np.uint32))
+        assert [st.sum_delta[k] for k in range(t)] == [de[k * p:(k + 1) * p].sum() for k in range(t)]
+    assert all(de[k * p:(k + 1) * p].sum() > 0 for k in range(t))
+    g.close()
