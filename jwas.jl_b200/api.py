@@ -452,7 +452,12 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             model.R.val = np.diag(vary * 0.5)
         model.R.val = np.array(model.R.val, dtype=np.float64)
         model.R.scale = model.R.val * (model.R.df - t - 1)
-        if isinstance(Mi.π, dict):
+        if Mi.G.constraint:
+            # megaBayesABC!: one pi per trait (MCMC_BayesianAlphabet.jl:96-99 starts them at zero)
+            big = np.zeros(t) if (np.isscalar(Mi.π) or isinstance(Mi.π, dict)) else np.array(Mi.π, dtype=np.float64)
+            if big.shape != (t,):
+                error("constraint=true needs one Pi per trait.")
+        elif isinstance(Mi.π, dict):
             big = np.zeros(1 << t)
             for key, v in Mi.π.items():
                 big[sum(int(round(k)) << i for i, k in enumerate(key))] = v
@@ -460,14 +465,17 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             big = np.zeros(1 << t); big[-1] = 1.0      # "all markers have effects on all traits"
         else:
             big = np.array(Mi.π, dtype=np.float64)
-        if abs(big.sum() - 1.0) > 1e-8:
+        if not Mi.G.constraint and abs(big.sum() - 1.0) > 1e-8:
             error("Summation of probabilities of Pi is not equal to one.")
         if Mi.G.val is False:
             gv = np.array(Mi.genetic_variance.val, float) if Mi.genetic_variance.val is not False else np.diag(vary * 0.5)
             denom = np.zeros((t, t))
             for i in range(t):
                 for j in range(t):
-                    denom[i, j] = Mi.sum2pq * sum(big[s] for s in range(1 << t) if (s >> i) & 1 and (s >> j) & 1)
+                    if Mi.G.constraint:
+                        denom[i, j] = Mi.sum2pq * (1 - big[i]) * (1 - big[j]) if i != j else Mi.sum2pq * (1 - big[i])
+                    else:
+                        denom[i, j] = Mi.sum2pq * sum(big[s] for s in range(1 << t) if (s >> i) & 1 and (s >> j) & 1)
             if np.any(denom <= 0):
                 error("Marker effects covariance matrix is not postive definite! Please modify the argument: Pi.")
             Mi.G.val = gv / denom
@@ -508,7 +516,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          estimate_vare=model.R.estimate_variance,
                          R=model.R.val if t > 1 else None, G=Mi.G.val if t > 1 else None,
                          big_pi=Mi.π if t > 1 else None, scale_G=Mi.G.scale if t > 1 else None,
-                         scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler)
+                         scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler,
+                         constraint_G=bool(t > 1 and Mi.G.constraint), constraint_R=bool(t > 1 and model.R.constraint))
 
     # ---- output dictionary (output.jl:108-212)
     ma, ma2, md = backend.get_means()
@@ -539,6 +548,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             labels = ["π"]
         elif t == 1:
             labels = [f"class{c + 1}" for c in range(len(pm))]
+        elif Mi.G.constraint:
+            labels = list(model.lhsVec)
         else:
             labels = [str([float((s >> i) & 1) for i in range(t)]) for s in range(1 << t)]
         output["pi_" + Mi.name] = _frame([[l, pm[i], math.sqrt(abs(pm2[i] - pm[i] ** 2))] for i, l in enumerate(labels)],

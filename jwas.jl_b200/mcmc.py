@@ -105,6 +105,9 @@ class GpuBackend:
     def sweep_mt2(self, schedule, R, G, big_pi, seed, it):
         return self._stats(self.s.sweep_mt2(schedule, R, G, big_pi, seed, it), self.s.t)
 
+    def sweep_mega(self, schedule, vare, var_effects, pi, seed, it):
+        return self._stats(self.s.sweep_mega(schedule, vare, var_effects, pi, seed, it), self.s.t)
+
     def sample_bayesb_variances(self, df, scale, seed, it):
         self.s.sample_bayesb_variances(df, scale, seed, it)
 
@@ -125,7 +128,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               seed, vare, var_effect, pi, df_effect, scale_effect, df_res, scale_res,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
-              mu0=None, iter0=0, want_ebv=False, mt_sampler="I"):
+              mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -176,6 +179,9 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                         first_bayesb = False
                     backend.fill_hyper("pi", pi)
                     st = backend.sweep_bayesabc(schedule, vare, None, None, seed, it)
+            elif constraint_G:
+                # megaBayesABC! (MCMC_BayesianAlphabet.jl:233-234): per-trait pi vector, diagonal variances
+                st = backend.sweep_mega(schedule, np.diag(R).copy(), np.diag(G).copy(), big_pi, seed, it)
             else:
                 st = (backend.sweep_mt2 if mt_sampler == "II" else backend.sweep_mt1)(schedule, R, G, big_pi, seed, it)
         elif method == "BayesR":
@@ -190,6 +196,8 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
             elif t == 1:
                 k_in = st["sum_delta"][0]
                 pi = rng.beta(p - k_in + 1, k_in + 1)                            # Pi.jl:7-9
+            elif constraint_G:                                                   # MCMC_BayesianAlphabet.jl:300-301
+                big_pi = np.array([rng.beta(p - st["sum_delta"][k] + 1, st["sum_delta"][k] + 1) for k in range(t)])
             else:
                 big_pi = rng.dirichlet(st["class_counts"][:1 << t] + 1.0)        # Pi.jl:20-42
         # [4] marker effect variance
@@ -203,12 +211,18 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                                               / rng.chisq(st["sum_delta"][0] + df_effect)))  # :166-168
             elif t == 1:
                 backend.sample_bayesb_variances(df_effect, scale_effect, seed, it)  # :169-172
+            elif constraint_G:                       # variance_components.jl:103-110: diagonal scaled-inv-chi2
+                G = np.diag([float(np.float32((st["beta_ss"][k, k] + df_effect * scale_G[k, k]) / rng.chisq(p + df_effect)))
+                             for k in range(t)])
             else:
                 G = rng.inverse_wishart(df_effect + p, scale_G + st["beta_ss"]).astype(np.float32).astype(np.float64)
         # [5] residual variance
         if estimate_vare:
             if t == 1:
                 vare = float(np.float32((st["ycorr_ss"][0, 0] + df_res * scale_res) / rng.chisq(n + df_res)))
+            elif constraint_R:
+                R = np.diag([float(np.float32((st["ycorr_ss"][k, k] + df_res * scale_R[k, k]) / rng.chisq(n + df_res)))
+                             for k in range(t)])
             else:
                 R = rng.inverse_wishart(df_res + n, scale_R + st["ycorr_ss"]).astype(np.float32).astype(np.float64)
         ysum = st["ycorr_sum"]

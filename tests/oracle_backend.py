@@ -115,6 +115,9 @@ class OracleBackend:
     def sweep_mt2(self, schedule, R, G, big_pi, seed, it):
         return self._sweep(orc.METHOD_MT2, schedule, 1, seed, it, R=R, G=G, bigPi=big_pi)
 
+    def sweep_mega(self, schedule, vare, var_effects, pi, seed, it):
+        return self._sweep(orc.METHOD_MEGA, schedule, 1, seed, it, R=np.diag(vare), G=np.diag(var_effects), bigPi=np.asarray(pi, float))
+
     def accumulate(self, nsamples, bayesr=False):
         a = self.alpha.astype(np.float64)
         d = (self.delta > 1).astype(np.float64) if bayesr else self.delta.astype(np.float64)

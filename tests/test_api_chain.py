@@ -182,3 +182,14 @@ def test_contract_arithmetic_tracks_reference_arithmetic():
         np.testing.assert_allclose(y2, y1, atol=1e-3)
         np.testing.assert_allclose(a3, a1, atol=1e-4)       # dense == stream (reference's own check)
     assert d2.sum() > 5
+
+
+def test_multitrait_constraint_runs_independent_traits():
+    # constraint=true: megaBayesABC! -- no genetic covariance among traits, one pi per trait
+    codes, ids, ph = make_data(ntraits=2, seed=8)
+    geno = jw.get_genotypes(codes, np.array([[1.0, 0.0], [0.0, 1.0]]), method="BayesC", obsID=ids, constraint=True)
+    model = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.array([[1.0, 0.2], [0.2, 1.0]]),
+                           genotypes={"geno": geno})
+    out = jw.runMCMC(model, ph, chain_length=12, burnin=2, seed=5, outputEBV=False, _backend_factory=factory)
+    assert len(out["pi_geno"]) == 2 and out["pi_geno"]["Estimate"].between(0, 1).all()
+    assert len(out["marker effects geno"]) == 2 * geno.nMarkers

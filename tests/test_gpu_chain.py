@@ -12,10 +12,10 @@ from test_api_chain import make_data
 pytestmark = pytest.mark.gpu
 
 
-def both(codes, ids, ph, eqs, G, R, method, Pi=0.0, engine=1, **kw):
+def both(codes, ids, ph, eqs, G, R, method, Pi=0.0, engine=1, geno_kw=None, **kw):
     outs = []
     for bf in (None, factory):
-        geno = jw.get_genotypes(codes, G, method=method, Pi=Pi, obsID=ids)
+        geno = jw.get_genotypes(codes, G, method=method, Pi=Pi, obsID=ids, **(geno_kw or {}))
         model = jw.build_model(eqs, R, genotypes={"geno": geno})
         outs.append(jw.runMCMC(model, ph, seed=77, engine=engine, _backend_factory=bf, **kw))
     return outs
@@ -73,4 +73,16 @@ def test_config1_bayesc_pi095(tmp_path):
     assert np.corrcoef(ebv, y)[0, 1] > 0.5                 # h2 = 0.5 simulation: EBVs track phenotypes
     assert 0.5 < out["pi_geno"]["Estimate"][0] < 1.0
     g, o = both(codes, ids, ph, "y1 = intercept + geno", False, False, "BayesC", 0.95, chain_length=60, burnin=10)
+    assert_same(g, o)
+
+
+@pytest.mark.parametrize("geno_kw", [dict(multi_trait_sampler="II"), dict(constraint=True)])
+def test_multitrait_variants_chain(geno_kw):
+    """Sampler II (joint states) and constraint=true (megaBayesABC!) through runMCMC: GPU chain == oracle chain."""
+    codes, ids, ph = make_data(n=250, p=300, seed=27, ntraits=2)
+    G = np.array([[1.0, 0.5], [0.5, 1.0]]) if "constraint" not in geno_kw else np.array([[1.0, 0.0], [0.0, 1.0]])
+    R = np.array([[1.0, 0.3], [0.3, 1.0]])
+    Pi = {(0.0, 0.0): 0.35, (1.0, 0.0): 0.20, (0.0, 1.0): 0.15, (1.0, 1.0): 0.30} if "constraint" not in geno_kw else 0.0
+    g, o = both(codes, ids, ph, "y1 = intercept + geno\ny2 = intercept + geno", G, R, "BayesC", Pi, geno_kw=geno_kw,
+                chain_length=12, burnin=2)
     assert_same(g, o)
