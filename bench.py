@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--burnin", type=int, default=40, help="untimed chain iterations before warm-up")
     ap.add_argument("--engine", type=int, default=1)
     ap.add_argument("--lag", type=int, default=1, help="1 = lagged exact schedule (chain k overlaps stream k+1)")
+    ap.add_argument("--chain-ctas", type=int, default=0, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
     ap.add_argument("--fixed-pi", action="store_true", help="keep pi=0.95 fixed (reference perf scripts: estimatePi=false)")
     ap.add_argument("--cpu-markers", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
@@ -168,6 +169,7 @@ def main():
     starts = np.array(list(range(0, p, args.panel)) + [p], dtype=np.int64)
     g.set_option("engine", args.engine)
     g.set_option("lag", args.lag if args.engine == 1 else 0)
+    g.set_option("chain_ctas", args.chain_ctas if (args.engine == 1 and args.lag) else 0)
     g.set_blocks(starts)
     means, xpx = g.marker_stats()
     # phenotype: y = sum_qtl x_j a_j + e, h2 = 0.5
@@ -265,7 +267,7 @@ def main():
     line = {"metric": "gibbs_marker_sweeps_per_sec", "value": value, "unit": "sweeps/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 dots / f64 scalars / f32 state",
-            "data": "synthetic", "config": dict(config, engine=args.engine, lag=args.lag, burnin=args.burnin, pi=("fixed 0.95" if args.fixed_pi else "estimated"),
+            "data": "synthetic", "config": dict(config, engine=args.engine, lag=args.lag, chain_ctas=args.chain_ctas, burnin=args.burnin, pi=("fixed 0.95" if args.fixed_pi else "estimated"),
                                                 markers_in_model=model_size, active_updates_per_sweep=active,
                                                 chain_rounds_per_sweep=rounds, setup_s=setup_s),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary()}

@@ -1,0 +1,355 @@
+// jw_chain_pipe.cuh -- the sequential Gibbs chain of the lagged exact schedule, pipelined over several
+// chain CTAs of the persistent sweep kernel (engine 1, option chain_ctas >= 1).
+//
+// The chain is walked in UNITS of up to 1024 markers (one thread per marker; a panel of the exact
+// schedule is 1..4 units).  Unit u is owned by chain CTA (u mod n_chain).  Everything that does not
+// depend on earlier units of the same sweep -- state and constant loads, the block rhs, Gram-row
+// prefetches, the write-back of alpha/beta/delta, the ordered active list -- runs off the critical
+// path on the owning CTA while the previous units are still being decided by other CTAs.  What is
+// sequential (BayesABC.jl:24-58 applied marker after marker) travels as COMMIT RECORDS:
+//
+//   one 64-bit word per (commit, trait):  [63:32] float bits of old-new alpha
+//                                         [31:16] sweep tag   [15:0] position inside the unit
+//   and one terminator word per unit (code 0x8000).
+//
+// A record is written with a single 64-bit store the moment the marker commits and is complete in
+// itself, so no flag / fence / second round trip is needed: consumers poll the word until the tag
+// is this sweep's.  Three consumers read the same records:
+//   * later units of the same panel      (rhs correction with the panel's Gram block,  BayesABC.jl:169)
+//   * the units of the next panel        (cross-Gram correction of the lagged schedule)
+//   * the streaming CTAs, two panels on  (ycorr <- ycorr + (old-new) x_j,             BayesABC.jl:48)
+// The additions happen in commit order everywhere, i.e. the same sums in the same order as the
+// one-CTA chain (jw_chain_block) and the oracle's lagged schedule: results are bit-identical.
+#pragma once
+#include "jw_sweep_kernels.cuh"
+
+#define JW_REC_END 0x8000u
+#define JW_REC_STRIDE (JW_CHAIN_SB + 1)       // commits of one unit + terminator
+#define JW_REC_BATCH 4                        // records peeked per poll (their Gram / genotype loads overlap)
+
+struct jw_pipe_args {
+    int n_chain;                              // chain CTAs (0 = one-CTA chain, jw_chain_block)
+    int nunits;
+    const int64_t* unit_start;                // nunits+1: first marker of every unit
+    const int32_t* unit_blk;                  // nunits: block (panel) of the unit
+    const int32_t* blk_unit0;                 // nblocks+1: first unit of every block
+    unsigned long long* rec;                  // nunits * JW_REC_STRIDE * T words
+    unsigned tag;                             // 1..65535, changes every sweep
+    int32_t* act_cnt_unit;                    // nunits: entries of the unit's ordered active list
+    int32_t* flags;                           // [2] sticky abort
+};
+
+__device__ __forceinline__ unsigned long long jw_ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void jw_st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long jw_rec_pack(float d, unsigned tag, unsigned code) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | ((unsigned long long)(tag & 0xffffu) << 16) | (code & 0xffffu);
+}
+
+// Reader of one unit's record stream.  next() returns how many commits (0..JW_REC_BATCH) became
+// available at the cursor and advances over them; w[q][k] holds their words.  done() is true once
+// the terminator has been consumed.  All lanes of a warp read the same addresses in the same
+// instruction, so the result is warp-uniform; different warps may be at different cursors.
+template <int T>
+struct jw_rec_reader {
+    const unsigned long long* base;
+    unsigned tag;
+    int e;
+    bool finished;
+    unsigned long long w[JW_REC_BATCH][T];
+
+    __device__ __forceinline__ void open(const jw_pipe_args& P, int unit) {
+        base = P.rec + (size_t)unit * JW_REC_STRIDE * T;
+        tag = P.tag & 0xffffu; e = 0; finished = false;
+    }
+    __device__ __forceinline__ int next() {
+#pragma unroll
+        for (int q = 0; q < JW_REC_BATCH; ++q)
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+                w[q][k] = (e + q < JW_REC_STRIDE) ? jw_ld_relaxed_u64(base + (size_t)(e + q) * T + k) : 0ull;
+        int nv = 0;
+#pragma unroll
+        for (int q = 0; q < JW_REC_BATCH; ++q) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < T; ++k) ok = ok && (((unsigned)(w[q][k] >> 16) & 0xffffu) == tag);
+            if (ok && nv == q && !finished) {
+                if ((unsigned)w[q][0] & JW_REC_END) finished = true; else nv = q + 1;
+            }
+        }
+        e += nv;
+        return nv;
+    }
+    __device__ __forceinline__ int code(int q) const { return (int)((unsigned)w[q][0] & 0x7fffu); }
+    __device__ __forceinline__ float d(int q, int k) const { return __uint_as_float((unsigned)(w[q][k] >> 32)); }
+};
+
+// spin bookkeeping shared by every record poller: returns false when the sweep must be abandoned
+__device__ __forceinline__ bool jw_spin_ok(unsigned& spins, unsigned long long& t0, int32_t* flags) {
+    if ((++spins & 2047u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        int ab;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(flags + 2) : "memory");
+        if (ab != 0) return false;
+        if (now - t0 > 20000000000ull) { atomicExch(&flags[2], 1); return false; }
+    }
+    return true;
+}
+
+// One unit of the chain.  B describes the unit's panel (s, b, Gram, cross-Gram towards the previous
+// panel, rhs source); wait_fn() blocks until the panel's rhs partial sums are complete.
+// Shared memory (caller-supplied): wmin[2][32] | cnt[32] | dc[T][1024].
+// Returns the number of commits, -1 when the sweep was aborted.
+template <int METHOD, int T, class WaitFn>
+__device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pipe_args& P, const jw_chain_blk& B,
+                                             const int u, WaitFn wait_fn, unsigned char* smem_base,
+                                             unsigned long long* ct /* 5 phase timers or nullptr */) {
+    int (*s_wmin)[32] = reinterpret_cast<int (*)[32]>(smem_base);
+    int* s_cnt = reinterpret_cast<int*>(smem_base + 256);
+    float* s_dc = reinterpret_cast<float*>(smem_base + 512);                  // [T][JW_CHAIN_SB]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = (int)(blockDim.x >> 5);
+    const int64_t p = A.p;
+    const int kb = P.unit_blk[u];
+    const int64_t s = B.s; const int b = B.b;
+    const int64_t us = P.unit_start[u];
+    const int m0 = (int)(us - s);                         // unit's first position inside the panel
+    const int ub = min(JW_CHAIN_SB, b - m0);
+    const int m = m0 + tid;
+    const bool valid = tid < ub;
+    const int64_t j = us + (valid ? tid : 0);
+    const float* G = A.gram + B.gram_off;
+    unsigned long long* myrec = P.rec + (size_t)u * JW_REC_STRIDE * T;
+    unsigned long long ctm = 0;
+    const bool ctimed = (ct != nullptr) && tid == 0;
+    if (ctimed) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ctm));
+#define JW_CT(i) do { if (ctimed) { unsigned long long n__; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(n__)); ct[i] += n__ - ctm; ctm = n__; } } while (0)
+
+    // the inputs of this CTA's NEXT unit are needed n_chain units from now: pull them towards L2 in bulk
+    if (warp == 0 && B.prefetch_b > 0) {
+        const int64_t ps = B.prefetch_s; const int pb = B.prefetch_b;
+        for (int kk = 0; kk < T; ++kk) {
+            const void* base = nullptr; unsigned esz = 0;
+            switch (lane) {
+                case 0: base = A.alpha + kk * p + ps; esz = 4; break;
+                case 1: base = A.delta + kk * p + ps; esz = 4; break;
+                case 2: if (kk == 0) { base = A.xpx + ps; esz = 4; } break;
+                case 3: if (kk == 0) { base = A.means + ps; esz = 4; } break;
+                case 4: if (METHOD != 1) { base = A.beta + kk * p + ps; esz = 4; } break;
+                case 5: if (A.prep_beta0 && kk == 0) { base = A.prep_beta0 + ps; esz = 4; } break;
+                case 6: case 7: case 8: case 9: case 10: case 11:
+                    if (A.prep && kk == 0) { base = A.prep + (int64_t)(lane - 6) * p + ps; esz = 8; } break;
+                case 12: case 13:
+                    if (A.draws_u) { base = (lane == 12 ? A.draws_u : A.draws_z) + kk * p + ps; esz = 8; } break;
+                default: break;
+            }
+            if (base) {
+                const unsigned long long a0 = (unsigned long long)base & ~15ull;
+                const unsigned bytes = (unsigned)((((unsigned long long)base + (unsigned long long)pb * esz + 15ull) & ~15ull) - a0);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+            }
+        }
+    }
+
+    // ---- state at unit entry, constants, draws (nothing here depends on other units) ----
+    double r[T];
+    float a_entry[T], a_cur[T], b_cur[T];
+    int d_cur[T];
+    const double mu = (double)A.means[j];
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        a_entry[k] = a_cur[k] = A.alpha[k * p + j];
+        b_cur[k] = (METHOD == 1) ? 0.0f : A.beta[k * p + j];
+        d_cur[k] = A.delta[k * p + j];
+    }
+    jw_marker_eval<METHOD, T> E;
+    E.load_constants(A, j);
+    E.load_draws(A, j, 0);
+    bool row_requested = false;
+    if (valid) {
+        bool nz = false;
+#pragma unroll
+        for (int k = 0; k < T; ++k) nz = nz || (a_cur[k] != 0.0f);
+        if (nz) {            // certain to need its Gram row: one bulk prefetch towards L2
+            row_requested = true;
+            const float* row = G + (int64_t)m * b;
+            const unsigned long long a0 = (unsigned long long)row & ~15ull;
+            const unsigned bytes = (unsigned)((((unsigned long long)(row + b) + 15ull) & ~15ull) - a0);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+        }
+    }
+    JW_CT(0);
+    if (!wait_fn()) return -1;
+    JW_CT(1);
+
+    // ---- rhs of this marker from the streamed partial sums ----
+    const int mc = valid ? m : m0;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        long long dq, mq, sqk;
+        if (B.xslots != nullptr) {
+            dq = 0; mq = 0; sqk = 0;
+            for (int rk = 0; rk < B.xworld; ++rk) {
+                const long long* sl = B.xslots + (int64_t)rk * B.slot_stride;
+                dq += __ldcg(sl + (int64_t)k * B.slot_b + mc);
+                if (A.mq) mq += __ldcg(sl + (int64_t)(T + k) * B.slot_b + mc);
+                sqk += __ldcg(sl + (int64_t)2 * T * B.slot_b + k);
+            }
+        } else {
+            dq = __ldcg(&A.dq[k * p + j]); mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
+            sqk = __ldcg(&B.sq[k]);
+        }
+        r[k] = ((double)dq - mu * (double)(sqk - mq)) * A.invscale;
+    }
+
+    // ---- corrections, in commit order: the previous panel's units (cross-Gram), then the earlier
+    //      units of this panel (Gram).  Records are consumed as they appear. ----
+    bool ok = true;
+    {
+        const int u_lo = (kb > 0 && B.xgram != nullptr) ? P.blk_unit0[kb - 1] : P.blk_unit0[kb];
+        const int u_own = P.blk_unit0[kb];
+        unsigned spins = 0; unsigned long long t0 = 0;
+        for (int us_ = u_lo; us_ < u && ok; ++us_) {
+            const bool prevblk = us_ < u_own;
+            const float* gsrc = prevblk ? B.xgram : G;
+            const int rowbase = (int)(P.unit_start[us_] - (prevblk ? B.xstart : s));
+            jw_rec_reader<T> R;
+            R.open(P, us_);
+            while (!R.finished) {
+                const int nv = R.next();
+                if (nv == 0) {
+                    if (!R.finished && !jw_spin_ok(spins, t0, P.flags)) { ok = false; break; }
+                    continue;
+                }
+                float g[JW_REC_BATCH];
+#pragma unroll
+                for (int q = 0; q < JW_REC_BATCH; ++q)
+                    g[q] = (q < nv && valid) ? gsrc[(int64_t)(rowbase + R.code(q)) * b + m] : 0.0f;
+#pragma unroll
+                for (int q = 0; q < JW_REC_BATCH; ++q) {
+                    if (q < nv) {
+#pragma unroll
+                        for (int k = 0; k < T; ++k) {
+                            const float d = R.d(q, k);
+                            if (d != 0.0f) r[k] += (double)d * (double)g[q];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (__syncthreads_or(ok ? 0 : 1)) return -1;          // a poller gave up: the whole CTA leaves together
+    JW_CT(2);
+
+    // ---- speculative rounds (one barrier each), every commit published at once ----
+    unsigned long long my_active = 0, my_rounds = 0;
+    int parity = 0, ncommit = 0, pos = 0;
+    while (true) {
+        const bool pending = valid && tid >= pos;
+        float newA[T], newB[T]; int newD[T];
+        bool active = false;
+        if (pending) {
+            active = E.eval(A, r, a_cur, b_cur, d_cur, newA, newB, newD);
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < T; ++k) s_dc[k * JW_CHAIN_SB + tid] = a_cur[k] - newA[k];
+                if (!row_requested) {
+                    row_requested = true;
+                    const float* row = G + (int64_t)m * b;
+                    const unsigned long long a0 = (unsigned long long)row & ~15ull;
+                    const unsigned bytes = (unsigned)((((unsigned long long)(row + b) + 15ull) & ~15ull) - a0);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+                }
+            }
+        }
+        const int key = (pending && active) ? tid : 0x7fffffff;
+        const int wmin = __reduce_min_sync(0xffffffffu, key);
+        if (lane == 0) s_wmin[parity][warp] = wmin;
+        __syncthreads();
+        const int v = (lane < nw) ? s_wmin[parity][lane] : 0x7fffffff;
+        const int first = __reduce_min_sync(0xffffffffu, v);
+        parity ^= 1;
+        my_rounds += (tid == 0);
+        if (pending && tid == first) {
+            // the committing marker publishes its own record before anything else happens
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+                jw_st_relaxed_u64(myrec + (size_t)ncommit * T + k, jw_rec_pack(a_cur[k] - newA[k], P.tag, (unsigned)first));
+            my_active += 1;
+        }
+        if (pending && tid <= first) {
+#pragma unroll
+            for (int k = 0; k < T; ++k) { a_cur[k] = newA[k]; b_cur[k] = newB[k]; d_cur[k] = newD[k]; }
+        }
+        if (first == 0x7fffffff) break;
+        const int fg = m0 + first;                       // committed marker's position inside the panel
+        if (valid && tid > first) {
+            const float g = G[(int64_t)fg * b + m];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const float d = s_dc[k * JW_CHAIN_SB + first];
+                if (d != 0.0f) r[k] += (double)d * (double)g;
+            }
+        }
+        if (B.xgram_next != nullptr && tid == 0) {
+            // the next panel's units will need this marker's cross-Gram row: start moving it to L2
+            const float* row = B.xgram_next + (int64_t)fg * B.b_next;
+            const unsigned long long a0 = (unsigned long long)row & ~15ull;
+            const unsigned bytes = (unsigned)((((unsigned long long)(row + B.b_next) + 15ull) & ~15ull) - a0);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
+        }
+        ncommit += 1;
+        pos = first + 1;
+        if (pos >= ub) break;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < T; ++k) jw_st_relaxed_u64(myrec + (size_t)ncommit * T + k, jw_rec_pack(0.0f, P.tag, JW_REC_END));
+    }
+    JW_CT(3);
+
+    // ---- off the critical path: publish state, net delta-alpha and the ordered active list ----
+    bool any = false;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            A.alpha[k * p + j] = a_cur[k];
+            if (METHOD != 1) A.beta[k * p + j] = b_cur[k];
+            A.delta[k * p + j] = d_cur[k];
+            const float d = a_entry[k] - a_cur[k];
+            A.dalpha[k * p + j] = d;
+            any = any || (d != 0.0f);
+        }
+    }
+    int act_total = 0;
+    if (__syncthreads_or(any ? 1 : 0)) {
+        const unsigned bal = __ballot_sync(0xffffffffu, any);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        const int c = (lane < nw) ? s_cnt[lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int vv = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += vv; }
+        const int warp_off = __shfl_sync(0xffffffffu, incl - c, warp);
+        act_total = __shfl_sync(0xffffffffu, incl, 31);
+        if (any) B.act_idx[warp_off + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
+    }
+    if (tid == 0) P.act_cnt_unit[u] = act_total;
+    __syncthreads();          // shared scratch is reused by this CTA's next unit
+    JW_CT(4);
+#undef JW_CT
+    if (A.counters) {
+        if (my_active) atomicAdd(&A.counters[0], my_active);
+        if (my_rounds) atomicAdd(&A.counters[1], my_rounds);
+    }
+    return ncommit;
+}

@@ -16,6 +16,7 @@
 #pragma once
 #include "jw_common.cuh"
 #include "jw_sweep_kernels.cuh"
+#include "jw_chain_pipe.cuh"
 #include <cooperative_groups.h>
 
 #define JW_FUSED_THREADS 1024
@@ -29,9 +30,16 @@ struct jw_fused_state {
     int* d_done = nullptr;           // 1
     long long* d_sq_acc = nullptr;   // nblocks * T
     int32_t* d_act_cnt_blk = nullptr;// nblocks
+    // pipelined chain (option chain_ctas): units of <= 1024 markers, commit records
+    int n_chain = 0, nunits = 0;
+    int64_t* d_unit_start = nullptr; int32_t* d_unit_blk = nullptr; int32_t* d_blk_unit0 = nullptr;
+    unsigned long long* d_rec = nullptr; size_t rec_bytes = 0;
+    int32_t* d_act_cnt_unit = nullptr;
+    unsigned rec_tag = 0;
+    std::vector<int64_t> unit_start;
     int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1, list_cap = 0, two_lists = 0;
     int64_t total_chunks = 0;
-    size_t smem = 0;
+    size_t smem = 0, smem_pipe = 0;
     bool ready = false;
 };
 
@@ -55,6 +63,7 @@ struct jw_fused_args {
     int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
     int32_t* flags;              // [0] overflow, [2] abort
     long long* dq; long long* mq;
+    jw_pipe_args P;
 };
 
 // ---- re-tiling: marker-major .jgb2 image -> [block][row slice][16-marker chunk][byte group][16] ----
@@ -153,9 +162,12 @@ jw_k_fused(jw_fused_args F) {
     // overlaps the streaming of block k+1 (which needs the updates of blocks <= k-1 only)
     const int lag = F.lag;
     const bool multi = F.world > 1;                      // needs lag = 1
-    const int n_stream = lag ? (int)gridDim.x - 1 - (multi ? 1 : 0) : (int)gridDim.x;
-    const bool is_chain_cta = lag ? (blockIdx.x == gridDim.x - 1) : (blockIdx.x == 0);
-    const bool is_comm_cta = multi && (blockIdx.x == gridDim.x - 2);
+    // pipelined chain: the last n_chain CTAs walk the chain unit by unit (jw_chain_pipe.cuh)
+    const bool pipe = F.P.n_chain > 0;
+    const int n_chain = pipe ? F.P.n_chain : 1;
+    const int n_stream = lag ? (int)gridDim.x - n_chain - (multi ? 1 : 0) : (int)gridDim.x;
+    const bool is_chain_cta = lag ? (blockIdx.x >= gridDim.x - n_chain) : (blockIdx.x == 0);
+    const bool is_comm_cta = multi && (blockIdx.x == gridDim.x - n_chain - 1);
     const bool is_stream_cta = lag ? (blockIdx.x < (unsigned)n_stream) : true;
     const int n_vs_local = F.vs1 - F.vs0;
     const bool single = n_vs_local <= n_stream;
@@ -170,13 +182,75 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
     for (int kk = 0; kk < T; ++kk) sq_keep[kk] = 0;
 
+    if (pipe && is_chain_cta) {
+        // ---- pipelined chain: this CTA owns units cidx, cidx + n_chain, ... ----
+        const int cidx = (int)blockIdx.x - ((int)gridDim.x - n_chain);
+        unsigned long long ct[5] = {0, 0, 0, 0, 0};
+        const bool ctimed = timed && cidx == 0;
+        int my_units = 0;
+        for (int u = cidx; u < F.P.nunits; u += n_chain, ++my_units) {
+            const int k = F.P.unit_blk[u];
+            jw_chain_blk B;
+            B.s = F.C.starts[k]; B.b = (int)(F.C.starts[k + 1] - B.s); B.gram_off = F.C.gram_off[k];
+            B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
+            B.xcount_smem = -1;
+            if (k > 0) { B.xgram = F.gramx + F.gramx_off[k]; B.xstart = F.C.starts[k - 1]; }
+            if (k + 1 < F.nblocks) {
+                B.xgram_next = F.gramx + F.gramx_off[k + 1];
+                B.b_next = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
+            }
+            B.prefetch_s = 0; B.prefetch_b = 0;
+            if (u + n_chain < F.P.nunits) {
+                B.prefetch_s = F.P.unit_start[u + n_chain];
+                B.prefetch_b = (int)(F.P.unit_start[u + n_chain + 1] - B.prefetch_s);
+            }
+            B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0;
+            if (multi) {
+                B.xslots = F.my_slots + (int64_t)(k & 3) * F.ring_stride;
+                B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
+            }
+            B.sq = F.sq_acc + k * T;
+            B.act_idx = F.act_idx_all + F.P.unit_start[u];
+            B.act_cnt = nullptr; B.write_active_list = 1;
+            auto wait_rhs = [&]() -> bool {
+                if (multi) {
+                    if (tid == 0) s_ok = 1;
+                    __syncthreads();
+                    if (tid < F.world) {
+                        const int* fl = F.my_flags + (k & 3) * F.world + tid;
+                        unsigned long long t0 = jw_globaltimer(); unsigned it = 0; int v;
+                        while (true) {
+                            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                            if (v >= F.flag_base + k + 1) break;
+                            if ((++it & 1023u) == 0) {
+                                if (jw_ld_acquire(&F.flags[2]) != 0) { s_ok = 0; break; }
+                                if (jw_globaltimer() - t0 > 20000000000ull) { atomicExch(&F.flags[2], 1); s_ok = 0; break; }
+                            }
+                        }
+                    }
+                } else if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+                __syncthreads();
+                return s_ok != 0;
+            };
+            const int nc = jw_chain_unit<METHOD, T>(F.C, F.P, B, u, wait_rhs,
+                                                    reinterpret_cast<unsigned char*>(jw_smem), ctimed ? ct : nullptr);
+            if (nc < 0) return;
+        }
+        if (ctimed) {
+            // [56..60] preload | wait for the panel's rhs | rhs + record corrections | rounds | epilogue; [61] units
+            for (int i = 0; i < 5; ++i) F.C.counters[56 + i] = ct[i];
+            F.C.counters[61] = (unsigned long long)my_units;
+        }
+        return;
+    }
+
     for (int k = 0; k < F.nblocks; ++k) {
         const int64_t s = F.C.starts[k];
         const int b = (int)(F.C.starts[k + 1] - s);
         if (is_stream_cta) {
         int prev_cnt = 0;
         const int ap = k - 1 - lag;              // block whose updates reach ycorr before this block streams
-        if (ap >= 0) {
+        if (ap >= 0 && !pipe) {
             if (tid == 0) s_ok = jw_spin_ge(F.done, ap + 1, F.flags) ? 1 : 0;
             __syncthreads();
             if (!s_ok) return;
@@ -185,13 +259,76 @@ jw_k_fused(jw_fused_args F) {
         JW_PHASE(0);
         const int nchunks = (b + 15) >> 4;
         const int32_t* prev_idx = F.act_idx_all + (ap >= 0 ? F.C.starts[ap] : 0);
-        const bool rebuild = (k == 0) || prev_cnt > 0 || !single;
+        bool rebuild = (k == 0) || prev_cnt > 0 || !single;
         long long sq_blk[T];
 #pragma unroll
         for (int kk = 0; kk < T; ++kk) sq_blk[kk] = 0;
 
         for (int vs = F.vs0 + blockIdx.x; vs < F.vs1; vs += n_stream) {
             const int64_t row0 = (int64_t)vs * R;
+            float v[T];
+#pragma unroll
+            for (int kk = 0; kk < T; ++kk) v[kk] = 0.0f;
+            const bool from_records = pipe && ap >= 0;
+            if (from_records) {
+                // ---- (1a) pipelined chain: block ap's commits arrive as records; every row of the slice
+                //      replays them in commit order against its own genotypes.  The bytes come from this CTA's
+                //      own tile of block ap (streamed two panels ago, still in L2). ----
+                bool okr = true;
+                int cnt = 0;
+                if (tid < R) {
+                    const int64_t row = row0 + tid;
+                    const bool rv = row < n;
+#pragma unroll
+                    for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
+                    const int sh = (tid & 3) << 1;
+                    const int64_t s_ap = F.C.starts[ap];
+                    const int nch_ap = ((int)(F.C.starts[ap + 1] - s_ap) + 15) >> 4;
+                    const uint8_t* tile_ap = F.tiled +
+                        ((size_t)(F.chunk_off[ap] * F.n_vs + (int64_t)vs * nch_ap) * Gs) * 16 + ((size_t)(tid >> 2) << 4);
+                    unsigned spins = 0; unsigned long long t0 = 0;
+                    for (int us_ = F.P.blk_unit0[ap]; us_ < F.P.blk_unit0[ap + 1] && okr; ++us_) {
+                        const int pbase = (int)(F.P.unit_start[us_] - s_ap);
+                        jw_rec_reader<T> RR;
+                        RR.open(F.P, us_);
+                        while (!RR.finished) {
+                            const int nv = RR.next();
+                            if (nv == 0) {
+                                if (!RR.finished && !jw_spin_ok(spins, t0, F.flags)) { okr = false; break; }
+                                continue;
+                            }
+                            unsigned bytes[JW_REC_BATCH]; float mus[JW_REC_BATCH];
+#pragma unroll
+                            for (int q = 0; q < JW_REC_BATCH; ++q) {
+                                bytes[q] = 0; mus[q] = 0.0f;
+                                if (q < nv && rv) {
+                                    const int pm = pbase + RR.code(q);
+                                    bytes[q] = tile_ap[((size_t)(pm >> 4) * Gs << 4) + (pm & 15)];
+                                    mus[q] = F.C.means[s_ap + pm];
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < JW_REC_BATCH; ++q) {
+                                if (q < nv && rv) {
+                                    const unsigned code = (bytes[q] >> sh) & 3u;
+                                    const float xv = (code == 3u ? mus[q] : (float)code) - mus[q];
+#pragma unroll
+                                    for (int kk = 0; kk < T; ++kk) {
+                                        const float d = RR.d(q, kk);
+                                        if (d != 0.0f) v[kk] = fmaf(d, xv, v[kk]);
+                                    }
+                                }
+                            }
+                            cnt += nv;
+                        }
+                    }
+                    if (tid == 0) s_ok = cnt;
+                }
+                if (__syncthreads_or(okr ? 0 : 1)) return;
+                prev_cnt = s_ok;
+                rebuild = (k == 0) || prev_cnt > 0 || !single;
+                JW_PHASE(0);
+            }
             if (rebuild) {
                 // ---- (1) fused axpy of the previous block + fixed-point image of the slice ----
                 long long qs[T];
@@ -200,21 +337,24 @@ jw_k_fused(jw_fused_args F) {
                 if (tid < R) {
                     const int64_t row = row0 + tid;
                     const bool rv = row < n;
-                    float v[T];
+                    if (!from_records) {
 #pragma unroll
-                    for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
+                        for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
+                    }
                     if (rv && prev_cnt > 0) {
-                        const int sh = (int)(row & 3) << 1;
-                        const int64_t byte = row >> 2;
-                        for (int a = 0; a < prev_cnt; ++a) {
-                            const int64_t j = __ldcg(prev_idx + a);
-                            const unsigned code = (F.packed[j * F.stride_d + byte] >> sh) & 3u;
-                            const float mu = F.C.means[j];
-                            const float xv = (code == 3u ? mu : (float)code) - mu;
+                        if (!from_records) {
+                            const int sh = (int)(row & 3) << 1;
+                            const int64_t byte = row >> 2;
+                            for (int a = 0; a < prev_cnt; ++a) {
+                                const int64_t j = __ldcg(prev_idx + a);
+                                const unsigned code = (F.packed[j * F.stride_d + byte] >> sh) & 3u;
+                                const float mu = F.C.means[j];
+                                const float xv = (code == 3u ? mu : (float)code) - mu;
 #pragma unroll
-                            for (int kk = 0; kk < T; ++kk) {
-                                const float d = __ldcg(&F.C.dalpha[kk * p + j]);
-                                if (d != 0.0f) v[kk] = fmaf(d, xv, v[kk]);
+                                for (int kk = 0; kk < T; ++kk) {
+                                    const float d = __ldcg(&F.C.dalpha[kk * p + j]);
+                                    if (d != 0.0f) v[kk] = fmaf(d, xv, v[kk]);
+                                }
                             }
                         }
 #pragma unroll
@@ -490,7 +630,8 @@ jw_k_apply_last(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n,
 static void jw_fused_free(jwas_handle* h) {
     jw_fused_state* f = (jw_fused_state*)h->fused;
     if (!f) return;
-    void* ptrs[] = {f->d_tiled, f->d_chunk_off, f->d_chunk_block, f->d_arrive, f->d_done, f->d_sq_acc, f->d_act_cnt_blk};
+    void* ptrs[] = {f->d_tiled, f->d_chunk_off, f->d_chunk_block, f->d_arrive, f->d_done, f->d_sq_acc, f->d_act_cnt_blk,
+                    f->d_unit_start, f->d_unit_blk, f->d_blk_unit0, f->d_rec, f->d_act_cnt_unit};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete f;
     h->fused = nullptr;
@@ -509,8 +650,11 @@ static int jw_fused_prepare(jwas_handle* h) {
     h->fused = f;
     const int64_t nbytes = (h->n + 3) / 4;
     f->W = (h->t == 2 || h->has_missing) ? 2 : 1;
-    // one SM is kept for the chain (lag = 1); a second one for the NVLink push when rows are sharded
-    const int64_t streamers = (int64_t)h->world * std::max(1, h->sm_count - (h->world > 1 ? 2 : 1));
+    // SMs kept for the chain (lag = 1): one, or chain_ctas of them for the pipelined chain; one more for the
+    // NVLink push when rows are sharded
+    f->n_chain = h->opt_chain_ctas > 0 ? (int)std::min<int64_t>(h->opt_chain_ctas, std::max(1, h->sm_count / 4)) : 0;
+    const int chain_sms = std::max(1, f->n_chain);
+    const int64_t streamers = (int64_t)h->world * std::max(1, h->sm_count - chain_sms - (h->world > 1 ? 1 : 0));
     int64_t gs = (nbytes + streamers - 1) / streamers;
     if (h->world > 1) gs = (gs + 3) / 4 * 4;                 // shard boundaries on 16-individual words
     if (gs > JW_FUSED_MAX_GS) gs = JW_FUSED_MAX_GS;
@@ -525,6 +669,8 @@ static int jw_fused_prepare(jwas_handle* h) {
     f->two_lists = (base_smem + jw_chain_smem_bytes(h->t, (int)h->maxb, 2) <= 227 * 1024) ? 1 : 0;
     f->list_cap = f->two_lists ? (int)h->maxb : (h->maxb > JW_MAX_BLOCK ? (int)h->maxb : 0);
     f->smem = base_smem + jw_chain_smem_bytes(h->t, f->list_cap, f->two_lists ? 2 : 1);
+    // pipelined chain CTAs never stream: their scratch (no commit lists) overlays the tables
+    f->smem_pipe = std::max(base_smem, jw_chain_smem_bytes(h->t, 0, 1));
     if (f->smem > 227 * 1024) { delete f; h->fused = nullptr; return 0; }   // engine 0 only for this shape
     std::vector<int64_t> coff(h->nblocks + 1, 0);
     std::vector<int32_t> cblk;
@@ -550,6 +696,30 @@ static int jw_fused_prepare(jwas_handle* h) {
     h->launches += 1;
     JW_CUDA(cudaGetLastError());
     JW_CUDA(cudaStreamSynchronize(h->stream));
+    if (f->n_chain > 0) {
+        // chain units: every block cut into pieces of <= JW_CHAIN_SB markers
+        std::vector<int32_t> ublk, bu0(h->nblocks + 1, 0);
+        f->unit_start.clear();
+        for (int64_t k = 0; k < h->nblocks; ++k) {
+            bu0[k] = (int32_t)ublk.size();
+            for (int64_t m = h->starts[k]; m < h->starts[k + 1]; m += JW_CHAIN_SB) { f->unit_start.push_back(m); ublk.push_back((int32_t)k); }
+        }
+        bu0[h->nblocks] = (int32_t)ublk.size();
+        f->nunits = (int)ublk.size();
+        f->unit_start.push_back(h->p);
+        f->rec_bytes = (size_t)f->nunits * JW_REC_STRIDE * h->t * sizeof(unsigned long long);
+        JW_CUDA(cudaMalloc((void**)&f->d_unit_start, f->unit_start.size() * sizeof(int64_t)));
+        JW_CUDA(cudaMalloc((void**)&f->d_unit_blk, ublk.size() * sizeof(int32_t)));
+        JW_CUDA(cudaMalloc((void**)&f->d_blk_unit0, bu0.size() * sizeof(int32_t)));
+        JW_CUDA(cudaMalloc((void**)&f->d_rec, f->rec_bytes));
+        JW_CUDA(cudaMalloc((void**)&f->d_act_cnt_unit, f->nunits * sizeof(int32_t)));
+        JW_CUDA(cudaMemcpyAsync(f->d_unit_start, f->unit_start.data(), f->unit_start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        JW_CUDA(cudaMemcpyAsync(f->d_unit_blk, ublk.data(), ublk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        JW_CUDA(cudaMemcpyAsync(f->d_blk_unit0, bu0.data(), bu0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        JW_CUDA(cudaMemsetAsync(f->d_rec, 0, f->rec_bytes, h->stream));          // tag 0 = never written
+        JW_CUDA(cudaStreamSynchronize(h->stream));
+        f->rec_tag = 0;
+    }
     f->ready = true;
     if (h->world > 1) {
         // contiguous byte-group slices per rank; individuals follow
@@ -566,14 +736,16 @@ static int jw_fused_prepare(jwas_handle* h) {
 template <int METHOD, int T, int W>
 static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
     auto kern = jw_k_fused<METHOD, T, W>;
-    JW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
+    const size_t smem = F.P.n_chain > 0 ? f->smem_pipe : f->smem;
+    JW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    JW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JW_FUSED_THREADS, f->smem));
+    JW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JW_FUSED_THREADS, smem));
     JW_REQUIRE(occ >= 1, "fused sweep kernel does not fit on an SM");
     void* args[] = {(void*)&F};
-    const int grid = F.world > 1 ? std::min<int>(h->sm_count, (F.vs1 - F.vs0) + 2)
-                                 : (F.lag ? std::min<int>(h->sm_count, f->n_vs + 1) : f->n_cta);
-    JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(JW_FUSED_THREADS), args, f->smem, h->stream));
+    const int chain_sms = std::max(1, F.P.n_chain);
+    const int grid = F.world > 1 ? std::min<int>(h->sm_count, (F.vs1 - F.vs0) + 1 + chain_sms)
+                                 : (F.lag ? std::min<int>(h->sm_count, f->n_vs + chain_sms) : f->n_cta);
+    JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(JW_FUSED_THREADS), args, smem, h->stream));
     h->launches += 1;
     return 0;
 }
@@ -614,6 +786,19 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.arrive = f->d_arrive; F.done = f->d_done; F.sq_acc = f->d_sq_acc;
     F.act_cnt_blk = f->d_act_cnt_blk; F.act_idx_all = h->d_act_idx;
     F.flags = h->d_flags; F.dq = h->d_dq; F.mq = h->d_mq;
+    memset(&F.P, 0, sizeof(F.P));
+    const bool pipe = F.lag && f->n_chain > 0;
+    if (pipe) {
+        f->rec_tag += 1;
+        if (f->rec_tag > 0xffffu) {              // tags wrapped: forget every old record
+            JW_CUDA(cudaMemsetAsync(f->d_rec, 0, f->rec_bytes, h->stream));
+            f->rec_tag = 1;
+        }
+        F.P.n_chain = f->n_chain; F.P.nunits = f->nunits;
+        F.P.unit_start = f->d_unit_start; F.P.unit_blk = f->d_unit_blk; F.P.blk_unit0 = f->d_blk_unit0;
+        F.P.rec = f->d_rec; F.P.tag = f->rec_tag; F.P.act_cnt_unit = f->d_act_cnt_unit; F.P.flags = h->d_flags;
+        JW_CUDA(cudaMemsetAsync(f->d_act_cnt_unit, 0, f->nunits * sizeof(int32_t), h->stream));
+    }
     if (h->opt_profile) {
         cudaEvent_t a, b;
         JW_CUDA(cudaEventCreate(&a)); JW_CUDA(cudaEventCreate(&b));
@@ -640,15 +825,24 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     if (h->opt_profile) JW_CUDA(cudaEventRecord(h->prof_events.back(), h->stream));
     // the axpy of the last block (and of the one before it under the lagged schedule)
     for (int64_t blk = std::max<int64_t>(0, h->nblocks - 1 - F.lag); blk < h->nblocks; ++blk) {
-        unsigned g = (unsigned)std::max<int64_t>(1, (h->row_end - h->row_begin + 255) / 256);
-        if (t == 1)
-            jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
-                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr, h->row_begin, h->row_end);
-        else
-            jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
-                h->d_act_idx + h->starts[blk], f->d_act_cnt_blk + blk, h->d_ycorr, h->row_begin, h->row_end);
-        h->launches += 1;
-        JW_CUDA(cudaGetLastError());
+        // one ordered active list per block, or per chain unit of the block (pipelined chain)
+        std::vector<std::pair<int64_t, const int32_t*>> lists;
+        if (pipe) {
+            for (int u = 0; u < f->nunits; ++u)
+                if (f->unit_start[u] >= h->starts[blk] && f->unit_start[u] < h->starts[blk + 1])
+                    lists.push_back({f->unit_start[u], f->d_act_cnt_unit + u});
+        } else lists.push_back({h->starts[blk], f->d_act_cnt_blk + blk});
+        for (auto& L : lists) {
+            unsigned g = (unsigned)std::max<int64_t>(1, (h->row_end - h->row_begin + 255) / 256);
+            if (t == 1)
+                jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+                    h->d_act_idx + L.first, L.second, h->d_ycorr, h->row_begin, h->row_end);
+            else
+                jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+                    h->d_act_idx + L.first, L.second, h->d_ycorr, h->row_begin, h->row_end);
+            h->launches += 1;
+            JW_CUDA(cudaGetLastError());
+        }
     }
     // abort flag -> error
     int32_t hf[4];

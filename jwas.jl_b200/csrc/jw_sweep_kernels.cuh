@@ -238,6 +238,289 @@ jw_k_prep_abc(jw_chain_args A, double* __restrict__ prep, float* __restrict__ be
     beta0[j] = (float)(z * jw_sqrt(ve));
 }
 
+// ------------------------------------------------------------------------------------------
+// One marker's single-site conditional, shared by every chain driver (jw_chain_block and the
+// pipelined jw_chain_unit): load_constants() gathers everything that does not depend on the rhs,
+// load_draws() the repetition's uniform / normal, eval() turns (rhs, current state) into the new
+// state and says whether the marker's effect changes (the only case that touches the rhs).
+//   METHOD 0 BayesABC (BayesABC.jl:24-58)      1 BayesR (BayesR.jl:58-95)
+//          2 multi-trait sampler I (MTBayesABC.jl:78-125)   3 sampler II (MTBayesABC.jl:163-208)
+//          4 megaBayesABC (BayesABC.jl:1-7)
+// ------------------------------------------------------------------------------------------
+template <int METHOD, int T>
+struct jw_marker_eval {
+    double x, invVarRes;
+    double Ginv[T * T];
+    // METHOD 0: draw-independent constants (from jw_k_prep_abc when available)
+    double c_invLhs, c_L, c_lpc, c_lp0, c_ve;
+    bool use_prep;
+    double u0, zs1_0; float beta0_0;
+    // METHOD 1: class terms that do not depend on the rhs (BayesR.jl:64-72); exactly JW_R_CLASSES = 4
+    // mixture classes (BAYESR_GAMMA, JWAS.jl:12), loops fully unrolled so the terms live in registers
+    double rc_invLhs[JW_R_CLASSES], rc_base[JW_R_CLASSES], rc_lpi[JW_R_CLASSES];
+    // METHOD 2: logs of the per-marker constants (MTBayesABC.jl:88-105)
+    double mt_lG[T], mt_lC[T], mt_lPi[1 << T];
+    // draws of the current repetition (u[] holds the log-odds threshold except for METHOD 1 / 3)
+    double u[T], z[T];
+    double zs1; float beta0;                   // METHOD 0: z*sqrt(invLhs), float(z*sqrt(ve))
+
+    __device__ __forceinline__ void load_constants(const jw_chain_args& A, const int64_t j) {
+        const int64_t p = A.p;
+        x = (double)A.xpx[j];
+        if (METHOD == 2 || METHOD == 3) {
+            if (A.per_marker_G) jw_inv_spd_fixed(A.Gmat + j * T * T, T, Ginv);
+            else for (int q = 0; q < T * T; ++q) Ginv[q] = A.Ginv[q];
+        }
+        invVarRes = (METHOD == 2 || METHOD == 3 || METHOD == 4) ? 0.0 : 1.0 / A.vare;
+        c_invLhs = 0; c_L = 0; c_lpc = 0; c_lp0 = 0; c_ve = 1;
+        use_prep = (METHOD == 0) && (A.prep != nullptr);
+        u0 = 0.0; zs1_0 = 0.0; beta0_0 = 0.0f;
+        if (METHOD == 0) {
+            if (use_prep) {
+                c_invLhs = A.prep[2 * p + j]; c_L = A.prep[3 * p + j];
+                c_lpc = A.prep[4 * p + j]; c_lp0 = A.prep[5 * p + j];
+                u0 = A.prep[j]; zs1_0 = A.prep[p + j]; beta0_0 = A.prep_beta0[j];
+            } else {
+                c_ve = A.ve[j];
+                double pi = A.pi[j];
+                double c_lhs = x * invVarRes + 1.0 / c_ve;
+                c_invLhs = 1.0 / c_lhs;
+                c_L = jw_log(c_lhs) + jw_log(c_ve);
+                c_lpc = jw_log(1.0 - pi);
+                c_lp0 = jw_log(pi);
+            }
+        }
+        if (METHOD == 1) {
+            rc_invLhs[0] = 0.0; rc_base[0] = 0.0;
+            if (A.prep_rm != nullptr && A.host_logs) {
+                const int K1 = JW_R_CLASSES - 1;
+                rc_lpi[0] = A.lpi[0];
+#pragma unroll
+                for (int c = 1; c < JW_R_CLASSES; ++c) {
+                    rc_invLhs[c] = A.prep_rm[(int64_t)(c - 1) * p + j];
+                    rc_base[c] = A.prep_rm[(int64_t)(K1 + c - 1) * p + j];
+                    rc_lpi[c] = A.lpi[c];
+                }
+            } else {
+                const double* pij = A.per_marker_pi ? A.pi + j * JW_R_CLASSES : A.pi;
+                rc_lpi[0] = jw_log(pij[0]);
+#pragma unroll
+                for (int c = 1; c < JW_R_CLASSES; ++c) {
+                    double varEffect = A.gamma[c] * A.sigmaSq;
+                    double lhs = x * invVarRes + 1.0 / varEffect;
+                    rc_invLhs[c] = 1.0 / lhs;
+                    rc_base[c] = jw_log(rc_invLhs[c]) - jw_log(varEffect);
+                    rc_lpi[c] = jw_log(pij[c]);
+                }
+            }
+        }
+        if (METHOD == 2) {
+            if (A.prep_rm != nullptr && A.host_logs) {
+#pragma unroll
+                for (int k = 0; k < T; ++k) { mt_lG[k] = A.mt_lG[k]; mt_lC[k] = A.prep_rm[(int64_t)k * p + j]; }
+#pragma unroll
+                for (int q = 0; q < (1 << T); ++q) mt_lPi[q] = A.mt_lPi[q];
+            } else {
+                const double* Pi = A.per_marker_pi ? A.bigPi + j * (1 << T) : A.bigPi;
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    mt_lG[k] = jw_log(Ginv[k * T + k]);
+                    mt_lC[k] = jw_log(Ginv[k * T + k] + A.Rinv[k * T + k] * x);
+                }
+#pragma unroll
+                for (int q = 0; q < (1 << T); ++q) mt_lPi[q] = jw_log(Pi[q]);
+            }
+        }
+    }
+
+    __device__ __forceinline__ void load_draws(const jw_chain_args& A, const int64_t j, const int rep) {
+        const int64_t p = A.p;
+        zs1 = 0.0; beta0 = 0.0f;
+        if (METHOD == 0 && use_prep && rep == 0) {
+            u[0] = u0; zs1 = zs1_0; beta0 = beta0_0; z[0] = 0.0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                if (rep == 0 && A.draws_u != nullptr) {
+                    u[k] = A.draws_u[k * p + j]; z[k] = A.draws_z[k * p + j];
+                } else {
+                    u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep);
+                    if (METHOD != 1 && METHOD != 3) u[k] = jw_logit_threshold(u[k]);
+                }
+            }
+            if (METHOD == 0) {
+                if (use_prep) c_ve = A.ve[j];
+                zs1 = z[0] * jw_sqrt(c_invLhs); beta0 = (float)(z[0] * jw_sqrt(c_ve));
+            }
+        }
+    }
+
+    // returns true when the marker's effect changes (a_cur != newA for some trait)
+    __device__ __forceinline__ bool eval(const jw_chain_args& A, const double* r, const float* a_cur,
+                                         const float* b_cur, const int* d_cur,
+                                         float* newA, float* newB, int* newD) const {
+        bool active = false;
+        if (METHOD == 0) {
+            double aold = (double)a_cur[0];
+            double rhs = (r[0] + x * aold) * invVarRes;
+            double gHat = rhs * c_invLhs;
+            double logDelta1 = -0.5 * (c_L - gHat * rhs) + c_lpc;
+            if (c_lp0 - logDelta1 < u[0]) {           // u[] holds the log-odds threshold of the draw
+                newD[0] = 1;
+                newA[0] = (float)(gHat + zs1);
+                newB[0] = newA[0];
+            } else {
+                newD[0] = 0;
+                newB[0] = beta0;
+                newA[0] = 0.0f;
+            }
+            active = (a_cur[0] - newA[0]) != 0.0f;
+        } else if (METHOD == 1) {
+            double aold = (double)a_cur[0];
+            double rhs = (r[0] + x * aold) * invVarRes;
+            double lp[JW_R_CLASSES], ex[JW_R_CLASSES];
+            lp[0] = rc_lpi[0];
+#pragma unroll
+            for (int c = 1; c < JW_R_CLASSES; ++c) {
+                double betaHat = rc_invLhs[c] * rhs;
+                lp[c] = 0.5 * (rc_base[c] + betaHat * rhs) + rc_lpi[c];
+            }
+            double mx = lp[0];
+#pragma unroll
+            for (int c = 1; c < JW_R_CLASSES; ++c) if (lp[c] > mx) mx = lp[c];
+            double se = 0.0;
+#pragma unroll
+            for (int c = 0; c < JW_R_CLASSES; ++c) { ex[c] = jw_exp(lp[c] - mx); se += ex[c]; }
+            // Categorical(exp(lp - logsumexp)) (BayesR.jl:74-79) drawn on the unnormalised weights:
+            // first class whose cumulative weight exceeds u * sum
+            const double target = u[0] * se;
+            int cls = 0; double cp = ex[0];
+#pragma unroll
+            for (int c = 1; c < JW_R_CLASSES; ++c) {
+                if (cls == c - 1 && cp <= target) { cls = c; cp += ex[c]; }
+            }
+            newD[0] = cls + 1;
+            newA[0] = 0.0f;
+            if (cls > 0) {
+                const double il = cls == 1 ? rc_invLhs[1] : (cls == 2 ? rc_invLhs[2] : rc_invLhs[3]);
+                double betaHat = il * rhs;
+                newA[0] = (float)(betaHat + z[0] * jw_sqrt(il));
+            }
+            newB[0] = 0.0f;
+            active = (a_cur[0] - newA[0]) != 0.0f;
+        } else if (METHOD == 4) {
+            // megaBayesABC! (BayesABC.jl:1-7): T independent BayesABC steps; trait k uses
+            // vare = 1/Rinv[k] (diagonal stored), varEffect = Ginv[k] (variance itself), pi = lpi[k]
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const double ivr = A.Rinv[k], vek = A.Ginv[k], pik = A.lpi[k];
+                const double aold = (double)a_cur[k];
+                const double rhs = (r[k] + x * aold) * ivr;
+                const double lhs = x * ivr + 1.0 / vek;
+                const double invLhs = 1.0 / lhs;
+                const double gHat = rhs * invLhs;
+                const double logDelta1 = -0.5 * (jw_log(lhs) + jw_log(vek) - gHat * rhs) + jw_log(1.0 - pik);
+                const double logDelta0 = jw_log(pik);
+                if (logDelta0 - logDelta1 < u[k]) {
+                    newD[k] = 1;
+                    newA[k] = (float)(gHat + z[k] * jw_sqrt(invLhs));
+                    newB[k] = newA[k];
+                } else {
+                    newD[k] = 0;
+                    newB[k] = (float)(z[k] * jw_sqrt(vek));
+                    newA[k] = 0.0f;
+                }
+                if ((a_cur[k] - newA[k]) != 0.0f) active = true;
+            }
+        } else if (METHOD == 3) {
+            // MTBayesABC.jl:163-208 (sampler II, joint states), T == 2; twin of the oracle's MT2 step
+            const double w0 = r[0] + x * (double)a_cur[0];
+            const double w1 = r[T - 1] + x * (double)a_cur[T - 1];
+            const double z0 = z[0], z1 = z[T - 1], uu = u[0];
+            double ld[4], bc0[4], bc1[4];
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                const double d0 = (double)(st & 1), d1 = (double)((st >> 1) & 1);
+                const double l00 = d0 * A.Rinv[0] * x + Ginv[0];
+                const double l01 = (d0 * d1) * A.Rinv[1] * x + Ginv[1];
+                const double l11 = d1 * A.Rinv[3] * x + Ginv[T * T - 1];
+                const double rhs0 = d0 * (A.Rinv[0] * w0 + A.Rinv[2] * w1);
+                const double rhs1 = d1 * (A.Rinv[1] * w0 + A.Rinv[3] * w1);
+                const double det = l00 * l11 - l01 * l01;
+                const double i00 = l11 / det, i11 = l00 / det, i01 = -l01 / det;
+                const double g0 = i00 * rhs0 + i01 * rhs1, g1 = i01 * rhs0 + i11 * rhs1;
+                ld[st] = -0.5 * (jw_log(det) - (rhs0 * g0 + rhs1 * g1)) + jw_log(A.bigPi[st]);
+                const double L00 = jw_sqrt(i00), L10 = i01 / L00, L11 = jw_sqrt(i11 - L10 * L10);
+                bc0[st] = g0 + L00 * z0;
+                bc1[st] = g1 + L10 * z0 + L11 * z1;
+            }
+            double mx = ld[0];
+#pragma unroll
+            for (int st = 1; st < 4; ++st) if (ld[st] > mx) mx = ld[st];
+            double ex[4], se = 0.0;
+#pragma unroll
+            for (int st = 0; st < 4; ++st) { ex[st] = jw_exp(ld[st] - mx); se += ex[st]; }
+            const double target = uu * se;
+            int lab = 0; double cp = ex[0];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) { if (lab == c - 1 && cp <= target) { lab = c; cp += ex[c]; } }
+            const float b0 = (float)(lab == 0 ? bc0[0] : lab == 1 ? bc0[1] : lab == 2 ? bc0[2] : bc0[3]);
+            const float b1 = (float)(lab == 0 ? bc1[0] : lab == 1 ? bc1[1] : lab == 2 ? bc1[2] : bc1[3]);
+            newB[0] = b0; newB[T - 1] = b1;
+            newD[0] = lab & 1; newD[T - 1] = (lab >> 1) & 1;
+            newA[0] = newD[0] ? b0 : 0.0f; newA[T - 1] = newD[T - 1] ? b1 : 0.0f;
+            active = ((a_cur[0] - newA[0]) != 0.0f) || ((a_cur[T - 1] - newA[T - 1]) != 0.0f);
+        } else {
+            // MTBayesABC.jl:78-125
+            double bb[T], olda[T], w[T]; int dd[T];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                bb[k] = (double)b_cur[k]; olda[k] = (double)a_cur[k]; dd[k] = d_cur[k] != 0;
+                w[k] = r[k] + x * olda[k];
+            }
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                double Ginv11 = Ginv[k * T + k];
+                double C11 = Ginv11 + A.Rinv[k * T + k] * x;
+                double rhs0 = 0.0, c12b = 0.0;
+#pragma unroll
+                for (int q = 0; q < T; ++q) if (q != k) {
+                    double Ginv12 = Ginv[k * T + q];
+                    double C12 = Ginv12 + x * (double)dd[q] * A.Rinv[k * T + q];
+                    rhs0 = rhs0 - Ginv12 * bb[q];
+                    c12b = c12b + C12 * bb[q];
+                }
+                double invLhs0 = 1.0 / Ginv11, gHat0 = rhs0 * invLhs0;
+                double invLhs1 = 1.0 / C11;
+                double wr = 0.0;
+#pragma unroll
+                for (int q = 0; q < T; ++q) wr = wr + w[q] * A.Rinv[q * T + k];
+                double gHat1 = (wr - c12b) * invLhs1;
+                int s0 = 0, s1 = 0;
+#pragma unroll
+                for (int q = 0; q < T; ++q) {
+                    int dqq = (q == k) ? 0 : dd[q];
+                    s0 |= dqq << q; s1 |= ((q == k) ? 1 : dqq) << q;
+                }
+                double logDelta0 = -0.5 * (mt_lG[k] - gHat0 * gHat0 * Ginv11) + mt_lPi[s0];
+                double logDelta1 = -0.5 * (mt_lC[k] - gHat1 * gHat1 * C11) + mt_lPi[s1];
+                if (logDelta0 - logDelta1 < u[k]) {
+                    dd[k] = 1;
+                    newA[k] = (float)(gHat1 + z[k] * jw_sqrt(invLhs1));
+                    bb[k] = (double)newA[k];
+                } else {
+                    dd[k] = 0;
+                    bb[k] = (double)(float)(gHat0 + z[k] * jw_sqrt(invLhs0));
+                    newA[k] = 0.0f;
+                }
+                newB[k] = (float)bb[k]; newD[k] = dd[k];
+                if ((a_cur[k] - newA[k]) != 0.0f) active = true;
+            }
+        }
+        return active;
+    }
+};
+
 struct jw_no_wait { __device__ __forceinline__ bool operator()() const { return true; } };
 
 // what changes from block to block (kept small so the big jw_chain_args can stay in parameter space)
@@ -346,7 +629,6 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
     const int m = sb * SB + tid;           // marker position inside the panel
     const bool valid = m < b;
     const int64_t j = s + (valid ? m : 0);
-    const double x = (double)A.xpx[j];
 
     // state at block entry
     double r[T];
@@ -359,32 +641,9 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         b_cur[k] = (METHOD == 1) ? 0.0f : A.beta[k * p + j];
         d_cur[k] = A.delta[k * p + j];
     }
-    double Ginv[T * T];
-    if (METHOD == 2 || METHOD == 3) {
-        if (A.per_marker_G) jw_inv_spd_fixed(A.Gmat + j * T * T, T, Ginv);
-        else for (int q = 0; q < T * T; ++q) Ginv[q] = A.Ginv[q];
-    }
-    const double invVarRes = (METHOD == 2 || METHOD == 3 || METHOD == 4) ? 0.0 : 1.0 / A.vare;
-
-    // draw-independent constants
-    double c_invLhs = 0, c_L = 0, c_lpc = 0, c_lp0 = 0, c_ve = 1;
-    const bool use_prep = (METHOD == 0) && (A.prep != nullptr);
-    double u0 = 0.0, zs1_0 = 0.0; float beta0_0 = 0.0f;
-    if (METHOD == 0) {
-        if (use_prep) {
-            c_invLhs = A.prep[2 * p + j]; c_L = A.prep[3 * p + j];
-            c_lpc = A.prep[4 * p + j]; c_lp0 = A.prep[5 * p + j];
-            u0 = A.prep[j]; zs1_0 = A.prep[p + j]; beta0_0 = A.prep_beta0[j];
-        } else {
-            c_ve = A.ve[j];
-            double pi = A.pi[j];
-            double c_lhs = x * invVarRes + 1.0 / c_ve;
-            c_invLhs = 1.0 / c_lhs;
-            c_L = jw_log(c_lhs) + jw_log(c_ve);
-            c_lpc = jw_log(1.0 - pi);
-            c_lp0 = jw_log(pi);
-        }
-    }
+    jw_marker_eval<METHOD, T> E;
+    E.load_constants(A, j);
+    const double x = E.x; (void)x;
     // markers that already carry an effect are certain to need their Gram row: start pulling it
     // towards L2 now (one bulk prefetch per row)
     bool row_requested = false;
@@ -479,76 +738,11 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         }
     }
 
-    // BayesR: class terms that do not depend on the rhs (BayesR.jl:64-72)
-    // (exactly JW_R_CLASSES = 4 mixture classes, as BAYESR_GAMMA in JWAS.jl:12; loops fully unrolled so
-    //  the per-class terms live in registers)
-    double rc_invLhs[JW_R_CLASSES], rc_base[JW_R_CLASSES], rc_lpi[JW_R_CLASSES];
-    if (METHOD == 1) {
-        rc_invLhs[0] = 0.0; rc_base[0] = 0.0;
-        if (A.prep_rm != nullptr && A.host_logs) {
-            const int K1 = JW_R_CLASSES - 1;
-            rc_lpi[0] = A.lpi[0];
-#pragma unroll
-            for (int c = 1; c < JW_R_CLASSES; ++c) {
-                rc_invLhs[c] = A.prep_rm[(int64_t)(c - 1) * p + j];
-                rc_base[c] = A.prep_rm[(int64_t)(K1 + c - 1) * p + j];
-                rc_lpi[c] = A.lpi[c];
-            }
-        } else {
-            const double* pij = A.per_marker_pi ? A.pi + j * JW_R_CLASSES : A.pi;
-            rc_lpi[0] = jw_log(pij[0]);
-#pragma unroll
-            for (int c = 1; c < JW_R_CLASSES; ++c) {
-                double varEffect = A.gamma[c] * A.sigmaSq;
-                double lhs = x * invVarRes + 1.0 / varEffect;
-                rc_invLhs[c] = 1.0 / lhs;
-                rc_base[c] = jw_log(rc_invLhs[c]) - jw_log(varEffect);
-                rc_lpi[c] = jw_log(pij[c]);
-            }
-        }
-    }
-    // multi-trait sampler I: logs of the per-marker constants (MTBayesABC.jl:88-105)
-    double mt_lG[T], mt_lC[T], mt_lPi[1 << T];
-    if (METHOD == 2) {
-        if (A.prep_rm != nullptr && A.host_logs) {
-#pragma unroll
-            for (int k = 0; k < T; ++k) { mt_lG[k] = A.mt_lG[k]; mt_lC[k] = A.prep_rm[(int64_t)k * p + j]; }
-#pragma unroll
-            for (int q = 0; q < (1 << T); ++q) mt_lPi[q] = A.mt_lPi[q];
-        } else {
-            const double* Pi = A.per_marker_pi ? A.bigPi + j * (1 << T) : A.bigPi;
-#pragma unroll
-            for (int k = 0; k < T; ++k) {
-                mt_lG[k] = jw_log(Ginv[k * T + k]);
-                mt_lC[k] = jw_log(Ginv[k * T + k] + A.Rinv[k * T + k] * x);
-            }
-#pragma unroll
-            for (int q = 0; q < (1 << T); ++q) mt_lPi[q] = jw_log(Pi[q]);
-        }
-    }
     JW_CT(2);
     const int nreps = A.nreps_mode ? b : 1;
 
     for (int rep = 0; rep < nreps; ++rep) {
-        double u[T], z[T];
-        double zs1 = 0.0; float beta0 = 0.0f;        // METHOD 0: z*sqrt(invLhs), float(z*sqrt(ve))
-        if (METHOD == 0 && use_prep && rep == 0) {
-            u[0] = u0; zs1 = zs1_0; beta0 = beta0_0; z[0] = 0.0;
-        } else {
-#pragma unroll
-            for (int k = 0; k < T; ++k) {
-                if (rep == 0 && A.draws_u != nullptr) {
-                    u[k] = A.draws_u[k * p + j]; z[k] = A.draws_z[k * p + j];
-                } else {
-                    u[k] = jw_get_u(A, j, k, rep); z[k] = jw_get_z(A, j, k, rep);
-                    if (METHOD != 1 && METHOD != 3) u[k] = jw_logit_threshold(u[k]);
-                }
-            }
-            if (METHOD == 0) {
-                if (use_prep) c_ve = A.ve[j];
-                zs1 = z[0] * jw_sqrt(c_invLhs); beta0 = (float)(z[0] * jw_sqrt(c_ve));
-            }
-        }
+        E.load_draws(A, j, rep);
         int pos = 0;                   // position inside the sub-block
         while (true) {
             // ---- evaluate this marker against the current rhs ----
@@ -556,163 +750,7 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
             float newA[T], newB[T]; int newD[T];
             bool active = false;
             if (pending) {
-                if (METHOD == 0) {
-                    double aold = (double)a_cur[0];
-                    double rhs = (r[0] + x * aold) * invVarRes;
-                    double gHat = rhs * c_invLhs;
-                    double logDelta1 = -0.5 * (c_L - gHat * rhs) + c_lpc;
-                    if (c_lp0 - logDelta1 < u[0]) {           // u[] holds the log-odds threshold of the draw
-                        newD[0] = 1;
-                        newA[0] = (float)(gHat + zs1);
-                        newB[0] = newA[0];
-                    } else {
-                        newD[0] = 0;
-                        newB[0] = beta0;
-                        newA[0] = 0.0f;
-                    }
-                    active = (a_cur[0] - newA[0]) != 0.0f;
-                } else if (METHOD == 1) {
-                    double aold = (double)a_cur[0];
-                    double rhs = (r[0] + x * aold) * invVarRes;
-                    double lp[JW_R_CLASSES], ex[JW_R_CLASSES];
-                    lp[0] = rc_lpi[0];
-#pragma unroll
-                    for (int c = 1; c < JW_R_CLASSES; ++c) {
-                        double betaHat = rc_invLhs[c] * rhs;
-                        lp[c] = 0.5 * (rc_base[c] + betaHat * rhs) + rc_lpi[c];
-                    }
-                    double mx = lp[0];
-#pragma unroll
-                    for (int c = 1; c < JW_R_CLASSES; ++c) if (lp[c] > mx) mx = lp[c];
-                    double se = 0.0;
-#pragma unroll
-                    for (int c = 0; c < JW_R_CLASSES; ++c) { ex[c] = jw_exp(lp[c] - mx); se += ex[c]; }
-                    // Categorical(exp(lp - logsumexp)) (BayesR.jl:74-79) drawn on the unnormalised weights:
-                    // first class whose cumulative weight exceeds u * sum
-                    const double target = u[0] * se;
-                    int cls = 0; double cp = ex[0];
-#pragma unroll
-                    for (int c = 1; c < JW_R_CLASSES; ++c) {
-                        if (cls == c - 1 && cp <= target) { cls = c; cp += ex[c]; }
-                    }
-                    newD[0] = cls + 1;
-                    newA[0] = 0.0f;
-                    if (cls > 0) {
-                        const double il = cls == 1 ? rc_invLhs[1] : (cls == 2 ? rc_invLhs[2] : rc_invLhs[3]);
-                        double betaHat = il * rhs;
-                        newA[0] = (float)(betaHat + z[0] * jw_sqrt(il));
-                    }
-                    newB[0] = 0.0f;
-                    active = (a_cur[0] - newA[0]) != 0.0f;
-                } else if (METHOD == 4) {
-                    // megaBayesABC! (BayesABC.jl:1-7): T independent BayesABC steps; trait k uses
-                    // vare = 1/Rinv[k] (diagonal stored), varEffect = Ginv[k] (variance itself), pi = lpi[k]
-#pragma unroll
-                    for (int k = 0; k < T; ++k) {
-                        const double ivr = A.Rinv[k], vek = A.Ginv[k], pik = A.lpi[k];
-                        const double aold = (double)a_cur[k];
-                        const double rhs = (r[k] + x * aold) * ivr;
-                        const double lhs = x * ivr + 1.0 / vek;
-                        const double invLhs = 1.0 / lhs;
-                        const double gHat = rhs * invLhs;
-                        const double logDelta1 = -0.5 * (jw_log(lhs) + jw_log(vek) - gHat * rhs) + jw_log(1.0 - pik);
-                        const double logDelta0 = jw_log(pik);
-                        if (logDelta0 - logDelta1 < u[k]) {
-                            newD[k] = 1;
-                            newA[k] = (float)(gHat + z[k] * jw_sqrt(invLhs));
-                            newB[k] = newA[k];
-                        } else {
-                            newD[k] = 0;
-                            newB[k] = (float)(z[k] * jw_sqrt(vek));
-                            newA[k] = 0.0f;
-                        }
-                        if ((a_cur[k] - newA[k]) != 0.0f) active = true;
-                    }
-                } else if (METHOD == 3) {
-                    // MTBayesABC.jl:163-208 (sampler II, joint states), T == 2; twin of the oracle's MT2 step
-                    const double w0 = r[0] + x * (double)a_cur[0];
-                    const double w1 = r[T - 1] + x * (double)a_cur[T - 1];
-                    const double z0 = z[0], z1 = z[T - 1], uu = u[0];
-                    double ld[4], bc0[4], bc1[4];
-#pragma unroll
-                    for (int st = 0; st < 4; ++st) {
-                        const double d0 = (double)(st & 1), d1 = (double)((st >> 1) & 1);
-                        const double l00 = d0 * A.Rinv[0] * x + Ginv[0];
-                        const double l01 = (d0 * d1) * A.Rinv[1] * x + Ginv[1];
-                        const double l11 = d1 * A.Rinv[3] * x + Ginv[T * T - 1];
-                        const double rhs0 = d0 * (A.Rinv[0] * w0 + A.Rinv[2] * w1);
-                        const double rhs1 = d1 * (A.Rinv[1] * w0 + A.Rinv[3] * w1);
-                        const double det = l00 * l11 - l01 * l01;
-                        const double i00 = l11 / det, i11 = l00 / det, i01 = -l01 / det;
-                        const double g0 = i00 * rhs0 + i01 * rhs1, g1 = i01 * rhs0 + i11 * rhs1;
-                        ld[st] = -0.5 * (jw_log(det) - (rhs0 * g0 + rhs1 * g1)) + jw_log(A.bigPi[st]);
-                        const double L00 = jw_sqrt(i00), L10 = i01 / L00, L11 = jw_sqrt(i11 - L10 * L10);
-                        bc0[st] = g0 + L00 * z0;
-                        bc1[st] = g1 + L10 * z0 + L11 * z1;
-                    }
-                    double mx = ld[0];
-#pragma unroll
-                    for (int st = 1; st < 4; ++st) if (ld[st] > mx) mx = ld[st];
-                    double ex[4], se = 0.0;
-#pragma unroll
-                    for (int st = 0; st < 4; ++st) { ex[st] = jw_exp(ld[st] - mx); se += ex[st]; }
-                    const double target = uu * se;
-                    int lab = 0; double cp = ex[0];
-#pragma unroll
-                    for (int c = 1; c < 4; ++c) { if (lab == c - 1 && cp <= target) { lab = c; cp += ex[c]; } }
-                    const float b0 = (float)(lab == 0 ? bc0[0] : lab == 1 ? bc0[1] : lab == 2 ? bc0[2] : bc0[3]);
-                    const float b1 = (float)(lab == 0 ? bc1[0] : lab == 1 ? bc1[1] : lab == 2 ? bc1[2] : bc1[3]);
-                    newB[0] = b0; newB[T - 1] = b1;
-                    newD[0] = lab & 1; newD[T - 1] = (lab >> 1) & 1;
-                    newA[0] = newD[0] ? b0 : 0.0f; newA[T - 1] = newD[T - 1] ? b1 : 0.0f;
-                    active = ((a_cur[0] - newA[0]) != 0.0f) || ((a_cur[T - 1] - newA[T - 1]) != 0.0f);
-                } else {
-                    // MTBayesABC.jl:78-125
-                    double bb[T], olda[T], w[T]; int dd[T];
-#pragma unroll
-                    for (int k = 0; k < T; ++k) {
-                        bb[k] = (double)b_cur[k]; olda[k] = (double)a_cur[k]; dd[k] = d_cur[k] != 0;
-                        w[k] = r[k] + x * olda[k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < T; ++k) {
-                        double Ginv11 = Ginv[k * T + k];
-                        double C11 = Ginv11 + A.Rinv[k * T + k] * x;
-                        double rhs0 = 0.0, c12b = 0.0;
-#pragma unroll
-                        for (int q = 0; q < T; ++q) if (q != k) {
-                            double Ginv12 = Ginv[k * T + q];
-                            double C12 = Ginv12 + x * (double)dd[q] * A.Rinv[k * T + q];
-                            rhs0 = rhs0 - Ginv12 * bb[q];
-                            c12b = c12b + C12 * bb[q];
-                        }
-                        double invLhs0 = 1.0 / Ginv11, gHat0 = rhs0 * invLhs0;
-                        double invLhs1 = 1.0 / C11;
-                        double wr = 0.0;
-#pragma unroll
-                        for (int q = 0; q < T; ++q) wr = wr + w[q] * A.Rinv[q * T + k];
-                        double gHat1 = (wr - c12b) * invLhs1;
-                        int s0 = 0, s1 = 0;
-#pragma unroll
-                        for (int q = 0; q < T; ++q) {
-                            int dqq = (q == k) ? 0 : dd[q];
-                            s0 |= dqq << q; s1 |= ((q == k) ? 1 : dqq) << q;
-                        }
-                        double logDelta0 = -0.5 * (mt_lG[k] - gHat0 * gHat0 * Ginv11) + mt_lPi[s0];
-                        double logDelta1 = -0.5 * (mt_lC[k] - gHat1 * gHat1 * C11) + mt_lPi[s1];
-                        if (logDelta0 - logDelta1 < u[k]) {
-                            dd[k] = 1;
-                            newA[k] = (float)(gHat1 + z[k] * jw_sqrt(invLhs1));
-                            bb[k] = (double)newA[k];
-                        } else {
-                            dd[k] = 0;
-                            bb[k] = (double)(float)(gHat0 + z[k] * jw_sqrt(invLhs0));
-                            newA[k] = 0.0f;
-                        }
-                        newB[k] = (float)bb[k]; newD[k] = dd[k];
-                        if ((a_cur[k] - newA[k]) != 0.0f) active = true;
-                    }
-                }
+                active = E.eval(A, r, a_cur, b_cur, d_cur, newA, newB, newD);
                 if (active) {
 #pragma unroll
                     for (int k = 0; k < T; ++k) s_dc[k * JW_CHAIN_SB + tid] = a_cur[k] - newA[k];

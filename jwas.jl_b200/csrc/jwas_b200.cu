@@ -1085,6 +1085,14 @@ extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
         }
         return 0;
     }
+    if (!strcmp(key, "chain_ctas")) {
+        JW_REQUIRE(value >= 0 && value <= 16, "chain_ctas must be in 0..16");
+        JW_CUDA(cudaSetDevice(h->device));
+        const bool changed = h->opt_chain_ctas != value;
+        h->opt_chain_ctas = value;
+        if (changed && h->nblocks > 0) return jw_fused_prepare(h);                      // slices are re-cut
+        return 0;
+    }
     if (!strcmp(key, "engine")) { JW_REQUIRE(value == 0 || value == 1, "engine must be 0 or 1"); h->opt_engine = value; return 0; }
     jw_set_error(std::string("unknown option: ") + key);
     return 2;

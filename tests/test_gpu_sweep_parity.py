@@ -21,12 +21,13 @@ def jw():
 
 
 def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=False, replay=False, engine=0,
-                 seed=11, lag=0):
+                 seed=11, lag=0, chain_ctas=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
+    g.set_option("chain_ctas", chain_ctas)
     gm, gx = g.marker_stats()
     np.testing.assert_array_equal(gm, prob.means)
     np.testing.assert_array_equal(gx, prob.xpx)
@@ -97,12 +98,13 @@ def test_bayesc_block_schedules(jw, oracle, schedule_name, missing):
     run_pair_abc(jw, oracle, prob, starts, sched, nsweeps=3, replay=(schedule_name == "block"))
 
 
-def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0):
+def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0, chain_ctas=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
+    g.set_option("chain_ctas", chain_ctas)
     yc, al, be, de = prob.fresh_state()
     de[:] = 1
     g.put_ycorr(yc); g.put_state(al, be, de)
@@ -144,12 +146,13 @@ def test_bayesr_block_schedules(jw, oracle, schedule_name, full_reps):
     run_pair_r(jw, oracle, prob, uniform_starts(90, 17), sched, full_reps, nsweeps=3)
 
 
-def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0, sampler="I"):
+def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0, sampler="I", chain_ctas=0):
     n, p, t = prob.n, prob.p, prob.t
     g = jw.GpuSweeper(prob.packed, n, t)
     g.set_blocks(starts)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
+    g.set_option("chain_ctas", chain_ctas)
     yc, al, be, de = prob.fresh_state()
     g.put_ycorr(yc); g.put_state(al, be, de)
     R = np.array([[1.0, 0.3], [0.3, 1.2]]) * prob.vary * 0.5
@@ -362,6 +365,42 @@ def test_fused_lagged_schedule(jw, oracle, n, p, b, missing):
                  pi=(0.97 if b > 1024 else 0.9))
 
 
+@pytest.mark.parametrize("chain_ctas", [1, 2, 4])
+@pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (501, 333, 64, 0.03), (67, 50, 1, 0.0),
+                                           (1030, 700, 700, 0.03), (60013, 150, 64, 0.0), (160, 3100, 1500, 0.0),
+                                           (300, 9000, 4096, 0.0), (200, 2500, 2048, 0.0)])
+def test_fused_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas):
+    """option chain_ctas: the chain of the lagged schedule walks units of <= 1024 markers on several chain CTAs
+    that hand each other commit records (jw_chain_pipe.cuh).  Same sums in the same order: bit-exact against
+    the oracle's lagged schedule, whatever the number of chain CTAs."""
+    prob = Problem(oracle, n, p, seed=n + p + 7, missing=missing)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1,
+                 pi=(0.97 if b > 1024 else 0.9), chain_ctas=chain_ctas)
+
+
+@pytest.mark.parametrize("chain_ctas", [2, 3])
+def test_fused_pipelined_chain_other_methods(jw, oracle, chain_ctas):
+    prob = Problem(oracle, 700, 900, seed=36, missing=0.02)
+    run_pair_r(jw, oracle, prob, uniform_starts(900, 256), jw.SCHED_EXACT, 1, nsweeps=3, engine=1, lag=1,
+               chain_ctas=chain_ctas)
+    prob = Problem(oracle, 350, 2600, seed=37)
+    run_pair_r(jw, oracle, prob, uniform_starts(2600, 2048), jw.SCHED_EXACT, 1, nsweeps=2, engine=1, lag=1,
+               chain_ctas=chain_ctas)
+    prob = Problem(oracle, 803, 500, seed=46, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(500, 128), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1,
+                chain_ctas=chain_ctas)
+    prob = Problem(oracle, 403, 2500, seed=47, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(2500, 1300), jw.SCHED_EXACT, nsweeps=2, engine=1, lag=1, sampler="II",
+                chain_ctas=chain_ctas)
+
+
+def test_pipelined_chain_dense_start(jw, oracle):
+    """pi = 0.2: most markers commit, units carry hundreds of records (the dense start of a chain)."""
+    prob = Problem(oracle, 400, 3000, seed=5)
+    run_pair_abc(jw, oracle, prob, uniform_starts(3000, 2048), jw.SCHED_EXACT, nsweeps=2, engine=1, lag=1, pi=0.2,
+                 chain_ctas=4)
+
+
 def test_fused_lagged_bayesr_and_multitrait(jw, oracle):
     prob = Problem(oracle, 700, 900, seed=36, missing=0.02)
     run_pair_r(jw, oracle, prob, uniform_starts(900, 256), jw.SCHED_EXACT, 1, nsweeps=3, engine=1, lag=1)
@@ -465,13 +504,13 @@ def test_fixed_point_overflow_is_reported(jw, oracle):
     g.close()
 
 
-@pytest.mark.parametrize("engine,lag,t", [(0, 0, 2), (1, 1, 2), (0, 0, 3)])
-def test_mega_bayesabc_independent_traits(jw, oracle, engine, lag, t):
+@pytest.mark.parametrize("engine,lag,t,chain_ctas", [(0, 0, 2, 0), (1, 1, 2, 0), (1, 1, 2, 2), (0, 0, 3, 0)])
+def test_mega_bayesabc_independent_traits(jw, oracle, engine, lag, t, chain_ctas):
     """megaBayesABC! (BayesABC.jl:1-7, constraint=true): one single-trait step per trait, one column read."""
     n, p = 300, 400
     prob = Problem(oracle, n, p, seed=80 + t, ntraits=t)
     g = jw.GpuSweeper(prob.packed, n, t)
-    g.set_option("engine", engine); g.set_option("lag", lag)
+    g.set_option("engine", engine); g.set_option("lag", lag); g.set_option("chain_ctas", chain_ctas)
     starts = uniform_starts(p, 128)
     g.set_blocks(starts)
     yc, al, be, de = prob.fresh_state()
