@@ -51,10 +51,11 @@ __device__ __forceinline__ unsigned long long jw_rec_pack(float d, unsigned tag,
     return ((unsigned long long)__float_as_uint(d) << 32) | ((unsigned long long)(tag & 0xffffu) << 16) | (code & 0xffffu);
 }
 
-// Reader of one unit's record stream.  next() returns how many commits (0..JW_REC_BATCH) became
-// available at the cursor and advances over them; w[q][k] holds their words.  done() is true once
-// the terminator has been consumed.  All lanes of a warp read the same addresses in the same
-// instruction, so the result is warp-uniform; different warps may be at different cursors.
+// Reader of one unit's record stream.  issue() starts the loads of the next JW_REC_BATCH words at the
+// cursor; resolve() looks at them: it returns how many commits (0..JW_REC_BATCH) have arrived, advances
+// over them and sets `finished` once the terminator has been seen.  w[q][k] holds the words.  All lanes
+// of a warp read the same addresses in the same instruction, so the result is warp-uniform; different
+// warps may be at different cursors.
 template <int T>
 struct jw_rec_reader {
     const unsigned long long* base;
@@ -63,16 +64,19 @@ struct jw_rec_reader {
     bool finished;
     unsigned long long w[JW_REC_BATCH][T];
 
-    __device__ __forceinline__ void open(const jw_pipe_args& P, int unit) {
-        base = P.rec + (size_t)unit * JW_REC_STRIDE * T;
-        tag = P.tag & 0xffffu; e = 0; finished = false;
+    __device__ __forceinline__ void open(const unsigned long long* rec, unsigned tag_, int unit) {
+        base = rec + (size_t)unit * JW_REC_STRIDE * T;
+        tag = tag_ & 0xffffu; e = 0; finished = false;
     }
-    __device__ __forceinline__ int next() {
+    __device__ __forceinline__ void open(const jw_pipe_args& P, int unit) { open(P.rec, P.tag, unit); }
+    __device__ __forceinline__ void issue() {
 #pragma unroll
         for (int q = 0; q < JW_REC_BATCH; ++q)
 #pragma unroll
             for (int k = 0; k < T; ++k)
                 w[q][k] = (e + q < JW_REC_STRIDE) ? jw_ld_relaxed_u64(base + (size_t)(e + q) * T + k) : 0ull;
+    }
+    __device__ __forceinline__ int resolve() {
         int nv = 0;
 #pragma unroll
         for (int q = 0; q < JW_REC_BATCH; ++q) {
@@ -92,7 +96,7 @@ struct jw_rec_reader {
 
 // spin bookkeeping shared by every record poller: returns false when the sweep must be abandoned
 __device__ __forceinline__ bool jw_spin_ok(unsigned& spins, unsigned long long& t0, int32_t* flags) {
-    if ((++spins & 2047u) == 0) {
+    if ((++spins & 255u) == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;
@@ -104,9 +108,85 @@ __device__ __forceinline__ bool jw_spin_ok(unsigned& spins, unsigned long long& 
     return true;
 }
 
+// Walks the commits of units [u0, u1) in commit order, handing them to fn(unit, nv, reader) in batches of
+// up to JW_REC_BATCH (fn starts the batch's dependent loads together, then adds in order).  The first
+// words of unit u+1 are requested before unit u is drained, so a run of finished units costs one memory
+// round trip for the records plus one for what fn loads, not two per unit.  Returns false on abort.
+// GENTLE pollers (the streaming CTAs' gather warps: ~150 of them, with slack) sleep between empty polls so
+// that they neither take issue slots from the streaming warps nor hammer the L2 slice of the record being
+// written; the chain CTAs (a handful, on the critical path) poll back to back.
+template <int T, bool GENTLE = false, class BatchFn>
+__device__ __forceinline__ bool jw_rec_foreach(const jw_pipe_args& P, const int u0, const int u1, BatchFn fn) {
+    if (u0 >= u1) return true;
+    unsigned spins = 0; unsigned long long t0 = 0;
+    jw_rec_reader<T> cur, nxt;
+    cur.open(P, u0); cur.issue();
+    for (int u = u0; u < u1; ++u) {
+        const bool more = u + 1 < u1;
+        if (more) { nxt.open(P, u + 1); nxt.issue(); }
+        while (true) {
+            const int nv = cur.resolve();
+            if (nv > 0) fn(u, nv, cur);
+            if (cur.finished) break;
+            if (nv == 0) {
+                if (!jw_spin_ok(spins, t0, P.flags)) return false;
+                if (GENTLE) __nanosleep(400);
+            }
+            cur.issue();
+        }
+        if (more) cur = nxt;
+    }
+    return true;
+}
+
+// Resumable walk over the commits of units [u0, u1) in commit order (the chain CTAs' view of the records):
+// poll() returns  n > 0: the next n commits (of unit `unit`, words in R);  0: nothing new yet;  -1: all units done.
+template <int T>
+struct jw_rec_walker {
+    const unsigned long long* rec;        // (no pointer to the argument struct: that would spill it to local memory)
+    unsigned tag;
+    int u, u1;
+    bool loaded;
+    jw_rec_reader<T> R;
+    __device__ __forceinline__ void init(const jw_pipe_args& P_, int u0, int u1_) {
+        rec = P_.rec; tag = P_.tag; u = u0; u1 = u1_; loaded = false;
+        if (u < u1) R.open(rec, tag, u);
+    }
+    __device__ __forceinline__ int poll(int& unit) {
+        while (true) {
+            if (u >= u1) return -1;
+            if (!loaded) R.issue();
+            loaded = false;
+            const int nv = R.resolve();
+            if (nv > 0 || R.finished) {
+                unit = u;
+                if (R.finished) { u += 1; if (u < u1) R.open(rec, tag, u); }   // open() keeps the words of this batch
+                if (nv > 0) return nv;
+                continue;
+            }
+            return 0;
+        }
+    }
+};
+
+#define JW_UNIT_PG 16          // corrections fetched ahead of the block's rhs (per thread, in shared memory)
+#define JW_UNIT_ROWS 8         // Gram rows of markers already in the model, cached in shared memory
+__host__ __device__ inline size_t jw_chain_unit_smem_bytes(int T) {
+    return 512 + (size_t)T * JW_CHAIN_SB * 4 + (size_t)32 * JW_UNIT_PG * T * 4 +
+           (size_t)JW_UNIT_PG * JW_CHAIN_SB * 4 + (size_t)JW_UNIT_ROWS * JW_CHAIN_SB * 4;
+}
+
 // One unit of the chain.  B describes the unit's panel (s, b, Gram, cross-Gram towards the previous
 // panel, rhs source); wait_fn() blocks until the panel's rhs partial sums are complete.
-// Shared memory (caller-supplied): wmin[2][32] | cnt[32] | dc[T][1024].
+// Shared memory (caller-supplied, jw_chain_unit_smem_bytes): wmin[2][32] | cnt[32] | misc[32] | dc[T][1024] |
+// pd[32 warps][PG][T] | pg[PG][1024] | rows[ROWS][1024].
+//
+// Everything that can be had before the block's rhs exists is fetched while the CTA would otherwise wait for
+// it: state, constants, draws; the Gram rows of the markers that already carry an effect (they are the
+// likely commits) into shared memory; and the cross-Gram / Gram values of every correction whose record has
+// already been published (all of the previous panel, normally).  After the wait the critical path is:
+// rhs partial sums (one L2 round trip) -> buffered corrections (shared memory) -> rounds (one barrier each;
+// a Gram round trip only when a marker ENTERS the model).
 // Returns the number of commits, -1 when the sweep was aborted.
 template <int METHOD, int T, class WaitFn>
 __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pipe_args& P, const jw_chain_blk& B,
@@ -114,7 +194,11 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
                                              unsigned long long* ct /* 5 phase timers or nullptr */) {
     int (*s_wmin)[32] = reinterpret_cast<int (*)[32]>(smem_base);
     int* s_cnt = reinterpret_cast<int*>(smem_base + 256);
+    int* s_misc = reinterpret_cast<int*>(smem_base + 384);                    // [0] cached rows, [1..ROWS] their positions
     float* s_dc = reinterpret_cast<float*>(smem_base + 512);                  // [T][JW_CHAIN_SB]
+    float* s_pd = s_dc + T * JW_CHAIN_SB;                                     // [32][PG][T]
+    float* s_pg = s_pd + 32 * JW_UNIT_PG * T;                                 // [PG][JW_CHAIN_SB]
+    float* s_rows = s_pg + JW_UNIT_PG * JW_CHAIN_SB;                          // [ROWS][JW_CHAIN_SB]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = (int)(blockDim.x >> 5);
@@ -175,17 +259,55 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
     E.load_constants(A, j);
     E.load_draws(A, j, 0);
     bool row_requested = false;
+    bool nz = false;
     if (valid) {
-        bool nz = false;
 #pragma unroll
         for (int k = 0; k < T; ++k) nz = nz || (a_cur[k] != 0.0f);
-        if (nz) {            // certain to need its Gram row: one bulk prefetch towards L2
+        if (nz) {            // certain to need its Gram row: one bulk prefetch towards L2 (later units read it too)
             row_requested = true;
             const float* row = G + (int64_t)m * b;
             const unsigned long long a0 = (unsigned long long)row & ~15ull;
             const unsigned bytes = (unsigned)((((unsigned long long)(row + b) + 15ull) & ~15ull) - a0);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
         }
+    }
+    // Gram rows of (up to ROWS) markers already in the model -> shared memory, this unit's columns only
+    if (tid == 0) s_misc[0] = 0;
+    __syncthreads();
+    if (nz) { const int slot = atomicAdd(&s_misc[0], 1); if (slot < JW_UNIT_ROWS) s_misc[1 + slot] = tid; }
+    __syncthreads();
+    const int nrow = min(s_misc[0], JW_UNIT_ROWS);
+    for (int q = 0; q < nrow; ++q)
+        s_rows[q * JW_CHAIN_SB + tid] = valid ? G[(int64_t)(m0 + s_misc[1 + q]) * b + m] : 0.0f;
+
+    // corrections whose records are already there: fetch their (cross-)Gram values now, add them after the rhs
+    const int u_own = P.blk_unit0[kb];
+    const int u_lo = (kb > 0 && B.xgram != nullptr) ? P.blk_unit0[kb - 1] : u_own;
+    jw_rec_walker<T> W;
+    W.init(P, u_lo, u);
+    int pgn = 0, wst = 0;
+    float* s_pd_w = s_pd + warp * (JW_UNIT_PG * T);
+    auto corr_row = [&](const int us_, const int code) -> const float* {
+        // units are cut every JW_CHAIN_SB markers inside a panel: no table look-up on this path
+        const bool prevblk = us_ < u_own;
+        const int rowpos = (prevblk ? (us_ - u_lo) : (us_ - u_own)) * JW_CHAIN_SB + code;
+        return (prevblk ? B.xgram : G) + (int64_t)rowpos * b + m;
+    };
+    while (pgn + JW_REC_BATCH <= JW_UNIT_PG) {
+        int us_ = 0;
+        wst = W.poll(us_);
+        if (wst <= 0) break;
+#pragma unroll
+        for (int q = 0; q < JW_REC_BATCH; ++q) {
+            if (q < wst) {
+                s_pg[(pgn + q) * JW_CHAIN_SB + tid] = valid ? *corr_row(us_, W.R.code(q)) : 0.0f;
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < T; ++k) s_pd_w[(pgn + q) * T + k] = W.R.d(q, k);
+                }
+            }
+        }
+        pgn += wst;
     }
     JW_CT(0);
     if (!wait_fn()) return -1;
@@ -211,37 +333,34 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
         r[k] = ((double)dq - mu * (double)(sqk - mq)) * A.invscale;
     }
 
-    // ---- corrections, in commit order: the previous panel's units (cross-Gram), then the earlier
-    //      units of this panel (Gram).  Records are consumed as they appear. ----
+    // ---- corrections in commit order: the buffered ones, then whatever is still being decided ----
+    __syncwarp();
+    for (int e = 0; e < pgn; ++e) {
+        const float g = s_pg[e * JW_CHAIN_SB + tid];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            const float d = s_pd_w[e * T + k];
+            if (d != 0.0f) r[k] += (double)d * (double)g;
+        }
+    }
     bool ok = true;
     {
-        const int u_lo = (kb > 0 && B.xgram != nullptr) ? P.blk_unit0[kb - 1] : P.blk_unit0[kb];
-        const int u_own = P.blk_unit0[kb];
         unsigned spins = 0; unsigned long long t0 = 0;
-        for (int us_ = u_lo; us_ < u && ok; ++us_) {
-            const bool prevblk = us_ < u_own;
-            const float* gsrc = prevblk ? B.xgram : G;
-            const int rowbase = (int)(P.unit_start[us_] - (prevblk ? B.xstart : s));
-            jw_rec_reader<T> R;
-            R.open(P, us_);
-            while (!R.finished) {
-                const int nv = R.next();
-                if (nv == 0) {
-                    if (!R.finished && !jw_spin_ok(spins, t0, P.flags)) { ok = false; break; }
-                    continue;
-                }
-                float g[JW_REC_BATCH];
+        while (wst >= 0) {
+            int us_ = 0;
+            wst = W.poll(us_);
+            if (wst < 0) break;
+            if (wst == 0) { if (!jw_spin_ok(spins, t0, P.flags)) { ok = false; break; } continue; }
+            float g[JW_REC_BATCH];
 #pragma unroll
-                for (int q = 0; q < JW_REC_BATCH; ++q)
-                    g[q] = (q < nv && valid) ? gsrc[(int64_t)(rowbase + R.code(q)) * b + m] : 0.0f;
+            for (int q = 0; q < JW_REC_BATCH; ++q) g[q] = (q < wst && valid) ? *corr_row(us_, W.R.code(q)) : 0.0f;
 #pragma unroll
-                for (int q = 0; q < JW_REC_BATCH; ++q) {
-                    if (q < nv) {
+            for (int q = 0; q < JW_REC_BATCH; ++q) {
+                if (q < wst) {
 #pragma unroll
-                        for (int k = 0; k < T; ++k) {
-                            const float d = R.d(q, k);
-                            if (d != 0.0f) r[k] += (double)d * (double)g[q];
-                        }
+                    for (int k = 0; k < T; ++k) {
+                        const float d = W.R.d(q, k);
+                        if (d != 0.0f) r[k] += (double)d * (double)g[q];
                     }
                 }
             }
@@ -293,7 +412,9 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
         if (first == 0x7fffffff) break;
         const int fg = m0 + first;                       // committed marker's position inside the panel
         if (valid && tid > first) {
-            const float g = G[(int64_t)fg * b + m];
+            int slot = -1;
+            for (int q = 0; q < nrow; ++q) if (s_misc[1 + q] == first) slot = q;
+            const float g = slot >= 0 ? s_rows[slot * JW_CHAIN_SB + tid] : G[(int64_t)fg * b + m];
 #pragma unroll
             for (int k = 0; k < T; ++k) {
                 const float d = s_dc[k * JW_CHAIN_SB + first];

@@ -692,7 +692,7 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
 
     JW_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int32_t), h->stream));
     JW_CUDA(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
-    JW_CUDA(cudaMemsetAsync(h->d_counters + 56, 0, 8 * sizeof(unsigned long long), h->stream));
+    JW_CUDA(cudaMemsetAsync(h->d_counters + 32, 0, 32 * sizeof(unsigned long long), h->stream));    // phase timers
 
     jw_chain_args A;
     memset(&A, 0, sizeof(A));
@@ -1083,6 +1083,13 @@ extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
             if (!h->opt_gram_popc && h->n < ((int64_t)1 << 22)) return build_gram_gemm(h, true);
             return build_gram(h, true);
         }
+        return 0;
+    }
+    if (!strcmp(key, "ring")) {
+        JW_CUDA(cudaSetDevice(h->device));
+        const bool changed = (h->opt_ring != 0) != (value != 0);
+        h->opt_ring = value != 0;
+        if (changed && h->nblocks > 0) return jw_fused_prepare(h);
         return 0;
     }
     if (!strcmp(key, "chain_ctas")) {
