@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--engine", type=int, default=1)
     ap.add_argument("--lag", type=int, default=1, help="1 = lagged exact schedule (chain k overlaps stream k+1)")
     ap.add_argument("--chain-ctas", type=int, default=0, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
-    ap.add_argument("--ring", action="store_true", help="stage the stream through the TMA shared-memory ring (A/B; default: direct 128-bit loads)")
+    ap.add_argument("--no-gather", action="store_true", help="replay commit records in line instead of on a gather warp (A/B)")
     ap.add_argument("--fixed-pi", action="store_true", help="keep pi=0.95 fixed (reference perf scripts: estimatePi=false)")
     ap.add_argument("--cpu-markers", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
@@ -171,7 +171,11 @@ def main():
     g.set_option("engine", args.engine)
     g.set_option("lag", args.lag if args.engine == 1 else 0)
     g.set_option("chain_ctas", args.chain_ctas if (args.engine == 1 and args.lag) else 0)
-    g.set_option("ring", 1 if args.ring else 0)
+    for key, val in (("gather", 0 if args.no_gather else 1),):
+        try:
+            g.set_option(key, val)
+        except jwas_b200.JwasError:
+            pass                                  # an older build under JWAS_B200_LIB does not know this A/B knob
     g.set_blocks(starts)
     means, xpx = g.marker_stats()
     # phenotype: y = sum_qtl x_j a_j + e, h2 = 0.5

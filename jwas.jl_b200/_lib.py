@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libjwasb200.so")
+# JWAS_B200_LIB selects another build of the same library (A/B measurements of two commits on one box)
+SO_PATH = os.environ.get("JWAS_B200_LIB") or os.path.join(_HERE, "libjwasb200.so")
 
 SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT = 0, 1, 2
 

@@ -20,9 +20,10 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(SO) and os.path.getmtime(SO) >= _newest_source_mtime():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    so = os.environ.get("JWAS_B200_BUILD_SO", SO)
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
            "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
-           "-o", SO, SRC, "-lcublas"]
+           "-o", so, SRC, "-lcublas"] + os.environ.get("JWAS_B200_BUILD_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
     subprocess.check_call(cmd)

@@ -103,8 +103,7 @@ struct jwas_handle {
     int64_t opt_timers = 0;        // 1 = in-kernel phase timers (tools/phase_probe.py)
     int64_t opt_lag = 0;           // 1 = lagged exact schedule (engine 1): chain k overlaps stream k+1
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
-    int64_t opt_ring = 0;          // engine 1: stage the genotype stream through a TMA ring in shared memory (measured slower
-                                   // than direct 128-bit loads behind the L2 prefetch: profiles/README.md; kept for A/B)
+    int64_t opt_gather = 1;        // pipelined chain: dedicated gather warp per streaming CTA (0 = replay records in line)
     int64_t opt_chain_ctas = 0;    // engine 1, lag 1: chain CTAs of the pipelined chain (0 = one-CTA chain)
     // row-sharded multi-GPU sweep: this rank streams rows [row_begin, row_end) of every column
     int64_t row_begin = 0, row_end = 0;

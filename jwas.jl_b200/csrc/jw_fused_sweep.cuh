@@ -40,7 +40,6 @@ struct jw_fused_state {
     int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1, list_cap = 0, two_lists = 0;
     int64_t total_chunks = 0;
     size_t smem = 0, smem_pipe = 0;
-    int ring_slots = 0, ring_slots_pipe = 0, ring_off = 0, ring_off_pipe = 0;
     bool ready = false;
 };
 
@@ -50,7 +49,7 @@ struct jw_fused_args {
     const int64_t* chunk_off;
     const uint8_t* packed; int64_t stride_d;
     int Gs, TS, n_vs, nblocks, list_cap, lag;
-    int ring_slots, ring_off;    // per-warp TMA ring of 16-marker chunks (0 slots = direct 128-bit loads)
+    int gather;                  // 1 = a gather warp replays the records under the stream (else: in line, before the tables)
     const float* gramx; const int64_t* gramx_off;
     int timers, two_lists;
     // multi-GPU (rows sharded over `world` GPUs of one node, one process each): this rank streams the
@@ -111,38 +110,6 @@ __device__ __forceinline__ void jw_st_release(int* p, int v) {
 __device__ __forceinline__ void jw_prefetch_l2(const void* ptr, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(ptr), "r"(bytes) : "memory");
 }
-// ---- TMA bulk copies into a shared-memory ring, completion on an mbarrier (one per slot) ----
-__device__ __forceinline__ unsigned jw_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void jw_mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(jw_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void jw_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(jw_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void jw_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(jw_smem_u32(dst)), "l"(src), "r"(bytes), "r"(jw_smem_u32(bar)) : "memory");
-}
-// waits for the phase with the given parity; gives up after ~2^24 polls (returns false) instead of hanging.
-// The loop lives inside one asm block so that the compiler sees straight-line, warp-convergent code.
-__device__ __forceinline__ bool jw_mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned left;
-    asm volatile("{\n"
-                 ".reg .pred p;\n"
-                 ".reg .u32 cnt;\n"
-                 "mov.u32 cnt, 0x1000000;\n"
-                 "JW_MBAR_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                 "@p bra JW_MBAR_DONE;\n"
-                 "sub.u32 cnt, cnt, 1;\n"
-                 "setp.ne.u32 p, cnt, 0;\n"
-                 "@p bra JW_MBAR_WAIT;\n"
-                 "JW_MBAR_DONE:\n"
-                 "mov.u32 %0, cnt;\n"
-                 "}"
-                 : "=r"(left) : "r"(jw_smem_u32(bar)), "r"(parity) : "memory");
-    return left != 0;
-}
 __device__ __forceinline__ unsigned long long jw_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -178,7 +145,11 @@ __host__ __device__ __forceinline__ constexpr int jw_tab_sub(int gb) {
 }
 #define JW_TAB_BYTES(W_) ((W_) == 1 ? 2 * 65536 : 3 * 65536)
 
-template <int METHOD, int T, int W, bool RING>
+// MODE 0: one chain CTA (lag 1) or CTA 0 streams and chains (lag 0), jw_chain_block
+//      1: pipelined chain (jw_chain_pipe.cuh), streaming CTAs replay the commit records in line
+//      2: pipelined chain, one gather warp per streaming CTA replays them under the stream (one slice per CTA)
+// The modes are compile-time: code of an unused role costs the streaming loop registers (measured: -13 %).
+template <int METHOD, int T, int W, int MODE>
 __global__ void __launch_bounds__(JW_FUSED_THREADS, 1)
 jw_k_fused(jw_fused_args F) {
     extern __shared__ __align__(16) int jw_smem[];
@@ -191,6 +162,7 @@ jw_k_fused(jw_fused_args F) {
     const int TRp = (T * R + 3) & ~3;
     float* s_y = reinterpret_cast<float*>(yqs + TRp);       // [T][R] this CTA's rows of ycorr (gather mode)
     float* s_yn = s_y + TRp;                                 // [T][R] the same rows after the next replay
+    __shared__ unsigned s_tmax;                              // (timers) last streaming warp's finish time in the block
     __shared__ int s_gcnt[2];                                // commits replayed into s_yn by the gather warp, by block parity
     (void)TS;
     __shared__ long long s_red[32 * JW_MAX_TRAITS];
@@ -201,7 +173,7 @@ jw_k_fused(jw_fused_args F) {
     const int lag = F.lag;
     const bool multi = F.world > 1;                      // needs lag = 1
     // pipelined chain: the last n_chain CTAs walk the chain unit by unit (jw_chain_pipe.cuh)
-    const bool pipe = F.P.n_chain > 0;
+    constexpr bool pipe = MODE >= 1;
     const int n_chain = pipe ? F.P.n_chain : 1;
     const int n_stream = lag ? (int)gridDim.x - n_chain - (multi ? 1 : 0) : (int)gridDim.x;
     const bool is_chain_cta = lag ? (blockIdx.x >= gridDim.x - n_chain) : (blockIdx.x == 0);
@@ -212,7 +184,13 @@ jw_k_fused(jw_fused_args F) {
     // phase timers (ns): [0] wait for previous chain, [1] axpy+quantise+tables, [2] stream,
     // [3] wait for all slices, [4] chain; CTA 0 -> counters[32..36], CTA 1 -> counters[40..44]
     unsigned long long ph[5] = {0, 0, 0, 0, 0};
+#ifdef JW_TIMERS          // phase timers are a build option (tools/phase_probe.py): their mere presence costs ~10 %
     const bool timed = (tid == 0) && (blockIdx.x <= 1 || is_chain_cta) && (F.C.counters != nullptr) && F.timers;
+    const bool timers_on = F.timers != 0;
+#else
+    constexpr bool timed = false;
+    constexpr bool timers_on = false;
+#endif
     unsigned long long tm = timed ? jw_globaltimer() : 0;
 #define JW_PHASE(i) do { if (timed) { unsigned long long now__ = jw_globaltimer(); ph[i] += now__ - tm; tm = now__; } } while (0)
     int prev_commits = 0;                  // chain CTA, lagged schedule: commits of the previous block (smem list)
@@ -220,60 +198,16 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
     for (int kk = 0; kk < T; ++kk) sq_keep[kk] = 0;
 
-    // ---- TMA ring (streaming CTAs, one slice per CTA).  The CTA's tile of a block is one contiguous region;
-    //      it is copied global -> shared in STAGES of consecutive 16-marker chunks (one chunk per streaming warp,
-    //      <= 48 KB per cp.async.bulk), `ring_slots` stages deep, across block boundaries.  Every warp waits
-    //      on the stage's mbarrier, turns its chunk into table lookups and reports the stage consumed; the
-    //      last warp to do so refills the slot with the stage `ring_slots` ahead.  The stream never waits on
-    //      memory (the first stages of the next block land while this block's tables are rebuilt) and needs
-    //      no staging registers. ----
     // gather mode (pipelined chain, one slice per CTA): the last warp does not stream; while the others
     // stream block k it replays the commit records of block k-1 against this CTA's rows of ycorr (kept
     // in shared memory for the whole sweep), so that block k+1 starts from finished values and the
     // record / genotype-byte round trips stay off the streaming CTAs' critical path
-    const bool gather_mode = pipe && is_stream_cta && single;
+    const bool gather_mode = (MODE == 2) && is_stream_cta && single;
     const int nws = gather_mode ? nwarps - 1 : nwarps;                // streaming warps
-    if (tid == 0) { s_gcnt[0] = 0; s_gcnt[1] = 0; }
+    if (tid == 0) { s_gcnt[0] = 0; s_gcnt[1] = 0; s_tmax = 0; }
     bool gather_failed = false;
-    const int S = (RING && is_stream_cta && single && F.vs0 + (int)blockIdx.x < F.vs1) ? F.ring_slots : 0;
-    const int Sd = S > 0 ? S : 1;          // divisor (the ring code is dead when S == 0)
-    const unsigned slot_bytes = (unsigned)Gs * 16u;                   // one chunk
-    const unsigned stage_bytes = slot_bytes * (unsigned)nws;          // one stage
-    unsigned char* ring = reinterpret_cast<unsigned char*>(jw_smem) + F.ring_off;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)S * stage_bytes);
-    int* s_cons = reinterpret_cast<int*>(bars + Sd);                  // warps that have consumed each slot
-    int seq = 0;                           // stages consumed by this warp (the same sequence in every warp)
-    int ik = 0, ist = 0;                   // request cursor (block, stage), kept identically by every warp
-    auto ring_advance = [&]() {
-        if (ik >= F.nblocks) return;
-        const int nch = ((int)(F.C.starts[ik + 1] - F.C.starts[ik]) + 15) >> 4;
-        ist += 1;
-        if (ist * nws >= nch) { ik += 1; ist = 0; }
-    };
-    auto ring_issue = [&](const int slot) {            // one thread: request stage (ik, ist) into `slot`
-        if (ik >= F.nblocks) return;
-        const int nch = ((int)(F.C.starts[ik + 1] - F.C.starts[ik]) + 15) >> 4;
-        const int c0 = ist * nws;
-        const unsigned bytes = (unsigned)min(nws, nch - c0) * slot_bytes;
-        const uint8_t* src = F.tiled +
-            ((size_t)(F.chunk_off[ik] * F.n_vs + (int64_t)(F.vs0 + blockIdx.x) * nch) * Gs + (size_t)c0 * Gs) * 16;
-        jw_mbar_expect_tx(&bars[slot], bytes);
-        jw_bulk_g2s(ring + (size_t)slot * stage_bytes, src, bytes, &bars[slot]);
-    };
-    if (RING && S > 0) {
-        if (tid == 0) {
-            for (int q = 0; q < S; ++q) { jw_mbar_init(&bars[q], 1); s_cons[q] = 0; }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncthreads();
-        for (int q = 0; q < S; ++q) {                  // prologue: the first S stages
-            if (tid == 0) ring_issue(q);
-            ring_advance();
-        }
-    }
 
-    if (pipe && is_chain_cta) {
+    if constexpr (MODE >= 1) { if (is_chain_cta) {
         // ---- pipelined chain: this CTA owns units cidx, cidx + n_chain, ... ----
         const int cidx = (int)blockIdx.x - ((int)gridDim.x - n_chain);
         unsigned long long ct[5] = {0, 0, 0, 0, 0};
@@ -333,12 +267,12 @@ jw_k_fused(jw_fused_args F) {
             F.C.counters[61] = (unsigned long long)my_units;
         }
         return;
-    }
+    } }
 
     // block metadata is fetched one iteration ahead: a dependent global load costs ~1 us inside this kernel
     int64_t md_s = F.C.starts[0], md_e = F.C.starts[1], md_co = F.chunk_off[0];
     for (int k = 0; k < F.nblocks; ++k) {
-        const unsigned long long t_blk = (F.timers && blockIdx.x == 0) ? jw_globaltimer() : 0ull;
+        const unsigned long long t_blk = (timers_on && blockIdx.x == 0) ? jw_globaltimer() : 0ull;
         const int64_t s = md_s;
         const int b = (int)(md_e - md_s);
         const int64_t chunk_off_k = md_co;
@@ -366,12 +300,12 @@ jw_k_fused(jw_fused_args F) {
             float v[T];
 #pragma unroll
             for (int kk = 0; kk < T; ++kk) v[kk] = 0.0f;
-            const bool from_records = pipe && ap >= 0 && !gather_mode;
+            const bool from_records = (MODE == 1) && ap >= 0;
             if (gather_mode) {
                 prev_cnt = s_gcnt[k & 1];                // written before the barrier that ended the previous block
                 rebuild = (k == 0) || prev_cnt > 0;
             }
-            if (from_records) {
+            if constexpr (MODE == 1) { if (from_records) {
                 // ---- (1a) pipelined chain: block ap's commits arrive as records; every row of the slice
                 //      replays them in commit order against its own genotypes.  The bytes come from this CTA's
                 //      own tile of block ap (streamed two panels ago, still in L2). ----
@@ -420,7 +354,7 @@ jw_k_fused(jw_fused_args F) {
                 prev_cnt = s_ok;
                 rebuild = (k == 0) || prev_cnt > 0 || !single;
                 JW_PHASE(0);
-            }
+            } }
             if (rebuild) {
                 // ---- (1) fused axpy of the previous block + fixed-point image of the slice ----
                 long long qs[T];
@@ -508,44 +442,27 @@ jw_k_fused(jw_fused_args F) {
             // ---- (3) stream the block's genotypes: one lookup per byte (4 individuals) ----
             const uint8_t* tile = F.tiled +
                 ((size_t)(chunk_off_k * F.n_vs + (int64_t)vs * nchunks) * Gs) * 16;
-            // direct path: every CTA walks its chunks in a different rotation, so that the 64-bit atomics of
-            // the ~150 CTAs do not all land on the same 16 markers at the same moment
-            const int rot = RING ? 0 : (int)((blockIdx.x * 37u) % (unsigned)nchunks);
-            const int mc_end = RING ? ((nchunks + nws - 1) / nws) * nws : nchunks;   // ring: whole stages
-            for (int mc0 = warp; mc0 < mc_end && warp < nws; mc0 += nws) {
-                const bool has = mc0 < nchunks;         // (ring) the last stage of a block may be partial
-                const int mc = RING ? mc0 : (mc0 + rot >= nchunks ? mc0 + rot - nchunks : mc0 + rot);
+            for (int mc = warp; mc < nchunks && warp < nws; mc += nws) {
                 int acc[16][W];
 #pragma unroll
                 for (int q = 0; q < 16; ++q)
 #pragma unroll
                     for (int comp = 0; comp < W; ++comp) acc[q][comp] = 0;
-                // direct path: all of this chunk's 128-bit loads are issued before the first lookup;
-                // ring path: the chunk is already in shared memory (requested ring_slots chunks ago)
+                // all of this chunk's 128-bit loads are issued before the first lookup
                 uint4 dv[JW_FUSED_MAX_GS / 32];
-                const uint4* slot_ptr = nullptr;
-                const int slot = seq % Sd;
-                if (RING) {
-                    const unsigned par = (unsigned)(seq / Sd) & 1u;
-                    if (!jw_mbar_wait(&bars[slot], par)) atomicExch(&F.flags[2], 1);       // never hang the device
-                    __syncwarp();
-                    slot_ptr = reinterpret_cast<const uint4*>(ring + (size_t)slot * stage_bytes + (size_t)warp * slot_bytes);
-                } else {
 #pragma unroll
-                    for (int gb = 0; gb < JW_FUSED_MAX_GS / 32; ++gb) {
-                        const int g = gb * 32 + lane;
-                        dv[gb] = make_uint4(0, 0, 0, 0);
-                        if (g < Gs) dv[gb] = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
-                    }
+                for (int gb = 0; gb < JW_FUSED_MAX_GS / 32; ++gb) {
+                    const int g = gb * 32 + lane;
+                    dv[gb] = make_uint4(0, 0, 0, 0);
+                    if (g < Gs) dv[gb] = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
                 }
 #pragma unroll
                 for (int gb = 0; gb < JW_FUSED_MAX_GS / 32; ++gb) {
                     const int g = gb * 32 + lane;
-                    if (g < Gs && has) {
+                    if (g < Gs) {
                         const unsigned char* tg = tab + jw_tab_sub<W>(gb);
                         const uint32_t laneoff = (uint32_t)lane * 4u * W;
-                        const uint4 dvv = RING ? slot_ptr[g] : dv[gb];
-                        const uint32_t wds[4] = {dvv.x, dvv.y, dvv.z, dvv.w};
+                        const uint32_t wds[4] = {dv[gb].x, dv[gb].y, dv[gb].z, dv[gb].w};
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             // byte1 = packed byte q, byte0 = lane offset: (byte << 8) | laneoff
@@ -558,21 +475,6 @@ jw_k_fused(jw_fused_args F) {
                             }
                         }
                     }
-                }
-                if (RING) {
-                    // every lane has turned its bytes into table addresses: this warp is done with the stage;
-                    // the last warp to say so refills the slot with the stage S ahead
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence_block();
-                        if (atomicAdd(&s_cons[slot], 1) == nws - 1) {
-                            s_cons[slot] = 0;
-                            ring_issue(slot);
-                        }
-                    }
-                    ring_advance();
-                    seq += 1;
-                    if (!has) continue;
                 }
                 // transposed butterfly: 16 markers x 32 lanes -> marker (lane>>1)&15 on every lane
 #pragma unroll
@@ -609,7 +511,8 @@ jw_k_fused(jw_fused_args F) {
                 }
             }
             if (timed && blockIdx.x == 0) F.C.counters[38] += jw_globaltimer() - t_blk;   // this warp's chunks are done
-            if (gather_mode && warp == nws) {
+            if (timers_on && blockIdx.x == 0 && lane == 0 && warp < nws) atomicMax(&s_tmax, (unsigned)(jw_globaltimer() - t_blk));
+            if constexpr (MODE == 2) { if (gather_mode && warp == nws) {
                 // ---- gather warp: replay block k-1's commits (in commit order) on this CTA's rows ----
                 bool okg = true;
                 int cnt = 0;
@@ -669,13 +572,17 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
                     for (int kk = 0; kk < T; ++kk) if (NG * 4 * lane + i < R) s_yn[kk * R + NG * 4 * lane + i] = gv[i][kk];
                 if (lane == 0) s_gcnt[(k + 1) & 1] = cnt;  // read by every thread at the start of block k+1
-                if (lane == 0 && blockIdx.x == 0 && F.C.counters != nullptr && F.timers) F.C.counters[37] += jw_globaltimer() - t_blk;
+                if (timers_on && lane == 0 && blockIdx.x == 0 && F.C.counters != nullptr) F.C.counters[37] += jw_globaltimer() - t_blk;
                 if (!okg) gather_failed = true;
-            }
+            } }
             if (!single) __syncthreads();       // the next slice overwrites the tables
         }
         // ---- (4) publish this CTA's contribution, then CTA 0 runs the chain ----
         if (__syncthreads_or(gather_failed ? 1 : 0)) return;
+        if (timed && blockIdx.x == 0) {
+            F.C.counters[39] += jw_globaltimer() - t_blk;        // end-of-block barrier passed
+            F.C.counters[47] += s_tmax; s_tmax = 0;               // last streaming warp done
+        }
         if (tid == 0) {
 #pragma unroll
             for (int kk = 0; kk < T; ++kk) {
@@ -684,6 +591,7 @@ jw_k_fused(jw_fused_args F) {
             }
             // release at gpu scope: cumulative over the CTA's atomics (ordered before by the barrier)
             asm volatile("red.release.gpu.global.add.s32 [%0], 1;" :: "l"(&F.arrive[k]) : "memory");
+            if (timed && blockIdx.x == 0) F.C.counters[45] += jw_globaltimer() - t_blk;   // arrive published
         }
         if (warp == 1 && k + 1 < F.nblocks) {
             // while the chain runs: pull the next block's tile(s) of this CTA into L2
@@ -724,7 +632,7 @@ jw_k_fused(jw_fused_args F) {
                 asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(fl), "r"(F.flag_base + k + 1) : "memory");
             }
         }
-        if (is_chain_cta) {
+        if constexpr (MODE == 0) { if (is_chain_cta) {
             jw_chain_blk B;
             B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
             if (lag && k > 0) {
@@ -779,7 +687,7 @@ jw_k_fused(jw_fused_args F) {
             __syncthreads();
             if (tid == 0) { __threadfence(); jw_st_release(F.done, k + 1); }
             JW_PHASE(4);
-        }
+        } }
     }
     if (timed) {
         const int base = (blockIdx.x == 0 && !(is_chain_cta && lag)) ? 32 : (is_chain_cta ? 48 : 40);
@@ -866,22 +774,6 @@ static int jw_fused_prepare(jwas_handle* h) {
     f->smem = base_smem + jw_chain_smem_bytes(h->t, f->list_cap, f->two_lists ? 2 : 1);
     // pipelined chain CTAs never stream: their scratch (no commit lists) overlays the tables
     f->smem_pipe = std::max(base_smem, jw_chain_unit_smem_bytes(h->t));
-    // per-warp TMA ring with whatever shared memory is left (>= 2 slots of Gs*16 bytes per warp, one slice per CTA)
-    {
-        const size_t limit = 227 * 1024 - 2048;                      // static shared memory of the kernel
-        const size_t per_slot = (size_t)(JW_FUSED_THREADS / 32) * (size_t)f->Gs * 16 + 16;    // stage + mbarrier + counter
-        auto slots_for = [&](size_t used) -> int {
-            const size_t off = (used + 127) & ~(size_t)127;
-            if (!h->opt_ring || f->W != 1 || off + 2 * per_slot > limit || f->n_vs > h->sm_count) return 0;
-            return (int)std::min<size_t>(4, (limit - off) / per_slot);
-        };
-        f->ring_off = (int)((f->smem + 127) & ~(size_t)127);
-        f->ring_slots = f->smem <= 227 * 1024 ? slots_for(f->smem) : 0;
-        f->ring_off_pipe = (int)((base_smem + 127) & ~(size_t)127);
-        f->ring_slots_pipe = slots_for(base_smem);
-        if (f->ring_slots) f->smem = f->ring_off + f->ring_slots * per_slot;
-        if (f->ring_slots_pipe) f->smem_pipe = std::max(f->smem_pipe, f->ring_off_pipe + f->ring_slots_pipe * per_slot);
-    }
     if (f->smem > 227 * 1024) { delete f; h->fused = nullptr; return 0; }   // engine 0 only for this shape
     std::vector<int64_t> coff(h->nblocks + 1, 0);
     std::vector<int32_t> cblk;
@@ -944,9 +836,9 @@ static int jw_fused_prepare(jwas_handle* h) {
     return 0;
 }
 
-template <int METHOD, int T, int W, bool RING = false>
-static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
-    auto kern = jw_k_fused<METHOD, T, W, RING>;
+template <int METHOD, int T, int W, int MODE>
+static int jw_fused_launch_mode(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
+    auto kern = jw_k_fused<METHOD, T, W, MODE>;
     const size_t smem = F.P.n_chain > 0 ? f->smem_pipe : f->smem;
     JW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -959,6 +851,14 @@ static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) 
     JW_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(JW_FUSED_THREADS), args, smem, h->stream));
     h->launches += 1;
     return 0;
+}
+template <int METHOD, int T, int W>
+static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
+    if (F.P.n_chain <= 0) return jw_fused_launch_mode<METHOD, T, W, 0>(h, f, F);
+    // the gather warp needs one slice per streaming CTA
+    const bool single = (F.vs1 - F.vs0) <= h->sm_count - F.P.n_chain - (F.world > 1 ? 1 : 0);
+    if (F.gather && single) return jw_fused_launch_mode<METHOD, T, W, 2>(h, f, F);
+    return jw_fused_launch_mode<METHOD, T, W, 1>(h, f, F);
 }
 
 static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
@@ -999,9 +899,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.flags = h->d_flags; F.dq = h->d_dq; F.mq = h->d_mq;
     memset(&F.P, 0, sizeof(F.P));
     const bool pipe = F.lag && f->n_chain > 0;
-    F.ring_slots = pipe ? f->ring_slots_pipe : f->ring_slots;
-    F.ring_off = pipe ? f->ring_off_pipe : f->ring_off;
-    if (h->world > 1 || f->W != 1 || (F.vs1 - F.vs0) > h->sm_count - (F.lag ? std::max(1, f->n_chain) : 0)) F.ring_slots = 0;
+    F.gather = (int)h->opt_gather;
     if (pipe) {
         f->rec_tag += 1;
         if (f->rec_tag > 0xffffu) {              // tags wrapped: forget every old record
@@ -1021,10 +919,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     }
     int rc = 2;
     const bool ms = h->has_missing != 0;
-    if (t == 1 && !ms && F.ring_slots > 0) {
-        if (A.method == 0) rc = jw_fused_launch<0, 1, 1, true>(h, f, F);
-        else if (A.method == 1) rc = jw_fused_launch<1, 1, 1, true>(h, f, F);
-    } else if (t == 1 && !ms) {
+    if (t == 1 && !ms) {
         if (A.method == 0) rc = jw_fused_launch<0, 1, 1>(h, f, F);
         else if (A.method == 1) rc = jw_fused_launch<1, 1, 1>(h, f, F);
     } else if (t == 1 && ms) {

@@ -1085,13 +1085,7 @@ extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
         }
         return 0;
     }
-    if (!strcmp(key, "ring")) {
-        JW_CUDA(cudaSetDevice(h->device));
-        const bool changed = (h->opt_ring != 0) != (value != 0);
-        h->opt_ring = value != 0;
-        if (changed && h->nblocks > 0) return jw_fused_prepare(h);
-        return 0;
-    }
+    if (!strcmp(key, "gather")) { h->opt_gather = value != 0; return 0; }
     if (!strcmp(key, "chain_ctas")) {
         JW_REQUIRE(value >= 0 && value <= 16, "chain_ctas must be in 0..16");
         JW_CUDA(cudaSetDevice(h->device));

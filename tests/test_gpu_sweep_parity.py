@@ -21,13 +21,14 @@ def jw():
 
 
 def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=False, replay=False, engine=0,
-                 seed=11, lag=0, chain_ctas=0):
+                 seed=11, lag=0, chain_ctas=0, gather=1):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
+    g.set_option("gather", gather)
     gm, gx = g.marker_stats()
     np.testing.assert_array_equal(gm, prob.means)
     np.testing.assert_array_equal(gx, prob.xpx)
@@ -392,6 +393,15 @@ def test_fused_pipelined_chain_other_methods(jw, oracle, chain_ctas):
     prob = Problem(oracle, 403, 2500, seed=47, ntraits=2)
     run_pair_mt(jw, oracle, prob, uniform_starts(2500, 1300), jw.SCHED_EXACT, nsweeps=2, engine=1, lag=1, sampler="II",
                 chain_ctas=chain_ctas)
+
+
+@pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (1030, 700, 700, 0.03), (300, 9000, 4096, 0.0)])
+def test_pipelined_chain_inline_replay(jw, oracle, n, p, b, missing):
+    """option gather=0: the streaming CTAs replay the commit records in line (kernel mode 1) instead of on a
+    gather warp (mode 2, the default when every streaming CTA owns one slice)."""
+    prob = Problem(oracle, n, p, seed=n + p + 9, missing=missing)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=1,
+                 pi=(0.97 if b > 1024 else 0.9), chain_ctas=2, gather=0)
 
 
 def test_pipelined_chain_dense_start(jw, oracle):

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sweep_parity.py -m gpu -q -x -k "pipelined" 2>&1 | tail -3
 run() {
 timeout 300 python bench.py --steps 20 --warmup 5 --burnin 40 --no-cpu "$@" 2>gpurun_out/bench_tmp.err | tail -1 > gpurun_out/bench_tmp.json
 python - "$@" <<PY
@@ -11,6 +10,10 @@ except Exception as e:
     print(' '.join(sys.argv[1:]), 'FAILED', e); print(open('gpurun_out/bench_tmp.err').read()[-1500:])
 PY
 }
+timeout 900 python -m pytest tests/test_gpu_sweep_parity.py -m gpu -q -x -k "pipelined or lagged or mega or fused or subblocks" 2>&1 | tail -3
+run --chain-ctas 2 --panel 2048 --no-gather
 run --chain-ctas 2 --panel 1984
-run --chain-ctas 2 --panel 2048
-timeout 300 python tools/phase_probe.py --panel 1984 --lag 1 --chain-ctas 2 --sweeps 8 2>&1 | tail -1
+run --chain-ctas 3 --panel 2976
+run --chain-ctas 4 --panel 3968
+run --chain-ctas 6 --panel 3968
+run --chain-ctas 0 --panel 2048
