@@ -125,8 +125,8 @@ def main():
     ap.add_argument("--burnin", type=int, default=40, help="untimed chain iterations before warm-up")
     ap.add_argument("--engine", type=int, default=1)
     ap.add_argument("--lag", type=int, default=1, help="1 = lagged exact schedule (chain k overlaps stream k+1)")
-    ap.add_argument("--chain-ctas", type=int, default=0, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
-    ap.add_argument("--no-gather", action="store_true", help="replay commit records in line instead of on a gather warp (A/B)")
+    ap.add_argument("--chain-ctas", type=int, default=2, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
+    ap.add_argument("--gather", action="store_true", help="gather warp per streaming CTA (kernel mode 2; use a panel that is a multiple of 496)")
     ap.add_argument("--fixed-pi", action="store_true", help="keep pi=0.95 fixed (reference perf scripts: estimatePi=false)")
     ap.add_argument("--cpu-markers", type=int, default=4000)
     ap.add_argument("--no-cpu", action="store_true")
@@ -171,7 +171,7 @@ def main():
     g.set_option("engine", args.engine)
     g.set_option("lag", args.lag if args.engine == 1 else 0)
     g.set_option("chain_ctas", args.chain_ctas if (args.engine == 1 and args.lag) else 0)
-    for key, val in (("gather", 0 if args.no_gather else 1),):
+    for key, val in (("gather", 1 if args.gather else 0),):
         try:
             g.set_option(key, val)
         except jwas_b200.JwasError:

@@ -26,7 +26,8 @@ try:  # pandas is what a DataFrame is here
 except Exception:  # pragma: no cover
     pd = None
 
-DEFAULT_PANEL = 2048          # look-ahead panel of the exact schedule (GPU-internal; 1024 with missing calls / multi-trait)
+DEFAULT_PANEL = 2048          # look-ahead panel of the exact schedule (GPU-internal)
+DEFAULT_CHAIN_CTAS = 2        # chain CTAs of the pipelined chain (engine 1, lag 1); 0 = one chain CTA
 
 
 def error(msg):
@@ -373,7 +374,7 @@ def _frame(rows, cols):
 def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=None, seed=False,
             fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
             double_precision=False, heterogeneous_residuals=False, output_folder="results", device=0,
-            panel=DEFAULT_PANEL, engine=1, lag=1, _backend_factory=None, **ignored):
+            panel=DEFAULT_PANEL, engine=1, lag=1, chain_ctas=DEFAULT_CHAIN_CTAS, _backend_factory=None, **ignored):
     """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
     Returns the reference's output dictionary keys for this path: "location parameters",
     "residual variance", "marker effects <name>", "pi_<name>", "EBV_<trait>"."""
@@ -421,7 +422,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     schedule = SCHED_EXACT if starts is None else (SCHED_INDEPENDENT if independent_blocks else SCHED_BLOCK)
     if starts is None:
         has_missing = bool(np.any((packed & (packed >> 1) & 0x55) != 0))
-        pmax = 2048 if (t == 1 and not has_missing) else 1024
+        pipelined = bool(lag) and engine == 1 and chain_ctas > 0
+        pmax = 4096 if pipelined else (2048 if (t == 1 and not has_missing) else 1024)
         starts = np.array(list(range(0, p, max(1, min(panel, pmax)))) + [p], dtype=np.int64)
 
     # ---- default priors (input_data_validation.jl:296-350) and marker hyper-parameters
@@ -494,6 +496,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         sw = GpuSweeper(packed, n, t, device=device)
         sw.set_option("engine", engine)
         sw.set_option("lag", use_lag)
+        sw.set_option("chain_ctas", int(chain_ctas) if use_lag else 0)
         sw.set_blocks(starts)
         backend = mcmc.GpuBackend(sw)
         Mi.stream_backend = sw

@@ -103,7 +103,8 @@ struct jwas_handle {
     int64_t opt_timers = 0;        // 1 = in-kernel phase timers (tools/phase_probe.py)
     int64_t opt_lag = 0;           // 1 = lagged exact schedule (engine 1): chain k overlaps stream k+1
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
-    int64_t opt_gather = 1;        // pipelined chain: dedicated gather warp per streaming CTA (0 = replay records in line)
+    int64_t opt_gather = 0;        // pipelined chain: 1 = a gather warp per streaming CTA replays the records under the
+                                   // stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line
     int64_t opt_chain_ctas = 0;    // engine 1, lag 1: chain CTAs of the pipelined chain (0 = one-CTA chain)
     // row-sharded multi-GPU sweep: this rank streams rows [row_begin, row_end) of every column
     int64_t row_begin = 0, row_end = 0;

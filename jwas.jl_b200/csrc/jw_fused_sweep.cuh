@@ -40,6 +40,7 @@ struct jw_fused_state {
     int Gs = 0, TS = 0, n_vs = 0, n_cta = 0, W = 1, list_cap = 0, two_lists = 0;
     int64_t total_chunks = 0;
     size_t smem = 0, smem_pipe = 0;
+    bool legacy_ok = true;           // the one-chain-CTA layout (with its commit lists) fits in shared memory
     bool ready = false;
 };
 
@@ -774,7 +775,9 @@ static int jw_fused_prepare(jwas_handle* h) {
     f->smem = base_smem + jw_chain_smem_bytes(h->t, f->list_cap, f->two_lists ? 2 : 1);
     // pipelined chain CTAs never stream: their scratch (no commit lists) overlays the tables
     f->smem_pipe = std::max(base_smem, jw_chain_unit_smem_bytes(h->t));
-    if (f->smem > 227 * 1024) { delete f; h->fused = nullptr; return 0; }   // engine 0 only for this shape
+    f->legacy_ok = f->smem <= 227 * 1024;
+    const bool pipe_ok = f->n_chain > 0 && f->smem_pipe <= 227 * 1024 - 2048;
+    if (!f->legacy_ok && !pipe_ok) { delete f; h->fused = nullptr; return 0; }   // engine 0 only for this shape
     std::vector<int64_t> coff(h->nblocks + 1, 0);
     std::vector<int32_t> cblk;
     for (int64_t k = 0; k < h->nblocks; ++k) {
@@ -854,7 +857,10 @@ static int jw_fused_launch_mode(jwas_handle* h, jw_fused_state* f, jw_fused_args
 }
 template <int METHOD, int T, int W>
 static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
-    if (F.P.n_chain <= 0) return jw_fused_launch_mode<METHOD, T, W, 0>(h, f, F);
+    if (F.P.n_chain <= 0) {
+        JW_REQUIRE(f->legacy_ok, "engine 1: this panel size needs the pipelined chain (option chain_ctas >= 1 with lag = 1)");
+        return jw_fused_launch_mode<METHOD, T, W, 0>(h, f, F);
+    }
     // the gather warp needs one slice per streaming CTA
     const bool single = (F.vs1 - F.vs0) <= h->sm_count - F.P.n_chain - (F.world > 1 ? 1 : 0);
     if (F.gather && single) return jw_fused_launch_mode<METHOD, T, W, 2>(h, f, F);

@@ -85,6 +85,7 @@ def bench_main(args, cfg, config):
     panel = args.panel
     g.set_option("engine", args.engine)
     g.set_option("lag", 1 if args.engine == 1 else 0)
+    g.set_option("chain_ctas", args.chain_ctas if args.engine == 1 else 0)
     starts = np.array(list(range(0, p, panel)) + [p], dtype=np.int64)
     g.set_blocks(starts)
     attach(g, rank, world, fused=(args.engine == 1))

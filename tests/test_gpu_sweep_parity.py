@@ -99,13 +99,14 @@ def test_bayesc_block_schedules(jw, oracle, schedule_name, missing):
     run_pair_abc(jw, oracle, prob, starts, sched, nsweeps=3, replay=(schedule_name == "block"))
 
 
-def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0, chain_ctas=0):
+def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0, chain_ctas=0, gather=1):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
+    g.set_option("gather", gather)
     yc, al, be, de = prob.fresh_state()
     de[:] = 1
     g.put_ycorr(yc); g.put_state(al, be, de)
@@ -147,13 +148,14 @@ def test_bayesr_block_schedules(jw, oracle, schedule_name, full_reps):
     run_pair_r(jw, oracle, prob, uniform_starts(90, 17), sched, full_reps, nsweeps=3)
 
 
-def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0, sampler="I", chain_ctas=0):
+def run_pair_mt(jw, oracle, prob, starts, schedule, nsweeps, seed=9, engine=0, lag=0, sampler="I", chain_ctas=0, gather=1):
     n, p, t = prob.n, prob.p, prob.t
     g = jw.GpuSweeper(prob.packed, n, t)
     g.set_blocks(starts)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
+    g.set_option("gather", gather)
     yc, al, be, de = prob.fresh_state()
     g.put_ycorr(yc); g.put_state(al, be, de)
     R = np.array([[1.0, 0.3], [0.3, 1.2]]) * prob.vary * 0.5
@@ -369,7 +371,7 @@ def test_fused_lagged_schedule(jw, oracle, n, p, b, missing):
 @pytest.mark.parametrize("chain_ctas", [1, 2, 4])
 @pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (501, 333, 64, 0.03), (67, 50, 1, 0.0),
                                            (1030, 700, 700, 0.03), (60013, 150, 64, 0.0), (160, 3100, 1500, 0.0),
-                                           (300, 9000, 4096, 0.0), (200, 2500, 2048, 0.0)])
+                                           (300, 9000, 4096, 0.0), (200, 2500, 2048, 0.0), (160, 3100, 1500, 0.03)])
 def test_fused_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas):
     """option chain_ctas: the chain of the lagged schedule walks units of <= 1024 markers on several chain CTAs
     that hand each other commit records (jw_chain_pipe.cuh).  Same sums in the same order: bit-exact against

@@ -5,12 +5,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import jwas_b200
 ap = argparse.ArgumentParser()
 ap.add_argument("--method", default="R"); ap.add_argument("--n", type=int, default=50000); ap.add_argument("--p", type=int, default=1000000)
-ap.add_argument("--panel", type=int, default=1024); ap.add_argument("--sweeps", type=int, default=12); ap.add_argument("--lag", type=int, default=1)
+ap.add_argument("--panel", type=int, default=2048); ap.add_argument("--chain-ctas", type=int, default=2); ap.add_argument("--sweeps", type=int, default=12); ap.add_argument("--lag", type=int, default=1)
 a = ap.parse_args()
 t = 2 if a.method == "MT" else 1
 t0 = time.time()
 g = jwas_b200.GpuSweeper.synthetic(a.n, a.p, t, seed=2026)
-g.set_option("lag", a.lag)
+g.set_option("lag", a.lag); g.set_option("chain_ctas", a.chain_ctas if a.lag else 0)
 g.set_blocks(np.array(list(range(0, a.p, a.panel)) + [a.p], dtype=np.int64)); g.set_option("engine", 1)
 print("setup %.1fs" % (time.time() - t0))
 rng = np.random.default_rng(1)

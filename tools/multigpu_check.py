@@ -17,10 +17,11 @@ n, p = 30011, 3000
 GAMMA = np.array([0.0, 0.01, 0.1, 1.0]); PI_R = np.array([0.95, 0.03, 0.015, 0.005])
 
 
-def run(t, method, sharded, engine, miss, lag=0):
+def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0):
     g = jwas_b200.GpuSweeper.synthetic(n, p, t, seed=11, missing_rate=miss, device=local)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
+    g.set_option("chain_ctas", chain_ctas)
     g.set_blocks(np.array(list(range(0, p, 512)) + [p], dtype=np.int64))
     if sharded:
         multigpu.attach(g, rank, world, fused=(engine == 1))
@@ -56,6 +57,12 @@ for t, method, miss in ((1, "C", 0.01), (1, "R", 0.0), (2, "M", 0.0), (1, "I", 0
         same1 = all(np.array_equal(x, y) for x, y in zip(ref1, sh1))
         print(f"rank {rank}/{world} method {method} t={t}: fused multi-GPU (NVLink push) == fused single GPU: {same1}", flush=True)
         same = same and same1
+        # the same with the chain pipelined over two chain CTAs (commit records), one GPU and sharded
+        ref2 = run(t, method, False, 1, miss, lag=1, chain_ctas=2)
+        sh2 = run(t, method, True, 1, miss, lag=1, chain_ctas=2)
+        same2 = all(np.array_equal(x, y) for x, y in zip(ref1, ref2)) and all(np.array_equal(x, y) for x, y in zip(ref1, sh2))
+        print(f"rank {rank}/{world} method {method} t={t}: pipelined chain, sharded == single == one-CTA chain: {same2}", flush=True)
+        same = same and same2
     nz = int(np.count_nonzero(ref[0]))
     print(f"rank {rank}/{world} method {method} t={t}: sharded==single==fused: {same} (nonzero effects {nz})", flush=True)
     ok = ok and same and nz > 0

@@ -7,12 +7,12 @@ import jwas_b200
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=50000); ap.add_argument("--p", type=int, default=600000)
 ap.add_argument("--panel", type=int, default=1024); ap.add_argument("--sweeps", type=int, default=6)
-ap.add_argument("--lag", type=int, default=0); ap.add_argument("--chain-ctas", type=int, default=0); ap.add_argument("--no-gather", action="store_true")
+ap.add_argument("--lag", type=int, default=0); ap.add_argument("--chain-ctas", type=int, default=0); ap.add_argument("--gather", action="store_true")
 ap.add_argument("--pi", type=float, default=0.999); ap.add_argument("--ve", type=float, default=2e-3)
 a = ap.parse_args()
 g = jwas_b200.GpuSweeper.synthetic(a.n, a.p, 1, seed=2026)
 starts = np.array(list(range(0, a.p, a.panel)) + [a.p], dtype=np.int64)
-g.set_option("chain_ctas", a.chain_ctas); g.set_option("gather", 0 if a.no_gather else 1)
+g.set_option("chain_ctas", a.chain_ctas); g.set_option("gather", 1 if a.gather else 0)
 g.set_blocks(starts); g.set_option("engine", 1); g.set_option("lag", a.lag); g.set_option("timers", 1)
 rng = np.random.default_rng(1)
 g.put_ycorr(rng.standard_normal(a.n).astype(np.float32))
