@@ -169,6 +169,16 @@ int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world * 64 bytes i
 
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 int64_t jwas_kernel_launches(jwas_handle* h);     /* kernels launched by this handle so far */
+/* Backend options (none changes a result bit):
+ *   "engine"      0 = multi-kernel engine, 1 = persistent fused sweep kernel
+ *   "lag"         1 = lagged exact schedule (engine 1): the chain of panel k overlaps the stream of panel k+1
+ *   "chain_ctas"  engine 1, lag 1: number of chain CTAs of the PIPELINED chain (units of <= 1024 markers handed
+ *                 from CTA to CTA as 64-bit commit records); 0 = one chain CTA.  Re-cuts the row slices.
+ *   "gather"      pipelined chain: 1 = one warp of every streaming CTA replays the commit records under the
+ *                 stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line (default)
+ *   "profile"     1 = time the streaming kernel(s) with CUDA events (jwas_last_stream_kernel_ms)
+ *   "timers"      1 = in-kernel phase timers; only in a library built with -DJW_TIMERS
+ *   "gram_popcount" 1 = popcount Gram kernel instead of the bf16 tensor-core GEMM */
 int jwas_set_option(jwas_handle* h, const char* key, int64_t value);
 /* last sweep's device time in milliseconds (CUDA events on the handle's stream) */
 double jwas_last_sweep_ms(jwas_handle* h);

@@ -53,6 +53,11 @@ function GpuBackend(packed::Matrix{UInt8}, nObs::Integer, ntraits::Integer; devi
     means = Vector{Float32}(undef, p); xpx = Vector{Float32}(undef, p)
     check(ccall((:jwas_get_marker_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), h[], means, xpx))
     b = GpuBackend(h[], nObs, p, ntraits, means, xpx, nothing)
+    # backend tuning (no effect on results): persistent fused kernel, lagged exact schedule, chain pipelined over
+    # two chain CTAs -- the configuration bench.py measures.  Must precede set_blocks!.
+    for (key, val) in (("engine", 1), ("lag", 1), ("chain_ctas", 2))
+        check(ccall((:jwas_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), h[], key, val))
+    end
     finalizer(x -> ccall((:jwas_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), b)   # like streaming_genotypes.jl:966-968
     return b
 end

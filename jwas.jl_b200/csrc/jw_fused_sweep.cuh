@@ -904,7 +904,12 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.act_cnt_blk = f->d_act_cnt_blk; F.act_idx_all = h->d_act_idx;
     F.flags = h->d_flags; F.dq = h->d_dq; F.mq = h->d_mq;
     memset(&F.P, 0, sizeof(F.P));
-    const bool pipe = F.lag && f->n_chain > 0;
+    // the pipelined chain pays when every streaming CTA owns ONE row slice (n up to ~55,000 rows per GPU): with
+    // several slices per CTA the stream dominates, the chain is idle anyway, and replaying the records once
+    // per slice costs more than the one-chain-CTA hand-off (400,000 x 61,440: 260 vs 284 sweeps/s)
+    const int my_slices = h->world > 1 ? (int)((int64_t)f->n_vs * (h->rank + 1) / h->world - (int64_t)f->n_vs * h->rank / h->world) : f->n_vs;
+    const bool one_slice = my_slices <= h->sm_count - std::max(1, f->n_chain) - (h->world > 1 ? 1 : 0);
+    const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok);
     F.gather = (int)h->opt_gather;
     if (pipe) {
         f->rec_tag += 1;

@@ -1,4 +1,7 @@
-"""Prints engine-1 phase timers (ns per block) at a given size: where a block's time goes."""
+"""Prints engine-1 phase timers (ns per block) at a given size: where a block's time goes.
+The timers are a BUILD option (their presence alone costs the sweep ~10 %): build the library with
+    JWAS_B200_BUILD_FLAGS=-DJW_TIMERS python jwas.jl_b200/build.py
+before running this tool; with the default build every phase reads 0."""
 import argparse, sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
