@@ -1,3 +1,4 @@
+# A/B of engine-1 options at cfg2 on one box (every run prints one summary line)
 mkdir -p gpurun_out
 run() {
 timeout 300 python bench.py --steps 20 --warmup 5 --burnin 40 --no-cpu "$@" 2>gpurun_out/bench_tmp.err | tail -1 > gpurun_out/bench_tmp.json
@@ -10,10 +11,8 @@ except Exception as e:
     print(' '.join(sys.argv[1:]), 'FAILED', e); print(open('gpurun_out/bench_tmp.err').read()[-1500:])
 PY
 }
-timeout 900 python -m pytest tests/test_gpu_sweep_parity.py -m gpu -q -x -k "pipelined or lagged or mega or fused or subblocks" 2>&1 | tail -3
-run --chain-ctas 2 --panel 2048 --no-gather
-run --chain-ctas 2 --panel 1984
-run --chain-ctas 3 --panel 2976
-run --chain-ctas 4 --panel 3968
-run --chain-ctas 6 --panel 3968
 run --chain-ctas 0 --panel 2048
+run --chain-ctas 2 --panel 2048
+run --chain-ctas 2 --panel 1984 --gather
+run --chain-ctas 4 --panel 3968 --gather
+# a second build of the library (another commit, or JWAS_B200_BUILD_FLAGS=-DJW_TIMERS) is selected with JWAS_B200_LIB=<path>
