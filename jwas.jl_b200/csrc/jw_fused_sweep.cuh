@@ -9,8 +9,11 @@
 //      + ONE integer add -- 4 genotypes per lookup instead of 3+ instructions per genotype;
 //   3. reduce across lanes and add the exact int64 partial rhs into global memory with
 //      red.add.u64 (integer atomics commute: any CTA order gives the same bits);
-//   4. CTA 0 waits for all slices (release/acquire counter), runs the in-block Gibbs chain
-//      (jw_chain_block, shared with engine 0) and publishes the block's ordered active list.
+//   4. the chain: lag 0 -- CTA 0 waits for all slices (release/acquire counter), runs the in-block Gibbs
+//      chain (jw_chain_block, shared with engine 0) and publishes the block's ordered active list;
+//      lag 1 -- dedicated chain CTA(s) do that while the other CTAs already stream the next block: one
+//      chain CTA (MODE 0), or several that walk units of 1024 markers and hand each other 64-bit commit
+//      records (MODE 1 / 2, jw_chain_pipe.cuh); the streaming CTAs replay the same records for the axpy.
 // No host round trip, no kernel boundary, ycorr never leaves L2 for the duration of the sweep.
 // Spin loops carry a time-out that raises a sticky abort flag instead of hanging the device.
 #pragma once
