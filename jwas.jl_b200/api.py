@@ -8,9 +8,9 @@ backend seam is the one the reference itself uses for `storage=:stream`
 genotypes 2-bit packed in HBM behind a libjwasb200 handle and every sweep runs there.
 
 Only what the sweep needs is implemented: `y = intercept + <genotypes>` models (single- or
-multi-trait), BayesA/B/C, BayesR, multi-trait BayesC sampler I.  Everything else the reference
-offers (pedigree, covariates, random terms, SEM, RRM, categorical traits, annotations, GBLUP,
-BayesL, RR-BLUP) is outside this backend's scope and raises JwasError with a message saying so.
+multi-trait), BayesA/B/C, BayesR, RR-BLUP and BayesL (single-trait), multi-trait BayesC samplers I / II.
+Everything else the reference offers (pedigree, covariates, random terms, SEM, RRM, categorical traits,
+annotations, GBLUP) is outside this backend's scope and raises JwasError with a message saying so.
 """
 import math
 import os
@@ -161,8 +161,8 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         error("multi_trait_sampler must be one of :auto, :I, or :II.")
     if storage not in ("gpu",):
         error("storage must be :gpu in this backend (:dense and :stream live in JWAS.jl).")
-    if method not in ("BayesA", "BayesB", "BayesC", "BayesR"):
-        error(f"method {method} is outside the GPU marker-sweep path (BayesA/B/C and BayesR only).")
+    if method not in ("BayesA", "BayesB", "BayesC", "BayesR", "RR-BLUP", "BayesL"):
+        error(f"method {method} is outside the GPU marker-sweep path (BayesA/B/C, BayesR, RR-BLUP and BayesL only).")
     if annotations is not False:
         error("annotations are outside the GPU marker-sweep path.")
     if double_precision:
@@ -224,6 +224,8 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
     g.genetic_variance = Variance(val=False if G_is_marker_variance else G, df=df)
     if method == "BayesA":                 # input_data_validation.jl:33-36
         g.method = "BayesB"; g.π = 0.0; g.estimatePi = False
+    if method in ("RR-BLUP", "BayesL"):    # input_data_validation.jl:24-31: "runs with π = false / estimatePi = false"
+        g.π = 0.0; g.estimatePi = False
     return g
 
 
@@ -448,6 +450,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         if not Mi.G.val > 0:
             error("Marker effects variance is negative!")
         Mi.G.scale = Mi.G.val * (Mi.G.df - 2) / Mi.G.df
+        if Mi.method == "BayesL":          # MCMC_BayesianAlphabet.jl:70-74: G.val is the scale "Sigma" of the lasso prior
+            Mi.G.val = Mi.G.val / 8; Mi.G.scale = Mi.G.scale / 8
         Mi.π = pi
     else:
         if model.R.val is False:

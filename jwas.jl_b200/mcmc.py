@@ -33,6 +33,12 @@ class HostRng:
     def normal(self):
         return float(self.g.standard_normal())
 
+    def gamma(self, shape, scale, size):
+        return self.g.gamma(shape, scale, size)
+
+    def uniform(self, size):
+        return self.g.random(size)
+
     def inverse_wishart(self, df, scale):
         """InverseWishart(df, scale) via Bartlett; scale is the sum-of-squares matrix."""
         scale = np.asarray(scale, dtype=np.float64)
@@ -153,6 +159,13 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
             out[key] = np.zeros((t, t))
         out["pi_mean"] = np.zeros_like(big_pi); out["pi_mean2"] = np.zeros_like(big_pi)
     ebv_m = ebv_s = None
+    gamma_arr = None
+    if method == "BayesL":
+        # Bayesian Lasso (BayesC0L.jl:25-47): marker j has variance var_effect * gamma_j; gamma ~ Gamma(1, 8) to
+        # start with (MCMC_BayesianAlphabet.jl:72-77; api.runMCMC has already divided var_effect and its scale by 8)
+        if t != 1:
+            raise ValueError("BayesL: single-trait only in this backend")
+        gamma_arr = rng.gamma(1.0, 8.0, p)
     first_bayesb = True
     nsamples = 0
     ysum = None
@@ -187,6 +200,13 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
         elif method == "BayesR":
             full = 1 if it > burnin else 0          # bayesr_block_nreps, BayesR.jl:22-25
             st = backend.sweep_bayesr(schedule, full, vare, var_effect, pi, BAYESR_GAMMA, seed, it)
+        elif method == "RR-BLUP" and t == 1:
+            # BayesC0! = BayesL! with gamma = [1.0] (BayesC0L.jl:19-23): every marker in the model with the common
+            # variance, i.e. the BayesC step with pi = 0 (log pi = -inf: the inclusion test always passes)
+            st = backend.sweep_bayesc(schedule, vare, var_effect, 0.0, seed, it)
+        elif method == "BayesL":
+            # BayesL! (BayesC0L.jl:25-47): lhs = xpx + (vare/var_effect)/gamma_j  <=>  marker variance var_effect*gamma_j
+            st = backend.sweep_bayesabc(schedule, vare, var_effect * gamma_arr, np.zeros(p), seed, it)
         else:
             raise ValueError(method)
         # [3] pi
@@ -209,6 +229,18 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
             elif t == 1 and method == "BayesR":
                 var_effect = float(np.float32((st["bayesr_ssq"] + df_effect * scale_effect)
                                               / rng.chisq(st["sum_delta"][0] + df_effect)))  # :166-168
+            elif t == 1 and method == "RR-BLUP":
+                var_effect = float(np.float32((st["alpha_ss"][0, 0] + df_effect * scale_effect)
+                                              / rng.chisq(p + df_effect)))      # :160-162 with nloci = nMarkers
+            elif method == "BayesL":
+                # :152-165: sample_variance on alpha ./ sqrt(gamma), then the MH update of gammaArray (:191-204)
+                a = backend.get_state()[0][:p].astype(np.float64)
+                var_effect = float(np.float32((float(np.sum(a * a / gamma_arr)) + df_effect * scale_effect)
+                                              / rng.chisq(p + df_effect)))
+                Q = a * a / var_effect
+                cand = 1.0 / rng.gamma(0.5, 4.0, p)
+                accept = rng.uniform(p) < np.exp(Q / 4.0 * (2.0 / gamma_arr - cand))
+                gamma_arr = np.where(accept, 2.0 / cand, gamma_arr)
             elif t == 1:
                 backend.sample_bayesb_variances(df_effect, scale_effect, seed, it)  # :169-172
             elif constraint_G:                       # variance_components.jl:103-110: diagonal scaled-inv-chi2

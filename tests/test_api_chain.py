@@ -62,6 +62,39 @@ def test_other_methods_run(method):
         assert (me["Model_Frequency"] == 1).all()
 
 
+@pytest.mark.parametrize("method", ["RR-BLUP", "BayesL"])
+def test_dense_methods_run_and_predict(method):
+    """RR-BLUP (BayesC0! = BayesL! with gamma = 1, BayesC0L.jl:19-47) and the Bayesian Lasso: every marker is in
+    the model every iteration, pi is not estimated (input_data_validation.jl:24-31), EBVs follow the simulated
+    genetic values, and the same seed reproduces the run."""
+    n, p = 150, 60
+    codes, ids, ph = make_data(n=n, p=p, seed=8)
+    outs = []
+    for _ in range(2):
+        geno = jw.get_genotypes(codes, 1.0, method=method, obsID=ids, Pi=0.5, estimatePi=True, quality_control=False)
+        assert geno.π == 0.0 and geno.estimatePi is False
+        model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+        outs.append(jw.runMCMC(model, ph, chain_length=60, burnin=20, seed=11, _backend_factory=factory))
+    out = outs[0]
+    me = out["marker effects geno"]
+    assert (me["Model_Frequency"] == 1).all()
+    assert "pi_geno" not in out
+    np.testing.assert_array_equal(outs[0]["marker effects geno"]["Estimate"], outs[1]["marker effects geno"]["Estimate"])
+    # the fitted genetic values explain the phenotype they were simulated from
+    ebv = out["EBV_y1"]["EBV"].to_numpy(dtype=float)
+    y = ph["y1"].to_numpy(dtype=float)
+    assert np.corrcoef(ebv, y)[0, 1] > 0.5
+    assert out["residual variance"]["Estimate"][0] > 0
+
+
+def test_rrblup_multitrait_is_rejected():
+    codes, ids, ph = make_data(ntraits=2, seed=4)
+    geno = jw.get_genotypes(codes, np.eye(2), method="RR-BLUP", obsID=ids, quality_control=False)
+    model = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.eye(2), genotypes={"geno": geno})
+    with pytest.raises(jw.JwasError, match="multi-trait"):
+        jw.runMCMC(model, ph, chain_length=4, seed=1, _backend_factory=factory)
+
+
 def test_multitrait_bayesc_run():
     codes, ids, ph = make_data(ntraits=2, seed=7)
     geno = jw.get_genotypes(codes, np.array([[1.0, 0.5], [0.5, 1.0]]), method="BayesC", obsID=ids)
@@ -102,7 +135,7 @@ def test_constraint_errors():
     # input_data_validation.jl:45-66, 81-111 style guards for what this backend does not cover
     codes, ids, ph = make_data(n=30, p=20)
     with pytest.raises(jw.JwasError, match="outside the GPU marker-sweep path"):
-        jw.get_genotypes(codes, 1.0, method="RR-BLUP")
+        jw.get_genotypes(codes, 1.0, method="GBLUP")
     with pytest.raises(jw.JwasError, match="Only 0/1/2 genotypes"):
         jw.get_genotypes(codes + 0.5, 1.0)
     with pytest.raises(jw.JwasError, match="outside the GPU marker-sweep path"):

@@ -32,7 +32,8 @@ def assert_same(a, b):
 
 
 @pytest.mark.parametrize("engine", [0, 1])
-@pytest.mark.parametrize("method,Pi", [("BayesC", 0.9), ("BayesB", 0.8), ("BayesA", 0.0), ("BayesR", 0.0)])
+@pytest.mark.parametrize("method,Pi", [("BayesC", 0.9), ("BayesB", 0.8), ("BayesA", 0.0), ("BayesR", 0.0),
+                                       ("RR-BLUP", 0.0), ("BayesL", 0.0)])
 def test_single_trait_chain_matches_oracle_chain(method, Pi, engine):
     codes, ids, ph = make_data(n=300, p=400, seed=21, missing=0.01)
     g, o = both(codes, ids, ph, "y1 = intercept + geno", 1.0, 1.0, method, Pi, engine=engine,
