@@ -1,4 +1,10 @@
-"""Builds libjwasb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libjwasb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Environment: JWAS_B200_BUILD_SO=<path> writes another file (select it at run time with JWAS_B200_LIB=<path>, e.g.
+for an A/B of two builds on one box); JWAS_B200_BUILD_FLAGS adds nvcc flags:
+  -DJW_TIMERS  in-kernel phase timers for tools/phase_probe.py (cost the sweep ~10 %)
+  -DJW_NEXT    round-2 candidates not yet measured on a GPU (arithmetic block metadata in the record replay,
+               L1 prefetch of the next chunk, red instead of atomicAdd; profiles/r1_fused_kernel_stall_hotspots.md)"""
 import os
 import subprocess
 import sys

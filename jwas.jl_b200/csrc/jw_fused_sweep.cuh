@@ -53,6 +53,7 @@ struct jw_fused_args {
     const int64_t* chunk_off;
     const uint8_t* packed; int64_t stride_d;
     int Gs, TS, n_vs, nblocks, list_cap, lag;
+    int uniform_b;               // > 0: every block has this many markers (the last one possibly fewer)
     int gather;                  // 1 = a gather warp replays the records under the stream (else: in line, before the tables)
     const float* gramx; const int64_t* gramx_off;
     int timers, two_lists;
@@ -321,13 +322,33 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
                     for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
                     const int sh = (tid & 3) << 1;
+#ifdef JW_NEXT
+                    // uniform panels (every block uniform_b markers, the last one possibly shorter): the block's
+                    // metadata is arithmetic, so the record words are requested at once instead of one dependent
+                    // L2 round trip later (profiles/r1_fused_kernel_stall_hotspots.md, item 1)
+                    const bool uni = F.uniform_b > 0;
+                    const int64_t s_ap = uni ? (int64_t)ap * F.uniform_b : F.C.starts[ap];
+                    const int64_t e_ap = uni ? min(p, s_ap + F.uniform_b) : F.C.starts[ap + 1];
+                    const int nch_ap = ((int)(e_ap - s_ap) + 15) >> 4;
+                    const int64_t co_ap = uni ? (int64_t)ap * ((F.uniform_b + 15) >> 4) : F.chunk_off[ap];
+                    const int upb = (F.uniform_b + JW_CHAIN_SB - 1) / JW_CHAIN_SB;
+                    const int u0_ap = uni ? ap * upb : F.P.blk_unit0[ap];
+                    const int u1_ap = uni ? u0_ap + ((int)(e_ap - s_ap) + JW_CHAIN_SB - 1) / JW_CHAIN_SB : F.P.blk_unit0[ap + 1];
+#else
                     const int64_t s_ap = F.C.starts[ap];
                     const int nch_ap = ((int)(F.C.starts[ap + 1] - s_ap) + 15) >> 4;
+                    const int64_t co_ap = F.chunk_off[ap];
+                    const int u0_ap = F.P.blk_unit0[ap], u1_ap = F.P.blk_unit0[ap + 1];
+#endif
                     const uint8_t* tile_ap = F.tiled +
-                        ((size_t)(F.chunk_off[ap] * F.n_vs + (int64_t)vs * nch_ap) * Gs) * 16 + ((size_t)(tid >> 2) << 4);
-                    okr = jw_rec_foreach<T>(F.P, F.P.blk_unit0[ap], F.P.blk_unit0[ap + 1],
+                        ((size_t)(co_ap * F.n_vs + (int64_t)vs * nch_ap) * Gs) * 16 + ((size_t)(tid >> 2) << 4);
+                    okr = jw_rec_foreach<T>(F.P, u0_ap, u1_ap,
                                             [&](const int us_, const int nv, const jw_rec_reader<T>& RR) {
+#ifdef JW_NEXT
+                        const int pbase = (us_ - u0_ap) * JW_CHAIN_SB;    // units are cut every JW_CHAIN_SB markers of a panel
+#else
                         const int pbase = (int)(F.P.unit_start[us_] - s_ap);
+#endif
                         unsigned bytes[JW_REC_BATCH]; float mus[JW_REC_BATCH];
 #pragma unroll
                         for (int q = 0; q < JW_REC_BATCH; ++q) {
@@ -460,6 +481,15 @@ jw_k_fused(jw_fused_args F) {
                     dv[gb] = make_uint4(0, 0, 0, 0);
                     if (g < Gs) dv[gb] = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
                 }
+#ifdef JW_NEXT
+                // the warp's next chunk -> L1 (no registers involved), so that its LDG.128 do not expose the L2
+                // round trip once per chunk (hotspots, item 2); one 128-byte line per lane
+                if (mc + nws < nchunks) {
+                    const uint8_t* nx = tile + ((size_t)(mc + nws) * Gs << 4);
+                    const uint8_t* line = reinterpret_cast<const uint8_t*>(((unsigned long long)nx & ~127ull)) + ((size_t)lane << 7);
+                    if (line < nx + ((size_t)Gs << 4)) asm volatile("prefetch.global.L1 [%0];" :: "l"(line));
+                }
+#endif
 #pragma unroll
                 for (int gb = 0; gb < JW_FUSED_MAX_GS / 32; ++gb) {
                     const int g = gb * 32 + lane;
@@ -510,7 +540,11 @@ jw_k_fused(jw_fused_args F) {
                     if ((lane & 1) == 0 && jj < b && tot != 0) {
                         long long* dst = (MISS && comp == 1) ? &F.mq[s + jj]
                                                              : &F.dq[(int64_t)(MISS ? 0 : comp) * p + s + jj];
+#ifdef JW_NEXT
+                        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst), "l"((unsigned long long)tot) : "memory");
+#else
                         atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)tot);
+#endif
                     }
                 }
             }
@@ -914,6 +948,16 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     const bool one_slice = my_slices <= h->sm_count - std::max(1, f->n_chain) - (h->world > 1 ? 1 : 0);
     const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok);
     F.gather = (int)h->opt_gather;
+    F.uniform_b = 0;
+    if (h->nblocks >= 1) {
+        const int64_t b0 = h->starts[1] - h->starts[0];
+        bool uni = b0 <= (int64_t)JW_MAX_PANEL;
+        for (int64_t k = 1; k < h->nblocks && uni; ++k) {
+            const int64_t bk = h->starts[k + 1] - h->starts[k];
+            uni = (k + 1 < h->nblocks) ? (bk == b0) : (bk <= b0);
+        }
+        if (uni) F.uniform_b = (int)b0;
+    }
     if (pipe) {
         f->rec_tag += 1;
         if (f->rec_tag > 0xffffu) {              // tags wrapped: forget every old record
