@@ -13,6 +13,7 @@ from .api import (get_genotypes, build_model, set_covariate, set_random, runMCMC
                   load_streaming_backend, Genotypes, MME, MCMCinfo, Variance, resolve_fast_blocks,
                   validate_fast_block_starts)
 from . import mcmc
+from .gwas import GWAS
 
 __all__ += ["get_genotypes", "build_model", "set_covariate", "set_random", "runMCMC", "prepare_streaming_genotypes",
-            "load_streaming_backend", "Genotypes", "MME", "MCMCinfo", "Variance", "mcmc"]
+            "load_streaming_backend", "Genotypes", "MME", "MCMCinfo", "Variance", "mcmc", "GWAS"]

@@ -376,7 +376,8 @@ def _frame(rows, cols):
 def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=None, seed=False,
             fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
             double_precision=False, heterogeneous_residuals=False, output_folder="results", device=0,
-            panel=DEFAULT_PANEL, engine=1, lag=1, chain_ctas=DEFAULT_CHAIN_CTAS, _backend_factory=None, **ignored):
+            panel=DEFAULT_PANEL, engine=1, lag=1, chain_ctas=DEFAULT_CHAIN_CTAS, output_marker_effect_samples=False,
+            _backend_factory=None, **ignored):
     """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
     Returns the reference's output dictionary keys for this path: "location parameters",
     "residual variance", "marker effects <name>", "pi_<name>", "EBV_<trait>"."""
@@ -514,7 +515,17 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     if np.any(alpha0 != 0):
         backend.sub_malpha()
 
+    # marker-effect sample files (output.jl:411, 467): <output_folder>/MCMC_samples_marker_effects_<geno>_<trait>.txt,
+    # header of marker IDs + one row per saved iteration -- what GWAS() (and the reference's GWAS) reads.  Off by
+    # default here: a row is p numbers per saved iteration and trait.
+    sample_rows = [[] for _ in range(t)] if output_marker_effect_samples else None
+
+    def sink(alpha):
+        for k in range(t):
+            sample_rows[k].append(np.array(alpha[k * p:(k + 1) * p], dtype=np.float32))
+
     out = mcmc.run_chain(backend, n=n, p=p, ntraits=t, method=Mi.method, schedule=schedule,
+                         sample_sink=(sink if output_marker_effect_samples else None),
                          chain_length=chain_length, burnin=burnin, output_samples_frequency=output_samples_frequency,
                          seed=seed_v, vare=model.R.val if t == 1 else None, var_effect=Mi.G.val if t == 1 else None,
                          pi=Mi.π if t == 1 else None, df_effect=Mi.G.df, scale_effect=Mi.G.scale if t == 1 else None,
@@ -566,6 +577,13 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         for k, tr in enumerate(model.lhsVec):
             em, ev = out["ebv_mean"][k], out["ebv_var"][k]
             output["EBV_" + tr] = _frame([[i, float(a), float(v)] for i, a, v in zip(ids, em, ev)], ["ID", "EBV", "PEV"])
+    if output_marker_effect_samples:
+        from .gwas import write_samples
+        model.sample_files = {}
+        for k, tr in enumerate(model.lhsVec):
+            path = os.path.join(output_folder, f"MCMC_samples_marker_effects_{Mi.name}_{tr}.txt")
+            write_samples(path, Mi.markerID, sample_rows[k])
+            model.sample_files[tr] = path
     model.output = output
     model.sol = out["mu"]
     return output

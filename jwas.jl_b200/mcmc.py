@@ -134,7 +134,8 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               seed, vare, var_effect, pi, df_effect, scale_effect, df_res, scale_res,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
-              mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False):
+              mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False,
+              sample_sink=None):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -276,6 +277,8 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                 pi_now = pi if t == 1 else big_pi
                 out["pi_mean"] = out["pi_mean"] + (pi_now - out["pi_mean"]) / nsamples
                 out["pi_mean2"] = out["pi_mean2"] + (pi_now ** 2 - out["pi_mean2"]) / nsamples
+            if sample_sink is not None:     # marker-effect sample rows (output.jl:467)
+                sample_sink(backend.get_state()[0])
             if want_ebv:                    # getEBV per saved sample (output.jl:281-306, 489-495)
                 e = np.array([backend.mul_alpha(k) for k in range(t)], dtype=np.float64)
                 if ebv_m is None:
