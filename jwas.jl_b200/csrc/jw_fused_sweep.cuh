@@ -22,6 +22,11 @@
 #include "jw_chain_pipe.cuh"
 #include <cooperative_groups.h>
 
+#ifdef JW_NEXT
+#define JW_NEXT_META
+#define JW_NEXT_L1PF
+#define JW_NEXT_RED
+#endif
 #define JW_FUSED_THREADS 1024
 #define JW_FUSED_MAX_GS 96          // 3 lookups per lane and marker keep the int32 partial < 2^31
 
@@ -322,7 +327,7 @@ jw_k_fused(jw_fused_args F) {
 #pragma unroll
                     for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
                     const int sh = (tid & 3) << 1;
-#ifdef JW_NEXT
+#ifdef JW_NEXT_META
                     // uniform panels (every block uniform_b markers, the last one possibly shorter): the block's
                     // metadata is arithmetic, so the record words are requested at once instead of one dependent
                     // L2 round trip later (profiles/r1_fused_kernel_stall_hotspots.md, item 1)
@@ -344,7 +349,7 @@ jw_k_fused(jw_fused_args F) {
                         ((size_t)(co_ap * F.n_vs + (int64_t)vs * nch_ap) * Gs) * 16 + ((size_t)(tid >> 2) << 4);
                     okr = jw_rec_foreach<T>(F.P, u0_ap, u1_ap,
                                             [&](const int us_, const int nv, const jw_rec_reader<T>& RR) {
-#ifdef JW_NEXT
+#ifdef JW_NEXT_META
                         const int pbase = (us_ - u0_ap) * JW_CHAIN_SB;    // units are cut every JW_CHAIN_SB markers of a panel
 #else
                         const int pbase = (int)(F.P.unit_start[us_] - s_ap);
@@ -481,7 +486,7 @@ jw_k_fused(jw_fused_args F) {
                     dv[gb] = make_uint4(0, 0, 0, 0);
                     if (g < Gs) dv[gb] = __ldg(reinterpret_cast<const uint4*>(tile + ((size_t)(mc * Gs + g) << 4)));
                 }
-#ifdef JW_NEXT
+#ifdef JW_NEXT_L1PF
                 // the warp's next chunk -> L1 (no registers involved), so that its LDG.128 do not expose the L2
                 // round trip once per chunk (hotspots, item 2); one 128-byte line per lane
                 if (mc + nws < nchunks) {
@@ -540,7 +545,7 @@ jw_k_fused(jw_fused_args F) {
                     if ((lane & 1) == 0 && jj < b && tot != 0) {
                         long long* dst = (MISS && comp == 1) ? &F.mq[s + jj]
                                                              : &F.dq[(int64_t)(MISS ? 0 : comp) * p + s + jj];
-#ifdef JW_NEXT
+#ifdef JW_NEXT_RED
                         asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(dst), "l"((unsigned long long)tot) : "memory");
 #else
                         atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)tot);
@@ -920,8 +925,8 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.tiled = f->d_tiled; F.chunk_off = f->d_chunk_off;
     F.packed = h->d_packed; F.stride_d = h->stride_d;
     F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks; F.list_cap = f->list_cap;
-    F.lag = (int)h->opt_lag; F.timers = (int)h->opt_timers; F.two_lists = f->two_lists;
-    JW_REQUIRE(!F.lag || (A.nreps_mode == 0 && h->d_gramx), "lag = 1 needs the exact schedule and the cross-Gram blocks");
+    F.lag = A.nreps_mode ? 0 : (int)h->opt_lag; F.timers = (int)h->opt_timers; F.two_lists = f->two_lists;
+    JW_REQUIRE(!F.lag || h->d_gramx, "lag = 1 needs the cross-Gram blocks");
     F.gramx = h->d_gramx; F.gramx_off = h->d_gramx_off;
     F.world = h->world; F.rank = h->rank; F.vs0 = 0; F.vs1 = f->n_vs;
     F.peer_slots = nullptr; F.peer_flags = nullptr; F.my_slots = nullptr; F.my_flags = nullptr;

@@ -745,7 +745,12 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
         }
     }
 
-    if (h->opt_engine == 1 && c.schedule != JWAS_SCHED_INDEPENDENT && (h->world == 1 || (h->ipc_ready && h->opt_lag))) {
+    // engine 1 (persistent fused kernel) where it covers the shape; engine 0 otherwise.  The lagged schedule is
+    // the exact schedule's; block repetitions (nreps = block size) run engine 1 without the lag.
+    const bool fused_ok = h->fused != nullptr && ((jw_fused_state*)h->fused)->ready;
+    const bool fused_multi_ok = h->world == 1 || (h->ipc_ready && h->opt_lag && A.nreps_mode == 0);
+    if (h->opt_engine == 1 && fused_ok && c.schedule != JWAS_SCHED_INDEPENDENT && fused_multi_ok &&
+        (A.nreps_mode == 0 || ((jw_fused_state*)h->fused)->legacy_ok)) {
         int rc = jw_fused_sweep(h, A, scale);
         if (rc) return rc;
         if (gather_ycorr(h)) return 13;

@@ -479,6 +479,240 @@ void jwo_mtbayesabc_II_ref(const float* X, int64_t n, int64_t p, const float* xp
     }
 }
 
+/* ------------------------------------------------------------------------ */
+/* block restatements for BayesR and the multi-trait samplers               */
+/* ------------------------------------------------------------------------ */
+
+/* Float32 Gram block Xb'Xb (tools4genotypes.jl:263, sgemm) and block rhs Xb'y (tools4genotypes.jl:64-66, sgemv) */
+static void ref_gram_f32(const float* X, int64_t n, int64_t s, int64_t b, float* G) {
+    for (int64_t a = 0; a < b; ++a)
+        for (int64_t c = 0; c < b; ++c)
+            G[a * b + c] = jwo_sdot(X + (s + a) * n, X + (s + c) * n, n, 1);
+}
+
+/* one BayesR marker step on a block rhs entry (BayesR.jl:149-183; same arithmetic as :58-95 of the dense
+ * sampler).  Returns oldAlpha - newAlpha (Float32), the coefficient of the Gram-column axpy (:182). */
+static float bayesr_step_ref(float r_j, float xpx_j, float* alpha_j, int32_t* delta_j, float invVarRes,
+                             float sigmaSq, const double* pij, const double* gamma, int nclasses,
+                             double u, double z) {
+    double log_probs[16], probs[16];
+    float rhs = (r_j + xpx_j * (*alpha_j)) * invVarRes;                 /* :150 */
+    float oldAlpha = *alpha_j;
+    log_probs[0] = log(pij[0]);                                          /* :154 */
+    for (int k = 1; k < nclasses; ++k) {
+        double varEffect = gamma[k] * (double)sigmaSq;
+        double lhs = (double)(xpx_j * invVarRes) + 1.0 / varEffect;
+        double invLhs = 1.0 / lhs;
+        double betaHat = invLhs * (double)rhs;
+        log_probs[k] = 0.5 * (log(invLhs) - log(varEffect) + betaHat * (double)rhs) + log(pij[k]);
+    }
+    double mx = log_probs[0];
+    for (int k = 1; k < nclasses; ++k) if (log_probs[k] > mx) mx = log_probs[k];
+    double se = 0.0;
+    for (int k = 0; k < nclasses; ++k) se += exp(log_probs[k] - mx);
+    double log_norm = mx + log(se);                                      /* BayesR.jl:1-4 */
+    for (int k = 0; k < nclasses; ++k) probs[k] = exp(log_probs[k] - log_norm);
+    int cls = categorical_from_uniform(probs, nclasses, u);              /* :168 */
+    *delta_j = cls + 1;
+    if (cls == 0) *alpha_j = 0.0f;                                       /* :171-172 */
+    else {
+        double varEffect = gamma[cls] * (double)sigmaSq;
+        double lhs = (double)(xpx_j * invVarRes) + 1.0 / varEffect;
+        double invLhs = 1.0 / lhs;
+        double betaHat = invLhs * (double)rhs;
+        *alpha_j = (float)(betaHat + z * sqrt(invLhs));                  /* :179 */
+    }
+    return oldAlpha - *alpha_j;
+}
+
+/* BayesR.jl:111-193 BayesR_block! (exact) and :195-273 BayesR_block_independent!.
+ * nreps_in = bayesr_block_nreps(iter, burnin, block_size) evaluated by the caller per sweep: 1 during
+ * burn-in, <= 0 -> the block size afterwards (:22-25, :144).  u,z indexed [rep*p + j]. */
+void jwo_bayesr_block_ref(const float* X, int64_t n, int64_t p, const float* xpx,
+                          const int64_t* starts, int64_t nblocks, int nreps_in, int independent,
+                          float* ycorr, float* alpha, int32_t* delta,
+                          float vare, float sigmaSq, const double* pi, int per_marker_pi,
+                          const double* gamma, int nclasses, const double* u, const double* z) {
+    float invVarRes = 1.0f / vare;                                       /* :130 */
+    float* snap = NULL; float* dsave = NULL;
+    if (independent) {
+        snap = (float*)malloc(sizeof(float) * (size_t)n);                /* :207 */
+        for (int64_t i = 0; i < n; ++i) snap[i] = ycorr[i];
+        dsave = (float*)malloc(sizeof(float) * (size_t)p);
+    }
+    for (int64_t ib = 0; ib < nblocks; ++ib) {
+        int64_t s = starts[ib], b = starts[ib + 1] - s;
+        float* G = (float*)malloc(sizeof(float) * (size_t)(b * b));
+        float* r = (float*)malloc(sizeof(float) * (size_t)b);
+        float* aold = (float*)malloc(sizeof(float) * (size_t)b);
+        ref_gram_f32(X, n, s, b, G);
+        for (int64_t a = 0; a < b; ++a) {
+            aold[a] = alpha[s + a];                                      /* :141 */
+            r[a] = jwo_sdot(X + (s + a) * n, independent ? snap : ycorr, n, 1);   /* :143 / :222 */
+        }
+        int nreps = nreps_in > 0 ? nreps_in : (int)b;                    /* :144 */
+        for (int rep = 0; rep < nreps; ++rep)
+            for (int64_t jj = 0; jj < b; ++jj) {
+                int64_t j = s + jj;
+                const double* pij = per_marker_pi ? pi + j * nclasses : pi;
+                float d = bayesr_step_ref(r[jj], xpx[j], &alpha[j], &delta[j], invVarRes, sigmaSq, pij, gamma,
+                                          nclasses, u[(int64_t)rep * p + j], z[(int64_t)rep * p + j]);
+                for (int64_t m = 0; m < b; ++m) r[m] += d * G[m * b + jj];        /* :182 (always) */
+            }
+        for (int64_t a = 0; a < b; ++a) aold[a] -= alpha[s + a];         /* :188 */
+        if (independent) for (int64_t a = 0; a < b; ++a) dsave[s + a] = aold[a];   /* :263-264 */
+        else for (int64_t a = 0; a < b; ++a)                             /* :189 mul!(yCorr, X_b, d, 1, 1) */
+            if (aold[a] != 0.0f) jwo_saxpy(aold[a], X + (s + a) * n, ycorr, n, 1);
+        free(G); free(r); free(aold);
+    }
+    if (independent) {                                                   /* :267-270 */
+        for (int64_t j = 0; j < p; ++j)
+            if (dsave[j] != 0.0f) jwo_saxpy(dsave[j], X + j * n, ycorr, n, 1);
+        free(snap); free(dsave);
+    }
+}
+
+/* MTBayesABC.jl:243-333 (block sampler I), :335-437 (independent I), :439-537 (block sampler II, t = 2),
+ * :539-646 (independent II).  Same per-marker arithmetic as jwo_mtbayesabc_I_ref / _II_ref with the
+ * dots replaced by the block rhs and the axpys by Gram-column updates of it (:309, :316, :524).
+ * nreps_in <= 0 -> block size (:272, :486).  u,z indexed [(rep*t + k)*p + j]; sampler II uses u of
+ * trait 0 for the state label and z of both traits as the shared normals (:499, :518). */
+void jwo_mtbayesabc_block_ref(const float* X, int64_t n, int64_t p, int t, int sampler, const float* xpx,
+                              const int64_t* starts, int64_t nblocks, int nreps_in, int independent,
+                              float* ycorr, float* alpha, float* beta, float* delta,
+                              const double* R, const double* G, const double* bigPi,
+                              const double* u, const double* z) {
+    double Rinv[64], Ginv[64];
+    inv_small(R, t, Rinv); inv_small(G, t, Ginv);
+    float* snap = NULL; float* dsave = NULL;
+    if (independent) {
+        snap = (float*)malloc(sizeof(float) * (size_t)(n * t));          /* :350 / :563 */
+        for (int64_t i = 0; i < n * t; ++i) snap[i] = ycorr[i];
+        dsave = (float*)calloc((size_t)(p * t), sizeof(float));
+    }
+    for (int64_t ib = 0; ib < nblocks; ++ib) {
+        int64_t s = starts[ib], b = starts[ib + 1] - s;
+        float* Gm = (float*)malloc(sizeof(float) * (size_t)(b * b));
+        float* r = (float*)malloc(sizeof(float) * (size_t)(b * t));
+        float* aold = (float*)malloc(sizeof(float) * (size_t)(b * t));
+        ref_gram_f32(X, n, s, b, Gm);
+        for (int k = 0; k < t; ++k)
+            for (int64_t a = 0; a < b; ++a) {
+                aold[k * b + a] = alpha[k * p + s + a];                  /* :270 */
+                r[k * b + a] = jwo_sdot(X + (s + a) * n, (independent ? snap : ycorr) + k * n, n, 1);  /* :268 */
+            }
+        int nreps = nreps_in > 0 ? nreps_in : (int)b;
+        for (int rep = 0; rep < nreps; ++rep)
+            for (int64_t jj = 0; jj < b; ++jj) {
+                int64_t m = s + jj;
+                const double* uu = u + (int64_t)rep * t * p;
+                const double* zz = z + (int64_t)rep * t * p;
+                if (sampler == 2) {
+                    double w[2], olda[2];
+                    for (int k = 0; k < 2; ++k) {
+                        olda[k] = alpha[k * p + m];
+                        w[k] = (double)(r[k * b + jj] + xpx[m] * alpha[k * p + m]);              /* :496 */
+                    }
+                    double logDelta[4], bcand[4][2];
+                    for (int st = 0; st < 4; ++st) {
+                        double D[2] = { (double)(st & 1), (double)((st >> 1) & 1) };
+                        double lhs[4], rhs[2], ilhs[4];
+                        for (int i = 0; i < 2; ++i) {
+                            for (int j = 0; j < 2; ++j)
+                                lhs[i * 2 + j] = D[i] * Rinv[i * 2 + j] * D[j] * (double)xpx[m] + Ginv[i * 2 + j]; /* :501 */
+                            rhs[i] = D[i] * (Rinv[0 * 2 + i] * w[0] + Rinv[1 * 2 + i] * w[1]);                    /* :502 */
+                        }
+                        double det = lhs[0] * lhs[3] - lhs[1] * lhs[2];
+                        ilhs[0] = lhs[3] / det; ilhs[3] = lhs[0] / det; ilhs[1] = -lhs[1] / det; ilhs[2] = -lhs[2] / det;
+                        double g0 = ilhs[0] * rhs[0] + ilhs[1] * rhs[1];
+                        double g1 = ilhs[2] * rhs[0] + ilhs[3] * rhs[1];
+                        logDelta[st] = -0.5 * (log(det) - (rhs[0] * g0 + rhs[1] * g1)) + log(bigPi[st]);          /* :506 */
+                        double L00 = sqrt(ilhs[0]), L10 = ilhs[2] / L00;
+                        double L11 = sqrt(ilhs[3] - L10 * L10);
+                        bcand[st][0] = g0 + L00 * zz[m];                                                           /* :507 */
+                        bcand[st][1] = g1 + L10 * zz[m] + L11 * zz[p + m];
+                    }
+                    double mx = logDelta[0];
+                    for (int st = 1; st < 4; ++st) if (logDelta[st] > mx) mx = logDelta[st];
+                    double probs[4], den = 0.0;
+                    for (int st = 0; st < 4; ++st) { probs[st] = exp(logDelta[st] - mx); den += probs[st]; }
+                    for (int st = 0; st < 4; ++st) probs[st] /= den;
+                    int st = categorical_from_uniform(probs, 4, uu[m]);                                            /* :518 */
+                    for (int k = 0; k < 2; ++k) {
+                        double dk = (double)((st >> k) & 1);
+                        float bk = (float)bcand[st][k];
+                        float na = (float)(dk * (double)bk);
+                        float d = (float)olda[k] - na;
+                        for (int64_t q = 0; q < b; ++q) r[k * b + q] += d * Gm[q * b + jj];                        /* :524 */
+                        beta[k * p + m] = bk; delta[k * p + m] = (float)dk; alpha[k * p + m] = na;
+                    }
+                } else {
+                    double bb[8], newa[8], olda[8], d[8], w[8];
+                    for (int k = 0; k < t; ++k) {                        /* :276-281 */
+                        bb[k] = beta[k * p + m];
+                        olda[k] = newa[k] = alpha[k * p + m];
+                        d[k] = delta[k * p + m];
+                        w[k] = (double)(r[k * b + jj] + xpx[m] * alpha[k * p + m]);
+                    }
+                    for (int k = 0; k < t; ++k) {                        /* :282-320 */
+                        double Ginv11 = Ginv[k * t + k];
+                        double C11 = Ginv11 + Rinv[k * t + k] * (double)xpx[m];
+                        double rhs0 = 0.0, c12b = 0.0;
+                        for (int q = 0; q < t; ++q) if (q != k) {
+                            double Ginv12 = Ginv[k * t + q];
+                            double C12 = Ginv12 + (double)xpx[m] * d[q] * Rinv[k * t + q];
+                            rhs0 -= Ginv12 * bb[q];
+                            c12b += C12 * bb[q];
+                        }
+                        double invLhs0 = 1.0 / Ginv11, gHat0 = rhs0 * invLhs0;
+                        double invLhs1 = 1.0 / C11;
+                        double wr = 0.0;
+                        for (int q = 0; q < t; ++q) wr += w[q] * Rinv[q * t + k];
+                        double gHat1 = (wr - c12b) * invLhs1;
+                        int s0 = 0, s1 = 0;
+                        for (int q = 0; q < t; ++q) {
+                            int dq = (q == k) ? 0 : (d[q] != 0.0);
+                            s0 |= dq << q; s1 |= ((q == k) ? 1 : dq) << q;
+                        }
+                        double logDelta0 = -0.5 * (log(Ginv11) - gHat0 * gHat0 * Ginv11) + log(bigPi[s0]);
+                        double logDelta1 = -0.5 * (log(C11) - gHat1 * gHat1 * C11) + log(bigPi[s1]);
+                        double prob1 = 1.0 / (1.0 + exp(logDelta0 - logDelta1));
+                        if (uu[k * p + m] < prob1) {                      /* :306 */
+                            d[k] = 1.0;
+                            float nb = (float)(gHat1 + zz[k * p + m] * sqrt(invLhs1));
+                            bb[k] = newa[k] = nb;
+                            float dd = (float)olda[k] - nb;
+                            for (int64_t q = 0; q < b; ++q) r[k * b + q] += dd * Gm[q * b + jj];   /* :309 */
+                        } else {
+                            bb[k] = (double)(float)(gHat0 + zz[k * p + m] * sqrt(invLhs0));
+                            d[k] = 0.0; newa[k] = 0.0;
+                            if (olda[k] != 0.0) {
+                                float dd = (float)olda[k];
+                                for (int64_t q = 0; q < b; ++q) r[k * b + q] += dd * Gm[q * b + jj]; /* :316 */
+                            }
+                        }
+                    }
+                    for (int k = 0; k < t; ++k) {
+                        beta[k * p + m] = (float)bb[k]; delta[k * p + m] = (float)d[k]; alpha[k * p + m] = (float)newa[k];
+                    }
+                }
+            }
+        for (int k = 0; k < t; ++k)
+            for (int64_t a = 0; a < b; ++a) {
+                float d = aold[k * b + a] - alpha[k * p + s + a];        /* :329 / :533 */
+                if (independent) dsave[k * p + s + a] = d;
+                else if (d != 0.0f) jwo_saxpy(d, X + (s + a) * n, ycorr + k * n, n, 1);
+            }
+        free(Gm); free(r); free(aold);
+    }
+    if (independent) {                                                   /* :432-436 / :641-645 */
+        for (int k = 0; k < t; ++k)
+            for (int64_t j = 0; j < p; ++j)
+                if (dsave[k * p + j] != 0.0f) jwo_saxpy(dsave[k * p + j], X + j * n, ycorr + k * n, n, 1);
+        free(snap); free(dsave);
+    }
+}
+
 /* ======================================================================== */
 /* schedule helpers                                                         */
 /* ======================================================================== */

@@ -87,6 +87,20 @@ void jwo_mtbayesabc_II_ref(const float* X, int64_t n, int64_t p, const float* xp
                            const double* R, const double* G, const double* bigPi,
                            const double* u, const double* z2 /* [j*2 + k] */);
 
+/* BayesR.jl:111-193 (exact block), :195-273 (independent); nreps <= 0 -> block size; u,z [rep*p + j] */
+void jwo_bayesr_block_ref(const float* X, int64_t n, int64_t p, const float* xpx,
+                          const int64_t* starts, int64_t nblocks, int nreps, int independent,
+                          float* ycorr, float* alpha, int32_t* delta,
+                          float vare, float sigmaSq, const double* pi, int per_marker_pi,
+                          const double* gamma, int nclasses, const double* u, const double* z);
+/* MTBayesABC.jl:243-333 / :335-437 (sampler = 1) and :439-537 / :539-646 (sampler = 2, t == 2);
+ * global G and Pi; u,z [(rep*t + k)*p + j] */
+void jwo_mtbayesabc_block_ref(const float* X, int64_t n, int64_t p, int t, int sampler, const float* xpx,
+                              const int64_t* starts, int64_t nblocks, int nreps, int independent,
+                              float* ycorr, float* alpha, float* beta, float* delta,
+                              const double* R, const double* G, const double* bigPi,
+                              const double* u, const double* z);
+
 /* ---- schedule helpers ---- */
 int jwo_bayesr_block_nreps(int64_t iter, int64_t burnin, int64_t block_size); /* BayesR.jl:22-25 */
 int jwo_validate_block_starts(const int64_t* starts, int64_t nstarts, int64_t nmarkers); /* JWAS.jl:73-79; 0 ok */

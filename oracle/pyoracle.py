@@ -183,6 +183,27 @@ def mtbayesabc_II_ref(X, xpx, ycorr, alpha, beta, delta, R, G, bigPi, u, z2):
                                 _p(_f64(u)), _p(_f64(z2)))
 
 
+def bayesr_block_ref(X, xpx, starts, nreps, independent, ycorr, alpha, delta, vare, sigmaSq, pi, gamma, u, z):
+    n, p = X.shape
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    pi = _f64(pi); gamma = _f64(gamma)
+    lib().jwo_bayesr_block_ref(_p(X), C.c_int64(n), C.c_int64(p), _p(_f32(xpx)), _p(st), C.c_int64(len(st) - 1),
+                               C.c_int(nreps), C.c_int(int(independent)), _p(ycorr), _p(alpha), _p(delta),
+                               C.c_float(vare), C.c_float(sigmaSq), _p(pi), C.c_int(int(pi.ndim == 2)),
+                               _p(gamma), C.c_int(len(gamma)), _p(_f64(u)), _p(_f64(z)))
+
+
+def mtbayesabc_block_ref(X, xpx, starts, nreps, independent, sampler, ycorr, alpha, beta, delta, R, G, bigPi, u, z):
+    """sampler: 1 or 2.  alpha/beta/delta: (t, p) Float32; ycorr (t*n,)."""
+    n, p = X.shape
+    t = alpha.shape[0]
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    lib().jwo_mtbayesabc_block_ref(_p(X), C.c_int64(n), C.c_int64(p), C.c_int(t), C.c_int(sampler), _p(_f32(xpx)),
+                                   _p(st), C.c_int64(len(st) - 1), C.c_int(nreps), C.c_int(int(independent)),
+                                   _p(ycorr), _p(alpha), _p(beta), _p(delta), _p(_f64(R)), _p(_f64(G)),
+                                   _p(_f64(bigPi)), _p(_f64(u)), _p(_f64(z)))
+
+
 def bayesr_block_nreps(it, burnin, bs):
     return lib().jwo_bayesr_block_nreps(it, burnin, bs)
 

@@ -1,0 +1,78 @@
+"""Bridge between the two arithmetic flavours of the oracle, for EVERY method and schedule of the path:
+the contract-arithmetic sweep (the bit-exact twin of the CUDA kernels) against the faithful `*_ref`
+restatements of the reference samplers, at BASELINE.json configs[0] size (500 x 2,000) with shared replayed
+draws (tests/bridge.py).  Bar = north_star's: inclusion indicators EQUAL after every sweep, effects and
+ycorr within 1e-5 relative (measured: <= 6e-7; the floor is the reference's own Float32 sdot).
+
+The shipped default schedule (lag = 1, look-ahead panels of 256 / 2048 markers) and the plain one (lag = 0)
+are both bridged.  tests/test_gpu_ref_parity.py repeats this with the CUDA library as the second arm."""
+import numpy as np
+import pytest
+
+import bridge as B
+from helpers import Problem
+
+N, P = 500, 2000
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def probs(oracle):
+    return {1: Problem(oracle, N, P, seed=2026), 2: Problem(oracle, N, P, seed=2027, ntraits=2)}
+
+
+@pytest.mark.parametrize("schedule", B.SCHEDULES)
+@pytest.mark.parametrize("method", B.METHODS)
+def test_contract_tracks_reference_arithmetic(oracle, probs, method, schedule):
+    t = 2 if method.startswith("MT") else 1
+    prob = probs[t]
+    hyp = B.Hyper(prob, method, 5)
+    if schedule == "exact":
+        ref_starts = np.array([0, P], dtype=np.int64)
+        variants = [(np.array(list(range(0, P, 256)) + [P], dtype=np.int64), 1),     # shipped default: lagged panels
+                    (np.array([0, P], dtype=np.int64), 1),                            # one panel of 2,000 (panel 2048)
+                    (np.array(list(range(0, P, 256)) + [P], dtype=np.int64), 0)]
+        nsweeps = 4
+    else:
+        ref_starts = B.fast_block_starts(N, P)             # fast_blocks=true: b = floor(sqrt(500)) = 22, nreps = b
+        variants = [(ref_starts, 0)]
+        nsweeps = 2
+    for starts, lag in variants:
+        sr = B.ref_state(prob, method)
+        sc = prob.fresh_state()
+        rng = np.random.default_rng(3)
+        for it in range(1, nsweeps + 1):
+            u, z = B.draws(rng, schedule, ref_starts, t, P)
+            B.ref_sweep(oracle, prob, hyp, schedule, ref_starts, sr, u, z)
+            B.contract_sweep(oracle, prob, hyp, schedule, starts, sc, u, z, it, lag=lag)
+            eq, ra, ry = B.compare(sr, sc, method)
+            assert eq, f"{method}/{schedule}: delta forks from the reference arithmetic at sweep {it} (lag={lag})"
+            assert ra <= REL and ry <= REL, (method, schedule, it, lag, ra, ry)
+        assert np.count_nonzero(sc[1]) > 5, "degenerate case: (almost) nothing in the model"
+
+
+def test_block_refs_with_one_repetition_equal_dense_refs(oracle, probs):
+    """BayesR_block! / MTBayesABC block samplers with nreps = 1 are the same chain as the dense samplers
+    (block rhs corrected by Gram columns == dot against the updated ycorr; BayesR.jl:150,182): pins the new
+    block restatements to the dense ones (Float32 rounding only)."""
+    prob = probs[1]
+    hyp = B.Hyper(prob, "BayesR", 5)
+    starts = B.fast_block_starts(N, P)
+    rng = np.random.default_rng(9)
+    u, z = rng.random(P), rng.standard_normal(P)
+    s1 = B.ref_state(prob, "BayesR"); s2 = B.ref_state(prob, "BayesR")
+    oracle.bayesr_ref(prob.X, prob.xpx, s1[0], s1[1], s1[3], hyp.vare, hyp.sigma_sq, B.PI_R, B.GAMMA, u, z)
+    oracle.bayesr_block_ref(prob.X, prob.xpx, starts, 1, False, s2[0], s2[1], s2[3], hyp.vare, hyp.sigma_sq, B.PI_R,
+                            B.GAMMA, u, z)
+    np.testing.assert_array_equal(s1[3], s2[3])
+    np.testing.assert_allclose(s2[1], s1[1], atol=2e-6 * np.abs(s1[1]).max())
+    prob = probs[2]
+    for sampler, name in ((1, "MT1"), (2, "MT2")):
+        hyp = B.Hyper(prob, name, 5)
+        u, z = rng.random(2 * P), rng.standard_normal(2 * P)
+        s1 = B.ref_state(prob, name); s2 = B.ref_state(prob, name)
+        B.ref_sweep(oracle, prob, hyp, "exact", None, s1, u, z)
+        oracle.mtbayesabc_block_ref(prob.X, prob.xpx, starts, 1, False, sampler, s2[0], s2[1], s2[2], s2[3], hyp.R, hyp.G,
+                                    hyp.big_pi, u, z)
+        np.testing.assert_array_equal(s1[3], s2[3])
+        np.testing.assert_allclose(s2[1], s1[1], atol=2e-6 * np.abs(s1[1]).max())
