@@ -67,8 +67,21 @@ int jwas_create(int64_t n_obs, int64_t n_markers, int n_traits,
  * Philox keyed by `seed` (benchmarks/bayesr_parity_common.jl:28-59 is the model). */
 int jwas_create_synthetic(int64_t n_obs, int64_t n_markers, int n_traits, uint64_t seed,
                           double missing_rate, int device, jwas_handle** out);
-/* copy of the packed image back to the host (p * stride bytes, stride = cld(n,4)) */
+/* Row shards (multi-GPU, one process per GPU): rank r of `world` stores rows [begin,end) of every column --
+ * words of 64 individuals split evenly (jwas_shard_range).  A shard is created from the bytes of its own rows
+ * only (column pitch stride_bytes >= cld(end-begin,4)); its marker statistics are completed by
+ * jwas_init_sharding, which sums the integer code counts over the ranks. */
+int jwas_shard_range(int64_t n_obs, int rank, int world, int64_t* begin, int64_t* end);
+int jwas_create_shard(int64_t n_obs, int64_t n_markers, int n_traits, int64_t row_begin, int64_t row_end,
+                      const uint8_t* packed_rows, int64_t stride_bytes, int device, jwas_handle** out);
+int jwas_create_synthetic_shard(int64_t n_obs, int64_t n_markers, int n_traits, uint64_t seed, double missing_rate,
+                                int64_t row_begin, int64_t row_end, int device, jwas_handle** out);
+/* copy of the packed rows stored by this handle back to the host (p * stride bytes, stride = cld(rows,4)) */
 int jwas_get_packed(jwas_handle* h, uint8_t* packed, int64_t stride_bytes);
+/* Centre on means computed elsewhere: get_genotypes centres on ALL genotyped individuals
+ * (markers/readgenotypes.jl:372-385) before the rows are aligned to the phenotyped ones (JWAS.jl:381-402).
+ * xpRinvx is recomputed for these means.  Call before jwas_set_blocks. */
+int jwas_set_marker_means(jwas_handle* h, const float* means);
 int jwas_destroy(jwas_handle* h);
 const char* jwas_last_error(void);
 int jwas_device_count(void);
@@ -150,19 +163,24 @@ int jwas_get_means(jwas_handle* h, float* mean_alpha, float* mean_alpha2, float*
 int jwas_get_gram(jwas_handle* h, int64_t ib, float* out);
 
 /* ---- multi-GPU: individuals (rows of M) shard across the GPUs of one node, one process per GPU.
- * Every rank holds the whole packed matrix and the replicated sampler state; rank r streams only
- * rows [begin,end) of every column.  Per marker block the exact int64 partial rhs are summed with
- * one NCCL all-reduce, every rank runs the identical chain (same draws -> same bits) and applies the
- * axpy to its own rows; the ycorr shards are re-assembled at the end of the sweep.  Results are
- * bit-identical for any number of ranks.  rank 0 calls jwas_nccl_unique_id and the host language
- * broadcasts the 128 bytes (torch.distributed, MPI, a file ...). */
+ * Rank r STORES and streams only its rows of every column (jwas_shard_range); ycorr and the sampler state
+ * (alpha, beta, delta, Gram blocks, marker statistics) are replicated.  Per marker block the exact int64
+ * partial rhs of every rank are summed, every rank runs the identical chain (same draws -> same bits) and
+ * applies the axpy to its own rows; the ycorr shards are all-gathered once at the end of the sweep (the host's
+ * hyper-parameter draws need ycorr'ycorr).  Results are bit-identical for any number of ranks.
+ * Order of calls: create (full matrix, or this rank's shard) -> jwas_init_sharding -> jwas_set_blocks ->
+ * jwas_ipc_export / all-gather the 64-byte handles / jwas_ipc_import -> sweeps.
+ * rank 0 calls jwas_nccl_unique_id and the host language broadcasts the 128 bytes (torch.distributed, MPI ...). */
 int jwas_nccl_unique_id(uint8_t* out128);
+/* A handle created from the full matrix keeps only its own rows from here on; a shard is checked against
+ * jwas_shard_range.  Marker statistics are summed over the ranks (NCCL, integer counts: exact). */
 int jwas_init_sharding(jwas_handle* h, int rank, int world, const uint8_t* unique_id128);
 int jwas_get_row_range(jwas_handle* h, int64_t* begin, int64_t* end);
 /* Fused multi-GPU sweep (engine 1, lag 1): every rank exports its exchange buffer as a CUDA IPC handle
  * (64 bytes), the host language all-gathers the handles, every rank imports them.  The persistent
- * kernel then pushes each block's exact int64 partial rhs straight into the peers' memory over NVLink
- * (one communication CTA per GPU) -- no NCCL call, no kernel boundary inside the sweep.  Without the
+ * kernel then pushes each block's exact int64 partial rhs straight into the peers' memory over NVLink as
+ * self-validating 16-byte words {lo32, tag, hi32, tag} (one communication CTA per GPU; no flag, no fence,
+ * no NCCL call, no kernel boundary inside the sweep); the chain's rhs read polls the tags.  Without the
  * import the sharded sweep falls back to engine 0 with one NCCL all-reduce per block. */
 int jwas_ipc_export(jwas_handle* h, uint8_t* out64);
 int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world * 64 bytes in rank order */);

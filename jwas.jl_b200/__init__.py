@@ -5,10 +5,10 @@ set_random / runMCMC with Genotypes / MME types), driving hand-written sm_100a C
 through the C ABI in include/jwas_b200.h.  There is no CPU fallback.
 """
 from ._lib import (GpuSweeper, JwasError, SweepStats, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT,
-                   device_count, SO_PATH)
+                   device_count, shard_range, SO_PATH)
 
 __all__ = ["GpuSweeper", "JwasError", "SweepStats", "SCHED_EXACT", "SCHED_BLOCK", "SCHED_INDEPENDENT",
-           "device_count", "SO_PATH"]
+           "device_count", "shard_range", "SO_PATH"]
 from .api import (get_genotypes, build_model, set_covariate, set_random, runMCMC, prepare_streaming_genotypes,
                   load_streaming_backend, Genotypes, MME, MCMCinfo, Variance, resolve_fast_blocks,
                   validate_fast_block_starts)

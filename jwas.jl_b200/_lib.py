@@ -43,6 +43,10 @@ def lib():
     sig = {
         "jwas_create": [i64, i64, i32, vp, i64, i32, C.POINTER(vp)],
         "jwas_create_synthetic": [i64, i64, i32, u64, dbl, i32, C.POINTER(vp)],
+        "jwas_shard_range": [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)],
+        "jwas_create_shard": [i64, i64, i32, i64, i64, vp, i64, i32, C.POINTER(vp)],
+        "jwas_create_synthetic_shard": [i64, i64, i32, u64, dbl, i64, i64, i32, C.POINTER(vp)],
+        "jwas_set_marker_means": [vp, vp],
         "jwas_get_packed": [vp, vp, i64],
         "jwas_get_gram": [vp, i64, vp],
         "jwas_last_stream_kernel_ms": [vp, C.POINTER(i64)],
@@ -113,10 +117,19 @@ def device_count():
     return lib().jwas_device_count()
 
 
+def shard_range(n_obs, rank, world):
+    """Rows [begin, end) stored by `rank` of a `world`-way row-sharded problem (jwas_shard_range)."""
+    b, e = C.c_int64(), C.c_int64()
+    _check(lib().jwas_shard_range(int(n_obs), int(rank), int(world), C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
 class GpuSweeper:
     """Owns one device-resident genotype matrix and the sampler state that lives beside it."""
 
-    def __init__(self, packed, n_obs, n_traits=1, device=0):
+    def __init__(self, packed, n_obs, n_traits=1, device=0, rows=None):
+        """packed: (p, stride) uint8 .jgb2 image of all n_obs individuals, or -- with rows=(begin, end), the range
+        shard_range() gives this rank -- of those rows only (a row shard; follow with init_sharding)."""
         self._h = C.c_void_p()
         self.starts = None
         if packed is None:
@@ -124,20 +137,36 @@ class GpuSweeper:
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         assert packed.ndim == 2
         self.n, self.p, self.t = int(n_obs), int(packed.shape[0]), int(n_traits)
-        _check(lib().jwas_create(self.n, self.p, self.t, _p(packed), packed.shape[1], device, C.byref(self._h)))
+        if rows is None:
+            _check(lib().jwas_create(self.n, self.p, self.t, _p(packed), packed.shape[1], device, C.byref(self._h)))
+        else:
+            _check(lib().jwas_create_shard(self.n, self.p, self.t, int(rows[0]), int(rows[1]), _p(packed), packed.shape[1],
+                                           device, C.byref(self._h)))
 
     @classmethod
-    def synthetic(cls, n_obs, n_markers, n_traits=1, seed=0, missing_rate=0.0, device=0):
+    def synthetic(cls, n_obs, n_markers, n_traits=1, seed=0, missing_rate=0.0, device=0, rows=None):
+        """Synthetic genotypes generated on the device; rows=(begin, end) generates this rank's shard only (the
+        same bytes the full matrix would hold in those rows)."""
         self = cls(None, 0)
         self.n, self.p, self.t = int(n_obs), int(n_markers), int(n_traits)
-        _check(lib().jwas_create_synthetic(self.n, self.p, self.t, int(seed), float(missing_rate), device,
-                                           C.byref(self._h)))
+        if rows is None:
+            _check(lib().jwas_create_synthetic(self.n, self.p, self.t, int(seed), float(missing_rate), device,
+                                               C.byref(self._h)))
+        else:
+            _check(lib().jwas_create_synthetic_shard(self.n, self.p, self.t, int(seed), float(missing_rate),
+                                                     int(rows[0]), int(rows[1]), device, C.byref(self._h)))
         return self
 
     def get_packed(self):
-        out = np.empty((self.p, (self.n + 3) // 4), np.uint8)
+        """The packed rows this handle stores (all rows unless it is a shard)."""
+        b, e = self.row_range()
+        out = np.empty((self.p, (e - b + 3) // 4), np.uint8)
         _check(lib().jwas_get_packed(self._h, _p(out), out.shape[1]))
         return out
+
+    def set_marker_means(self, means):
+        m = _arr(means, np.float32); assert m.size == self.p
+        _check(lib().jwas_set_marker_means(self._h, _p(m)))
 
     def get_gram(self, ib):
         b = int(self.starts[ib + 1] - self.starts[ib])
@@ -180,8 +209,10 @@ class GpuSweeper:
         y = _arr(y, np.float32); assert y.size == self.t * self.n
         _check(lib().jwas_put_ycorr(self._h, _p(y)))
 
-    def get_ycorr(self):
-        y = np.empty(self.t * self.n, np.float32)
+    def get_ycorr(self, out=None):
+        """out: optional caller-owned Float32 buffer (e.g. pinned memory) the device copies straight into."""
+        y = np.empty(self.t * self.n, np.float32) if out is None else out
+        assert y.dtype == np.float32 and y.size == self.t * self.n and y.flags.c_contiguous
         _check(lib().jwas_get_ycorr(self._h, _p(y)))
         return y
 
@@ -191,8 +222,13 @@ class GpuSweeper:
             assert x is None or x.size == self.t * self.p
         _check(lib().jwas_put_state(self._h, _p(a), _p(b), _p(d)))
 
-    def get_state(self):
-        a = np.empty(self.t * self.p, np.float32); b = np.empty_like(a); d = np.empty(self.t * self.p, np.int32)
+    def get_state(self, out=None):
+        """out: optional (alpha, beta, delta) caller-owned buffers (e.g. pinned memory) filled in place."""
+        if out is None:
+            a = np.empty(self.t * self.p, np.float32); b = np.empty_like(a); d = np.empty(self.t * self.p, np.int32)
+        else:
+            a, b, d = out
+            assert a.dtype == np.float32 and b.dtype == np.float32 and d.dtype == np.int32
         _check(lib().jwas_get_state(self._h, _p(a), _p(b), _p(d)))
         return a, b, d
 

@@ -319,11 +319,15 @@ def build_model(model_equations, R=False, *, df=4.0, genotypes=None, estimate_va
             error(f"{nm} is not a genotype term known to this backend: covariates, factors, pedigree and "
                   "random terms are outside the GPU marker-sweep path.")
         gi = genotypes[nm]; gi.name = nm; gi.ntraits = len(lhs)
+        if len(lhs) != 1 and not getattr(gi, "_df_bumped", False):
+            gi.G.df = gi.G.df + len(lhs)                     # build_MME.jl:108-110
+            gi._df_bumped = True
         M.append(gi)
     if len(M) != 1:
         error("exactly one genotype term is supported with storage=:gpu.")
+    df_R = df if len(lhs) == 1 else df + len(lhs)            # build_MME.jl:128-134
     return MME(model_equations=model_equations, lhsVec=lhs, nModels=len(lhs), M=M,
-               R=Variance(val=R, df=df, estimate_variance=estimate_variance, constraint=constraint))
+               R=Variance(val=R, df=df_R, estimate_variance=estimate_variance, constraint=constraint))
 
 
 def set_covariate(*a, **k):
@@ -415,10 +419,11 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     if n != Mi.nObs or not np.array_equal(rows, np.arange(n)):
         packed = _pack_codes(_unpack_codes(Mi.packed, Mi.nObs)[rows])
 
-    starts, chain_length = resolve_fast_blocks(fast_blocks, chain_length, n, p)
-    if output_samples_frequency is None:
+    if output_samples_frequency is None:                 # evaluated on the user's chain_length (JWAS.jl:168), before :312
         output_samples_frequency = chain_length // 1000 if chain_length > 1000 else 1
-    seed_v = 0 if seed is False else int(seed)
+    starts, chain_length = resolve_fast_blocks(fast_blocks, chain_length, n, p)
+    # seed=false: unseeded run (JWAS.jl:239-241 only seeds when a number is given)
+    seed_v = int.from_bytes(os.urandom(4), "little") if seed is False else int(seed)
     model.MCMCinfo = MCMCinfo(chain_length=chain_length, burnin=burnin, output_samples_frequency=output_samples_frequency,
                               seed=seed, fast_blocks=(False if starts is None else [int(s) + 1 for s in starts[:-1]]),
                               independent_blocks=independent_blocks, outputEBV=outputEBV, output_folder=output_folder)
@@ -458,7 +463,13 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         if model.R.val is False:
             model.R.val = np.diag(vary * 0.5)
         model.R.val = np.array(model.R.val, dtype=np.float64)
-        model.R.scale = model.R.val * (model.R.df - t - 1)
+        # df already carries the + nModels of build_model (build_MME.jl:128-134): scale = R * (df_user - 1);
+        # R_constraint! (input_data_validation.jl:530-540) then takes the traits back out and makes it diagonal
+        df_R = model.R.df
+        model.R.scale = model.R.val * (df_R - t - 1)         # input_data_validation.jl:345
+        if model.R.constraint:
+            df_R = df_R - t
+            model.R.scale = np.diag(np.diag(model.R.scale) / (df_R - 1)) * (df_R - 2) / df_R
         if Mi.G.constraint:
             # megaBayesABC!: one pi per trait (MCMC_BayesianAlphabet.jl:96-99 starts them at zero)
             big = np.zeros(t) if (np.isscalar(Mi.π) or isinstance(Mi.π, dict)) else np.array(Mi.π, dtype=np.float64)
@@ -489,7 +500,11 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         Mi.G.val = np.array(Mi.G.val, dtype=np.float64)
         if np.any(np.linalg.eigvalsh(Mi.G.val) <= 0):
             error("Marker effects covariance matrix is not postive definite! Please modify the argument: Pi.")
-        Mi.G.scale = Mi.G.val * (Mi.G.df - t - 1)
+        df_G = Mi.G.df                                       # user df + nModels (build_MME.jl:108-110)
+        Mi.G.scale = Mi.G.val * (df_G - t - 1)               # tools4genotypes.jl:417
+        if Mi.G.constraint:                                  # G_constraint! (input_data_validation.jl:543-558)
+            df_G = df_G - t
+            Mi.G.scale = np.diag(np.diag(Mi.G.scale) / (df_G - 1)) * (df_G - 2) / df_G
         Mi.π = big
 
     # ---- device-resident backend: GibbsMats (MCMC_BayesianAlphabet.jl:58) + ycorr (:131-147)
@@ -528,8 +543,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          sample_sink=(sink if output_marker_effect_samples else None),
                          chain_length=chain_length, burnin=burnin, output_samples_frequency=output_samples_frequency,
                          seed=seed_v, vare=model.R.val if t == 1 else None, var_effect=Mi.G.val if t == 1 else None,
-                         pi=Mi.π if t == 1 else None, df_effect=Mi.G.df, scale_effect=Mi.G.scale if t == 1 else None,
-                         df_res=model.R.df, scale_res=model.R.scale if t == 1 else None,
+                         pi=Mi.π if t == 1 else None, df_effect=(Mi.G.df if t == 1 else df_G),
+                         scale_effect=Mi.G.scale if t == 1 else None,
+                         df_res=(model.R.df if t == 1 else df_R), scale_res=model.R.scale if t == 1 else None,
                          estimate_pi=Mi.estimatePi, estimate_variance=Mi.G.estimate_variance,
                          estimate_vare=model.R.estimate_variance,
                          R=model.R.val if t > 1 else None, G=Mi.G.val if t > 1 else None,

@@ -315,17 +315,13 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
 
     // ---- rhs of this marker from the streamed partial sums ----
     const int mc = valid ? m : m0;
+    bool ok = true;
 #pragma unroll
     for (int k = 0; k < T; ++k) {
         long long dq, mq, sqk;
         if (B.xslots != nullptr) {
             dq = 0; mq = 0; sqk = 0;
-            for (int rk = 0; rk < B.xworld; ++rk) {
-                const long long* sl = B.xslots + (int64_t)rk * B.slot_stride;
-                dq += __ldcg(sl + (int64_t)k * B.slot_b + mc);
-                if (A.mq) mq += __ldcg(sl + (int64_t)(T + k) * B.slot_b + mc);
-                sqk += __ldcg(sl + (int64_t)2 * T * B.slot_b + k);
-            }
+            ok = jw_ll_rhs(B, T, k, mc, A.mq != nullptr, dq, mq, sqk) && ok;
         } else {
             dq = __ldcg(&A.dq[k * p + j]); mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
             sqk = __ldcg(&B.sq[k]);
@@ -343,10 +339,9 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
             if (d != 0.0f) r[k] += (double)d * (double)g;
         }
     }
-    bool ok = true;
     {
         unsigned spins = 0; unsigned long long t0 = 0;
-        while (wst >= 0) {
+        while (wst >= 0 && ok) {
             int us_ = 0;
             wst = W.poll(us_);
             if (wst < 0) break;

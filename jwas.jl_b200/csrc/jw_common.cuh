@@ -31,7 +31,8 @@ void jw_set_error(const std::string& s);
 
 struct jwas_handle {
     int device = 0;
-    int64_t n = 0, p = 0, stride = 0, stride_d = 0;   // stride_d: device column pitch (16B multiple)
+    int64_t n = 0, p = 0, stride = 0, stride_d = 0;   // n: ALL individuals; stride_d: device column pitch (16B multiple)
+                                                      // of the rows this rank stores, [row_begin, row_end)
     int t = 1;
     int has_missing = 0;
     int sm_count = 148;
@@ -46,6 +47,9 @@ struct jwas_handle {
     float* d_xpx = nullptr;
     int32_t* d_colsum = nullptr;   // sum of codes over observed rows
     int32_t* d_nvalid = nullptr;   // observed rows
+    int32_t* d_cnt = nullptr;      // 3*p: counts of codes 1, 2, 3 over this rank's rows (summed over ranks before use)
+    int stats_ready = 0;           // means / xpx / colsum / nvalid are final (after the all-reduce when rows are sharded)
+    int ext_means = 0;             // means were supplied by the host (jwas_set_marker_means)
 
     // sampler state
     float* d_ycorr = nullptr;      // t * n
@@ -106,19 +110,25 @@ struct jwas_handle {
     int64_t opt_gather = 0;        // pipelined chain: 1 = a gather warp per streaming CTA replays the records under the
                                    // stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line
     int64_t opt_chain_ctas = 0;    // engine 1, lag 1: chain CTAs of the pipelined chain (0 = one-CTA chain)
-    // row-sharded multi-GPU sweep: this rank streams rows [row_begin, row_end) of every column
+    // row-sharded multi-GPU sweep: this rank STORES and streams rows [row_begin, row_end) of every column
+    // (row_begin is a multiple of 64); ycorr and the sampler state are replicated
     int64_t row_begin = 0, row_end = 0;
+    float* d_gath = nullptr; size_t cap_gath = 0;     // all-gather staging (world * chunk * t floats, twice)
     int world = 1, rank = 0;
     void* nccl_comm = nullptr;
     std::vector<int64_t> shard_bounds;   // world+1 row boundaries (multiples of 16 except the last)
-    // fused multi-GPU exchange (IPC-mapped peer memory): one allocation = [flags 1 KB][4 rings x 8 ranks x slot]
+    // fused multi-GPU exchange (IPC-mapped peer memory): one allocation = [4 rings][8 source ranks][slot of 16-byte words]
     unsigned char* d_xbuf = nullptr; size_t xbuf_bytes = 0; int64_t x_slot_words = 0; int x_slot_b = 0;
     void* peer_bufs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    long long** d_peer_slots = nullptr; int** d_peer_flags = nullptr;
+    long long** d_peer_slots = nullptr;
     int ipc_ready = 0; int64_t sweep_seq = 0;
     void* fused = nullptr;         // jw_fused_state (engine 1)
     float next_maxabs = -1.0f;     // carried from the previous sweep's stats when ycorr untouched
 };
+
+// number of rows stored on this rank, and the packed image addressed by GLOBAL row (byte row>>2 of a column)
+static inline int64_t jw_nloc(const jwas_handle* h) { return h->row_end - h->row_begin; }
+static inline const uint8_t* jw_packed_g(const jwas_handle* h) { return h->d_packed - (h->row_begin >> 2); }
 
 __device__ __forceinline__ unsigned jw_dcode(const uint8_t* col, int64_t i) {
     return (col[i >> 2] >> ((i & 3) << 1)) & 3u;

@@ -63,13 +63,14 @@ struct jw_fused_args {
     const float* gramx; const int64_t* gramx_off;
     int timers, two_lists;
     // multi-GPU (rows sharded over `world` GPUs of one node, one process each): this rank streams the
-    // byte-group slices [vs0, vs1); a communication CTA pushes the block's exact int64 partial rhs into
-    // every peer's exchange slots over NVLink (IPC-mapped peer memory) and raises a flag there.
+    // byte-group slices [vs0, vs1) of the rows it stores; a communication CTA pushes the block's exact int64
+    // partial rhs into every peer's exchange slots over NVLink (IPC-mapped peer memory) as self-validating
+    // 16-byte words (value + tag): no flag, no fence; the chain's own rhs read is the wait.
     int world, rank, vs0, vs1;
-    long long* const* peer_slots;       // world pointers: each rank's slot buffer as seen from this GPU
-    int* const* peer_flags;             // world pointers: each rank's flag array [ring][world]
-    long long* my_slots; int* my_flags; // this rank's own buffers (local addresses)
-    int64_t slot_stride; int slot_b; int64_t ring_stride; int flag_base;
+    uint4* const* peer_slots;           // world pointers: each rank's exchange buffer as seen from this GPU
+    const uint4* my_slots;              // this rank's own buffer (local address)
+    int64_t slot_stride; int slot_b; int64_t ring_stride; unsigned tag_base;   // strides in 16-byte words
+    int64_t row_off, nloc;              // this rank stores rows [row_off, row_off + nloc) of the n individuals
     float* ycorr; float scale;
     int* arrive; int* done; long long* sq_acc; int32_t* act_cnt_blk; int32_t* act_idx_all;
     int32_t* flags;              // [0] overflow, [2] abort
@@ -178,6 +179,9 @@ jw_k_fused(jw_fused_args F) {
     __shared__ long long s_red[32 * JW_MAX_TRAITS];
     __shared__ int s_ok;
     const int64_t n = F.C.n, p = F.C.p;
+    // rows are LOCAL (0 .. nloc) in everything that touches the genotype image; ycorr holds all n individuals
+    const int64_t nloc = F.nloc;
+    float* const ycorr_l = F.ycorr + F.row_off;
     // lag = 1: the last CTA only runs chains, the others only stream, so that the chain of block k
     // overlaps the streaming of block k+1 (which needs the updates of blocks <= k-1 only)
     const int lag = F.lag;
@@ -239,31 +243,18 @@ jw_k_fused(jw_fused_args F) {
                 B.prefetch_s = F.P.unit_start[u + n_chain];
                 B.prefetch_b = (int)(F.P.unit_start[u + n_chain + 1] - B.prefetch_s);
             }
-            B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0;
+            B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = F.flags;
             if (multi) {
                 B.xslots = F.my_slots + (int64_t)(k & 3) * F.ring_stride;
                 B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
+                B.xtag = F.tag_base + (unsigned)k + 1u;
             }
             B.sq = F.sq_acc + k * T;
             B.act_idx = F.act_idx_all + F.P.unit_start[u];
             B.act_cnt = nullptr; B.write_active_list = 1;
             auto wait_rhs = [&]() -> bool {
-                if (multi) {
-                    if (tid == 0) s_ok = 1;
-                    __syncthreads();
-                    if (tid < F.world) {
-                        const int* fl = F.my_flags + (k & 3) * F.world + tid;
-                        unsigned long long t0 = jw_globaltimer(); unsigned it = 0; int v;
-                        while (true) {
-                            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
-                            if (v >= F.flag_base + k + 1) break;
-                            if ((++it & 1023u) == 0) {
-                                if (jw_ld_acquire(&F.flags[2]) != 0) { s_ok = 0; break; }
-                                if (jw_globaltimer() - t0 > 20000000000ull) { atomicExch(&F.flags[2], 1); s_ok = 0; break; }
-                            }
-                        }
-                    }
-                } else if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+                if (multi) return true;            // the rhs words carry their own tags: reading them is the wait
+                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
                 __syncthreads();
                 return s_ok != 0;
             };
@@ -323,9 +314,9 @@ jw_k_fused(jw_fused_args F) {
                 int cnt = 0;
                 if (tid < R) {
                     const int64_t row = row0 + tid;
-                    const bool rv = row < n;
+                    const bool rv = row < nloc;
 #pragma unroll
-                    for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
+                    for (int kk = 0; kk < T; ++kk) v[kk] = rv ? ycorr_l[kk * n + row] : 0.0f;
                     const int sh = (tid & 3) << 1;
 #ifdef JW_NEXT_META
                     // uniform panels (every block uniform_b markers, the last one possibly shorter): the block's
@@ -392,16 +383,16 @@ jw_k_fused(jw_fused_args F) {
                 for (int kk = 0; kk < T; ++kk) qs[kk] = 0;
                 if (tid < R) {
                     const int64_t row = row0 + tid;
-                    const bool rv = row < n;
+                    const bool rv = row < nloc;
                     if (gather_mode) {
 #pragma unroll
                         for (int kk = 0; kk < T; ++kk) {
-                            v[kk] = (k == 0) ? (rv ? F.ycorr[kk * n + row] : 0.0f) : s_yn[kk * R + tid];
+                            v[kk] = (k == 0) ? (rv ? ycorr_l[kk * n + row] : 0.0f) : s_yn[kk * R + tid];
                             s_y[kk * R + tid] = v[kk];
                         }
                     } else if (!from_records) {
 #pragma unroll
-                        for (int kk = 0; kk < T; ++kk) v[kk] = rv ? F.ycorr[kk * n + row] : 0.0f;
+                        for (int kk = 0; kk < T; ++kk) v[kk] = rv ? ycorr_l[kk * n + row] : 0.0f;
                     }
                     if (rv && prev_cnt > 0) {
                         if (!from_records && !gather_mode) {
@@ -420,7 +411,7 @@ jw_k_fused(jw_fused_args F) {
                             }
                         }
 #pragma unroll
-                        for (int kk = 0; kk < T; ++kk) F.ycorr[kk * n + row] = v[kk];
+                        for (int kk = 0; kk < T; ++kk) ycorr_l[kk * n + row] = v[kk];
                     }
                     int ovf = 0;
 #pragma unroll
@@ -598,7 +589,7 @@ jw_k_fused(jw_fused_args F) {
                                 for (int i = 0; i < NG * 4; ++i) {
                                     const unsigned code = (bytes[q][i >> 2] >> ((i & 3) << 1)) & 3u;
                                     const float xv = (code == 3u ? mus[q] : (float)code) - mus[q];
-                                    const bool rowv = (NG * 4 * lane + i < R) && (row0 + NG * 4 * lane + i < n);
+                                    const bool rowv = (NG * 4 * lane + i < R) && (row0 + NG * 4 * lane + i < nloc);
 #pragma unroll
                                     for (int kk = 0; kk < T; ++kk) {
                                         const float d = RR.d(q, kk);
@@ -656,23 +647,23 @@ jw_k_fused(jw_fused_args F) {
             __syncthreads();
             if (!s_ok) return;
             const int ring = k & 3;
-            const int per = 2 * T * F.slot_b + T;                 // int64 words of one slot
-            for (int rk = 0; rk < F.world; ++rk) {
-                long long* dst = F.peer_slots[rk] + (int64_t)ring * F.ring_stride + (int64_t)F.rank * F.slot_stride;
-                for (int e = tid; e < per; e += JW_FUSED_THREADS) {
-                    long long v;
-                    if (e < T * F.slot_b) { const int kk = e / F.slot_b, mm = e % F.slot_b; v = mm < b ? __ldcg(&F.dq[(int64_t)kk * p + s + mm]) : 0; }
-                    else if (e < 2 * T * F.slot_b) { const int e2 = e - T * F.slot_b; const int kk = e2 / F.slot_b, mm = e2 % F.slot_b;
-                                                     v = (mm < b && F.C.mq) ? __ldcg(&F.mq[(int64_t)kk * p + s + mm]) : 0; }
-                    else v = __ldcg(&F.sq_acc[k * T + (e - 2 * T * F.slot_b)]);
-                    dst[e] = v;
+            const unsigned tag = F.tag_base + (unsigned)k + 1u;
+            const int64_t slot0 = (int64_t)ring * F.ring_stride + (int64_t)F.rank * F.slot_stride;
+            // value e of the slot: dq[kk][mm] | mq[kk][mm] (only when calls are missing) | sq[kk]; only the
+            // entries the chain reads are sent (mm < b)
+            const int nmq = F.C.mq ? 2 : 1;
+            for (int e = tid; e < nmq * T * b + T; e += JW_FUSED_THREADS) {
+                long long v; int64_t w;
+                if (e < nmq * T * b) {
+                    const int part = e / (T * b), e2 = e - part * T * b, kk = e2 / b, mm = e2 - kk * b;
+                    v = part == 0 ? __ldcg(&F.dq[(int64_t)kk * p + s + mm]) : __ldcg(&F.mq[(int64_t)kk * p + s + mm]);
+                    w = (int64_t)(part * T + kk) * F.slot_b + mm;
+                } else {
+                    const int kk = e - nmq * T * b;
+                    v = __ldcg(&F.sq_acc[k * T + kk]);
+                    w = (int64_t)2 * T * F.slot_b + kk;
                 }
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < F.world) {
-                int* fl = F.peer_flags[tid] + ring * F.world + F.rank;
-                asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(fl), "r"(F.flag_base + k + 1) : "memory");
+                for (int rk = 0; rk < F.world; ++rk) jw_ll_store(F.peer_slots[rk] + slot0 + w, v, tag);
             }
         }
         if constexpr (MODE == 0) { if (is_chain_cta) {
@@ -692,33 +683,19 @@ jw_k_fused(jw_fused_args F) {
             B.xcount_smem = (lag && F.two_lists) ? prev_commits : -1;
             B.prefetch_s = 0; B.prefetch_b = 0;
             if (k + 1 < F.nblocks) { B.prefetch_s = F.C.starts[k + 1]; B.prefetch_b = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]); }
-            B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0;
+            B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = F.flags;
             if (multi) {
                 B.xslots = F.my_slots + (int64_t)(k & 3) * F.ring_stride;
                 B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
+                B.xtag = F.tag_base + (unsigned)k + 1u;
             }
             B.sq = F.sq_acc + k * T;
             B.act_idx = F.act_idx_all + s;
             B.act_cnt = F.act_cnt_blk + k;
             B.write_active_list = 1;
             auto wait_all = [&]() -> bool {
-                if (multi) {
-                    // every rank's partial rhs of this block has landed in my slots
-                    if (tid == 0) s_ok = 1;
-                    __syncthreads();
-                    if (tid < F.world) {
-                        const int* fl = F.my_flags + (k & 3) * F.world + tid;
-                        unsigned long long t0 = jw_globaltimer(); unsigned it = 0; int v;
-                        while (true) {
-                            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
-                            if (v >= F.flag_base + k + 1) break;
-                            if ((++it & 1023u) == 0) {
-                                if (jw_ld_acquire(&F.flags[2]) != 0) { s_ok = 0; break; }
-                                if (jw_globaltimer() - t0 > 20000000000ull) { atomicExch(&F.flags[2], 1); s_ok = 0; break; }
-                            }
-                        }
-                    }
-                } else if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+                if (multi) return true;            // every rank's partial rhs arrives as tagged words: the read waits
+                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
                 __syncthreads();
                 JW_PHASE(3);
                 return s_ok != 0;
@@ -793,15 +770,14 @@ static int jw_fused_prepare(jwas_handle* h) {
     if (!jw_fused_supported(h)) return 0;
     jw_fused_state* f = new jw_fused_state();
     h->fused = f;
-    const int64_t nbytes = (h->n + 3) / 4;
+    const int64_t nbytes = (jw_nloc(h) + 3) / 4;          // the rows stored on this rank
     f->W = (h->t == 2 || h->has_missing) ? 2 : 1;
     // SMs kept for the chain (lag = 1): one, or chain_ctas of them for the pipelined chain; one more for the
     // NVLink push when rows are sharded
     f->n_chain = h->opt_chain_ctas > 0 ? (int)std::min<int64_t>(h->opt_chain_ctas, std::max(1, h->sm_count / 4)) : 0;
     const int chain_sms = std::max(1, f->n_chain);
-    const int64_t streamers = (int64_t)h->world * std::max(1, h->sm_count - chain_sms - (h->world > 1 ? 1 : 0));
+    const int64_t streamers = std::max(1, h->sm_count - chain_sms - (h->world > 1 ? 1 : 0));
     int64_t gs = (nbytes + streamers - 1) / streamers;
-    if (h->world > 1) gs = (gs + 3) / 4 * 4;                 // shard boundaries on 16-individual words
     if (gs > JW_FUSED_MAX_GS) gs = JW_FUSED_MAX_GS;
     if (gs < 1) gs = 1;
     f->Gs = (int)gs;
@@ -869,15 +845,6 @@ static int jw_fused_prepare(jwas_handle* h) {
         f->rec_tag = 0;
     }
     f->ready = true;
-    if (h->world > 1) {
-        // contiguous byte-group slices per rank; individuals follow
-        const int64_t R = (int64_t)f->Gs * 4;
-        h->shard_bounds.assign(h->world + 1, 0);
-        for (int r = 0; r <= h->world; ++r)
-            h->shard_bounds[r] = std::min<int64_t>(h->n, ((int64_t)f->n_vs * r / h->world) * R);
-        h->shard_bounds[h->world] = h->n;
-        h->row_begin = h->shard_bounds[h->rank]; h->row_end = h->shard_bounds[h->rank + 1];
-    }
     return 0;
 }
 
@@ -928,17 +895,22 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.lag = A.nreps_mode ? 0 : (int)h->opt_lag; F.timers = (int)h->opt_timers; F.two_lists = f->two_lists;
     JW_REQUIRE(!F.lag || h->d_gramx, "lag = 1 needs the cross-Gram blocks");
     F.gramx = h->d_gramx; F.gramx_off = h->d_gramx_off;
-    F.world = h->world; F.rank = h->rank; F.vs0 = 0; F.vs1 = f->n_vs;
-    F.peer_slots = nullptr; F.peer_flags = nullptr; F.my_slots = nullptr; F.my_flags = nullptr;
-    F.slot_stride = 0; F.slot_b = 0; F.ring_stride = 0; F.flag_base = 0;
+    F.world = h->world; F.rank = h->rank; F.vs0 = 0; F.vs1 = f->n_vs;     // every slice of the tile is this rank's
+    F.row_off = h->row_begin; F.nloc = jw_nloc(h);
+    F.peer_slots = nullptr; F.my_slots = nullptr;
+    F.slot_stride = 0; F.slot_b = 0; F.ring_stride = 0; F.tag_base = 0;
     if (h->world > 1) {
         JW_REQUIRE(h->ipc_ready && F.lag, "multi-GPU fused sweep needs lag = 1 and jwas_ipc_import");
         JW_REQUIRE(h->maxb <= h->x_slot_b, "exchange slots are smaller than the largest block (call jwas_ipc_export after jwas_set_blocks)");
-        F.vs0 = (int)((int64_t)f->n_vs * h->rank / h->world); F.vs1 = (int)((int64_t)f->n_vs * (h->rank + 1) / h->world);
-        F.peer_slots = h->d_peer_slots; F.peer_flags = h->d_peer_flags;
-        F.my_flags = (int*)h->d_xbuf; F.my_slots = (long long*)(h->d_xbuf + 1024);
+        F.peer_slots = (uint4* const*)h->d_peer_slots;
+        F.my_slots = (const uint4*)h->d_xbuf;
         F.slot_b = h->x_slot_b; F.slot_stride = h->x_slot_words; F.ring_stride = 8 * h->x_slot_words;
-        F.flag_base = (int)(h->sweep_seq * (h->nblocks + 1));
+        // one tag per (sweep, block), never 0 (the cleared buffer) and never reused within 2^32 blocks
+        if (h->sweep_seq * (h->nblocks + 1) + h->nblocks + 2 >= ((int64_t)1 << 32)) {
+            JW_CUDA(cudaMemsetAsync(h->d_xbuf, 0, h->xbuf_bytes, h->stream));
+            h->sweep_seq = 0;
+        }
+        F.tag_base = (unsigned)(h->sweep_seq * (h->nblocks + 1));
         h->sweep_seq += 1;
     }
     F.ycorr = h->d_ycorr; F.scale = scale;
@@ -949,7 +921,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     // the pipelined chain pays when every streaming CTA owns ONE row slice (n up to ~55,000 rows per GPU): with
     // several slices per CTA the stream dominates, the chain is idle anyway, and replaying the records once
     // per slice costs more than the one-chain-CTA hand-off (400,000 x 61,440: 260 vs 284 sweeps/s)
-    const int my_slices = h->world > 1 ? (int)((int64_t)f->n_vs * (h->rank + 1) / h->world - (int64_t)f->n_vs * h->rank / h->world) : f->n_vs;
+    const int my_slices = f->n_vs;
     const bool one_slice = my_slices <= h->sm_count - std::max(1, f->n_chain) - (h->world > 1 ? 1 : 0);
     const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok);
     F.gather = (int)h->opt_gather;
@@ -1010,10 +982,10 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
         for (auto& L : lists) {
             unsigned g = (unsigned)std::max<int64_t>(1, (h->row_end - h->row_begin + 255) / 256);
             if (t == 1)
-                jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+                jw_k_apply_last<1><<<g, 256, 0, h->stream>>>(jw_packed_g(h), h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
                     h->d_act_idx + L.first, L.second, h->d_ycorr, h->row_begin, h->row_end);
             else
-                jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
+                jw_k_apply_last<2><<<g, 256, 0, h->stream>>>(jw_packed_g(h), h->stride_d, h->n, h->p, h->d_means, h->d_dalpha,
                     h->d_act_idx + L.first, L.second, h->d_ycorr, h->row_begin, h->row_end);
             h->launches += 1;
             JW_CUDA(cudaGetLastError());

@@ -1,7 +1,7 @@
 // jw_nccl.cuh -- NCCL through dlopen: the library has no link-time NCCL dependency, and inside a
 // process that already loaded an NCCL (e.g. torch's bundled one) the same instance is reused
-// (same soname).  Used only by the row-sharded multi-GPU sweep: one all-reduce of the exact int64
-// block rhs per marker block, one broadcast-gather of the ycorr shards per sweep.
+// (same soname).  Used only by the row-sharded multi-GPU sweep: set-up all-reduces of the integer marker / pair counts, one
+// all-gather of the ycorr shards per sweep, and (engine 0 only) one all-reduce of the exact int64 block rhs per block.
 #pragma once
 #include <dlfcn.h>
 #include "jw_common.cuh"
@@ -17,6 +17,7 @@ struct jw_nccl_api {
     int (*CommDestroy)(jw_nccl_comm) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, jw_nccl_comm, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, jw_nccl_comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, jw_nccl_comm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -36,6 +37,7 @@ static jw_nccl_api* jw_nccl() {
     JW_SYM(CommDestroy, "ncclCommDestroy")
     JW_SYM(AllReduce, "ncclAllReduce")
     JW_SYM(Broadcast, "ncclBroadcast")
+    JW_SYM(AllGather, "ncclAllGather")
     JW_SYM(GroupStart, "ncclGroupStart")
     JW_SYM(GroupEnd, "ncclGroupEnd")
     JW_SYM(GetErrorString, "ncclGetErrorString")
@@ -43,6 +45,7 @@ static jw_nccl_api* jw_nccl() {
     return &api;
 }
 
+#define JW_NCCL_INT32 2
 #define JW_NCCL_INT64 4
 #define JW_NCCL_FLOAT32 7
 #define JW_NCCL_SUM 0

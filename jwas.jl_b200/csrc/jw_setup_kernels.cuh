@@ -16,12 +16,9 @@ __device__ __forceinline__ float jw_gram_value(long long Nab, long long Sa_vb, l
     return (float)g;
 }
 
-// one warp per marker: counts of codes 1, 2 and 3 -> mean, xpx
+// one warp per marker: counts of codes 1, 2 and 3 over the rows this rank stores (zero padding counts nothing)
 __global__ void __launch_bounds__(256)
-jw_k_marker_stats(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
-                  float* __restrict__ means, float* __restrict__ xpx,
-                  int32_t* __restrict__ colsum, int32_t* __restrict__ nvalid,
-                  int* __restrict__ has_missing) {
+jw_k_marker_counts(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t p, int32_t* __restrict__ cnt) {
     int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (j >= p) return;
@@ -40,16 +37,27 @@ jw_k_marker_stats(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t 
         n2 += __shfl_xor_sync(0xffffffffu, n2, o);
         nm += __shfl_xor_sync(0xffffffffu, nm, o);
     }
-    if (lane == 0) {
-        long long nn = (long long)n - nm;
-        long long sum = (long long)n1 + 2ll * n2;
-        float mu = nn > 0 ? (float)sum / (float)nn : 0.0f;
-        means[j] = mu;
-        xpx[j] = jw_gram_value((long long)n1 + 4ll * n2, sum, sum, nn, mu, mu);
-        colsum[j] = (int32_t)sum;
-        nvalid[j] = (int32_t)nn;
-        if (nm > 0) atomicOr(has_missing, 1);
-    }
+    if (lane == 0) { cnt[j] = n1; cnt[p + j] = n2; cnt[2 * p + j] = nm; }
+}
+
+// counts (summed over the ranks when rows are sharded) -> mean, xpx, colsum, nvalid.  ext_means: the means
+// were supplied by the host (centring on a larger sample than the analysed rows, readgenotypes.jl:372-385
+// before the alignment of JWAS.jl:381-402); xpx follows from the same closed form.
+__global__ void __launch_bounds__(256)
+jw_k_marker_finalize(const int32_t* __restrict__ cnt, int64_t n, int64_t p, int ext_means,
+                     float* __restrict__ means, float* __restrict__ xpx,
+                     int32_t* __restrict__ colsum, int32_t* __restrict__ nvalid, int* __restrict__ has_missing) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    const int n1 = cnt[j], n2 = cnt[p + j], nm = cnt[2 * p + j];
+    long long nn = (long long)n - nm;
+    long long sum = (long long)n1 + 2ll * n2;
+    float mu = ext_means ? means[j] : (nn > 0 ? (float)sum / (float)nn : 0.0f);
+    means[j] = mu;
+    xpx[j] = jw_gram_value((long long)n1 + 4ll * n2, sum, sum, nn, mu, mu);
+    colsum[j] = (int32_t)sum;
+    nvalid[j] = (int32_t)nn;
+    if (nm > 0) atomicOr(has_missing, 1);
 }
 
 // Gram blocks.  One CTA computes a 64x64 tile of one block's b*b matrix, streaming both

@@ -534,15 +534,67 @@ struct jw_chain_blk {
     // (c) previous block's commits kept in shared memory by the dedicated chain CTA (lagged schedule)
     int xcount_smem;                        // >= 0: number of entries in the shared list; -1: use xlist/xcount
     // multi-GPU fused sweep: the block's partial rhs of every rank, pushed over NVLink into this GPU's
-    // exchange slots: [rank][ dq: T*slot_b | mq: T*slot_b | sq: T ] (int64); NULL = single GPU
-    const long long* xslots; int xworld; int64_t slot_stride; int slot_b;
+    // exchange slots: [rank][ dq: T*slot_b | mq: T*slot_b | sq: T ] 16-byte self-validating words
+    // {lo32, tag, hi32, tag}; NULL = single GPU
+    const uint4* xslots; int xworld; int64_t slot_stride; int slot_b; unsigned xtag; int32_t* xflags;
 };
+
+// ---- 16-byte words of the multi-GPU exchange: value + tag in each 8-byte half, so a word is complete in
+//      itself -- one vector store over NVLink, no flag, no fence; readers poll until both tags match ----
+__device__ __forceinline__ void jw_ll_store(void* dst, long long v, unsigned tag) {
+    const unsigned lo = (unsigned)(unsigned long long)v, hi = (unsigned)((unsigned long long)v >> 32);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 jw_ll_load(const void* src) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+    return v;
+}
+// exact int64 sum over the W ranks' copies of one value (copies `stride` words apart): all loads of a round are
+// issued together, ranks that have not arrived are polled again.  false = the sweep was abandoned.
+__device__ __forceinline__ bool jw_ll_sum(const uint4* base, const int64_t stride, const int W, const unsigned tag,
+                                          int32_t* flags, long long& out) {
+    unsigned pend = (1u << W) - 1u;
+    long long acc = 0;
+    unsigned spins = 0; unsigned long long t0 = 0;
+    while (pend) {
+        uint4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if ((pend >> q) & 1u) v[q] = jw_ll_load(base + (int64_t)q * stride);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (((pend >> q) & 1u) && v[q].y == tag && v[q].w == tag) {
+                acc += (long long)(((unsigned long long)v[q].z << 32) | (unsigned long long)v[q].x);
+                pend &= ~(1u << q);
+            }
+        if (pend && (++spins & 255u) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            int ab;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(flags + 2) : "memory");
+            if (ab != 0) return false;
+            if (now - t0 > 20000000000ull) { atomicExch(&flags[2], 1); return false; }
+        }
+    }
+    out = acc;
+    return true;
+}
+// the three integer sums a marker's rhs needs, over all ranks
+__device__ __forceinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
+                                          long long& dq, long long& mq, long long& sqk) {
+    bool ok = jw_ll_sum(B.xslots + (int64_t)k * B.slot_b + m, B.slot_stride, B.xworld, B.xtag, B.xflags, dq);
+    mq = 0;
+    if (has_mq) ok = jw_ll_sum(B.xslots + (int64_t)(T + k) * B.slot_b + m, B.slot_stride, B.xworld, B.xtag, B.xflags, mq) && ok;
+    ok = jw_ll_sum(B.xslots + (int64_t)2 * T * B.slot_b + k, B.slot_stride, B.xworld, B.xtag, B.xflags, sqk) && ok;
+    return ok;
+}
 __device__ __forceinline__ jw_chain_blk jw_chain_blk_from(const jw_chain_args& A) {
     jw_chain_blk B;
     B.sq = A.sq; B.act_idx = A.act_idx; B.act_cnt = A.act_cnt; B.write_active_list = A.write_active_list;
     B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
     B.prefetch_s = 0; B.prefetch_b = 0; B.s = 0; B.b = 0; B.gram_off = 0; B.xcount_smem = -1;
-    B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0;
+    B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = nullptr;
     return B;
 }
 
@@ -665,6 +717,7 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
     JW_CT(1);
 
     // rhs of this marker for every trait
+    bool ll_ok = true;
 #pragma unroll
     for (int k = 0; k < T; ++k) {
         // .cg loads: these words were produced by other CTAs' atomics in the fused engine
@@ -672,18 +725,14 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         if (B.xslots != nullptr) {
             // exact int64 sums over the ranks' partial rhs (any order gives the same bits)
             dq = 0; mq = 0; sqk = 0;
-            for (int rk = 0; rk < B.xworld; ++rk) {
-                const long long* sl = B.xslots + (int64_t)rk * B.slot_stride;
-                dq += __ldcg(sl + (int64_t)k * B.slot_b + m);
-                if (A.mq) mq += __ldcg(sl + (int64_t)(T + k) * B.slot_b + m);
-                sqk += __ldcg(sl + (int64_t)2 * T * B.slot_b + k);
-            }
+            ll_ok = jw_ll_rhs(B, T, k, valid ? m : 0, A.mq != nullptr, dq, mq, sqk) && ll_ok;
         } else {
             dq = __ldcg(&A.dq[k * p + j]); mq = A.mq ? __ldcg(&A.mq[k * p + j]) : 0ll;
             sqk = __ldcg(&B.sq[k]);
         }
         r[k] = ((double)dq - mu * (double)(sqk - mq)) * A.invscale;
     }
+    if (B.xslots != nullptr) { if (__syncthreads_or(ll_ok ? 0 : 1)) return -1; }
     if (B.xgram != nullptr && valid && two_lists) {
         // previous block's commits from shared memory; four cross-Gram loads in flight, adds in order
         const int xc = B.xcount_smem;
@@ -930,12 +979,13 @@ jw_k_apply(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int6
 }
 
 // out = M * alpha (getEBV / ycorr init): same column walk, alpha as the coefficient, no list
+// (rows [r0, r1) of this rank; `packed` is addressed by global row)
 __global__ void __launch_bounds__(256)
-jw_k_mul_alpha(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
+jw_k_mul_alpha(const uint8_t* __restrict__ packed, int64_t stride_d, int64_t r0, int64_t r1, int64_t p,
                const float* __restrict__ means, const float* __restrict__ alpha,
                float sign, float* __restrict__ out, int accumulate) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
     float v = accumulate ? out[i] : 0.0f;
     const int sh = (int)(i & 3) << 1;
     const int64_t byte = i >> 2;
@@ -1052,6 +1102,17 @@ jw_k_maxabs(const float* __restrict__ y, int64_t n, unsigned* __restrict__ out) 
         m = fmaxf(m, fabsf(y[i]));
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+// all-gather staging: recv = [rank][trait][chunk] -> y[trait][bounds[rank] + i]
+struct jw_bounds { int64_t b[9]; };
+__global__ void __launch_bounds__(256)
+jw_k_scatter_rows(const float* __restrict__ recv, int64_t chunk, int t, int world, jw_bounds B,
+                  float* __restrict__ y, int64_t n, int skip_rank) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y / t, k = blockIdx.y % t;
+    if (r == skip_rank) return;
+    const int64_t len = B.b[r + 1] - B.b[r];
+    if (i < len) y[(int64_t)k * n + B.b[r] + i] = recv[((int64_t)r * t + k) * chunk + i];
 }
 __global__ void __launch_bounds__(256)
 jw_k_shift(float* __restrict__ y, int64_t n, float shift) {

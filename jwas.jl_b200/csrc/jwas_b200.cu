@@ -46,21 +46,38 @@ static int ensure_cap(T** ptr, size_t* cap, size_t need) {
 }
 
 // ------------------------------------------------------------------------------------------
-static int create_common(int64_t n, int64_t p, int t, int device, jwas_handle** out) {
+// Row shards: words of 64 individuals (16 packed bytes) split evenly, the remainder to the first ranks.
+static void shard_range(int64_t n, int rank, int world, int64_t* b, int64_t* e) {
+    const int64_t nw = ceil_div(n, 64);
+    auto bound = [&](int r) { return std::min<int64_t>(n, (nw / world * r + std::min<int64_t>(r, nw % world)) * 64); };
+    *b = bound(rank); *e = rank + 1 == world ? n : bound(rank + 1);
+}
+extern "C" int jwas_shard_range(int64_t n_obs, int rank, int world, int64_t* begin, int64_t* end) {
+    JW_REQUIRE(begin && end, "jwas_shard_range: null argument");
+    JW_REQUIRE(n_obs > 0 && world >= 1 && rank >= 0 && rank < world, "jwas_shard_range: bad arguments");
+    shard_range(n_obs, rank, world, begin, end);
+    return 0;
+}
+
+static int create_common(int64_t n, int64_t p, int t, int64_t row_begin, int64_t row_end, int device, jwas_handle** out) {
     JW_REQUIRE(out != nullptr, "jwas_create: out is NULL");
     *out = nullptr;
     JW_REQUIRE(n > 0 && p > 0, "Genotype data is empty.");
     JW_REQUIRE(p < (int64_t)2147483647, "jwas_create: too many markers for 32-bit marker ids");
     JW_REQUIRE(t >= 1 && t <= JW_MAX_TRAITS, "jwas_create: number of traits must be 1..4");
+    JW_REQUIRE(row_begin >= 0 && row_begin < row_end && row_end <= n && (row_begin & 63) == 0,
+               "jwas_create: the row range must lie inside 0..nObs and begin on a multiple of 64");
     int ndev = jwas_device_count();
     JW_REQUIRE(ndev > 0, "no CUDA device is visible: libjwasb200 has no CPU fallback");
     JW_REQUIRE(device >= 0 && device < ndev, "jwas_create: device index out of range");
     JW_CUDA(cudaSetDevice(device));
 
     jwas_handle* h = new jwas_handle();
-    h->device = device; h->n = n; h->p = p; h->t = t; h->stride = (n + 3) / 4;
-    h->stride_d = ceil_div((n + 3) / 4, 16) * 16;
-    h->row_begin = 0; h->row_end = n;
+    h->device = device; h->n = n; h->p = p; h->t = t;
+    h->row_begin = row_begin; h->row_end = row_end;
+    const int64_t nloc = row_end - row_begin;
+    h->stride = (nloc + 3) / 4;
+    h->stride_d = ceil_div((nloc + 3) / 4, 16) * 16;
     cudaDeviceProp prop;
     JW_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
@@ -75,6 +92,7 @@ static int create_common(int64_t n, int64_t p, int t, int device, jwas_handle** 
     JW_CUDA(cudaMalloc((void**)&h->d_xpx, p * sizeof(float)));
     JW_CUDA(cudaMalloc((void**)&h->d_colsum, p * sizeof(int32_t)));
     JW_CUDA(cudaMalloc((void**)&h->d_nvalid, p * sizeof(int32_t)));
+    JW_CUDA(cudaMalloc((void**)&h->d_cnt, (size_t)3 * p * sizeof(int32_t)));
     JW_CUDA(cudaMalloc((void**)&h->d_ycorr, tn * sizeof(float)));
     JW_CUDA(cudaMalloc((void**)&h->d_alpha, tp * sizeof(float)));
     JW_CUDA(cudaMalloc((void**)&h->d_beta, tp * sizeof(float)));
@@ -102,40 +120,66 @@ static int create_common(int64_t n, int64_t p, int t, int device, jwas_handle** 
     return 0;
 }
 
-// per-marker statistics (GibbsMats: xpRinvx, tools4genotypes.jl:28-36, 247-250)
-static int finish_create(jwas_handle* h) {
+// per-marker statistics (GibbsMats: xpRinvx, tools4genotypes.jl:28-36, 247-250): integer counts over the
+// rows stored here, summed over the ranks when rows are sharded, then one closed form per marker
+static int marker_counts(jwas_handle* h) {
+    jw_k_marker_counts<<<(unsigned)ceil_div(h->p, 8), 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->p, h->d_cnt);
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+static int marker_finalize(jwas_handle* h) {
+    if (h->world > 1) {
+        jw_nccl_api* N = jw_nccl();
+        JW_REQUIRE(N && h->nccl_comm, "sharded handle without an initialised NCCL communicator");
+        JW_NCCL(N->AllReduce(h->d_cnt, h->d_cnt, (size_t)3 * h->p, JW_NCCL_INT32, JW_NCCL_SUM, h->nccl_comm, h->stream));
+    }
     int* d_hm = (int*)&h->d_flags[1];
-    jw_k_marker_stats<<<(unsigned)ceil_div(h->p, 8), 256, 0, h->stream>>>(
-        h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, d_hm);
+    JW_CUDA(cudaMemsetAsync(d_hm, 0, sizeof(int), h->stream));
+    jw_k_marker_finalize<<<(unsigned)ceil_div(h->p, 256), 256, 0, h->stream>>>(
+        h->d_cnt, h->n, h->p, h->ext_means, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, d_hm);
     JW_LAUNCH_CHECK(h);
     JW_CUDA(cudaMemcpyAsync(&h->has_missing, d_hm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats_ready = 1;
+    return 0;
+}
+// full handles finish here; a shard (rows of a larger problem) waits for jwas_init_sharding
+static int finish_create(jwas_handle* h) {
+    int rc = marker_counts(h);
+    if (rc) return rc;
+    if (h->row_begin == 0 && h->row_end == h->n) return marker_finalize(h);
     JW_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-extern "C" int jwas_create(int64_t n, int64_t p, int t, const uint8_t* packed, int64_t stride,
-                           int device, jwas_handle** out) {
+extern "C" int jwas_create_shard(int64_t n, int64_t p, int t, int64_t row_begin, int64_t row_end,
+                                 const uint8_t* packed_rows, int64_t stride, int device, jwas_handle** out) {
     JW_REQUIRE(n > 0 && p > 0, "Genotype data is empty.");
-    JW_REQUIRE(stride >= (n + 3) / 4, "jwas_create: stride_bytes is smaller than cld(nObs,4)");
-    JW_REQUIRE(packed != nullptr, "jwas_create: packed is NULL");
-    int rc = create_common(n, p, t, device, out);
+    JW_REQUIRE(packed_rows != nullptr, "jwas_create: packed is NULL");
+    JW_REQUIRE(row_end > row_begin && stride >= (row_end - row_begin + 3) / 4, "jwas_create: stride_bytes is smaller than cld(rows,4)");
+    int rc = create_common(n, p, t, row_begin, row_end, device, out);
     if (rc) return rc;
     jwas_handle* h = *out;
-    JW_CUDA(cudaMemcpy2DAsync(h->d_packed, h->stride_d, packed, stride, (n + 3) / 4, p,
+    JW_CUDA(cudaMemcpy2DAsync(h->d_packed, h->stride_d, packed_rows, stride, (row_end - row_begin + 3) / 4, p,
                               cudaMemcpyHostToDevice, h->stream));
     rc = finish_create(h);
     if (rc) { jwas_destroy(h); *out = nullptr; }
     return rc;
 }
+extern "C" int jwas_create(int64_t n, int64_t p, int t, const uint8_t* packed, int64_t stride,
+                           int device, jwas_handle** out) {
+    JW_REQUIRE(n > 0 && p > 0, "Genotype data is empty.");
+    JW_REQUIRE(stride >= (n + 3) / 4, "jwas_create: stride_bytes is smaller than cld(nObs,4)");
+    return jwas_create_shard(n, p, t, 0, n, packed, stride, device, out);
+}
 
-// synthetic genotypes: one thread per packed byte (4 individuals)
+// synthetic genotypes: one thread per packed byte (4 individuals); bytes [b0, b0 + nbytes_loc) of every column
 __global__ void __launch_bounds__(256)
-jw_k_synth(uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p, uint64_t seed,
-           uint32_t miss_thr) {
-    int64_t nbytes = (n + 3) >> 2;
+jw_k_synth(uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p, int64_t b0, int64_t nbytes_loc,
+           uint64_t seed, uint32_t miss_thr) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nbytes * p) return;
-    int64_t j = idx / nbytes, b = idx % nbytes;
+    if (idx >= nbytes_loc * p) return;
+    int64_t j = idx / nbytes_loc, lb = idx % nbytes_loc, b = b0 + lb;
     jw_u32x4 rf = jw_philox4x32_10((uint32_t)j, 0u, 0xF00Du, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
     double f = 0.05 + 0.45 * jw_u53(rf.v[0], rf.v[1]);
     uint32_t thr = (uint32_t)(f * 65536.0);
@@ -150,32 +194,54 @@ jw_k_synth(uint8_t* __restrict__ packed, int64_t stride_d, int64_t n, int64_t p,
         if (miss_thr && (rm.v[k] >> 16) < miss_thr) code = 3u;
         byte |= code << (2 * k);
     }
-    packed[j * stride_d + b] = (uint8_t)byte;
+    packed[j * stride_d + lb] = (uint8_t)byte;
 }
 
-extern "C" int jwas_create_synthetic(int64_t n, int64_t p, int t, uint64_t seed, double missing_rate,
-                                     int device, jwas_handle** out) {
+extern "C" int jwas_create_synthetic_shard(int64_t n, int64_t p, int t, uint64_t seed, double missing_rate,
+                                           int64_t row_begin, int64_t row_end, int device, jwas_handle** out) {
     JW_REQUIRE(missing_rate >= 0.0 && missing_rate < 0.5, "missing_rate must be in [0,0.5)");
-    int rc = create_common(n, p, t, device, out);
+    int rc = create_common(n, p, t, row_begin, row_end, device, out);
     if (rc) return rc;
     jwas_handle* h = *out;
-    int64_t total = ((n + 3) / 4) * p;
-    jw_k_synth<<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, p, seed,
-                                                                     (uint32_t)(missing_rate * 65536.0));
+    const int64_t nbytes_loc = (row_end - row_begin + 3) / 4;
+    const int64_t total = nbytes_loc * p;
+    // every byte depends on (seed, marker, GLOBAL byte) only: a shard holds exactly the rows of the full matrix
+    jw_k_synth<<<(unsigned)ceil_div(total, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, p, row_begin >> 2,
+                                                                     nbytes_loc, seed, (uint32_t)(missing_rate * 65536.0));
     JW_LAUNCH_CHECK(h);
     rc = finish_create(h);
     if (rc) { jwas_destroy(h); *out = nullptr; }
     return rc;
 }
+extern "C" int jwas_create_synthetic(int64_t n, int64_t p, int t, uint64_t seed, double missing_rate,
+                                     int device, jwas_handle** out) {
+    return jwas_create_synthetic_shard(n, p, t, seed, missing_rate, 0, n, device, out);
+}
 
+// the rows stored on this rank (all rows of an unsharded handle): p columns of cld(rows,4) bytes
 extern "C" int jwas_get_packed(jwas_handle* h, uint8_t* packed, int64_t stride) {
     JW_REQUIRE(h && packed, "jwas_get_packed: null argument");
-    JW_REQUIRE(stride >= (h->n + 3) / 4, "jwas_get_packed: stride too small");
+    JW_REQUIRE(stride >= (jw_nloc(h) + 3) / 4, "jwas_get_packed: stride too small");
     JW_CUDA(cudaSetDevice(h->device));
-    JW_CUDA(cudaMemcpy2DAsync(packed, stride, h->d_packed, h->stride_d, (h->n + 3) / 4, h->p,
+    JW_CUDA(cudaMemcpy2DAsync(packed, stride, h->d_packed, h->stride_d, (jw_nloc(h) + 3) / 4, h->p,
                               cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// centring on means computed elsewhere (the reference centres on ALL genotyped individuals in get_genotypes,
+// readgenotypes.jl:372-385, and only then aligns rows to the phenotypes, JWAS.jl:381-402); xpx follows.
+extern "C" int jwas_set_marker_means(jwas_handle* h, const float* means) {
+    JW_REQUIRE(h && means, "jwas_set_marker_means: null argument");
+    JW_REQUIRE(h->nblocks == 0, "jwas_set_marker_means must be called before jwas_set_blocks");
+    JW_REQUIRE(h->stats_ready, "jwas_set_marker_means: call jwas_init_sharding first on a sharded handle");
+    JW_CUDA(cudaSetDevice(h->device));
+    JW_CUDA(cudaMemcpyAsync(h->d_means, means, h->p * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->ext_means = 1;
+    const int world = h->world; h->world = 1;            // the counts are already global
+    int rc = marker_finalize(h);
+    h->world = world;
+    return rc;
 }
 
 extern "C" int jwas_get_gram(jwas_handle* h, int64_t ib, float* out) {
@@ -192,14 +258,14 @@ extern "C" int jwas_destroy(jwas_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_ycorr, h->d_alpha,
+    void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_cnt, h->d_gath, h->d_ycorr, h->d_alpha,
                     h->d_beta, h->d_delta, h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta, h->d_ve,
                     h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_draws, h->d_prep_rm, h->d_gramx, h->d_gramx_off, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (int r = 0; r < 8; ++r) if (h->peer_bufs[r]) cudaIpcCloseMemHandle(h->peer_bufs[r]);
-    for (void* q : {(void*)h->d_xbuf, (void*)h->d_peer_slots, (void*)h->d_peer_flags}) if (q) cudaFree(q);
+    for (void* q : {(void*)h->d_xbuf, (void*)h->d_peer_slots}) if (q) cudaFree(q);
     if (h->nccl_comm && jw_nccl()) jw_nccl()->CommDestroy(h->nccl_comm);
     jw_fused_free(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -234,8 +300,11 @@ extern "C" int jwas_get_marker_stats(jwas_handle* h, float* means, float* xpx) {
 // 0/1/2 codes; integer-exact (see jw_setup_kernels.cuh).  One pass over the blocks, the previous
 // block's unpacked panel is kept for the cross product.
 static int build_gram_gemm(jwas_handle* h, bool want_cross) {
-    const int64_t nb = h->nblocks, n = h->n;
+    // rows stored on this rank; the integer pair counts (exact as FP32 below 2^24) are summed over the ranks
+    const int64_t nb = h->nblocks, n = jw_nloc(h);
     const int64_t n_pad = ceil_div(n, 16) * 16;
+    jw_nccl_api* N = h->world > 1 ? jw_nccl() : nullptr;
+    JW_REQUIRE(h->world == 1 || (N && h->nccl_comm), "sharded handle without an initialised NCCL communicator");
     const int64_t maxb = h->maxb;
     const bool ms = h->has_missing != 0;
     cublasHandle_t cb = nullptr;
@@ -281,11 +350,19 @@ static int build_gram_gemm(jwas_handle* h, bool want_cross) {
                 JW_CUBLAS(gemm(V[cur], b, C[r], b_r, cnt[1]));                   // sum_i C_r[i,a] V_c[i,c]
                 JW_CUBLAS(gemm(C[cur], b, V[r], b_r, cnt[2]));                   // sum_i V_r[i,a] C_c[i,c]
                 JW_CUBLAS(gemm(V[cur], b, V[r], b_r, cnt[3]));
+            }
+            if (N) {
+                JW_NCCL(N->GroupStart());
+                for (int q = 0; q < (ms ? 4 : 1); ++q)
+                    JW_NCCL(N->AllReduce(cnt[q], cnt[q], (size_t)b_r * b, JW_NCCL_FLOAT32, JW_NCCL_SUM, h->nccl_comm, h->stream));
+                JW_NCCL(N->GroupEnd());
+            }
+            if (ms) {
                 jw_k_gram_finalize<true><<<(unsigned)ceil_div((int64_t)b_r * b, 256), 256, 0, h->stream>>>(
-                    cnt[0], cnt[1], cnt[2], cnt[3], n, h->d_means, h->d_colsum, s_r, b_r, s, b, out);
+                    cnt[0], cnt[1], cnt[2], cnt[3], h->n, h->d_means, h->d_colsum, s_r, b_r, s, b, out);
             } else {
                 jw_k_gram_finalize<false><<<(unsigned)ceil_div((int64_t)b_r * b, 256), 256, 0, h->stream>>>(
-                    cnt[0], nullptr, nullptr, nullptr, n, h->d_means, h->d_colsum, s_r, b_r, s, b, out);
+                    cnt[0], nullptr, nullptr, nullptr, h->n, h->d_means, h->d_colsum, s_r, b_r, s, b, out);
             }
             JW_LAUNCH_CHECK(h);
         }
@@ -299,6 +376,7 @@ static int build_gram_gemm(jwas_handle* h, bool want_cross) {
 
 // Gram blocks (cross = false) or cross-Gram of consecutive blocks (cross = true): every 64x64 tile
 static int build_gram(jwas_handle* h, bool cross) {
+    JW_REQUIRE(h->world == 1, "the popcount Gram kernel does not support sharded rows (use the default GEMM path, nObs < 2^22)");
     const int64_t nb = h->nblocks;
     std::vector<int32_t> tblk, tab; std::vector<int64_t> toff;
     std::vector<int64_t> xoff(nb, 0);
@@ -343,6 +421,7 @@ static int build_gram(jwas_handle* h, bool cross) {
 
 extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nblocks) {
     JW_REQUIRE(h, "null handle");
+    JW_REQUIRE(h->stats_ready, "jwas_set_blocks: a row shard needs jwas_init_sharding first (marker statistics are summed over the ranks)");
     JW_REQUIRE(starts && nblocks > 0, "fast_blocks block start vector cannot be empty.");
     JW_REQUIRE(starts[0] == 0, "fast_blocks block starts must begin with 1.");
     JW_REQUIRE(starts[nblocks] == h->p, "fast_blocks block boundaries must end at nMarkers.");
@@ -419,15 +498,40 @@ extern "C" int jwas_get_state(jwas_handle* h, float* alpha, float* beta, int32_t
     return 0;
 }
 
+// multi-GPU: every rank holds (or has just updated) only its own rows [row_begin,row_end) of the t vectors at
+// `y` (pitch n); one NCCL all-gather makes them whole on every rank
+static int gather_rows(jwas_handle* h, float* y) {
+    if (h->world == 1) return 0;
+    jw_nccl_api* N = jw_nccl();
+    JW_REQUIRE(N && h->nccl_comm, "multi-GPU call without an initialised NCCL communicator");
+    const int t = h->t, W = h->world;
+    int64_t chunk = 0;
+    for (int r = 0; r < W; ++r) chunk = std::max(chunk, h->shard_bounds[r + 1] - h->shard_bounds[r]);
+    const size_t need = (size_t)(W + 1) * t * chunk;
+    if (ensure_cap(&h->d_gath, &h->cap_gath, need)) return 10;
+    float* send = h->d_gath; float* recv = h->d_gath + (size_t)t * chunk;
+    for (int k = 0; k < t; ++k)
+        JW_CUDA(cudaMemcpyAsync(send + (size_t)k * chunk, y + (size_t)k * h->n + h->row_begin,
+                                (size_t)(h->row_end - h->row_begin) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    JW_NCCL(N->AllGather(send, recv, (size_t)t * chunk, JW_NCCL_FLOAT32, h->nccl_comm, h->stream));
+    jw_bounds B;
+    for (int r = 0; r <= W; ++r) B.b[r] = h->shard_bounds[r];
+    dim3 grid((unsigned)ceil_div(chunk, 256), (unsigned)(W * t));
+    jw_k_scatter_rows<<<grid, 256, 0, h->stream>>>(recv, chunk, t, W, B, y, h->n, h->rank);
+    JW_LAUNCH_CHECK(h);
+    return 0;
+}
+
 extern "C" int jwas_ycorr_sub_malpha(jwas_handle* h) {
     JW_REQUIRE(h, "null handle");
     JW_CUDA(cudaSetDevice(h->device));
     for (int k = 0; k < h->t; ++k) {
-        jw_k_mul_alpha<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(
-            h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_alpha + (size_t)k * h->p, -1.0f,
+        jw_k_mul_alpha<<<(unsigned)ceil_div(jw_nloc(h), 256), 256, 0, h->stream>>>(
+            jw_packed_g(h), h->stride_d, h->row_begin, h->row_end, h->p, h->d_means, h->d_alpha + (size_t)k * h->p, -1.0f,
             h->d_ycorr + (size_t)k * h->n, 1);
         JW_LAUNCH_CHECK(h);
     }
+    if (gather_rows(h, h->d_ycorr)) return 13;
     JW_CUDA(cudaStreamSynchronize(h->stream));
     h->next_maxabs = -1.0f;
     return 0;
@@ -436,10 +540,13 @@ extern "C" int jwas_mul_alpha(jwas_handle* h, int trait, float* out) {
     JW_REQUIRE(h && out, "jwas_mul_alpha: null argument");
     JW_REQUIRE(trait >= 0 && trait < h->t, "jwas_mul_alpha: trait out of range");
     JW_CUDA(cudaSetDevice(h->device));
-    float* d_out = (float*)h->d_yq;   // scratch of n floats (re-quantised by the next sweep anyway)
-    jw_k_mul_alpha<<<(unsigned)ceil_div(h->n, 256), 256, 0, h->stream>>>(
-        h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_alpha + (size_t)trait * h->p, 1.0f, d_out, 0);
+    float* d_out = (float*)h->d_yq + (size_t)trait * h->n;   // scratch (re-quantised by the next sweep anyway)
+    jw_k_mul_alpha<<<(unsigned)ceil_div(jw_nloc(h), 256), 256, 0, h->stream>>>(
+        jw_packed_g(h), h->stride_d, h->row_begin, h->row_end, h->p, h->d_means, h->d_alpha + (size_t)trait * h->p, 1.0f, d_out, 0);
     JW_LAUNCH_CHECK(h);
+    if (h->world > 1) {                 // the other ranks' rows (gather_rows moves all t vectors of the scratch)
+        if (gather_rows(h, (float*)h->d_yq)) return 13;
+    }
     JW_CUDA(cudaMemcpyAsync(out, d_out, h->n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     JW_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
@@ -555,7 +662,7 @@ static int dispatch_dot(jwas_handle* h, int64_t j0, int64_t nj) {
     const int64_t w0 = h->row_begin >> 4, w1 = ceil_div(h->row_end, 16);
     dim3 grid((unsigned)ceil_div(nj, 8), (unsigned)std::max<int64_t>(1, ceil_div(w1 - w0, JW_DOT_SLAB_WORDS)));
     long long* mq = h->d_mq;
-#define JW_DOT(T_, M_) jw_k_block_dot<T_, M_><<<grid, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, j0, nj, h->d_yq, h->d_dq, mq, w0, w1)
+#define JW_DOT(T_, M_) jw_k_block_dot<T_, M_><<<grid, 256, 0, h->stream>>>(jw_packed_g(h), h->stride_d, h->n, h->p, j0, nj, h->d_yq, h->d_dq, mq, w0, w1)
     bool ms = h->has_missing != 0;
     switch (h->t) {
         case 1: if (ms) JW_DOT(1, true); else JW_DOT(1, false); break;
@@ -570,7 +677,7 @@ static int dispatch_dot(jwas_handle* h, int64_t j0, int64_t nj) {
 }
 static int dispatch_apply(jwas_handle* h) {
     unsigned g = (unsigned)std::max<int64_t>(1, ceil_div(h->row_end - h->row_begin, 256));
-#define JW_APPLY(T_) jw_k_apply<T_><<<g, 256, 0, h->stream>>>(h->d_packed, h->stride_d, h->n, h->p, h->d_means, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_ycorr, h->row_begin, h->row_end)
+#define JW_APPLY(T_) jw_k_apply<T_><<<g, 256, 0, h->stream>>>(jw_packed_g(h), h->stride_d, h->n, h->p, h->d_means, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_ycorr, h->row_begin, h->row_end)
     switch (h->t) { case 1: JW_APPLY(1); break; case 2: JW_APPLY(2); break; case 3: JW_APPLY(3); break; default: JW_APPLY(4); }
 #undef JW_APPLY
     JW_LAUNCH_CHECK(h);
@@ -652,23 +759,7 @@ static int reduce_block_rhs(jwas_handle* h, int64_t j0, int64_t nj) {
     JW_NCCL(N->GroupEnd());
     return 0;
 }
-// multi-GPU: every rank updated only its own rows of ycorr; make the vector whole again
-static int gather_ycorr(jwas_handle* h) {
-    if (h->world == 1) return 0;
-    jw_nccl_api* N = jw_nccl();
-    JW_REQUIRE(N && h->nccl_comm, "multi-GPU sweep without an initialised NCCL communicator");
-    JW_NCCL(N->GroupStart());
-    for (int r = 0; r < h->world; ++r) {
-        int64_t b0 = h->shard_bounds[r], b1 = h->shard_bounds[r + 1];
-        if (b1 <= b0) continue;
-        for (int k = 0; k < h->t; ++k) {
-            float* ptr = h->d_ycorr + (size_t)k * h->n + b0;
-            JW_NCCL(N->Broadcast(ptr, ptr, (size_t)(b1 - b0), JW_NCCL_FLOAT32, r, h->nccl_comm, h->stream));
-        }
-    }
-    JW_NCCL(N->GroupEnd());
-    return 0;
-}
+static int gather_ycorr(jwas_handle* h) { return gather_rows(h, h->d_ycorr); }
 
 static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     JW_REQUIRE(h->nblocks > 0, "jwas_set_blocks must be called before a sweep");
@@ -984,33 +1075,54 @@ extern "C" int jwas_nccl_unique_id(uint8_t* out128) {
     memcpy(out128, id.internal, JW_NCCL_UNIQUE_ID_BYTES);
     return 0;
 }
+// Turns the handle into rank `rank` of a `world`-way row-sharded sweep.  A handle created with the full matrix
+// keeps only its own rows from here on (the rest of the image is freed); a handle created as a shard
+// (jwas_create_shard / jwas_create_synthetic_shard with the range of jwas_shard_range) is checked against it.
+// Marker statistics are (re)computed from integer counts summed over the ranks.  Call before jwas_set_blocks.
 extern "C" int jwas_init_sharding(jwas_handle* h, int rank, int world, const uint8_t* unique_id128) {
     JW_REQUIRE(h, "null handle");
-    JW_REQUIRE(world >= 1 && rank >= 0 && rank < world, "jwas_init_sharding: bad rank/world");
+    JW_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "jwas_init_sharding: bad rank/world (1..8 ranks)");
+    JW_REQUIRE(h->nblocks == 0, "jwas_init_sharding must be called before jwas_set_blocks");
+    JW_REQUIRE(h->world == 1 && !h->nccl_comm, "jwas_init_sharding: the handle is already sharded");
     JW_CUDA(cudaSetDevice(h->device));
-    // row shards: equal numbers of 16-individual words per rank, the remainder to the first ranks
-    const int64_t nwords = ceil_div(h->n, 16);
     h->shard_bounds.assign(world + 1, 0);
-    for (int r = 0; r < world; ++r) {
-        int64_t w = nwords / world + (r < nwords % world ? 1 : 0);
-        h->shard_bounds[r + 1] = std::min<int64_t>(h->n, h->shard_bounds[r] + w * 16);
-    }
-    h->shard_bounds[world] = h->n;
+    for (int r = 0; r < world; ++r) { int64_t b, e; shard_range(h->n, r, world, &b, &e); h->shard_bounds[r] = b; h->shard_bounds[r + 1] = e; }
+    const int64_t rb = h->shard_bounds[rank], re = h->shard_bounds[rank + 1];
+    JW_REQUIRE(re > rb, "jwas_init_sharding: more ranks than 64-individual words");
+    const bool full = h->row_begin == 0 && h->row_end == h->n;
+    JW_REQUIRE(full || (h->row_begin == rb && h->row_end == re),
+               "jwas_init_sharding: the handle's row range is not this rank's shard (see jwas_shard_range)");
+    if (world == 1) { h->rank = 0; return 0; }
+    JW_REQUIRE(unique_id128, "jwas_init_sharding: unique id required for world > 1");
+    JW_REQUIRE(!h->ext_means, "jwas_init_sharding: call jwas_set_marker_means after sharding");
+    jw_nccl_api* N = jw_nccl();
+    JW_REQUIRE(N, "libnccl.so.2 could not be loaded");
+    jw_nccl_id id;
+    memcpy(id.internal, unique_id128, JW_NCCL_UNIQUE_ID_BYTES);
+    JW_NCCL(N->CommInitRank(&h->nccl_comm, world, id, rank));
     h->rank = rank; h->world = world;
-    h->row_begin = h->shard_bounds[rank]; h->row_end = h->shard_bounds[rank + 1];
-    if (world > 1) {
-        JW_REQUIRE(unique_id128, "jwas_init_sharding: unique id required for world > 1");
-        jw_nccl_api* N = jw_nccl();
-        JW_REQUIRE(N, "libnccl.so.2 could not be loaded");
-        jw_nccl_id id;
-        memcpy(id.internal, unique_id128, JW_NCCL_UNIQUE_ID_BYTES);
-        JW_NCCL(N->CommInitRank(&h->nccl_comm, world, id, rank));
-        if (h->nblocks > 0) { int rc = jw_fused_prepare(h); if (rc) return rc; }   // slices re-cut for `world` GPUs
+    if (full) {
+        // keep rows [rb, re) only
+        const int64_t nloc = re - rb;
+        const int64_t new_pitch = ceil_div((nloc + 3) / 4, 16) * 16;
+        uint8_t* d_new = nullptr;
+        JW_CUDA(cudaMalloc((void**)&d_new, (size_t)h->p * new_pitch));
+        JW_CUDA(cudaMemsetAsync(d_new, 0, (size_t)h->p * new_pitch, h->stream));
+        JW_CUDA(cudaMemcpy2DAsync(d_new, new_pitch, h->d_packed + (rb >> 2), h->stride_d, (nloc + 3) / 4, h->p,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+        JW_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_packed);
+        h->d_packed = d_new; h->stride_d = new_pitch; h->stride = (nloc + 3) / 4;
+        h->row_begin = rb; h->row_end = re;
+        if (marker_counts(h)) return 11;
     }
-    return 0;
+    return marker_finalize(h);
 }
 
 // ---- fused multi-GPU exchange buffers over CUDA IPC ------------------------------------------
+// One allocation per rank: [ring 4][source rank 8][slot], a slot = 2*t*maxb + t values, each value one 16-byte
+// word {lo32, tag, hi32, tag} written with a single vector store over NVLink and valid when both tags match
+// (8-byte halves are self-validating: no flag, no fence, no second round trip).
 extern "C" int jwas_ipc_export(jwas_handle* h, uint8_t* out64) {
     JW_REQUIRE(h && out64, "jwas_ipc_export: null argument");
     JW_REQUIRE(h->nblocks > 0, "jwas_ipc_export: call jwas_set_blocks first");
@@ -1018,7 +1130,7 @@ extern "C" int jwas_ipc_export(jwas_handle* h, uint8_t* out64) {
     if (!h->d_xbuf) {
         h->x_slot_b = (int)h->maxb;
         h->x_slot_words = (int64_t)2 * h->t * h->x_slot_b + h->t;
-        h->xbuf_bytes = 1024 + (size_t)4 * 8 * h->x_slot_words * sizeof(long long);
+        h->xbuf_bytes = (size_t)4 * 8 * h->x_slot_words * 16;
         JW_CUDA(cudaMalloc((void**)&h->d_xbuf, h->xbuf_bytes));
         JW_CUDA(cudaMemset(h->d_xbuf, 0, h->xbuf_bytes));
     }
@@ -1033,7 +1145,7 @@ extern "C" int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world *
     JW_REQUIRE(h->world > 1 && h->world <= 8, "jwas_ipc_import: call jwas_init_sharding first (2..8 ranks)");
     JW_REQUIRE(h->d_xbuf, "jwas_ipc_import: call jwas_ipc_export first");
     JW_CUDA(cudaSetDevice(h->device));
-    long long* slots[8]; int* flags[8];
+    long long* slots[8];
     for (int r = 0; r < h->world; ++r) {
         void* base = h->d_xbuf;
         if (r != h->rank) {
@@ -1042,15 +1154,10 @@ extern "C" int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world *
             JW_CUDA(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
             h->peer_bufs[r] = base;
         }
-        flags[r] = (int*)base;
-        slots[r] = (long long*)((unsigned char*)base + 1024);
+        slots[r] = (long long*)base;
     }
-    if (!h->d_peer_slots) {
-        JW_CUDA(cudaMalloc((void**)&h->d_peer_slots, 8 * sizeof(long long*)));
-        JW_CUDA(cudaMalloc((void**)&h->d_peer_flags, 8 * sizeof(int*)));
-    }
+    if (!h->d_peer_slots) JW_CUDA(cudaMalloc((void**)&h->d_peer_slots, 8 * sizeof(long long*)));
     JW_CUDA(cudaMemcpy(h->d_peer_slots, slots, h->world * sizeof(long long*), cudaMemcpyHostToDevice));
-    JW_CUDA(cudaMemcpy(h->d_peer_flags, flags, h->world * sizeof(int*), cudaMemcpyHostToDevice));
     h->ipc_ready = 1;
     return 0;
 }

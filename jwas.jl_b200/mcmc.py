@@ -172,13 +172,22 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
     ysum = None
     for it in range(iter0 + 1, iter0 + chain_length + 1):
         # [1] intercept: ycorr += mu; mu ~ N(mean(ycorr), vare/n); ycorr -= mu
-        if sample_intercept:
+        if sample_intercept and t == 1:
+            s = ysum[0] if ysum is not None else backend.ycorr_sum(0)
+            new_mu = mu[0] + s / n + rng.normal() * math.sqrt(vare / n)      # Gibbs(A,x,b,vare), solver.jl:143-151
+            backend.shift_ycorr(0, np.float32(mu[0] - new_mu))
+            mu[0] = new_mu
+        elif sample_intercept:
+            # multi-trait: mmeLhs = X'RiX with Ri = kron(inv(R), I) (MCMC_BayesianAlphabet.jl:196-217) and one pass of
+            # Gibbs(A,x,b) (solver.jl:154-162): each intercept from its FULL CONDITIONAL given the other traits'
+            # current intercepts -- variance 1/(n Rinv_kk), mean through the off-diagonals of inv(R)
+            Rinv = np.linalg.inv(R)
+            ssum = np.array([ysum[k] if ysum is not None else backend.ycorr_sum(k) for k in range(t)], dtype=np.float64)
             for k in range(t):
-                s = ysum[k] if ysum is not None else backend.ycorr_sum(k)
-                vk = vare if t == 1 else R[k, k]
-                mu_hat = mu[k] + s / n
-                new_mu = mu_hat + rng.normal() * math.sqrt(vk / n)
+                invlhs = 1.0 / (n * Rinv[k, k])
+                new_mu = mu[k] + invlhs * float(Rinv[k] @ ssum) + rng.normal() * math.sqrt(invlhs)
                 backend.shift_ycorr(k, np.float32(mu[k] - new_mu))
+                ssum[k] += n * (mu[k] - new_mu)              # later traits see this trait's updated residual sum
                 mu[k] = new_mu
         # [2] marker effects
         if method in ("BayesC", "BayesB", "BayesA"):

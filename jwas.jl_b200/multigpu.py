@@ -14,15 +14,11 @@ import numpy as np
 
 
 def shard_bounds(n, world):
-    """Row boundaries of every rank: equal numbers of 16-individual words, remainder to the first
-    ranks (mirrors jwas_init_sharding)."""
-    nwords = (n + 15) // 16
-    b = [0]
-    for r in range(world):
-        w = nwords // world + (1 if r < nwords % world else 0)
-        b.append(min(n, b[-1] + w * 16))
-    b[-1] = n
-    return b
+    """Row boundaries of every rank: words of 64 individuals (16 packed bytes) split evenly, the remainder to
+    the first ranks (mirrors jwas_shard_range)."""
+    nw = (n + 63) // 64
+    b = [min(n, (nw // world * r + min(r, nw % world)) * 64) for r in range(world)]
+    return b + [n]
 
 
 def init_process_group(backend=None):
@@ -49,15 +45,20 @@ def broadcast_bytes(payload, nbytes, src=0):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach(sweeper, rank, world, fused=True):
-    """Turn a GpuSweeper holding the full matrix into rank `rank` of a `world`-way row-sharded sweep."""
+def shard(sweeper, rank, world):
+    """Make the sweeper rank `rank` of a `world`-way row-sharded sweep (before set_blocks): a sweeper holding the
+    full matrix keeps only its rows, one created with rows=shard_range(...) is checked; marker statistics are
+    summed over the ranks inside the library (NCCL)."""
     from ._lib import nccl_unique_id
     uid = broadcast_bytes(nccl_unique_id() if rank == 0 else b"", 128, src=0) if world > 1 else None
     sweeper.init_sharding(rank, world, uid)
-    if world > 1 and fused:
-        # exchange buffers for the in-kernel NVLink reduction: all-gather the 64-byte IPC handles
-        handles = all_gather_bytes(sweeper.ipc_export(), 64)
-        sweeper.ipc_import(handles)
+    return sweeper
+
+
+def connect(sweeper, world):
+    """After set_blocks: exchange buffers of the in-kernel NVLink reduction (all-gather of the 64-byte IPC handles)."""
+    if world > 1:
+        sweeper.ipc_import(all_gather_bytes(sweeper.ipc_export(), 64))
     return sweeper
 
 

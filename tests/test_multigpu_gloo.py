@@ -32,6 +32,20 @@ def _worker(rank, world, port, n, p, seed, out_dir):
         t = torch.from_numpy(arr)
         dist.all_reduce(t)
 
+    # marker statistics of a sharded handle (jwas_init_sharding): integer code counts over the local rows, summed
+    # over the ranks, then the closed form -- must equal the statistics of the whole matrix
+    codes = prob.codes[lo:hi]
+    cnt = np.array([(codes == 1).sum(axis=0), (codes == 2).sum(axis=0), (~np.isin(codes, (0, 1, 2))).sum(axis=0)], dtype=np.int64)
+    allreduce(cnt.reshape(-1))
+    nn = n - cnt[2]; ssum = cnt[0] + 2 * cnt[1]
+    mu = (ssum.astype(np.float32) / nn.astype(np.float32)).astype(np.float32)
+    m64 = mu.astype(np.float64)
+    g = (cnt[0] + 4 * cnt[1]).astype(np.float64) - m64 * ssum
+    g = g - m64 * ssum
+    g = g + (m64 * m64) * nn
+    np.testing.assert_array_equal(mu, prob.means)
+    np.testing.assert_array_equal(g.astype(np.float32), prob.xpx)
+
     ve = np.full(p, 0.02); pi = np.full(p, 0.85)
     for it in (1, 2, 3):
         rc, _ = orc.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
@@ -72,5 +86,6 @@ def test_shard_bounds():
     from jwas_b200 import multigpu
     assert multigpu.shard_bounds(50000, 1) == [0, 50000]
     b = multigpu.shard_bounds(50000, 8)
-    assert b[0] == 0 and b[-1] == 50000 and all(x % 16 == 0 for x in b[:-1]) and all(y > x for x, y in zip(b, b[1:]))
-    assert multigpu.shard_bounds(20, 4) == [0, 16, 20, 20, 20]      # fewer words than ranks: empty shards allowed
+    assert b[0] == 0 and b[-1] == 50000 and all(x % 64 == 0 for x in b[:-1]) and all(y > x for x, y in zip(b, b[1:]))
+    assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) < 128
+    assert multigpu.shard_bounds(20, 4) == [0, 20, 20, 20, 20]      # fewer 64-row words than ranks (the library refuses)

@@ -1,6 +1,7 @@
-"""torchrun --nproc-per-node N tools/multigpu_check.py : the row-sharded NCCL sweep on N GPUs must give
-the same bits as the single-GPU sweep (engine 0 and engine 1) for BayesC (with missing data), BayesR
-and 2-trait BayesC."""
+"""torchrun --nproc-per-node N tools/multigpu_check.py : the row-sharded sweep on N GPUs (every rank stores only
+its own rows; marker statistics and Gram blocks summed over the ranks) must give the same bits as the single-GPU
+sweep (engine 0 and engine 1) for BayesC (with missing data), BayesR and 2-trait BayesC -- state, ycorr, marker
+statistics and M*alpha."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,14 +18,20 @@ n, p = 30011, 3000
 GAMMA = np.array([0.0, 0.01, 0.1, 1.0]); PI_R = np.array([0.95, 0.03, 0.015, 0.005])
 
 
-def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0):
-    g = jwas_b200.GpuSweeper.synthetic(n, p, t, seed=11, missing_rate=miss, device=local)
+def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0, from_full=False):
+    # sharded: this rank creates (and stores) only its own rows, or -- from_full -- creates the whole matrix and
+    # lets jwas_init_sharding drop the other ranks' rows
+    rows = jwas_b200.shard_range(n, rank, world) if (sharded and not from_full) else None
+    g = jwas_b200.GpuSweeper.synthetic(n, p, t, seed=11, missing_rate=miss, device=local, rows=rows)
+    if sharded:
+        multigpu.shard(g, rank, world)
+        assert g.row_range() == jwas_b200.shard_range(n, rank, world)
     g.set_option("engine", engine)
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
     g.set_blocks(np.array(list(range(0, p, 512)) + [p], dtype=np.int64))
-    if sharded:
-        multigpu.attach(g, rank, world, fused=(engine == 1))
+    if sharded and engine == 1:
+        multigpu.connect(g, world)
     y = np.random.default_rng(3).standard_normal(t * n).astype(np.float32)
     g.put_ycorr(y)
     if method == "R":
@@ -40,8 +47,10 @@ def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0):
             g.sweep_mt1(jwas_b200.SCHED_EXACT, np.array([[1.0, 0.3], [0.3, 1.0]]), np.array([[2e-3, 5e-4], [5e-4, 2e-3]]),
                         np.array([0.97, 0.01, 0.01, 0.01]), 5, it)
     a, b, d = g.get_state(); yc = g.get_ycorr()
+    m, x = g.marker_stats()
+    ebv = g.mul_alpha(0)
     g.close()
-    return a, b, d, yc
+    return a, b, d, yc, m, x, ebv
 
 
 ok = True
@@ -54,7 +63,8 @@ for t, method, miss in ((1, "C", 0.01), (1, "R", 0.0), (2, "M", 0.0), (1, "I", 0
         # fused persistent kernel with the in-kernel NVLink reduction (lagged schedule) vs one GPU
         ref1 = run(t, method, False, 1, miss, lag=1)
         sh1 = run(t, method, True, 1, miss, lag=1)
-        same1 = all(np.array_equal(x, y) for x, y in zip(ref1, sh1))
+        sh1f = run(t, method, True, 1, miss, lag=1, from_full=True)
+        same1 = all(np.array_equal(x, y) for x, y in zip(ref1, sh1)) and all(np.array_equal(x, y) for x, y in zip(ref1, sh1f))
         print(f"rank {rank}/{world} method {method} t={t}: fused multi-GPU (NVLink push) == fused single GPU: {same1}", flush=True)
         same = same and same1
         # the same with the chain pipelined over two chain CTAs (commit records), one GPU and sharded
