@@ -121,6 +121,12 @@ int jwas_sweep_bayesabc(jwas_handle* h, int schedule, double vare,
 /* scalar convenience forms (device-side fill) */
 int jwas_sweep_bayesc(jwas_handle* h, int schedule, double vare, double var_effect, double pi,
                       uint64_t seed, uint32_t iter, jwas_sweep_stats* stats);
+/* The reference call itself -- BayesABC!(xArray, xRinvArray, xpRinvx, yCorr, alpha, beta, delta, vare, varEffects, pi)
+ * mutating the CALLER's host arrays in place (BayesABC.jl:60-63): host -> device copies, the sweep, device -> host
+ * copies, enqueued back to back with one synchronisation (use pinned buffers for asynchronous copies). */
+int jwas_sweep_bayesc_host(jwas_handle* h, int schedule, double vare, double var_effect, double pi,
+                           uint64_t seed, uint32_t iter, float* ycorr, float* alpha, float* beta, int32_t* delta,
+                           jwas_sweep_stats* stats);
 /* BayesR! (BayesR.jl:45-97), BayesR_block! (:111-193), _independent! (:195-273).
  * full_reps: the burn-in gate of bayesr_block_nreps (:22-25) evaluated by the caller. */
 int jwas_sweep_bayesr(jwas_handle* h, int schedule, int full_reps, double vare, double sigma_sq,
@@ -194,6 +200,9 @@ int64_t jwas_kernel_launches(jwas_handle* h);     /* kernels launched by this ha
  *                 from CTA to CTA as 64-bit commit records); 0 = one chain CTA.  Re-cuts the row slices.
  *   "gather"      pipelined chain: 1 = one warp of every streaming CTA replays the commit records under the
  *                 stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line (default)
+ *   "stream_variant", "stream_pf"   independent schedule, engine 1: launch shape of the streamed block-rhs kernel
+ *                 (0 = 512 threads + register double buffer, 1 = 1024 threads, 2 = 768 + double buffer,
+ *                 3 = 1024 + double buffer) and its L2 prefetch distance in chunk iterations (0 = off)
  *   "profile"     1 = time the streaming kernel(s) with CUDA events (jwas_last_stream_kernel_ms)
  *   "timers"      1 = in-kernel phase timers; only in a library built with -DJW_TIMERS
  *   "gram_popcount" 1 = popcount Gram kernel instead of the bf16 tensor-core GEMM */

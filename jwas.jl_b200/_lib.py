@@ -67,6 +67,7 @@ def lib():
         "jwas_put_state": [vp, vp, vp, vp], "jwas_get_state": [vp, vp, vp, vp],
         "jwas_sweep_bayesabc": [vp, i32, dbl, vp, vp, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_bayesc": [vp, i32, dbl, dbl, dbl, u64, u32, C.POINTER(SweepStats)],
+        "jwas_sweep_bayesc_host": [vp, i32, dbl, dbl, dbl, u64, u32, vp, vp, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_bayesr": [vp, i32, i32, dbl, dbl, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_mt1": [vp, i32, vp, vp, i32, vp, i32, u64, u32, vp, vp, C.POINTER(SweepStats)],
         "jwas_sweep_mt2": [vp, i32, vp, vp, vp, u64, u32, vp, vp, C.POINTER(SweepStats)],
@@ -260,6 +261,16 @@ class GpuSweeper:
         st = SweepStats()
         _check(lib().jwas_sweep_bayesc(self._h, schedule, float(vare), float(var_effect), float(pi),
                                        int(seed), int(it), C.byref(st)))
+        return st
+
+    def sweep_bayesc_host(self, schedule, vare, var_effect, pi, seed, it, ycorr, alpha, beta, delta):
+        """BayesABC!(…, yCorr, α, β, δ, …) on the caller's HOST arrays, mutated in place (BayesABC.jl:60-63)."""
+        st = SweepStats()
+        for a, dt, sz in ((ycorr, np.float32, self.n), (alpha, np.float32, self.p), (beta, np.float32, self.p),
+                          (delta, np.int32, self.p)):
+            assert a.dtype == dt and a.size == sz and a.flags.c_contiguous
+        _check(lib().jwas_sweep_bayesc_host(self._h, schedule, float(vare), float(var_effect), float(pi), int(seed),
+                                            int(it), _p(ycorr), _p(alpha), _p(beta), _p(delta), C.byref(st)))
         return st
 
     def sweep_bayesr(self, schedule, full_reps, vare, sigma_sq, pi, gamma, seed, it, u=None, z=None):

@@ -188,6 +188,10 @@ __host__ __device__ inline size_t jw_chain_unit_smem_bytes(int T) {
 // rhs partial sums (one L2 round trip) -> buffered corrections (shared memory) -> rounds (one barrier each;
 // a Gram round trip only when a marker ENTERS the model).
 // Returns the number of commits, -1 when the sweep was aborted.
+// Inlined into the persistent kernel on purpose: as a function of its own (measured) the chain runs ~2x slower --
+// the call ABI and a second spill set under the kernel's 64-register cap land on the chain's critical path, and the
+// chain, not the stream, bounds the exact schedule.  Rarely used paths called from here (the multi-GPU exchange
+// reads) are therefore kept OUT of line so that they do not disturb this function's register allocation.
 template <int METHOD, int T, class WaitFn>
 __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pipe_args& P, const jw_chain_blk& B,
                                              const int u, WaitFn wait_fn, unsigned char* smem_base,
@@ -281,17 +285,19 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
         s_rows[q * JW_CHAIN_SB + tid] = valid ? G[(int64_t)(m0 + s_misc[1 + q]) * b + m] : 0.0f;
 
     // corrections whose records are already there: fetch their (cross-)Gram values now, add them after the rhs
+    // corrections come from the units of the `lag` previous panels (oldest first) and the earlier units of this one
     const int u_own = P.blk_unit0[kb];
-    const int u_lo = (kb > 0 && B.xgram != nullptr) ? P.blk_unit0[kb - 1] : u_own;
+    const int u_l1 = (kb > 0 && B.xgram != nullptr) ? P.blk_unit0[kb - 1] : u_own;
+    const int u_lo = (kb > 1 && B.xgram2 != nullptr) ? P.blk_unit0[kb - 2] : u_l1;
     jw_rec_walker<T> W;
     W.init(P, u_lo, u);
     int pgn = 0, wst = 0;
     float* s_pd_w = s_pd + warp * (JW_UNIT_PG * T);
     auto corr_row = [&](const int us_, const int code) -> const float* {
         // units are cut every JW_CHAIN_SB markers inside a panel: no table look-up on this path
-        const bool prevblk = us_ < u_own;
-        const int rowpos = (prevblk ? (us_ - u_lo) : (us_ - u_own)) * JW_CHAIN_SB + code;
-        return (prevblk ? B.xgram : G) + (int64_t)rowpos * b + m;
+        const int ubase = us_ >= u_own ? u_own : (us_ >= u_l1 ? u_l1 : u_lo);
+        const float* M = us_ >= u_own ? G : (us_ >= u_l1 ? B.xgram : B.xgram2);
+        return M + (int64_t)((us_ - ubase) * JW_CHAIN_SB + code) * b + m;
     };
     while (pgn + JW_REC_BATCH <= JW_UNIT_PG) {
         int us_ = 0;

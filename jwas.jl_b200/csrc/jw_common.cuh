@@ -11,6 +11,7 @@
 #define JW_MAX_BLOCK 1024      // chain threads per CTA (one marker each per sub-block)
 #define JW_MAX_PANEL 4096      // largest block of the exact schedule (walked in sub-blocks)
 #define JW_MAX_CLASSES 8
+#define JW_MAX_LAG 2            // deepest lagged exact schedule on the device (the oracle goes to 3)
 #define JW_R_CLASSES 4          // BayesR mixture classes on the device (BAYESR_GAMMA, JWAS.jl:12)
 
 void jw_set_error(const std::string& s);
@@ -79,9 +80,11 @@ struct jwas_handle {
     int64_t* d_starts = nullptr;
     int64_t* d_gram_off = nullptr;
     float* d_gram = nullptr;
-    float* d_gramx = nullptr;      // cross-Gram X_{k-1}'X_k of consecutive blocks (lagged schedule), on demand
-    int64_t* d_gramx_off = nullptr;
-    std::vector<int64_t> gramx_off;
+    // cross-Gram X_{k-d}'X_k towards the d-th previous block, d = 1..lag (lagged schedule), on demand
+    float* d_gramx[2] = {nullptr, nullptr};
+    int64_t* d_gramx_off[2] = {nullptr, nullptr};
+    std::vector<int64_t> gramx_off[2];
+    int gramx_built = 0;
     int64_t nblocks = 0, maxb = 0;
 
     // sweep workspace
@@ -105,11 +108,14 @@ struct jwas_handle {
     double prof_ms = 0.0; int64_t prof_launches = 0;
     int64_t opt_gram_popc = 0;     // 1 = build Gram blocks with the popcount kernel (default: bf16 tensor-core GEMM)
     int64_t opt_timers = 0;        // 1 = in-kernel phase timers (tools/phase_probe.py)
-    int64_t opt_lag = 0;           // 1 = lagged exact schedule (engine 1): chain k overlaps stream k+1
+    int64_t opt_lag = 0;           // L = lagged exact schedule (engine 1): the chains of blocks k-L..k-1 overlap the stream of block k
     int64_t opt_engine = 0;        // 0 = multi-kernel engine, 1 = persistent fused kernel
     int64_t opt_gather = 0;        // pipelined chain: 1 = a gather warp per streaming CTA replays the records under the
                                    // stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line
     int64_t opt_chain_ctas = 0;    // engine 1, lag 1: chain CTAs of the pipelined chain (0 = one-CTA chain)
+    int64_t opt_stream_variant = 0;// streamed block rhs (independent schedule): 0 = 512 thr + register double buffer,
+                                   // 1 = 1024 thr, 2 = 768 thr + double buffer, 3 = 1024 thr + double buffer
+    int64_t opt_stream_pf = 4;     // L2 prefetch distance of the streamed block rhs, in chunk iterations (0 = off)
     // row-sharded multi-GPU sweep: this rank STORES and streams rows [row_begin, row_end) of every column
     // (row_begin is a multiple of 64); ycorr and the sampler state are replicated
     int64_t row_begin = 0, row_end = 0;

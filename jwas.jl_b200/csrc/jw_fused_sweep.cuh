@@ -28,6 +28,8 @@
 #define JW_NEXT_RED
 #endif
 #define JW_FUSED_THREADS 1024
+// multi-GPU exchange ring: a sender may run lag+3 blocks ahead of the slowest reader's chain
+#define JW_X_RING 8
 #define JW_FUSED_MAX_GS 96          // 3 lookups per lane and marker keep the int32 partial < 2^31
 
 struct jw_fused_state {
@@ -60,7 +62,8 @@ struct jw_fused_args {
     int Gs, TS, n_vs, nblocks, list_cap, lag;
     int uniform_b;               // > 0: every block has this many markers (the last one possibly fewer)
     int gather;                  // 1 = a gather warp replays the records under the stream (else: in line, before the tables)
-    const float* gramx; const int64_t* gramx_off;
+    const float* gramx; const int64_t* gramx_off;        // cross-Gram X_{k-1}'X_k
+    const float* gramx2; const int64_t* gramx2_off;      // cross-Gram X_{k-2}'X_k (lag 2), else NULL
     int timers, two_lists;
     // multi-GPU (rows sharded over `world` GPUs of one node, one process each): this rank streams the
     // byte-group slices [vs0, vs1) of the rows it stores; a communication CTA pushes the block's exact int64
@@ -156,6 +159,30 @@ __host__ __device__ __forceinline__ constexpr int jw_tab_sub(int gb) {
 }
 #define JW_TAB_BYTES(W_) ((W_) == 1 ? 2 * 65536 : 3 * 65536)
 
+// communication CTA (rows sharded over several GPUs): the block's exact int64 partial rhs of this GPU -> every rank's
+// exchange slots, as self-validating 16-byte words.  Value e of the slot: dq[kk][mm] | mq[kk][mm] (only when calls
+// are missing) | sq[kk]; only the entries the chain reads are sent (mm < b).  Not inlined (see jw_chain_unit).
+template <int T>
+__device__ __noinline__ void jw_comm_push(const long long* dq, const long long* mq, const long long* sq_k, uint4* const* peer_slots,
+                                          const int world, const int64_t slot0, const int slot_b, const unsigned tag,
+                                          const int64_t p, const int64_t s, const int b) {
+    const int tid = threadIdx.x;
+    const int nmq = mq ? 2 : 1;
+    for (int e = tid; e < nmq * T * b + T; e += JW_FUSED_THREADS) {
+        long long v; int64_t w;
+        if (e < nmq * T * b) {
+            const int part = e / (T * b), e2 = e - part * T * b, kk = e2 / b, mm = e2 - kk * b;
+            v = part == 0 ? __ldcg(&dq[(int64_t)kk * p + s + mm]) : __ldcg(&mq[(int64_t)kk * p + s + mm]);
+            w = (int64_t)(part * T + kk) * slot_b + mm;
+        } else {
+            const int kk = e - nmq * T * b;
+            v = __ldcg(&sq_k[kk]);
+            w = (int64_t)2 * T * slot_b + kk;
+        }
+        for (int rk = 0; rk < world; ++rk) jw_ll_store(peer_slots[rk] + slot0 + w, v, tag);
+    }
+}
+
 // MODE 0: one chain CTA (lag 1) or CTA 0 streams and chains (lag 0), jw_chain_block
 //      1: pipelined chain (jw_chain_pipe.cuh), streaming CTAs replay the commit records in line
 //      2: pipelined chain, one gather warp per streaming CTA replays them under the stream (one slice per CTA)
@@ -231,9 +258,10 @@ jw_k_fused(jw_fused_args F) {
             const int k = F.P.unit_blk[u];
             jw_chain_blk B;
             B.s = F.C.starts[k]; B.b = (int)(F.C.starts[k + 1] - B.s); B.gram_off = F.C.gram_off[k];
-            B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
+            B.xgram = nullptr; B.xgram2 = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
             B.xcount_smem = -1;
             if (k > 0) { B.xgram = F.gramx + F.gramx_off[k]; B.xstart = F.C.starts[k - 1]; }
+            if (k > 1 && F.gramx2 != nullptr) B.xgram2 = F.gramx2 + F.gramx2_off[k];
             if (k + 1 < F.nblocks) {
                 B.xgram_next = F.gramx + F.gramx_off[k + 1];
                 B.b_next = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
@@ -245,7 +273,7 @@ jw_k_fused(jw_fused_args F) {
             }
             B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = F.flags;
             if (multi) {
-                B.xslots = F.my_slots + (int64_t)(k & 3) * F.ring_stride;
+                B.xslots = F.my_slots + (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride;
                 B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
                 B.xtag = F.tag_base + (unsigned)k + 1u;
             }
@@ -550,7 +578,7 @@ jw_k_fused(jw_fused_args F) {
                 // ---- gather warp: replay block k-1's commits (in commit order) on this CTA's rows ----
                 bool okg = true;
                 int cnt = 0;
-                const int gp = k - 1;
+                const int gp = k - lag;                                // the block whose updates block k+1 starts from
                 constexpr int NG = JW_FUSED_MAX_GS / 32;              // consecutive byte groups (4 rows each) per lane
                 float gv[NG * 4][T];
 #pragma unroll
@@ -646,29 +674,13 @@ jw_k_fused(jw_fused_args F) {
             if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
             __syncthreads();
             if (!s_ok) return;
-            const int ring = k & 3;
-            const unsigned tag = F.tag_base + (unsigned)k + 1u;
-            const int64_t slot0 = (int64_t)ring * F.ring_stride + (int64_t)F.rank * F.slot_stride;
-            // value e of the slot: dq[kk][mm] | mq[kk][mm] (only when calls are missing) | sq[kk]; only the
-            // entries the chain reads are sent (mm < b)
-            const int nmq = F.C.mq ? 2 : 1;
-            for (int e = tid; e < nmq * T * b + T; e += JW_FUSED_THREADS) {
-                long long v; int64_t w;
-                if (e < nmq * T * b) {
-                    const int part = e / (T * b), e2 = e - part * T * b, kk = e2 / b, mm = e2 - kk * b;
-                    v = part == 0 ? __ldcg(&F.dq[(int64_t)kk * p + s + mm]) : __ldcg(&F.mq[(int64_t)kk * p + s + mm]);
-                    w = (int64_t)(part * T + kk) * F.slot_b + mm;
-                } else {
-                    const int kk = e - nmq * T * b;
-                    v = __ldcg(&F.sq_acc[k * T + kk]);
-                    w = (int64_t)2 * T * F.slot_b + kk;
-                }
-                for (int rk = 0; rk < F.world; ++rk) jw_ll_store(F.peer_slots[rk] + slot0 + w, v, tag);
-            }
+            jw_comm_push<T>(F.dq, F.C.mq ? F.mq : nullptr, F.sq_acc + k * T, F.peer_slots, F.world,
+                            (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride + (int64_t)F.rank * F.slot_stride, F.slot_b,
+                            F.tag_base + (unsigned)k + 1u, p, s, b);
         }
         if constexpr (MODE == 0) { if (is_chain_cta) {
             jw_chain_blk B;
-            B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
+            B.xgram = nullptr; B.xgram2 = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
             if (lag && k > 0) {
                 B.xgram = F.gramx + F.gramx_off[k];
                 B.xlist = F.act_idx_all + F.C.starts[k - 1];
@@ -685,7 +697,7 @@ jw_k_fused(jw_fused_args F) {
             if (k + 1 < F.nblocks) { B.prefetch_s = F.C.starts[k + 1]; B.prefetch_b = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]); }
             B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = F.flags;
             if (multi) {
-                B.xslots = F.my_slots + (int64_t)(k & 3) * F.ring_stride;
+                B.xslots = F.my_slots + (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride;
                 B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
                 B.xtag = F.tag_base + (unsigned)k + 1u;
             }
@@ -893,18 +905,20 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     F.packed = h->d_packed; F.stride_d = h->stride_d;
     F.Gs = f->Gs; F.TS = f->TS; F.n_vs = f->n_vs; F.nblocks = (int)h->nblocks; F.list_cap = f->list_cap;
     F.lag = A.nreps_mode ? 0 : (int)h->opt_lag; F.timers = (int)h->opt_timers; F.two_lists = f->two_lists;
-    JW_REQUIRE(!F.lag || h->d_gramx, "lag = 1 needs the cross-Gram blocks");
-    F.gramx = h->d_gramx; F.gramx_off = h->d_gramx_off;
+    JW_REQUIRE(h->gramx_built >= F.lag, "the lagged schedule needs the cross-Gram blocks (set the lag option before jwas_set_blocks or again after it)");
+    JW_REQUIRE(F.lag < 2 || f->n_chain > 0, "lag = 2 needs the pipelined chain (option chain_ctas >= 1)");
+    F.gramx = h->d_gramx[0]; F.gramx_off = h->d_gramx_off[0];
+    F.gramx2 = F.lag >= 2 ? h->d_gramx[1] : nullptr; F.gramx2_off = F.lag >= 2 ? h->d_gramx_off[1] : nullptr;
     F.world = h->world; F.rank = h->rank; F.vs0 = 0; F.vs1 = f->n_vs;     // every slice of the tile is this rank's
     F.row_off = h->row_begin; F.nloc = jw_nloc(h);
     F.peer_slots = nullptr; F.my_slots = nullptr;
     F.slot_stride = 0; F.slot_b = 0; F.ring_stride = 0; F.tag_base = 0;
     if (h->world > 1) {
-        JW_REQUIRE(h->ipc_ready && F.lag, "multi-GPU fused sweep needs lag = 1 and jwas_ipc_import");
+        JW_REQUIRE(h->ipc_ready && F.lag, "multi-GPU fused sweep needs lag >= 1 and jwas_ipc_import");
         JW_REQUIRE(h->maxb <= h->x_slot_b, "exchange slots are smaller than the largest block (call jwas_ipc_export after jwas_set_blocks)");
         F.peer_slots = (uint4* const*)h->d_peer_slots;
         F.my_slots = (const uint4*)h->d_xbuf;
-        F.slot_b = h->x_slot_b; F.slot_stride = h->x_slot_words; F.ring_stride = 8 * h->x_slot_words;
+        F.slot_b = h->x_slot_b; F.slot_stride = h->x_slot_words; F.ring_stride = 8 * h->x_slot_words;   // 8 source ranks per ring entry
         // one tag per (sweep, block), never 0 (the cleared buffer) and never reused within 2^32 blocks
         if (h->sweep_seq * (h->nblocks + 1) + h->nblocks + 2 >= ((int64_t)1 << 32)) {
             JW_CUDA(cudaMemsetAsync(h->d_xbuf, 0, h->xbuf_bytes, h->stream));
@@ -923,7 +937,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     // per slice costs more than the one-chain-CTA hand-off (400,000 x 61,440: 260 vs 284 sweeps/s)
     const int my_slices = f->n_vs;
     const bool one_slice = my_slices <= h->sm_count - std::max(1, f->n_chain) - (h->world > 1 ? 1 : 0);
-    const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok);
+    const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok || F.lag >= 2);
     F.gather = (int)h->opt_gather;
     F.uniform_b = 0;
     if (h->nblocks >= 1) {

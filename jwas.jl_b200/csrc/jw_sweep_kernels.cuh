@@ -528,6 +528,7 @@ struct jw_chain_blk {
     const long long* sq;
     int32_t* act_idx; int32_t* act_cnt; int write_active_list;
     const float* xgram; const int32_t* xlist; const int32_t* xcount; int64_t xstart;
+    const float* xgram2;                    // lag 2 (pipelined chain): cross-Gram X_{k-2}'X_k, NULL otherwise
     const float* xgram_next; int b_next;
     int64_t prefetch_s; int prefetch_b;     // next block's chain inputs to pull towards L2 (0 = none)
     int64_t s; int b; int64_t gram_off;     // this block: first marker, size, Gram offset (b = 0: look them up)
@@ -580,8 +581,8 @@ __device__ __forceinline__ bool jw_ll_sum(const uint4* base, const int64_t strid
     out = acc;
     return true;
 }
-// the three integer sums a marker's rhs needs, over all ranks
-__device__ __forceinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
+// the three integer sums a marker's rhs needs, over all ranks (out of line: see jw_chain_unit)
+__device__ __noinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
                                           long long& dq, long long& mq, long long& sqk) {
     bool ok = jw_ll_sum(B.xslots + (int64_t)k * B.slot_b + m, B.slot_stride, B.xworld, B.xtag, B.xflags, dq);
     mq = 0;
@@ -592,7 +593,7 @@ __device__ __forceinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, co
 __device__ __forceinline__ jw_chain_blk jw_chain_blk_from(const jw_chain_args& A) {
     jw_chain_blk B;
     B.sq = A.sq; B.act_idx = A.act_idx; B.act_cnt = A.act_cnt; B.write_active_list = A.write_active_list;
-    B.xgram = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
+    B.xgram = nullptr; B.xgram2 = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
     B.prefetch_s = 0; B.prefetch_b = 0; B.s = 0; B.b = 0; B.gram_off = 0; B.xcount_smem = -1;
     B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = nullptr;
     return B;

@@ -9,6 +9,7 @@
 #include "jw_setup_kernels.cuh"
 #include "jw_sweep_kernels.cuh"
 #include "jw_fused_sweep.cuh"
+#include "jw_stream_kernel.cuh"
 #include "jw_nccl.cuh"
 #include <cublas_v2.h>
 
@@ -260,7 +261,7 @@ extern "C" int jwas_destroy(jwas_handle* h) {
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_packed, h->d_means, h->d_xpx, h->d_colsum, h->d_nvalid, h->d_cnt, h->d_gath, h->d_ycorr, h->d_alpha,
                     h->d_beta, h->d_delta, h->d_mean_alpha, h->d_mean_alpha2, h->d_mean_delta, h->d_ve,
-                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_draws, h->d_prep_rm, h->d_gramx, h->d_gramx_off, h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
+                    h->d_pi, h->d_u, h->d_z, h->d_prep, h->d_prep_beta0, h->d_draws, h->d_prep_rm, h->d_gramx[0], h->d_gramx[1], h->d_gramx_off[0], h->d_gramx_off[1], h->d_starts, h->d_gram_off, h->d_gram, h->d_yq, h->d_sq,
                     h->d_dq, h->d_mq, h->d_dalpha, h->d_act_idx, h->d_act_cnt, h->d_flags, h->d_counters,
                     h->d_maxabs, h->d_stats, h->d_partials};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -296,10 +297,31 @@ extern "C" int jwas_get_marker_stats(jwas_handle* h, float* means, float* xpx) {
         }                                                                               \
     } while (0)
 
-// Gram blocks (and the cross-Gram of consecutive blocks) as bf16 tensor-core GEMMs on unpacked
-// 0/1/2 codes; integer-exact (see jw_setup_kernels.cuh).  One pass over the blocks, the previous
-// block's unpacked panel is kept for the cross product.
-static int build_gram_gemm(jwas_handle* h, bool want_cross) {
+// (re)allocates the cross-Gram storage for distances 1..dmax: X_{k-d}' X_k, rows = markers of block k-d
+static int alloc_gramx(jwas_handle* h, int dmax) {
+    const int64_t nb = h->nblocks;
+    for (int d = 1; d <= JW_MAX_LAG; ++d) {
+        if (h->d_gramx[d - 1]) { cudaFree(h->d_gramx[d - 1]); h->d_gramx[d - 1] = nullptr; }
+        if (h->d_gramx_off[d - 1]) { cudaFree(h->d_gramx_off[d - 1]); h->d_gramx_off[d - 1] = nullptr; }
+        h->gramx_off[d - 1].clear();
+    }
+    h->gramx_built = 0;
+    for (int d = 1; d <= dmax; ++d) {
+        std::vector<int64_t> xoff(nb, 0);
+        int64_t total = 0;
+        for (int64_t i = d; i < nb; ++i) { xoff[i] = total; total += (h->starts[i - d + 1] - h->starts[i - d]) * (h->starts[i + 1] - h->starts[i]); }
+        h->gramx_off[d - 1] = xoff;
+        JW_CUDA(cudaMalloc((void**)&h->d_gramx[d - 1], std::max<size_t>(1, (size_t)total) * sizeof(float)));
+        JW_CUDA(cudaMalloc((void**)&h->d_gramx_off[d - 1], nb * sizeof(int64_t)));
+        JW_CUDA(cudaMemcpyAsync(h->d_gramx_off[d - 1], xoff.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    return 0;
+}
+
+// Gram blocks (and the cross-Gram towards the `cross_max` previous blocks) as bf16 tensor-core GEMMs on unpacked
+// 0/1/2 codes; integer-exact (see jw_setup_kernels.cuh).  One pass over the blocks, the previous blocks'
+// unpacked panels are kept in a ring for the cross products.
+static int build_gram_gemm(jwas_handle* h, int cross_max) {
     // rows stored on this rank; the integer pair counts (exact as FP32 below 2^24) are summed over the ranks
     const int64_t nb = h->nblocks, n = jw_nloc(h);
     const int64_t n_pad = ceil_div(n, 16) * 16;
@@ -307,25 +329,18 @@ static int build_gram_gemm(jwas_handle* h, bool want_cross) {
     JW_REQUIRE(h->world == 1 || (N && h->nccl_comm), "sharded handle without an initialised NCCL communicator");
     const int64_t maxb = h->maxb;
     const bool ms = h->has_missing != 0;
+    const int NR = cross_max + 1;                       // ring of unpacked panels
     cublasHandle_t cb = nullptr;
     JW_CUBLAS(cublasCreate(&cb));
     JW_CUBLAS(cublasSetStream(cb, h->stream));
-    __nv_bfloat16 *C[2] = {nullptr, nullptr}, *V[2] = {nullptr, nullptr};
+    __nv_bfloat16 *C[JW_MAX_LAG + 1] = {nullptr}, *V[JW_MAX_LAG + 1] = {nullptr};
     float* cnt[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < NR; ++q) {
         JW_CUDA(cudaMalloc((void**)&C[q], (size_t)n_pad * maxb * sizeof(__nv_bfloat16)));
         if (ms) JW_CUDA(cudaMalloc((void**)&V[q], (size_t)n_pad * maxb * sizeof(__nv_bfloat16)));
     }
     for (int q = 0; q < (ms ? 4 : 1); ++q) JW_CUDA(cudaMalloc((void**)&cnt[q], (size_t)maxb * maxb * sizeof(float)));
-    if (want_cross) {
-        std::vector<int64_t> xoff(nb, 0);
-        int64_t total = 0;
-        for (int64_t i = 1; i < nb; ++i) { xoff[i] = total; total += (h->starts[i] - h->starts[i - 1]) * (h->starts[i + 1] - h->starts[i]); }
-        h->gramx_off = xoff;
-        JW_CUDA(cudaMalloc((void**)&h->d_gramx, std::max<size_t>(1, (size_t)total) * sizeof(float)));
-        JW_CUDA(cudaMalloc((void**)&h->d_gramx_off, nb * sizeof(int64_t)));
-        JW_CUDA(cudaMemcpyAsync(h->d_gramx_off, xoff.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    }
+    if (alloc_gramx(h, cross_max)) return 10;
     const float one = 1.0f, zero = 0.0f;
     auto gemm = [&](const __nv_bfloat16* A, int m, const __nv_bfloat16* B, int nn, float* out) -> cublasStatus_t {
         // out (column-major m x nn, ld m) = A^T (m x n) * B (n x nn): out[c + a*m] = sum_i A[i,c] * B[i,a]
@@ -333,18 +348,18 @@ static int build_gram_gemm(jwas_handle* h, bool want_cross) {
                             B, CUDA_R_16BF, (int)n_pad, &zero, out, CUDA_R_32F, m, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
     };
     for (int64_t k = 0; k < nb; ++k) {
-        const int cur = (int)(k & 1), prv = cur ^ 1;
+        const int cur = (int)(k % NR);
         const int64_t s = h->starts[k]; const int b = (int)(h->starts[k + 1] - s);
         const int64_t units = (int64_t)b * (n_pad >> 2);
         if (ms) jw_k_unpack_bf16<true><<<(unsigned)ceil_div(units, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, n_pad, s, b, C[cur], V[cur]);
         else jw_k_unpack_bf16<false><<<(unsigned)ceil_div(units, 256), 256, 0, h->stream>>>(h->d_packed, h->stride_d, n, n_pad, s, b, C[cur], nullptr);
         JW_LAUNCH_CHECK(h);
-        for (int pass = 0; pass < (want_cross && k > 0 ? 2 : 1); ++pass) {
-            // pass 0: rows = cols = block k ; pass 1: rows = block k-1, cols = block k
-            const int r = pass == 0 ? cur : prv;
-            const int64_t s_r = pass == 0 ? s : h->starts[k - 1];
-            const int b_r = pass == 0 ? b : (int)(h->starts[k] - h->starts[k - 1]);
-            float* out = pass == 0 ? h->d_gram + h->gram_off[k] : h->d_gramx + h->gramx_off[k];
+        for (int d = 0; d <= cross_max && d <= k; ++d) {
+            // d = 0: rows = cols = block k ; d >= 1: rows = block k-d, cols = block k
+            const int r = (int)((k - d) % NR);
+            const int64_t s_r = h->starts[k - d];
+            const int b_r = (int)(h->starts[k - d + 1] - s_r);
+            float* out = d == 0 ? h->d_gram + h->gram_off[k] : h->d_gramx[d - 1] + h->gramx_off[d - 1][k];
             JW_CUBLAS(gemm(C[cur], b, C[r], b_r, cnt[0]));                       // Nab[a][c]
             if (ms) {
                 JW_CUBLAS(gemm(V[cur], b, C[r], b_r, cnt[1]));                   // sum_i C_r[i,a] V_c[i,c]
@@ -368,21 +383,23 @@ static int build_gram_gemm(jwas_handle* h, bool want_cross) {
         }
     }
     JW_CUDA(cudaStreamSynchronize(h->stream));
-    for (int q = 0; q < 2; ++q) { cudaFree(C[q]); if (V[q]) cudaFree(V[q]); }
+    for (int q = 0; q < NR; ++q) { cudaFree(C[q]); if (V[q]) cudaFree(V[q]); }
     for (int q = 0; q < 4; ++q) if (cnt[q]) cudaFree(cnt[q]);
     cublasDestroy(cb);
+    h->gramx_built = cross_max;
     return 0;
 }
 
 // Gram blocks (cross = false) or cross-Gram of consecutive blocks (cross = true): every 64x64 tile
-static int build_gram(jwas_handle* h, bool cross) {
+static int build_gram(jwas_handle* h, int dist) {
     JW_REQUIRE(h->world == 1, "the popcount Gram kernel does not support sharded rows (use the default GEMM path, nObs < 2^22)");
+    const bool cross = dist > 0;
     const int64_t nb = h->nblocks;
     std::vector<int32_t> tblk, tab; std::vector<int64_t> toff;
     std::vector<int64_t> xoff(nb, 0);
     int64_t total = 0;
-    for (int64_t i = cross ? 1 : 0; i < nb; ++i) {
-        const int64_t rb = cross ? i - 1 : i, cb = i;
+    for (int64_t i = dist; i < nb; ++i) {
+        const int64_t rb = i - dist, cb = i;
         const int64_t br = h->starts[rb + 1] - h->starts[rb], bc = h->starts[cb + 1] - h->starts[cb];
         const int64_t off = cross ? total : h->gram_off[i];
         if (cross) { xoff[i] = total; total += br * bc; }
@@ -392,13 +409,7 @@ static int build_gram(jwas_handle* h, bool cross) {
         }
     }
     float* out = h->d_gram;
-    if (cross) {
-        h->gramx_off = xoff;
-        JW_CUDA(cudaMalloc((void**)&h->d_gramx, std::max<size_t>(1, (size_t)total) * sizeof(float)));
-        JW_CUDA(cudaMalloc((void**)&h->d_gramx_off, nb * sizeof(int64_t)));
-        JW_CUDA(cudaMemcpyAsync(h->d_gramx_off, xoff.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-        out = h->d_gramx;
-    }
+    if (cross) out = h->d_gramx[dist - 1];       // allocated (with these offsets) by alloc_gramx
     if (toff.empty()) return 0;
     int32_t *d_tb = nullptr, *d_tab = nullptr; int64_t* d_toff = nullptr;
     JW_CUDA(cudaMalloc((void**)&d_tb, tblk.size() * sizeof(int32_t)));
@@ -416,6 +427,16 @@ static int build_gram(jwas_handle* h, bool cross) {
     JW_LAUNCH_CHECK(h);
     JW_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(d_tb); cudaFree(d_tab); cudaFree(d_toff);
+    return 0;
+}
+
+// the blocks' own Gram and the cross-Gram towards the `lag` previous blocks
+static int build_all_gram(jwas_handle* h, int lag) {
+    const bool use_gemm = !h->opt_gram_popc && h->n < ((int64_t)1 << 22);   // 4n < 2^24: FP32 sums exact
+    if (use_gemm) return build_gram_gemm(h, lag);
+    if (alloc_gramx(h, lag)) return 10;
+    for (int d = 0; d <= lag; ++d) { int rc = build_gram(h, d); if (rc) return rc; }
+    h->gramx_built = lag;
     return 0;
 }
 
@@ -444,16 +465,8 @@ extern "C" int jwas_set_blocks(jwas_handle* h, const int64_t* starts, int64_t nb
     JW_CUDA(cudaMalloc((void**)&h->d_gram, (size_t)total * sizeof(float)));
     JW_CUDA(cudaMemcpyAsync(h->d_starts, starts, (nblocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     JW_CUDA(cudaMemcpyAsync(h->d_gram_off, off.data(), nblocks * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    if (h->d_gramx) { cudaFree(h->d_gramx); h->d_gramx = nullptr; }
-    if (h->d_gramx_off) { cudaFree(h->d_gramx_off); h->d_gramx_off = nullptr; }
-    int rc0;
-    const bool use_gemm = !h->opt_gram_popc && h->n < ((int64_t)1 << 22);   // 4n < 2^24: FP32 sums exact
-    if (use_gemm) { rc0 = build_gram_gemm(h, h->opt_lag != 0); if (rc0) return rc0; }
-    else {
-        rc0 = build_gram(h, false);
-        if (rc0) return rc0;
-        if (h->opt_lag) { rc0 = build_gram(h, true); if (rc0) return rc0; }
-    }
+    int rc0 = build_all_gram(h, (int)h->opt_lag);
+    if (rc0) return rc0;
     int rc = jw_fused_prepare(h);
     if (rc) return rc;
     return 0;
@@ -855,9 +868,18 @@ static int run_sweep(jwas_handle* h, sweep_cfg& c, jwas_sweep_stats* st) {
     if (c.schedule == JWAS_SCHED_INDEPENDENT) {
         // all blocks read the entry snapshot (BayesABC.jl:205); one GEMV over all of M
         JW_CUDA(cudaMemsetAsync(h->d_sq, 0, JW_MAX_TRAITS * sizeof(long long), h->stream));
-        jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags, h->row_begin, h->row_end);
-        JW_LAUNCH_CHECK(h);
-        if (dispatch_dot(h, 0, p)) return 11;
+        if (h->opt_engine == 1 && jw_stream_supported(h)) {
+            // engine 1: the rhs of every block in ONE streamed pass over the tiled image (lookup-table stream,
+            // tables built once per row slice, no per-panel barrier)
+            if (prof_begin(h)) return 10;
+            int rcs = jw_stream_all(h, scale);
+            if (rcs) return rcs;
+            if (prof_end(h)) return 10;
+        } else {
+            jw_k_quantize<<<qgrid, 256, 0, h->stream>>>(h->d_ycorr, n, t, scale, h->d_yq, h->d_sq, h->d_flags, h->row_begin, h->row_end);
+            JW_LAUNCH_CHECK(h);
+            if (dispatch_dot(h, 0, p)) return 11;
+        }
         if (reduce_block_rhs(h, 0, p)) return 13;
         A.block0 = 0; A.write_active_list = 0;
         if (dispatch_chain(h, A, (int)h->nblocks, threads)) return 11;
@@ -932,6 +954,31 @@ extern "C" int jwas_sweep_bayesc(jwas_handle* h, int schedule, double vare, doub
     if (fill_doubles(h, &h->d_pi, &h->cap_pi, pi, (size_t)h->p)) return 10;
     sweep_cfg c; c.method = 0; c.schedule = schedule; c.full_reps = 1; c.vare = vare; c.seed = seed; c.iter = iter;
     return run_sweep(h, c, stats);
+}
+
+// BayesABC!(xArray, xRinvArray, xpRinvx, yCorr, alpha, beta, delta, vare, varEffects, pi) mutates the caller's
+// arrays in place (BayesABC.jl:60-63).  This is that call for host arrays: copies in, the sweep, copies out, enqueued
+// back to back on the handle's stream with ONE synchronisation at the end (pinned buffers copy asynchronously).
+extern "C" int jwas_sweep_bayesc_host(jwas_handle* h, int schedule, double vare, double var_effect, double pi,
+                                      uint64_t seed, uint32_t iter, float* ycorr, float* alpha, float* beta,
+                                      int32_t* delta, jwas_sweep_stats* stats) {
+    JW_REQUIRE(h && ycorr && alpha && beta && delta, "jwas_sweep_bayesc_host: null argument");
+    JW_REQUIRE(h->t == 1, "jwas_sweep_bayesc_host: single-trait handle required");
+    JW_CUDA(cudaSetDevice(h->device));
+    const size_t nb = (size_t)h->n * sizeof(float), pb = (size_t)h->p * sizeof(float);
+    JW_CUDA(cudaMemcpyAsync(h->d_ycorr, ycorr, nb, cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(h->d_alpha, alpha, pb, cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(h->d_beta, beta, pb, cudaMemcpyHostToDevice, h->stream));
+    JW_CUDA(cudaMemcpyAsync(h->d_delta, delta, pb, cudaMemcpyHostToDevice, h->stream));
+    h->next_maxabs = -1.0f;
+    int rc = jwas_sweep_bayesc(h, schedule, vare, var_effect, pi, seed, iter, stats);
+    if (rc) return rc;
+    JW_CUDA(cudaMemcpyAsync(ycorr, h->d_ycorr, nb, cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(alpha, h->d_alpha, pb, cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(beta, h->d_beta, pb, cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaMemcpyAsync(delta, h->d_delta, pb, cudaMemcpyDeviceToHost, h->stream));
+    JW_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 extern "C" int jwas_sweep_bayesr(jwas_handle* h, int schedule, int full_reps, double vare, double sigma_sq,
@@ -1120,7 +1167,7 @@ extern "C" int jwas_init_sharding(jwas_handle* h, int rank, int world, const uin
 }
 
 // ---- fused multi-GPU exchange buffers over CUDA IPC ------------------------------------------
-// One allocation per rank: [ring 4][source rank 8][slot], a slot = 2*t*maxb + t values, each value one 16-byte
+// One allocation per rank: [ring JW_X_RING][source rank 8][slot], a slot = 2*t*maxb + t values, each value one 16-byte
 // word {lo32, tag, hi32, tag} written with a single vector store over NVLink and valid when both tags match
 // (8-byte halves are self-validating: no flag, no fence, no second round trip).
 extern "C" int jwas_ipc_export(jwas_handle* h, uint8_t* out64) {
@@ -1130,7 +1177,7 @@ extern "C" int jwas_ipc_export(jwas_handle* h, uint8_t* out64) {
     if (!h->d_xbuf) {
         h->x_slot_b = (int)h->maxb;
         h->x_slot_words = (int64_t)2 * h->t * h->x_slot_b + h->t;
-        h->xbuf_bytes = (size_t)4 * 8 * h->x_slot_words * 16;
+        h->xbuf_bytes = (size_t)JW_X_RING * 8 * h->x_slot_words * 16;
         JW_CUDA(cudaMalloc((void**)&h->d_xbuf, h->xbuf_bytes));
         JW_CUDA(cudaMemset(h->d_xbuf, 0, h->xbuf_bytes));
     }
@@ -1188,16 +1235,15 @@ extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "timers")) { h->opt_timers = value; return 0; }
     if (!strcmp(key, "gram_popcount")) { h->opt_gram_popc = value; return 0; }   // 1 = popcount kernel instead of the GEMM
     if (!strcmp(key, "lag")) {
-        JW_REQUIRE(value == 0 || value == 1, "lag must be 0 or 1");
+        JW_REQUIRE(value >= 0 && value <= JW_MAX_LAG, "lag must be 0, 1 or 2");
         JW_CUDA(cudaSetDevice(h->device));
         h->opt_lag = value;
-        if (value == 1 && h->nblocks > 0 && !h->d_gramx) {                             // cross-Gram on demand
-            if (!h->opt_gram_popc && h->n < ((int64_t)1 << 22)) return build_gram_gemm(h, true);
-            return build_gram(h, true);
-        }
+        if (h->nblocks > 0 && h->gramx_built < value) return build_all_gram(h, (int)value);    // cross-Gram on demand
         return 0;
     }
     if (!strcmp(key, "gather")) { h->opt_gather = value != 0; return 0; }
+    if (!strcmp(key, "stream_variant")) { JW_REQUIRE(value >= 0 && value <= 3, "stream_variant must be 0..3"); h->opt_stream_variant = value; return 0; }
+    if (!strcmp(key, "stream_pf")) { JW_REQUIRE(value >= 0 && value <= 64, "stream_pf must be 0..64"); h->opt_stream_pf = value; return 0; }
     if (!strcmp(key, "chain_ctas")) {
         JW_REQUIRE(value >= 0 && value <= 16, "chain_ctas must be in 0..16");
         JW_CUDA(cudaSetDevice(h->device));

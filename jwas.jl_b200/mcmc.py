@@ -60,6 +60,10 @@ class GpuBackend:
 
     def __init__(self, sweeper: GpuSweeper):
         self.s = sweeper
+        # record = True (bench.py): per-sweep device times -- (streaming-kernel ms, launches) needs option "profile"
+        self.record = False
+        self.kernel_ms = []
+        self.sweep_ms = []
 
     # ycorr lifecycle
     def put_ycorr(self, y):
@@ -84,8 +88,10 @@ class GpuBackend:
         self.s.ycorr_sub_malpha()
 
     # sweeps return a dict of the reductions the hyper-parameter draws need
-    @staticmethod
-    def _stats(st, t):
+    def _stats(self, st, t):
+        if self.record:
+            self.kernel_ms.append(self.s.stream_kernel_ms())
+            self.sweep_ms.append(self.s.last_sweep_ms)
         return {
             "ycorr_ss": np.array(st.ycorr_ss[:t * t]).reshape(t, t),
             "alpha_ss": np.array(st.alpha_ss[:t * t]).reshape(t, t),

@@ -886,8 +886,8 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
     if (a->method == JWO_METHOD_MT1 && t < 2) return 1;
     if (a->method == JWO_METHOD_MT2 && t != 2) return 1;
     const int lag = a->lag;
-    if (lag != 0 && lag != 1) return 1;
-    if (lag == 1 && (a->independent || a->nreps_mode)) return 1;   /* exact schedule only */
+    if (lag < 0 || lag > 3) return 1;
+    if (lag >= 1 && (a->independent || a->nreps_mode)) return 1;   /* exact schedule only */
 
     /* fixed-point scale from max|ycorr| over all traits (one S per sweep) */
     float maxabs = 0.0f;
@@ -912,8 +912,8 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
     int have_q = 0;
     for (int64_t ib = 0; ib < a->nblocks; ++ib) {
         int64_t s = a->starts[ib], e = a->starts[ib + 1], b = e - s;
-        /* (0) lagged schedule: the updates of block ib-2 reach ycorr only now */
-        if (lag && ib >= 2) apply_block_deltas(a, dall, a->starts[ib - 2], a->starts[ib - 1], r0, r1, xbuf);
+        /* (0) lagged schedule: the updates of block ib-lag-1 reach ycorr only now */
+        if (lag && ib >= lag + 1) apply_block_deltas(a, dall, a->starts[ib - lag - 1], a->starts[ib - lag], r0, r1, xbuf);
         /* (1) fixed-point image of ycorr.  Independent blocks all see the entry snapshot
          *     (BayesABC.jl:205, BayesR.jl:209, MTBayesABC.jl:350). */
         if (!a->independent || !have_q) {
@@ -957,7 +957,8 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
         /* (2b) lagged schedule: block ib-1's updates are not in ycorr yet -- correct the rhs with the
          *      cross-Gram rows of its non-zero deltas, in commit (= marker) order */
         if (lag && ib >= 1) {
-            for (int64_t ja = a->starts[ib - 1]; ja < a->starts[ib]; ++ja) {
+            /* blocks ib-lag .. ib-1, oldest first, each in commit (= marker) order */
+            for (int64_t ja = a->starts[ib > lag ? ib - lag : 0]; ja < a->starts[ib]; ++ja) {
                 int any = 0;
                 for (int k = 0; k < t; ++k) any = any || (dall[k * p + ja] != 0.0f);
                 if (!any) continue;
@@ -1108,9 +1109,9 @@ int jwo_sweep_contract(jwo_sweep_args* a) {
             }
         free(r); free(G); free(aold);
     }
-    if (lag) {                                  /* the last two blocks' updates */
-        if (a->nblocks >= 2) apply_block_deltas(a, dall, a->starts[a->nblocks - 2], a->starts[a->nblocks - 1], r0, r1, xbuf);
-        apply_block_deltas(a, dall, a->starts[a->nblocks - 1], a->starts[a->nblocks], r0, r1, xbuf);
+    if (lag) {                                  /* the updates of the last lag+1 blocks */
+        for (int64_t ib = a->nblocks > lag + 1 ? a->nblocks - lag - 1 : 0; ib < a->nblocks; ++ib)
+            apply_block_deltas(a, dall, a->starts[ib], a->starts[ib + 1], r0, r1, xbuf);
         free(dall);
     } else if (a->independent) {                /* BayesABC.jl:251-253 */
         for (int k = 0; k < t; ++k)

@@ -155,10 +155,10 @@ typedef struct {
     int64_t row_begin, row_end;
     void (*allreduce)(void* ctx, int64_t* buf, int64_t count);
     void* ctx;
-    /* lag = 1 (exact schedule only): block k's rhs is computed from ycorr carrying the updates of
-     * blocks <= k-2 and corrected by the cross-Gram of block k-1's updates,
-     *   r_j += sum_{a in block k-1, commit order} d_a * x_a'x_j,
-     * so that the chain of block k-1 can overlap the streaming of block k on the device.  Same
+    /* lag = L in 1..3 (exact schedule only): block k's rhs is computed from ycorr carrying the updates of
+     * blocks <= k-L-1 and corrected by the cross-Gram of the updates of blocks k-L .. k-1,
+     *   r_j += sum_{a in blocks k-L..k-1, oldest block first, commit order} d_a * x_a'x_j,
+     * so that the chains of the L previous blocks can overlap the streaming of block k on the device.  Same
      * chain in exact arithmetic; differs from lag = 0 in rounding only. */
     int lag;
 } jwo_sweep_args;

@@ -381,6 +381,34 @@ def test_fused_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas):
                  pi=(0.97 if b > 1024 else 0.9), chain_ctas=chain_ctas)
 
 
+@pytest.mark.parametrize("chain_ctas", [1, 2, 4])
+@pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (501, 333, 64, 0.03), (67, 50, 1, 0.0),
+                                           (1030, 700, 700, 0.03), (60013, 150, 64, 0.0), (160, 3100, 1500, 0.0),
+                                           (300, 9000, 4096, 0.0), (200, 2500, 2048, 0.0), (160, 3100, 1500, 0.03),
+                                           (300, 4100, 1024, 0.0)])
+@pytest.mark.parametrize("gather", [0, 1])
+def test_fused_lag2_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas, gather):
+    """option lag=2: the stream of block k carries the updates of blocks <= k-3; the chain corrects the rhs with the
+    cross-Grams of blocks k-2 and k-1 (oldest first, commit order).  Three panels in flight hide the chain and the
+    multi-GPU hand-off behind the stream.  Bit-exact against the oracle's lag-2 schedule."""
+    prob = Problem(oracle, n, p, seed=n + p + 9, missing=missing)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=2,
+                 pi=(0.97 if b > 1024 else 0.9), chain_ctas=chain_ctas, gather=gather)
+
+
+def test_fused_lag2_other_methods(jw, oracle):
+    prob = Problem(oracle, 700, 900, seed=36, missing=0.02)
+    run_pair_r(jw, oracle, prob, uniform_starts(900, 128), jw.SCHED_EXACT, 1, nsweeps=3, engine=1, lag=2, chain_ctas=4)
+    prob = Problem(oracle, 803, 500, seed=46, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(500, 64), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=2, chain_ctas=2)
+    prob = Problem(oracle, 403, 2500, seed=47, ntraits=2)
+    run_pair_mt(jw, oracle, prob, uniform_starts(2500, 1300), jw.SCHED_EXACT, nsweeps=2, engine=1, lag=2, sampler="II",
+                chain_ctas=3)
+    prob = Problem(oracle, 300, 1200, seed=48)
+    run_pair_abc(jw, oracle, prob, uniform_starts(1200, 100), jw.SCHED_EXACT, nsweeps=2, engine=1, lag=2, pi=0.0,
+                 chain_ctas=2)          # BayesA regime: every marker commits
+
+
 @pytest.mark.parametrize("chain_ctas", [2, 3])
 def test_fused_pipelined_chain_other_methods(jw, oracle, chain_ctas):
     prob = Problem(oracle, 700, 900, seed=36, missing=0.02)

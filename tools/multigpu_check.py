@@ -73,6 +73,12 @@ for t, method, miss in ((1, "C", 0.01), (1, "R", 0.0), (2, "M", 0.0), (1, "I", 0
         same2 = all(np.array_equal(x, y) for x, y in zip(ref1, ref2)) and all(np.array_equal(x, y) for x, y in zip(ref1, sh2))
         print(f"rank {rank}/{world} method {method} t={t}: pipelined chain, sharded == single == one-CTA chain: {same2}", flush=True)
         same = same and same2
+        # lag 2 (three panels in flight), four chain CTAs
+        ref3 = run(t, method, False, 1, miss, lag=2, chain_ctas=4)
+        sh3 = run(t, method, True, 1, miss, lag=2, chain_ctas=4)
+        same3 = all(np.array_equal(x, y) for x, y in zip(ref3, sh3))
+        print(f"rank {rank}/{world} method {method} t={t}: lag 2, sharded == single: {same3}", flush=True)
+        same = same and same3
     nz = int(np.count_nonzero(ref[0]))
     print(f"rank {rank}/{world} method {method} t={t}: sharded==single==fused: {same} (nonzero effects {nz})", flush=True)
     ok = ok and same and nz > 0
