@@ -335,7 +335,7 @@ def _max_over_ranks(x, world):
     return float(v.item())
 
 
-def e2e_leg(w, steps):
+def e2e_leg(w, steps, units):
     """Plugin-style call with HOST buffers (pinned): BayesABC!(..., yCorr, alpha, beta, delta, ...) mutating host arrays."""
     import torch
     g = w.g
@@ -353,7 +353,7 @@ def e2e_leg(w, steps):
     dt = _max_over_ranks(time.perf_counter() - t0, w.world)
     w.it0 += steps + 2
     io = (h_y.nbytes + h_a.nbytes + h_b.nbytes + h_d.nbytes) * w.world
-    return {"value": w.world * steps / dt, "unit": UNIT, "problem_sweeps_per_s": steps / dt,
+    return {"value": units * steps / dt, "unit": UNIT, "problem_sweeps_per_s": steps / dt,
             "h2d_bytes_per_step": io, "d2h_bytes_per_step": io,
             "call": "jwas_sweep_bayesc_host (host arrays mutated in place, pinned; every rank moves its replica of ycorr and the state)"}
 
@@ -397,8 +397,8 @@ def main():
     ap.add_argument("--panel", type=int, default=2048, help="look-ahead panel of the exact schedule (markers per block)")
     ap.add_argument("--burnin", type=int, default=40, help="untimed chain iterations before warm-up")
     ap.add_argument("--engine", type=int, default=1)
-    ap.add_argument("--lag", type=int, default=1, help="L = lagged exact schedule (the chains of blocks k-L..k-1 overlap the stream of block k)")
-    ap.add_argument("--chain-ctas", type=int, default=2, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
+    ap.add_argument("--lag", type=int, default=2, help="L = lagged exact schedule (the chains of blocks k-L..k-1 overlap the stream of block k)")
+    ap.add_argument("--chain-ctas", type=int, default=4, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
     ap.add_argument("--fixed-pi", action="store_true", help="keep pi fixed at its start value (reference perf scripts: estimatePi=false)")
     ap.add_argument("--pi0", type=float, default=None)
     ap.add_argument("--cpu-markers", type=int, default=0)
@@ -458,7 +458,7 @@ def main():
     crc = w.crc()
     e2e = None
     if w.t == 1 and w.method == "BayesC":
-        e2e = e2e_leg(w, max(3, min(args.steps, 10)))
+        e2e = e2e_leg(w, max(3, min(args.steps, 10)), units)
     roof = w.roofline(res, peak, peak_src, "exact single-site chain; the lookup-table stream is bound by CUDA-core issue slots and per-panel "
                                            "fixed costs before HBM (DESIGN.md section 5)")
     if (args.config, n, p, world, args.schedule) == ("cfg2", 50000, 600000, 1, "exact"):

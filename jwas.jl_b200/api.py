@@ -27,7 +27,8 @@ except Exception:  # pragma: no cover
     pd = None
 
 DEFAULT_PANEL = 2048          # look-ahead panel of the exact schedule (GPU-internal)
-DEFAULT_CHAIN_CTAS = 2        # chain CTAs of the pipelined chain (engine 1, lag 1); 0 = one chain CTA
+DEFAULT_CHAIN_CTAS = 4        # chain CTAs of the pipelined chain (engine 1, lag >= 1); 0 = one chain CTA
+DEFAULT_LAG = 2               # lagged exact schedule: three look-ahead panels in flight (0 = plain, 1, 2)
 
 
 def error(msg):
@@ -380,7 +381,7 @@ def _frame(rows, cols):
 def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=None, seed=False,
             fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
             double_precision=False, heterogeneous_residuals=False, output_folder="results", device=0,
-            panel=DEFAULT_PANEL, engine=1, lag=1, chain_ctas=DEFAULT_CHAIN_CTAS, output_marker_effect_samples=False,
+            panel=DEFAULT_PANEL, engine=1, lag=DEFAULT_LAG, chain_ctas=DEFAULT_CHAIN_CTAS, output_marker_effect_samples=False,
             _backend_factory=None, **ignored):
     """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
     Returns the reference's output dictionary keys for this path: "location parameters",
@@ -416,8 +417,15 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         error("missing phenotypes are not supported with storage=:gpu.")
     n = len(ids); p = Mi.nMarkers
     packed = Mi.packed
+    subset_means = None
     if n != Mi.nObs or not np.array_equal(rows, np.arange(n)):
-        packed = _pack_codes(_unpack_codes(Mi.packed, Mi.nObs)[rows])
+        # the reference centres on ALL genotyped individuals in get_genotypes (readgenotypes.jl:372-385) and only then
+        # aligns rows to the phenotyped ones (JWAS.jl:381-402): keep the full-sample means, recompute xpx for them
+        sub = _unpack_codes(Mi.packed, Mi.nObs)[rows]
+        if np.any((sub != 3).sum(axis=0) == 0):
+            error("a marker has no observed genotype among the phenotyped individuals.")
+        packed = _pack_codes(sub)
+        subset_means = np.asarray(Mi.marker_means, dtype=np.float32)
 
     if output_samples_frequency is None:                 # evaluated on the user's chain_length (JWAS.jl:168), before :312
         output_samples_frequency = chain_length // 1000 if chain_length > 1000 else 1
@@ -508,12 +516,17 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         Mi.π = big
 
     # ---- device-resident backend: GibbsMats (MCMC_BayesianAlphabet.jl:58) + ycorr (:131-147)
-    use_lag = int(bool(lag) and schedule == SCHED_EXACT and engine == 1)
+    use_lag = int(lag) if (schedule == SCHED_EXACT and engine == 1) else 0
+    if use_lag >= 2 and not chain_ctas:
+        use_lag = 1                                     # lag 2 needs the pipelined chain
     if _backend_factory is not None:
-        backend = _backend_factory(packed, n, t, starts)
+        backend = _backend_factory(packed, n, t, starts) if subset_means is None else \
+            _backend_factory(packed, n, t, starts, means=subset_means)
         backend.lag = use_lag
     else:
         sw = GpuSweeper(packed, n, t, device=device)
+        if subset_means is not None:
+            sw.set_marker_means(subset_means)
         sw.set_option("engine", engine)
         sw.set_option("lag", use_lag)
         sw.set_option("chain_ctas", int(chain_ctas) if use_lag else 0)

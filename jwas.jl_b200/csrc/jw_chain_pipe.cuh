@@ -192,7 +192,7 @@ __host__ __device__ inline size_t jw_chain_unit_smem_bytes(int T) {
 // the call ABI and a second spill set under the kernel's 64-register cap land on the chain's critical path, and the
 // chain, not the stream, bounds the exact schedule.  Rarely used paths called from here (the multi-GPU exchange
 // reads) are therefore kept OUT of line so that they do not disturb this function's register allocation.
-template <int METHOD, int T, class WaitFn>
+template <int METHOD, int T, bool MULTI, class WaitFn>
 __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pipe_args& P, const jw_chain_blk& B,
                                              const int u, WaitFn wait_fn, unsigned char* smem_base,
                                              unsigned long long* ct /* 5 phase timers or nullptr */) {
@@ -325,7 +325,7 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
 #pragma unroll
     for (int k = 0; k < T; ++k) {
         long long dq, mq, sqk;
-        if (B.xslots != nullptr) {
+        if (MULTI) {
             dq = 0; mq = 0; sqk = 0;
             ok = jw_ll_rhs(B, T, k, mc, A.mq != nullptr, dq, mq, sqk) && ok;
         } else {

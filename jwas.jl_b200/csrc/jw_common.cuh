@@ -113,9 +113,10 @@ struct jwas_handle {
     int64_t opt_gather = 0;        // pipelined chain: 1 = a gather warp per streaming CTA replays the records under the
                                    // stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line
     int64_t opt_chain_ctas = 0;    // engine 1, lag 1: chain CTAs of the pipelined chain (0 = one-CTA chain)
-    int64_t opt_stream_variant = 0;// streamed block rhs (independent schedule): 0 = 512 thr + register double buffer,
-                                   // 1 = 1024 thr, 2 = 768 thr + double buffer, 3 = 1024 thr + double buffer
-    int64_t opt_stream_pf = 4;     // L2 prefetch distance of the streamed block rhs, in chunk iterations (0 = off)
+    int64_t opt_stream_variant = 1;// streamed block rhs (independent schedule): 0 = 512 thr + register double buffer,
+                                   // 1 = 1024 thr (measured best: 2.27 ms at cfg2), 2 = 768 thr + double buffer, 3 = 1024 thr + double buffer
+    int64_t opt_stream_pf = 0;     // L2 prefetch distance of the streamed block rhs, in chunk iterations (0 = off: measured best)
+    int64_t opt_l2_prefetch = 1;   // engine 1: pull the next panel's tile into L2 at the end of a panel
     // row-sharded multi-GPU sweep: this rank STORES and streams rows [row_begin, row_end) of every column
     // (row_begin is a multiple of 64); ycorr and the sampler state are replicated
     int64_t row_begin = 0, row_end = 0;

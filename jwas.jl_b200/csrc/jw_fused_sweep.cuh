@@ -64,7 +64,7 @@ struct jw_fused_args {
     int gather;                  // 1 = a gather warp replays the records under the stream (else: in line, before the tables)
     const float* gramx; const int64_t* gramx_off;        // cross-Gram X_{k-1}'X_k
     const float* gramx2; const int64_t* gramx2_off;      // cross-Gram X_{k-2}'X_k (lag 2), else NULL
-    int timers, two_lists;
+    int timers, two_lists, l2_prefetch;
     // multi-GPU (rows sharded over `world` GPUs of one node, one process each): this rank streams the
     // byte-group slices [vs0, vs1) of the rows it stores; a communication CTA pushes the block's exact int64
     // partial rhs into every peer's exchange slots over NVLink (IPC-mapped peer memory) as self-validating
@@ -187,7 +187,8 @@ __device__ __noinline__ void jw_comm_push(const long long* dq, const long long* 
 //      1: pipelined chain (jw_chain_pipe.cuh), streaming CTAs replay the commit records in line
 //      2: pipelined chain, one gather warp per streaming CTA replays them under the stream (one slice per CTA)
 // The modes are compile-time: code of an unused role costs the streaming loop registers (measured: -13 %).
-template <int METHOD, int T, int W, int MODE>
+// MULTI (rows sharded over several GPUs) is compile-time as well: the single-GPU instantiations contain no exchange code.
+template <int METHOD, int T, int W, int MODE, bool MULTI>
 __global__ void __launch_bounds__(JW_FUSED_THREADS, 1)
 jw_k_fused(jw_fused_args F) {
     extern __shared__ __align__(16) int jw_smem[];
@@ -212,7 +213,7 @@ jw_k_fused(jw_fused_args F) {
     // lag = 1: the last CTA only runs chains, the others only stream, so that the chain of block k
     // overlaps the streaming of block k+1 (which needs the updates of blocks <= k-1 only)
     const int lag = F.lag;
-    const bool multi = F.world > 1;                      // needs lag = 1
+    constexpr bool multi = MULTI;                        // host: MULTI == (world > 1); needs lag >= 1
     // pipelined chain: the last n_chain CTAs walk the chain unit by unit (jw_chain_pipe.cuh)
     constexpr bool pipe = MODE >= 1;
     const int n_chain = pipe ? F.P.n_chain : 1;
@@ -286,7 +287,7 @@ jw_k_fused(jw_fused_args F) {
                 __syncthreads();
                 return s_ok != 0;
             };
-            const int nc = jw_chain_unit<METHOD, T>(F.C, F.P, B, u, wait_rhs,
+            const int nc = jw_chain_unit<METHOD, T, MULTI>(F.C, F.P, B, u, wait_rhs,
                                                     reinterpret_cast<unsigned char*>(jw_smem), ctimed ? ct : nullptr);
             if (nc < 0) return;
         }
@@ -655,7 +656,7 @@ jw_k_fused(jw_fused_args F) {
             asm volatile("red.release.gpu.global.add.s32 [%0], 1;" :: "l"(&F.arrive[k]) : "memory");
             if (timed && blockIdx.x == 0) F.C.counters[45] += jw_globaltimer() - t_blk;   // arrive published
         }
-        if (warp == 1 && k + 1 < F.nblocks) {
+        if (warp == 1 && k + 1 < F.nblocks && F.l2_prefetch) {
             // while the chain runs: pull the next block's tile(s) of this CTA into L2
             const int nb1 = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]);
             const int nch1 = (nb1 + 15) >> 4;
@@ -669,7 +670,7 @@ jw_k_fused(jw_fused_args F) {
         }
         JW_PHASE(2);
         }   // streaming role
-        if (is_comm_cta) {
+        if constexpr (MULTI) { if (is_comm_cta) {
             // wait for this GPU's slices, then push the block's partial rhs to every rank (own included)
             if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
             __syncthreads();
@@ -677,7 +678,7 @@ jw_k_fused(jw_fused_args F) {
             jw_comm_push<T>(F.dq, F.C.mq ? F.mq : nullptr, F.sq_acc + k * T, F.peer_slots, F.world,
                             (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride + (int64_t)F.rank * F.slot_stride, F.slot_b,
                             F.tag_base + (unsigned)k + 1u, p, s, b);
-        }
+        } }
         if constexpr (MODE == 0) { if (is_chain_cta) {
             jw_chain_blk B;
             B.xgram = nullptr; B.xgram2 = nullptr; B.xlist = nullptr; B.xcount = nullptr; B.xstart = 0; B.xgram_next = nullptr; B.b_next = 0;
@@ -713,7 +714,7 @@ jw_k_fused(jw_fused_args F) {
                 return s_ok != 0;
             };
             unsigned char* chain_smem = reinterpret_cast<unsigned char*>(yqs + 3 * TRp);
-            const int nc = jw_chain_block<METHOD, T>(F.C, B, k, wait_all, chain_smem, F.list_cap);
+            const int nc = jw_chain_block<METHOD, T, MULTI>(F.C, B, k, wait_all, chain_smem, F.list_cap);
             if (nc < 0) return;
             prev_commits = nc;
             __syncthreads();
@@ -862,7 +863,7 @@ static int jw_fused_prepare(jwas_handle* h) {
 
 template <int METHOD, int T, int W, int MODE>
 static int jw_fused_launch_mode(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
-    auto kern = jw_k_fused<METHOD, T, W, MODE>;
+    auto kern = F.world > 1 ? jw_k_fused<METHOD, T, W, MODE, true> : jw_k_fused<METHOD, T, W, MODE, false>;
     const size_t smem = F.P.n_chain > 0 ? f->smem_pipe : f->smem;
     JW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -938,7 +939,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     const int my_slices = f->n_vs;
     const bool one_slice = my_slices <= h->sm_count - std::max(1, f->n_chain) - (h->world > 1 ? 1 : 0);
     const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok || F.lag >= 2);
-    F.gather = (int)h->opt_gather;
+    F.gather = (int)h->opt_gather; F.l2_prefetch = (int)h->opt_l2_prefetch;
     F.uniform_b = 0;
     if (h->nblocks >= 1) {
         const int64_t b0 = h->starts[1] - h->starts[0];

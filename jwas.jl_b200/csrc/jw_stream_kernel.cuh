@@ -224,10 +224,10 @@ static int jw_stream_launch_v(jwas_handle* h, jw_fused_state* f, jw_stream_args&
 template <int T, int W>
 static int jw_stream_launch_tw(jwas_handle* h, jw_fused_state* f, jw_stream_args& S) {
     switch ((int)h->opt_stream_variant) {
-        case 1: return jw_stream_launch_v<T, W, 1024, 0>(h, f, S);
+        case 0: return jw_stream_launch_v<T, W, 512, 1>(h, f, S);
         case 2: return jw_stream_launch_v<T, W, 768, 1>(h, f, S);
         case 3: return jw_stream_launch_v<T, W, 1024, 1>(h, f, S);
-        default: return jw_stream_launch_v<T, W, 512, 1>(h, f, S);
+        default: return jw_stream_launch_v<T, W, 1024, 0>(h, f, S);
     }
 }
 

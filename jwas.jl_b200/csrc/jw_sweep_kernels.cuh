@@ -581,8 +581,8 @@ __device__ __forceinline__ bool jw_ll_sum(const uint4* base, const int64_t strid
     out = acc;
     return true;
 }
-// the three integer sums a marker's rhs needs, over all ranks (out of line: see jw_chain_unit)
-__device__ __noinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
+// the three integer sums a marker's rhs needs, over all ranks
+__device__ __forceinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
                                           long long& dq, long long& mq, long long& sqk) {
     bool ok = jw_ll_sum(B.xslots + (int64_t)k * B.slot_b + m, B.slot_stride, B.xworld, B.xtag, B.xflags, dq);
     mq = 0;
@@ -617,7 +617,7 @@ __host__ __device__ inline size_t jw_chain_smem_bytes(int T, int list_cap, int n
 // Panels larger than the thread block are walked in sub-blocks of blockDim.x markers; every commit is
 // appended to a list so that a later sub-block starts from  base rhs + sum_commits d*G[commit][j]
 // (added in commit order: the same sums, in the same order, as the one-thread-per-marker chain).
-template <int METHOD, int T, class WaitFn>
+template <int METHOD, int T, bool MULTI, class WaitFn>
 __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_chain_blk& B, const int ib,
                                               WaitFn wait_fn, unsigned char* smem_base, const int list_cap) {
     int (*s_wmin)[32] = reinterpret_cast<int (*)[32]>(smem_base);
@@ -723,7 +723,7 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
     for (int k = 0; k < T; ++k) {
         // .cg loads: these words were produced by other CTAs' atomics in the fused engine
         long long dq, mq, sqk;
-        if (B.xslots != nullptr) {
+        if (MULTI) {
             // exact int64 sums over the ranks' partial rhs (any order gives the same bits)
             dq = 0; mq = 0; sqk = 0;
             ll_ok = jw_ll_rhs(B, T, k, valid ? m : 0, A.mq != nullptr, dq, mq, sqk) && ll_ok;
@@ -733,7 +733,7 @@ __device__ __forceinline__ int jw_chain_block(const jw_chain_args& A, const jw_c
         }
         r[k] = ((double)dq - mu * (double)(sqk - mq)) * A.invscale;
     }
-    if (B.xslots != nullptr) { if (__syncthreads_or(ll_ok ? 0 : 1)) return -1; }
+    if (MULTI) { if (__syncthreads_or(ll_ok ? 0 : 1)) return -1; }
     if (B.xgram != nullptr && valid && two_lists) {
         // previous block's commits from shared memory; four cross-Gram loads in flight, adds in order
         const int xc = B.xcount_smem;
@@ -909,7 +909,7 @@ template <int METHOD, int T>
 __global__ void __launch_bounds__(JW_MAX_BLOCK)
 jw_k_chain(jw_chain_args A, int list_cap) {
     extern __shared__ __align__(16) unsigned char jw_chain_dyn[];
-    jw_chain_block<METHOD, T>(A, jw_chain_blk_from(A), A.block0 + (int)blockIdx.x, jw_no_wait(), jw_chain_dyn, list_cap);
+    jw_chain_block<METHOD, T, false>(A, jw_chain_blk_from(A), A.block0 + (int)blockIdx.x, jw_no_wait(), jw_chain_dyn, list_cap);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,11 +12,23 @@ SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT = 0, 1, 2
 class OracleBackend:
     name = "oracle"
 
-    def __init__(self, packed, n, t, starts):
+    def __init__(self, packed, n, t, starts, means=None):
         self.packed = np.ascontiguousarray(packed); self.n, self.t = n, t
         self.p = packed.shape[0]
         self.starts = np.asarray(starts, dtype=np.int64)
         self.means, self.xpx = orc.marker_stats(self.packed, n)
+        if means is not None:
+            # centring on means computed on a larger sample (twin of jwas_set_marker_means): xpx from the integer
+            # counts through the contract's closed form (gram_value), binary64, in that order
+            self.means = np.asarray(means, dtype=np.float32).copy()
+            codes = np.stack([(self.packed >> (2 * k)) & 3 for k in range(4)], axis=2).reshape(self.p, -1)[:, :n]
+            n1 = (codes == 1).sum(axis=1).astype(np.float64); n2 = (codes == 2).sum(axis=1).astype(np.float64)
+            nn = (codes != 3).sum(axis=1).astype(np.float64)
+            ssum = n1 + 2 * n2; m64 = self.means.astype(np.float64)
+            g = (n1 + 4 * n2) - m64 * ssum
+            g = g - m64 * ssum
+            g = g + (m64 * m64) * nn
+            self.xpx = g.astype(np.float32)
         tp = t * self.p
         self.y = np.zeros(t * n, np.float32)
         self.alpha = np.zeros(tp, np.float32); self.beta = np.zeros(tp, np.float32); self.delta = np.zeros(tp, np.int32)
@@ -129,5 +141,5 @@ class OracleBackend:
         return self.ma.copy(), self.ma2.copy(), self.md.copy()
 
 
-def factory(packed, n, t, starts):
-    return OracleBackend(packed, n, t, starts)
+def factory(packed, n, t, starts, means=None):
+    return OracleBackend(packed, n, t, starts, means=means)

@@ -159,8 +159,55 @@ def test_quality_control_and_phenotype_subset():
     assert geno.nMarkers == 28 and "m4" not in geno.markerID and "m8" not in geno.markerID
     model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
     sub = ph.iloc[::-1].iloc[:40].reset_index(drop=True)     # subset + reorder: genotypes follow phenotypes
-    out = jw.runMCMC(model, sub, chain_length=5, seed=1, _backend_factory=factory)
+    seen = {}
+
+    def fac(packed, n, t, starts, means=None):
+        seen["b"] = factory(packed, n, t, starts, means=means)
+        return seen["b"]
+
+    out = jw.runMCMC(model, sub, chain_length=5, seed=1, _backend_factory=fac)
     assert list(out["EBV_y1"]["ID"]) == list(sub["ID"])
+    # centring stays on ALL genotyped individuals (readgenotypes.jl:372-385 runs before the alignment of
+    # JWAS.jl:381-402): the backend keeps the full-sample means and xpx is the subset's sum of squares about them
+    b = seen["b"]
+    np.testing.assert_array_equal(b.means, np.asarray(geno.marker_means, np.float32))
+    rows = [ids.index(i) for i in sub["ID"]]
+    keep = [j for j in range(30) if j not in (3, 7)]
+    x = codes[np.ix_(rows, keep)].astype(np.float64) - np.asarray(geno.marker_means, np.float64)[None, :]
+    np.testing.assert_allclose(b.xpx, (x * x).sum(axis=0), rtol=1e-6)
+
+
+@pytest.mark.parametrize("t", [2, 3, 4])
+def test_multitrait_prior_df_and_scale_follow_the_reference(t):
+    """build_MME.jl:108-110, 128-134: df += nModels for t > 1; scale = val * (df - t - 1) = val * (df_user - 1)
+    (tools4genotypes.jl:417, input_data_validation.jl:345); constraint=true takes the traits back out and uses
+    diag(scale / (df - 1)) * (df - 2) / df (input_data_validation.jl:530-558)."""
+    codes, ids, ph = make_data(ntraits=t, seed=5)
+    for constraint in (False, True):
+        geno = jw.get_genotypes(codes, np.eye(t), method="BayesC", obsID=ids, constraint=constraint)
+        eq = "\n".join(f"y{k + 1} = intercept + geno" for k in range(t))
+        model = jw.build_model(eq, np.eye(t) * 2.0, genotypes={"geno": geno}, constraint=constraint)
+        assert model.R.df == 4.0 + t and geno.G.df == 4.0 + t
+        seen = {}
+        orig = jw.mcmc.run_chain
+
+        def spy(backend, **kw):
+            seen.update(kw)
+            return orig(backend, **kw)
+
+        jw.api.mcmc.run_chain = spy
+        try:
+            jw.runMCMC(model, ph, chain_length=2, seed=1, outputEBV=False, _backend_factory=factory)
+        finally:
+            jw.api.mcmc.run_chain = orig
+        if not constraint:
+            assert seen["df_res"] == 4.0 + t and seen["df_effect"] == 4.0 + t
+            np.testing.assert_allclose(seen["scale_R"], np.eye(t) * 2.0 * 3.0)              # R * (df_user - 1)
+            np.testing.assert_allclose(seen["scale_G"], np.asarray(geno.G.val) * 3.0)
+        else:
+            assert seen["df_res"] == 4.0 and seen["df_effect"] == 4.0
+            np.testing.assert_allclose(seen["scale_R"], np.eye(t) * 2.0 * 3.0 / 3.0 * 2.0 / 4.0)   # diag(R) * (nu-2)/nu
+            assert np.all(np.linalg.eigvalsh(seen["scale_G"]) > 0)
 
 
 def test_jgb2_backend_files_roundtrip(tmp_path):

@@ -571,3 +571,61 @@ def test_mega_bayesabc_independent_traits(jw, oracle, engine, lag, t, chain_ctas
         assert [st.sum_delta[k] for k in range(t)] == [de[k * p:(k + 1) * p].sum() for k in range(t)]
     assert all(de[k * p:(k + 1) * p].sum() > 0 for k in range(t))
     g.close()
+
+
+def test_external_marker_means(jw, oracle):
+    """jwas_set_marker_means: centring on means computed on a larger sample (get_genotypes centres on all genotyped
+    individuals, readgenotypes.jl:372-385, before JWAS.jl:381-402 aligns rows): xpx, Gram blocks, dots and the axpy all
+    follow the supplied means -- bit-exact against the contract sweep fed the same means / xpx."""
+    from oracle_backend import OracleBackend
+    prob = Problem(oracle, 300, 200, seed=77, missing=0.02)
+    means = (prob.means + np.random.default_rng(1).normal(0, 0.05, 200)).astype(np.float32)
+    starts = uniform_starts(200, 64)
+    ob = OracleBackend(prob.packed, 300, 1, starts, means=means)
+    for engine, lag, cc in ((0, 0, 0), (1, 2, 2)):
+        g = jw.GpuSweeper(prob.packed, 300, 1)
+        g.set_marker_means(means)
+        g.set_option("engine", engine); g.set_option("lag", lag); g.set_option("chain_ctas", cc)
+        g.set_blocks(starts)
+        gm, gx = g.marker_stats()
+        np.testing.assert_array_equal(gm, means)
+        np.testing.assert_array_equal(gx, ob.xpx)
+        yc, al, be, de = prob.fresh_state()
+        g.put_ycorr(yc); g.put_state(al, be, de)
+        ve = np.full(200, 0.02); pi = np.full(200, 0.8)
+        for it in (1, 2):
+            rc, _ = oracle.sweep_contract(prob.packed, 300, means, ob.xpx, starts, yc, al, be, de, vare=1.0, varEffects=ve,
+                                          pi=pi, seed=4, it=it, lag=lag)
+            assert rc == 0
+            g.sweep_bayesabc(jw.SCHED_EXACT, 1.0, ve, pi, 4, it)
+        ga, gb, gd = g.get_state()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(g.get_ycorr().view(np.uint32), yc.view(np.uint32))
+        assert de.sum() > 0
+        g.close()
+
+
+def test_host_array_sweep_call(jw, oracle):
+    """jwas_sweep_bayesc_host = BayesABC!(..., yCorr, alpha, beta, delta, ...) mutating the caller's arrays
+    (BayesABC.jl:60-63): same result as put / sweep / get."""
+    prob = Problem(oracle, 400, 300, seed=12)
+    starts = uniform_starts(300, 128)
+    outs = []
+    for host in (False, True):
+        g = jw.GpuSweeper(prob.packed, 400, 1)
+        g.set_option("engine", 1); g.set_option("lag", 2); g.set_option("chain_ctas", 2)
+        g.set_blocks(starts)
+        yc, al, be, de = prob.fresh_state()
+        for it in (1, 2, 3):
+            if host:
+                g.sweep_bayesc_host(jw.SCHED_EXACT, 1.0, 0.02, 0.9, 9, it, yc, al, be, de)
+            else:
+                g.put_ycorr(yc); g.put_state(al, be, de)
+                g.sweep_bayesc(jw.SCHED_EXACT, 1.0, 0.02, 0.9, 9, it)
+                al, be, de = g.get_state(); yc = g.get_ycorr()
+        outs.append((yc.copy(), al.copy(), be.copy(), de.copy()))
+        g.close()
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)
+    assert outs[0][3].sum() > 0

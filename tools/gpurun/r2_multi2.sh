@@ -1,0 +1,20 @@
+# N-GPU scaling probe (weak: 50,000 rows per GPU; strong: cfg2 itself), lag / chain CTA / panel variants
+N=${1:-2}
+mkdir -p gpurun_out
+run() {
+  tag=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29720 bench.py --gpus $N --steps 10 --warmup 3 --no-extras --no-cpu "$@" > gpurun_out/m${N}_$tag.json 2> gpurun_out/m${N}_$tag.err
+  python - "$tag" "$N" "$@" <<PY
+import json, sys
+try:
+    d = json.loads(open('gpurun_out/m%s_%s.json' % (sys.argv[2], sys.argv[1])).read().strip().splitlines()[-1])
+    print('N=%s' % sys.argv[2], ' '.join(sys.argv[3:]), '| value %.1f' % d['value'], 'problem %.1f' % d['problem_sweeps_per_s'], 'ms/step %.2f' % d['ms_per_step'], 'kernel ms %.3f' % d['roofline']['kernel_ms_per_launch'], 'frac %.3f' % d['roofline']['frac'], 'e2e %.1f' % (d['e2e']['value'] if d['e2e'] else 0), d['state_crc'])
+except Exception as e:
+    print(' '.join(sys.argv[1:]), 'FAILED', e); print(open('gpurun_out/m%s_%s.err' % (sys.argv[2], sys.argv[1])).read()[-1200:])
+PY
+}
+run weak_l2c4p3072 --lag 2 --chain-ctas 4 --panel 3072
+run weak_l1c2 --lag 1 --chain-ctas 2
+run weak_l2c4 --lag 2 --chain-ctas 4
+run strong_l2c4p3072 --strong --lag 2 --chain-ctas 4 --panel 3072
+run strong_l2c4 --strong --lag 2 --chain-ctas 4

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sweep_parity.py -q -x -k "lag2 or pipelined or independent or block_sched" 2>&1 | tail -3
 run() {
   tag=$1; shift
   timeout 300 python bench.py --steps 20 --warmup 5 --burnin 40 --no-cpu --no-extras "$@" 2>gpurun_out/ab_tmp.err | tail -1 > gpurun_out/ro_$tag.json
@@ -14,11 +13,11 @@ PY
 }
 run lag1c2 --lag 1 --chain-ctas 2
 run lag2c4 --lag 2 --chain-ctas 4
+run lag2c3 --lag 2 --chain-ctas 3
 run lag2c4p3072 --lag 2 --chain-ctas 4 --panel 3072
+run lag2c4p1536 --lag 2 --chain-ctas 4 --panel 1536
 run lag1c2g --lag 1 --chain-ctas 2 --panel 1984 --opt gather=1
 run lag2c4g --lag 2 --chain-ctas 4 --panel 1984 --opt gather=1
-run lag2c4gp2976 --lag 2 --chain-ctas 4 --panel 2976 --opt gather=1
 run lag2c6gp3968 --lag 2 --chain-ctas 6 --panel 3968 --opt gather=1
-for v in 0 1 2 3; do run ind_v${v}_pf0 --schedule independent --steps 4 --burnin 30 --opt stream_variant=$v --opt stream_pf=0; done
-run ind_v0_pf4 --schedule independent --steps 4 --burnin 30 --opt stream_variant=0 --opt stream_pf=4
-run ind_v1_pf4 --schedule independent --steps 4 --burnin 30 --opt stream_variant=1 --opt stream_pf=4
+run fixedpi_l2c4 --lag 2 --chain-ctas 4 --fixed-pi --steps 5
+run fixedpi_l2c8 --lag 2 --chain-ctas 8 --fixed-pi --steps 5
