@@ -25,7 +25,9 @@
 
 #define JW_REC_END 0x8000u
 #define JW_REC_STRIDE (JW_CHAIN_SB + 1)       // commits of one unit + terminator
+#ifndef JW_REC_BATCH
 #define JW_REC_BATCH 4                        // records peeked per poll (their Gram / genotype loads overlap)
+#endif
 
 struct jw_pipe_args {
     int n_chain;                              // chain CTAs (0 = one-CTA chain, jw_chain_block)
@@ -37,6 +39,9 @@ struct jw_pipe_args {
     unsigned tag;                             // 1..65535, changes every sweep
     int32_t* act_cnt_unit;                    // nunits: entries of the unit's ordered active list
     int32_t* flags;                           // [2] sticky abort
+    // optional back-off (ns) after an EMPTY poll of a record word (A/B knob: 0 / 300 / 1000 ns measured identical at
+    // cfg2 in the sparse and in the dense regime, so polling pressure is not what bounds the chain)
+    unsigned sleep_stream, sleep_chain;
 };
 
 __device__ __forceinline__ unsigned long long jw_ld_relaxed_u64(const unsigned long long* p) {
@@ -131,6 +136,7 @@ __device__ __forceinline__ bool jw_rec_foreach(const jw_pipe_args& P, const int 
             if (nv == 0) {
                 if (!jw_spin_ok(spins, t0, P.flags)) return false;
                 if (GENTLE) __nanosleep(400);
+                else if (P.sleep_stream) __nanosleep(P.sleep_stream);
             }
             cur.issue();
         }
@@ -170,23 +176,32 @@ struct jw_rec_walker {
 };
 
 #define JW_UNIT_PG 16          // corrections fetched ahead of the block's rhs (per thread, in shared memory)
-#define JW_UNIT_ROWS 8         // Gram rows of markers already in the model, cached in shared memory
+#define JW_UNIT_RING 16        // Gram rows of the predicted commits (markers already in the model) in flight / in shared memory
 __host__ __device__ inline size_t jw_chain_unit_smem_bytes(int T) {
     return 512 + (size_t)T * JW_CHAIN_SB * 4 + (size_t)32 * JW_UNIT_PG * T * 4 +
-           (size_t)JW_UNIT_PG * JW_CHAIN_SB * 4 + (size_t)JW_UNIT_ROWS * JW_CHAIN_SB * 4;
+           (size_t)JW_UNIT_PG * JW_CHAIN_SB * 4 + (size_t)JW_UNIT_RING * JW_CHAIN_SB * 4 + (size_t)JW_CHAIN_SB * 4;
 }
+// 4-byte asynchronous global -> shared copy (LDGSTS): the Gram-row ring is filled without holding registers
+__device__ __forceinline__ void jw_cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void jw_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void jw_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // One unit of the chain.  B describes the unit's panel (s, b, Gram, cross-Gram towards the previous
 // panel, rhs source); wait_fn() blocks until the panel's rhs partial sums are complete.
 // Shared memory (caller-supplied, jw_chain_unit_smem_bytes): wmin[2][32] | cnt[32] | misc[32] | dc[T][1024] |
-// pd[32 warps][PG][T] | pg[PG][1024] | rows[ROWS][1024].
+// pd[32 warps][PG][T] | pg[PG][1024] | ring[RING][1024] | list[1024].
 //
 // Everything that can be had before the block's rhs exists is fetched while the CTA would otherwise wait for
-// it: state, constants, draws; the Gram rows of the markers that already carry an effect (they are the
-// likely commits) into shared memory; and the cross-Gram / Gram values of every correction whose record has
-// already been published (all of the previous panel, normally).  After the wait the critical path is:
-// rhs partial sums (one L2 round trip) -> buffered corrections (shared memory) -> rounds (one barrier each;
-// a Gram round trip only when a marker ENTERS the model).
+// it: state, constants, draws; and the cross-Gram / Gram values of every correction whose record has already been
+// published (all of the previous panels, normally).  The markers that already carry an effect are the PREDICTED
+// commits of the unit (a marker in the model changes its effect every time it is sampled): their Gram rows stream
+// through a ring of JW_UNIT_RING rows in shared memory, filled by asynchronous copies (cp.async) that run RING
+// commits ahead of the chain.  After the wait the critical path is: rhs partial sums (one L2 round trip) -> buffered
+// corrections (shared memory) -> rounds (evaluation + one barrier + a shared-memory read each; a Gram round trip
+// only when a marker ENTERS the model).
 // Returns the number of commits, -1 when the sweep was aborted.
 // Inlined into the persistent kernel on purpose: as a function of its own (measured) the chain runs ~2x slower --
 // the call ABI and a second spill set under the kernel's 64-register cap land on the chain's critical path, and the
@@ -202,7 +217,9 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
     float* s_dc = reinterpret_cast<float*>(smem_base + 512);                  // [T][JW_CHAIN_SB]
     float* s_pd = s_dc + T * JW_CHAIN_SB;                                     // [32][PG][T]
     float* s_pg = s_pd + 32 * JW_UNIT_PG * T;                                 // [PG][JW_CHAIN_SB]
-    float* s_rows = s_pg + JW_UNIT_PG * JW_CHAIN_SB;                          // [ROWS][JW_CHAIN_SB]
+    float* s_ring = s_pg + JW_UNIT_PG * JW_CHAIN_SB;                          // [RING][JW_CHAIN_SB]
+    int* s_list = reinterpret_cast<int*>(s_ring + JW_UNIT_RING * JW_CHAIN_SB); // [JW_CHAIN_SB] ordered positions of the predicted commits
+    (void)s_misc;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = (int)(blockDim.x >> 5);
@@ -275,14 +292,32 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a0), "r"(bytes) : "memory");
         }
     }
-    // Gram rows of (up to ROWS) markers already in the model -> shared memory, this unit's columns only
-    if (tid == 0) s_misc[0] = 0;
-    __syncthreads();
-    if (nz) { const int slot = atomicAdd(&s_misc[0], 1); if (slot < JW_UNIT_ROWS) s_misc[1 + slot] = tid; }
-    __syncthreads();
-    const int nrow = min(s_misc[0], JW_UNIT_ROWS);
-    for (int q = 0; q < nrow; ++q)
-        s_rows[q * JW_CHAIN_SB + tid] = valid ? G[(int64_t)(m0 + s_misc[1 + q]) * b + m] : 0.0f;
+    // The PREDICTED commits of the unit = the markers already in the model (a marker in the model changes its effect
+    // every time it is sampled), and their Gram rows (this unit's columns only: thread tid copies and later reads
+    // column tid): the rows start streaming into the ring while the CTA waits for the rhs.  (Predicting the markers about
+    // to ENTER the model as well, from one extra evaluation after the rhs, was measured and is not worth its barrier:
+    // 50.5 vs 47.3 ms per sweep with pi fixed at 0.95.)
+    int nlist = 0;
+    auto build_list = [&](const bool flag) {
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        const int c = (lane < nw) ? s_cnt[lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int vv = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += vv; }
+        const int warp_off = __shfl_sync(0xffffffffu, incl - c, warp);
+        nlist = __shfl_sync(0xffffffffu, incl, 31);
+        if (flag) s_list[warp_off + __popc(bal & ((1u << lane) - 1u))] = tid;
+        __syncthreads();
+    };
+    auto ring_issue = [&](const int i) {      // row of predicted commit i -> slot i % RING (an empty group when there is none)
+        if (i < nlist && valid) jw_cp_async4(s_ring + (i % JW_UNIT_RING) * JW_CHAIN_SB + tid, G + (int64_t)(m0 + s_list[i]) * b + m);
+        jw_cp_async_commit();
+    };
+    build_list(nz);
+    for (int i = 0; i < JW_UNIT_RING; ++i) ring_issue(i);
+    int li = 0;                                // next predicted commit (uniform across the CTA)
 
     // corrections whose records are already there: fetch their (cross-)Gram values now, add them after the rhs
     // corrections come from the units of the `lag` previous panels (oldest first) and the earlier units of this one
@@ -351,7 +386,11 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
             int us_ = 0;
             wst = W.poll(us_);
             if (wst < 0) break;
-            if (wst == 0) { if (!jw_spin_ok(spins, t0, P.flags)) { ok = false; break; } continue; }
+            if (wst == 0) {
+                if (!jw_spin_ok(spins, t0, P.flags)) { ok = false; break; }
+                if (P.sleep_chain) __nanosleep(P.sleep_chain);
+                continue;
+            }
             float g[JW_REC_BATCH];
 #pragma unroll
             for (int q = 0; q < JW_REC_BATCH; ++q) g[q] = (q < wst && valid) ? *corr_row(us_, W.R.code(q)) : 0.0f;
@@ -412,10 +451,18 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
         }
         if (first == 0x7fffffff) break;
         const int fg = m0 + first;                       // committed marker's position inside the panel
+        // the committed marker's Gram row: from the ring when it was predicted (the usual case), else from L2.
+        // Every predicted commit at or before `first` retires its ring slot: wait for the oldest copy group, take the
+        // value, refill the slot with the row RING predictions ahead (keeps exactly RING groups in flight).
+        float g = 0.0f; bool hit = false;
+        while (li < nlist && s_list[li] <= first) {
+            jw_cp_async_wait<JW_UNIT_RING - 1>();
+            if (s_list[li] == first) { hit = true; g = s_ring[(li % JW_UNIT_RING) * JW_CHAIN_SB + tid]; }
+            ring_issue(li + JW_UNIT_RING);
+            li += 1;
+        }
         if (valid && tid > first) {
-            int slot = -1;
-            for (int q = 0; q < nrow; ++q) if (s_misc[1 + q] == first) slot = q;
-            const float g = slot >= 0 ? s_rows[slot * JW_CHAIN_SB + tid] : G[(int64_t)fg * b + m];
+            if (!hit) g = G[(int64_t)fg * b + m];
 #pragma unroll
             for (int k = 0; k < T; ++k) {
                 const float d = s_dc[k * JW_CHAIN_SB + first];
@@ -466,6 +513,7 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
         if (any) B.act_idx[warp_off + __popc(bal & ((1u << lane) - 1u))] = (int32_t)j;
     }
     if (tid == 0) P.act_cnt_unit[u] = act_total;
+    jw_cp_async_wait<0>();    // no copy of this unit may land in the ring after the next unit starts filling it
     __syncthreads();          // shared scratch is reused by this CTA's next unit
     JW_CT(4);
 #undef JW_CT

@@ -116,6 +116,7 @@ struct jwas_handle {
     int64_t opt_stream_variant = 1;// streamed block rhs (independent schedule): 0 = 512 thr + register double buffer,
                                    // 1 = 1024 thr (measured best: 2.27 ms at cfg2), 2 = 768 thr + double buffer, 3 = 1024 thr + double buffer
     int64_t opt_stream_pf = 0;     // L2 prefetch distance of the streamed block rhs, in chunk iterations (0 = off: measured best)
+    int64_t opt_poll_ns_stream = 0, opt_poll_ns_chain = 0;     // back-off after an empty record poll (measured: no effect)
     int64_t opt_l2_prefetch = 1;   // engine 1: pull the next panel's tile into L2 at the end of a panel
     // row-sharded multi-GPU sweep: this rank STORES and streams rows [row_begin, row_end) of every column
     // (row_begin is a multiple of 64); ycorr and the sampler state are replicated

@@ -959,6 +959,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
         F.P.n_chain = f->n_chain; F.P.nunits = f->nunits;
         F.P.unit_start = f->d_unit_start; F.P.unit_blk = f->d_unit_blk; F.P.blk_unit0 = f->d_blk_unit0;
         F.P.rec = f->d_rec; F.P.tag = f->rec_tag; F.P.act_cnt_unit = f->d_act_cnt_unit; F.P.flags = h->d_flags;
+        F.P.sleep_stream = (unsigned)h->opt_poll_ns_stream; F.P.sleep_chain = (unsigned)h->opt_poll_ns_chain;
         JW_CUDA(cudaMemsetAsync(f->d_act_cnt_unit, 0, f->nunits * sizeof(int32_t), h->stream));
     }
     if (h->opt_profile) {
