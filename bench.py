@@ -182,8 +182,8 @@ class Workload:
     """One chain on one configuration: device-resident genotypes (this rank's rows), simulated phenotypes, the
     reference's default priors, driven through mcmc.run_chain (the host side of MCMC_BayesianAlphabet)."""
 
-    def __init__(self, name, n, p, rank, world, device, *, schedule="exact", block=0, panel=2048, engine=1, lag=1,
-                 chain_ctas=2, estimate_pi=True, pi0=None, method=None, seed=2026, opts=None):
+    def __init__(self, name, n, p, rank, world, device, *, schedule="exact", block=0, panel=4096, engine=1, lag=2,
+                 chain_ctas=6, estimate_pi=True, pi0=None, method=None, seed=2026, opts=None):
         import jwas_b200
         from jwas_b200 import mcmc, multigpu
         self.jw, self.mcmc = jwas_b200, mcmc
@@ -394,11 +394,11 @@ def main():
     ap.add_argument("--strong", action="store_true", help="N > 1: shard the configuration's own rows instead of growing them with N")
     ap.add_argument("--schedule", default="exact", choices=["exact", "block", "independent"])
     ap.add_argument("--block", type=int, default=223, help="fast_blocks block size for --schedule block|independent")
-    ap.add_argument("--panel", type=int, default=2048, help="look-ahead panel of the exact schedule (markers per block)")
+    ap.add_argument("--panel", type=int, default=4096, help="look-ahead panel of the exact schedule (markers per block)")
     ap.add_argument("--burnin", type=int, default=40, help="untimed chain iterations before warm-up")
     ap.add_argument("--engine", type=int, default=1)
     ap.add_argument("--lag", type=int, default=2, help="L = lagged exact schedule (the chains of blocks k-L..k-1 overlap the stream of block k)")
-    ap.add_argument("--chain-ctas", type=int, default=4, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
+    ap.add_argument("--chain-ctas", type=int, default=6, help="chain CTAs of the pipelined chain (0 = one-CTA chain)")
     ap.add_argument("--fixed-pi", action="store_true", help="keep pi fixed at its start value (reference perf scripts: estimatePi=false)")
     ap.add_argument("--pi0", type=float, default=None)
     ap.add_argument("--cpu-markers", type=int, default=0)

@@ -195,11 +195,17 @@ int jwas_ipc_import(jwas_handle* h, const uint8_t* handles /* world * 64 bytes i
 int64_t jwas_kernel_launches(jwas_handle* h);     /* kernels launched by this handle so far */
 /* Backend options (none changes a result bit):
  *   "engine"      0 = multi-kernel engine, 1 = persistent fused sweep kernel
- *   "lag"         1 = lagged exact schedule (engine 1): the chain of panel k overlaps the stream of panel k+1
+ *   "lag"         L = 1, 2: lagged exact schedule (engine 1): the stream of panel k carries the updates of panels <= k-L-1,
+ *                 the chains of panels k-L..k-1 overlap it (cross-Gram corrections); 2 needs chain_ctas >= 1
  *   "chain_ctas"  engine 1, lag 1: number of chain CTAs of the PIPELINED chain (units of <= 1024 markers handed
  *                 from CTA to CTA as 64-bit commit records); 0 = one chain CTA.  Re-cuts the row slices.
  *   "gather"      pipelined chain: 1 = one warp of every streaming CTA replays the commit records under the
  *                 stream (pays off with panels that are a multiple of 31*16 markers), 0 = in line (default)
+ *   "ws"          engine 1, pipelined chain, one trait without missing calls: 1 (default) = warp-specialised streaming
+ *                 role (builder warps rebuild one lookup-table set while the streaming warps run through the other;
+ *                 per-warp release of a panel), 0 = the plain role (record replay, rebuild, stream in turn)
+ *   "l2_prefetch" 1 = pull the next panel's tile into L2 at the end of a panel (default 0: measured slower)
+ *   "poll_ns_stream", "poll_ns_chain"  back-off in ns after an empty poll of a commit record (default 0)
  *   "stream_variant", "stream_pf"   independent schedule, engine 1: launch shape of the streamed block-rhs kernel
  *                 (0 = 512 threads + register double buffer, 1 = 1024 threads, 2 = 768 + double buffer,
  *                 3 = 1024 + double buffer) and its L2 prefetch distance in chunk iterations (0 = off)

@@ -26,8 +26,8 @@ try:  # pandas is what a DataFrame is here
 except Exception:  # pragma: no cover
     pd = None
 
-DEFAULT_PANEL = 2048          # look-ahead panel of the exact schedule (GPU-internal)
-DEFAULT_CHAIN_CTAS = 4        # chain CTAs of the pipelined chain (engine 1, lag >= 1); 0 = one chain CTA
+DEFAULT_PANEL = 4096          # look-ahead panel of the exact schedule (GPU-internal)
+DEFAULT_CHAIN_CTAS = 6        # chain CTAs of the pipelined chain (engine 1, lag >= 1); 0 = one chain CTA
 DEFAULT_LAG = 2               # lagged exact schedule: three look-ahead panels in flight (0 = plain, 1, 2)
 
 

@@ -117,7 +117,9 @@ struct jwas_handle {
                                    // 1 = 1024 thr (measured best: 2.27 ms at cfg2), 2 = 768 thr + double buffer, 3 = 1024 thr + double buffer
     int64_t opt_stream_pf = 0;     // L2 prefetch distance of the streamed block rhs, in chunk iterations (0 = off: measured best)
     int64_t opt_poll_ns_stream = 0, opt_poll_ns_chain = 0;     // back-off after an empty record poll (measured: no effect)
-    int64_t opt_l2_prefetch = 1;   // engine 1: pull the next panel's tile into L2 at the end of a panel
+    int64_t opt_ws = 1;            // engine 1, pipelined chain, one trait without missing calls: warp-specialised streaming role
+                                   // (builder warps + streaming warps, two table sets; jw_fused_ws.cuh)
+    int64_t opt_l2_prefetch = 0;   // engine 1: pull the next panel's tile into L2 at the end of a panel (measured: slower, off)
     // row-sharded multi-GPU sweep: this rank STORES and streams rows [row_begin, row_end) of every column
     // (row_begin is a multiple of 64); ycorr and the sampler state are replicated
     int64_t row_begin = 0, row_end = 0;

@@ -65,6 +65,7 @@ struct jw_fused_args {
     const float* gramx; const int64_t* gramx_off;        // cross-Gram X_{k-1}'X_k
     const float* gramx2; const int64_t* gramx2_off;      // cross-Gram X_{k-2}'X_k (lag 2), else NULL
     int timers, two_lists, l2_prefetch;
+    int arrive_mult;             // arrivals per streaming CTA and panel (1; the warp-specialised role: one per streaming warp)
     // multi-GPU (rows sharded over `world` GPUs of one node, one process each): this rank streams the
     // byte-group slices [vs0, vs1) of the rows it stores; a communication CTA pushes the block's exact int64
     // partial rhs into every peer's exchange slots over NVLink (IPC-mapped peer memory) as self-validating
@@ -159,6 +160,8 @@ __host__ __device__ __forceinline__ constexpr int jw_tab_sub(int gb) {
 }
 #define JW_TAB_BYTES(W_) ((W_) == 1 ? 2 * 65536 : 3 * 65536)
 
+#include "jw_fused_ws.cuh"
+
 // communication CTA (rows sharded over several GPUs): the block's exact int64 partial rhs of this GPU -> every rank's
 // exchange slots, as self-validating 16-byte words.  Value e of the slot: dq[kk][mm] | mq[kk][mm] (only when calls
 // are missing) | sq[kk]; only the entries the chain reads are sent (mm < b).  Not inlined (see jw_chain_unit).
@@ -181,6 +184,35 @@ __device__ __noinline__ void jw_comm_push(const long long* dq, const long long* 
         }
         for (int rk = 0; rk < world; ++rk) jw_ll_store(peer_slots[rk] + slot0 + w, v, tag);
     }
+}
+
+// ... and the way back: the block's partial rhs of EVERY rank (pushed into this GPU's slots by the ranks' communication
+// CTAs) summed -- exact int64, any order -- and written over this GPU's own partial sums, so that the chain reads
+// complete sums from dq / mq / sq exactly as on one GPU (no exchange code, and no extra registers, inside the chain).
+// Returns false when the sweep was abandoned.
+template <int T>
+__device__ __noinline__ bool jw_comm_pull(long long* dq, long long* mq, long long* sq_k, const uint4* my_slots, const int world,
+                                          const int64_t ring_off, const int64_t slot_stride, const int slot_b, const unsigned tag,
+                                          const int64_t p, const int64_t s, const int b, int32_t* flags) {
+    const int tid = threadIdx.x;
+    const int nmq = mq ? 2 : 1;
+    bool ok = true;
+    for (int e = tid; e < nmq * T * b + T && ok; e += JW_FUSED_THREADS) {
+        long long* dst; int64_t w;
+        if (e < nmq * T * b) {
+            const int part = e / (T * b), e2 = e - part * T * b, kk = e2 / b, mm = e2 - kk * b;
+            dst = (part == 0 ? dq : mq) + (int64_t)kk * p + s + mm;
+            w = (int64_t)(part * T + kk) * slot_b + mm;
+        } else {
+            const int kk = e - nmq * T * b;
+            dst = sq_k + kk;
+            w = (int64_t)2 * T * slot_b + kk;
+        }
+        long long tot = 0;
+        ok = jw_ll_sum(my_slots + ring_off + w, slot_stride, world, tag, flags, tot);
+        if (ok) __stcg(dst, tot);
+    }
+    return ok;
 }
 
 // MODE 0: one chain CTA (lag 1) or CTA 0 streams and chains (lag 0), jw_chain_block
@@ -273,21 +305,17 @@ jw_k_fused(jw_fused_args F) {
                 B.prefetch_b = (int)(F.P.unit_start[u + n_chain + 1] - B.prefetch_s);
             }
             B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = F.flags;
-            if (multi) {
-                B.xslots = F.my_slots + (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride;
-                B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
-                B.xtag = F.tag_base + (unsigned)k + 1u;
-            }
             B.sq = F.sq_acc + k * T;
             B.act_idx = F.act_idx_all + F.P.unit_start[u];
             B.act_cnt = nullptr; B.write_active_list = 1;
             auto wait_rhs = [&]() -> bool {
-                if (multi) return true;            // the rhs words carry their own tags: reading them is the wait
-                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+                // one GPU: every streaming CTA (or warp) has arrived; several: + the communication CTA, which has
+                // then replaced this GPU's partial sums in dq / mq / sq by the sums over all ranks
+                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream * F.arrive_mult + (multi ? 1 : 0), F.flags) ? 1 : 0;
                 __syncthreads();
                 return s_ok != 0;
             };
-            const int nc = jw_chain_unit<METHOD, T, MULTI>(F.C, F.P, B, u, wait_rhs,
+            const int nc = jw_chain_unit<METHOD, T, false>(F.C, F.P, B, u, wait_rhs,
                                                     reinterpret_cast<unsigned char*>(jw_smem), ctimed ? ct : nullptr);
             if (nc < 0) return;
         }
@@ -296,6 +324,12 @@ jw_k_fused(jw_fused_args F) {
             for (int i = 0; i < 5; ++i) F.C.counters[56 + i] = ct[i];
             F.C.counters[61] = (unsigned long long)my_units;
         }
+        return;
+    } }
+
+    if constexpr (MODE == 3) { if (is_stream_cta) {
+        // warp-specialised streaming role (jw_fused_ws.cuh): builder warps and streaming warps, two table sets
+        if ((int)blockIdx.x < n_vs_local) jw_stream_ws<T>(F, jw_smem, F.vs0 + (int)blockIdx.x);
         return;
     } }
 
@@ -672,12 +706,18 @@ jw_k_fused(jw_fused_args F) {
         }   // streaming role
         if constexpr (MULTI) { if (is_comm_cta) {
             // wait for this GPU's slices, then push the block's partial rhs to every rank (own included)
-            if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+            if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream * F.arrive_mult, F.flags) ? 1 : 0;
             __syncthreads();
             if (!s_ok) return;
             jw_comm_push<T>(F.dq, F.C.mq ? F.mq : nullptr, F.sq_acc + k * T, F.peer_slots, F.world,
                             (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride + (int64_t)F.rank * F.slot_stride, F.slot_b,
                             F.tag_base + (unsigned)k + 1u, p, s, b);
+            const bool okp = jw_comm_pull<T>(F.dq, F.C.mq ? F.mq : nullptr, F.sq_acc + k * T, F.my_slots, F.world,
+                                             (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride, F.slot_stride, F.slot_b,
+                                             F.tag_base + (unsigned)k + 1u, p, s, b, F.flags);
+            if (__syncthreads_or(okp ? 0 : 1)) return;
+            // the sums are in place: one more arrival releases the chain (release is cumulative over the CTA's stores)
+            if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" :: "l"(&F.arrive[k]) : "memory");
         } }
         if constexpr (MODE == 0) { if (is_chain_cta) {
             jw_chain_blk B;
@@ -697,24 +737,18 @@ jw_k_fused(jw_fused_args F) {
             B.prefetch_s = 0; B.prefetch_b = 0;
             if (k + 1 < F.nblocks) { B.prefetch_s = F.C.starts[k + 1]; B.prefetch_b = (int)(F.C.starts[k + 2] - F.C.starts[k + 1]); }
             B.xslots = nullptr; B.xworld = 1; B.slot_stride = 0; B.slot_b = 0; B.xtag = 0; B.xflags = F.flags;
-            if (multi) {
-                B.xslots = F.my_slots + (int64_t)(k & (JW_X_RING - 1)) * F.ring_stride;
-                B.xworld = F.world; B.slot_stride = F.slot_stride; B.slot_b = F.slot_b;
-                B.xtag = F.tag_base + (unsigned)k + 1u;
-            }
             B.sq = F.sq_acc + k * T;
             B.act_idx = F.act_idx_all + s;
             B.act_cnt = F.act_cnt_blk + k;
             B.write_active_list = 1;
             auto wait_all = [&]() -> bool {
-                if (multi) return true;            // every rank's partial rhs arrives as tagged words: the read waits
-                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream, F.flags) ? 1 : 0;
+                if (tid == 0) s_ok = jw_spin_ge(&F.arrive[k], n_stream + (multi ? 1 : 0), F.flags) ? 1 : 0;
                 __syncthreads();
                 JW_PHASE(3);
                 return s_ok != 0;
             };
             unsigned char* chain_smem = reinterpret_cast<unsigned char*>(yqs + 3 * TRp);
-            const int nc = jw_chain_block<METHOD, T, MULTI>(F.C, B, k, wait_all, chain_smem, F.list_cap);
+            const int nc = jw_chain_block<METHOD, T, false>(F.C, B, k, wait_all, chain_smem, F.list_cap);
             if (nc < 0) return;
             prev_commits = nc;
             __syncthreads();
@@ -864,7 +898,8 @@ static int jw_fused_prepare(jwas_handle* h) {
 template <int METHOD, int T, int W, int MODE>
 static int jw_fused_launch_mode(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) {
     auto kern = F.world > 1 ? jw_k_fused<METHOD, T, W, MODE, true> : jw_k_fused<METHOD, T, W, MODE, false>;
-    const size_t smem = F.P.n_chain > 0 ? f->smem_pipe : f->smem;
+    const size_t smem = MODE == 3 ? std::max<size_t>(jw_chain_unit_smem_bytes(T), (size_t)JW_WS_SMEM)
+                                  : (F.P.n_chain > 0 ? f->smem_pipe : f->smem);
     JW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     JW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, JW_FUSED_THREADS, smem));
@@ -883,8 +918,11 @@ static int jw_fused_launch(jwas_handle* h, jw_fused_state* f, jw_fused_args& F) 
         JW_REQUIRE(f->legacy_ok, "engine 1: this panel size needs the pipelined chain (option chain_ctas >= 1 with lag = 1)");
         return jw_fused_launch_mode<METHOD, T, W, 0>(h, f, F);
     }
-    // the gather warp needs one slice per streaming CTA
+    // the gather warp and the warp-specialised role need one slice per streaming CTA
     const bool single = (F.vs1 - F.vs0) <= h->sm_count - F.P.n_chain - (F.world > 1 ? 1 : 0);
+    if constexpr (T == 1 && W == 1) {
+        if (h->opt_ws && single) { F.arrive_mult = JW_WS_NS; return jw_fused_launch_mode<METHOD, T, W, 3>(h, f, F); }
+    }
     if (F.gather && single) return jw_fused_launch_mode<METHOD, T, W, 2>(h, f, F);
     return jw_fused_launch_mode<METHOD, T, W, 1>(h, f, F);
 }
@@ -939,7 +977,7 @@ static int jw_fused_sweep(jwas_handle* h, const jw_chain_args& A, float scale) {
     const int my_slices = f->n_vs;
     const bool one_slice = my_slices <= h->sm_count - std::max(1, f->n_chain) - (h->world > 1 ? 1 : 0);
     const bool pipe = F.lag && f->n_chain > 0 && (one_slice || !f->legacy_ok || F.lag >= 2);
-    F.gather = (int)h->opt_gather; F.l2_prefetch = (int)h->opt_l2_prefetch;
+    F.gather = (int)h->opt_gather; F.l2_prefetch = (int)h->opt_l2_prefetch; F.arrive_mult = 1;
     F.uniform_b = 0;
     if (h->nblocks >= 1) {
         const int64_t b0 = h->starts[1] - h->starts[0];

@@ -551,38 +551,47 @@ __device__ __forceinline__ uint4 jw_ll_load(const void* src) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
     return v;
 }
-// exact int64 sum over the W ranks' copies of one value (copies `stride` words apart): all loads of a round are
-// issued together, ranks that have not arrived are polled again.  false = the sweep was abandoned.
-__device__ __forceinline__ bool jw_ll_sum(const uint4* base, const int64_t stride, const int W, const unsigned tag,
-                                          int32_t* flags, long long& out) {
-    unsigned pend = (1u << W) - 1u;
+// exact int64 sum over the W ranks' copies of one value (copies `stride` words apart): the loads of up to JW_LL_CHUNK
+// ranks are issued together, ranks that have not arrived are polled again.  false = the sweep was abandoned.
+#ifndef JW_LL_CHUNK
+#define JW_LL_CHUNK 4
+#endif
+#ifndef JW_LL_INLINE
+#define JW_LL_INLINE __forceinline__
+#endif
+__device__ JW_LL_INLINE bool jw_ll_sum(const uint4* base, const int64_t stride, const int W, const unsigned tag,
+                                       int32_t* flags, long long& out) {
     long long acc = 0;
     unsigned spins = 0; unsigned long long t0 = 0;
-    while (pend) {
-        uint4 v[8];
+    for (int r0 = 0; r0 < W; r0 += JW_LL_CHUNK) {
+        const int nr = min(JW_LL_CHUNK, W - r0);
+        unsigned pend = (1u << nr) - 1u;
+        while (pend) {
+            uint4 v[JW_LL_CHUNK];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) if ((pend >> q) & 1u) v[q] = jw_ll_load(base + (int64_t)q * stride);
+            for (int q = 0; q < JW_LL_CHUNK; ++q) if ((pend >> q) & 1u) v[q] = jw_ll_load(base + (int64_t)(r0 + q) * stride);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (((pend >> q) & 1u) && v[q].y == tag && v[q].w == tag) {
-                acc += (long long)(((unsigned long long)v[q].z << 32) | (unsigned long long)v[q].x);
-                pend &= ~(1u << q);
+            for (int q = 0; q < JW_LL_CHUNK; ++q)
+                if (((pend >> q) & 1u) && v[q].y == tag && v[q].w == tag) {
+                    acc += (long long)(((unsigned long long)v[q].z << 32) | (unsigned long long)v[q].x);
+                    pend &= ~(1u << q);
+                }
+            if (pend && (++spins & 255u) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                int ab;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(flags + 2) : "memory");
+                if (ab != 0) return false;
+                if (now - t0 > 20000000000ull) { atomicExch(&flags[2], 1); return false; }
             }
-        if (pend && (++spins & 255u) == 0) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            int ab;
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ab) : "l"(flags + 2) : "memory");
-            if (ab != 0) return false;
-            if (now - t0 > 20000000000ull) { atomicExch(&flags[2], 1); return false; }
         }
     }
     out = acc;
     return true;
 }
 // the three integer sums a marker's rhs needs, over all ranks
-__device__ __forceinline__ bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
+__device__ JW_LL_INLINE bool jw_ll_rhs(const jw_chain_blk& B, const int T, const int k, const int m, const bool has_mq,
                                           long long& dq, long long& mq, long long& sqk) {
     bool ok = jw_ll_sum(B.xslots + (int64_t)k * B.slot_b + m, B.slot_stride, B.xworld, B.xtag, B.xflags, dq);
     mq = 0;

@@ -1245,6 +1245,7 @@ extern "C" int jwas_set_option(jwas_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "stream_variant")) { JW_REQUIRE(value >= 0 && value <= 3, "stream_variant must be 0..3"); h->opt_stream_variant = value; return 0; }
     if (!strcmp(key, "poll_ns_stream")) { JW_REQUIRE(value >= 0 && value <= 100000, "poll_ns_stream out of range"); h->opt_poll_ns_stream = value; return 0; }
     if (!strcmp(key, "poll_ns_chain")) { JW_REQUIRE(value >= 0 && value <= 100000, "poll_ns_chain out of range"); h->opt_poll_ns_chain = value; return 0; }
+    if (!strcmp(key, "ws")) { h->opt_ws = value != 0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { h->opt_l2_prefetch = value != 0; return 0; }
     if (!strcmp(key, "stream_pf")) { JW_REQUIRE(value >= 0 && value <= 64, "stream_pf must be 0..64"); h->opt_stream_pf = value; return 0; }
     if (!strcmp(key, "chain_ctas")) {

@@ -21,7 +21,7 @@ def jw():
 
 
 def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=False, replay=False, engine=0,
-                 seed=11, lag=0, chain_ctas=0, gather=1):
+                 seed=11, lag=0, chain_ctas=0, gather=1, ws=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
@@ -29,6 +29,7 @@ def run_pair_abc(jw, oracle, prob, starts, schedule, nsweeps, *, pi=0.9, bayesb=
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
     g.set_option("gather", gather)
+    g.set_option("ws", ws)
     gm, gx = g.marker_stats()
     np.testing.assert_array_equal(gm, prob.means)
     np.testing.assert_array_equal(gx, prob.xpx)
@@ -99,7 +100,7 @@ def test_bayesc_block_schedules(jw, oracle, schedule_name, missing):
     run_pair_abc(jw, oracle, prob, starts, sched, nsweeps=3, replay=(schedule_name == "block"))
 
 
-def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0, chain_ctas=0, gather=1):
+def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, engine=0, lag=0, chain_ctas=0, gather=1, ws=0):
     n, p = prob.n, prob.p
     g = jw.GpuSweeper(prob.packed, n, 1)
     g.set_blocks(starts)
@@ -107,6 +108,7 @@ def run_pair_r(jw, oracle, prob, starts, schedule, full_reps, nsweeps, seed=3, e
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
     g.set_option("gather", gather)
+    g.set_option("ws", ws)
     yc, al, be, de = prob.fresh_state()
     de[:] = 1
     g.put_ycorr(yc); g.put_state(al, be, de)
@@ -629,3 +631,23 @@ def test_host_array_sweep_call(jw, oracle):
     for a, b in zip(*outs):
         np.testing.assert_array_equal(a, b)
     assert outs[0][3].sum() > 0
+
+
+@pytest.mark.parametrize("lag,chain_ctas", [(1, 2), (2, 1), (2, 4)])
+@pytest.mark.parametrize("n,p,b", [(500, 2000, 256), (501, 333, 64), (67, 50, 1), (1030, 700, 700), (60013, 150, 64),
+                                   (160, 3100, 1500), (300, 9000, 4096), (200, 2500, 2048), (52000, 4000, 448)])
+def test_fused_warp_specialised_stream(jw, oracle, n, p, b, lag, chain_ctas):
+    """option ws=1 (kernel MODE 3, jw_fused_ws.cuh): builder warps rebuild one table set while the streaming warps
+    run through the other; per-warp release of the panel, no CTA barrier.  Same sums, same order of the per-row
+    updates: bit-exact against the oracle's lagged schedules."""
+    prob = Problem(oracle, n, p, seed=n + p + 13)
+    run_pair_abc(jw, oracle, prob, uniform_starts(p, b), jw.SCHED_EXACT, nsweeps=3, engine=1, lag=lag,
+                 pi=(0.97 if b > 1024 else 0.9), chain_ctas=chain_ctas, gather=0, ws=1)
+
+
+def test_fused_warp_specialised_stream_bayesr_and_dense(jw, oracle):
+    prob = Problem(oracle, 700, 900, seed=36)
+    run_pair_r(jw, oracle, prob, uniform_starts(900, 128), jw.SCHED_EXACT, 1, nsweeps=3, engine=1, lag=2, chain_ctas=4, ws=1)
+    prob = Problem(oracle, 300, 1200, seed=48)
+    run_pair_abc(jw, oracle, prob, uniform_starts(1200, 100), jw.SCHED_EXACT, nsweeps=2, engine=1, lag=2, pi=0.0,
+                 chain_ctas=2, gather=0, ws=1)      # every marker commits: the builders replay long record lists

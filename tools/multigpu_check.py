@@ -18,7 +18,7 @@ n, p = 30011, 3000
 GAMMA = np.array([0.0, 0.01, 0.1, 1.0]); PI_R = np.array([0.95, 0.03, 0.015, 0.005])
 
 
-def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0, from_full=False):
+def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0, from_full=False, ws=0):
     # sharded: this rank creates (and stores) only its own rows, or -- from_full -- creates the whole matrix and
     # lets jwas_init_sharding drop the other ranks' rows
     rows = jwas_b200.shard_range(n, rank, world) if (sharded and not from_full) else None
@@ -29,6 +29,7 @@ def run(t, method, sharded, engine, miss, lag=0, chain_ctas=0, from_full=False):
     g.set_option("engine", engine)
     g.set_option("lag", lag)
     g.set_option("chain_ctas", chain_ctas)
+    g.set_option("ws", ws)
     g.set_blocks(np.array(list(range(0, p, 512)) + [p], dtype=np.int64))
     if sharded and engine == 1:
         multigpu.connect(g, world)
@@ -79,6 +80,12 @@ for t, method, miss in ((1, "C", 0.01), (1, "R", 0.0), (2, "M", 0.0), (1, "I", 0
         same3 = all(np.array_equal(x, y) for x, y in zip(ref3, sh3))
         print(f"rank {rank}/{world} method {method} t={t}: lag 2, sharded == single: {same3}", flush=True)
         same = same and same3
+        if miss == 0.0 and t == 1:
+            # warp-specialised streaming role (kernel MODE 3), sharded, against the plain role on one GPU
+            sh4 = run(t, method, True, 1, miss, lag=2, chain_ctas=4, ws=1)
+            same4 = all(np.array_equal(x, y) for x, y in zip(ref3, sh4))
+            print(f"rank {rank}/{world} method {method} t={t}: warp-specialised stream, sharded == plain single: {same4}", flush=True)
+            same = same and same4
     nz = int(np.count_nonzero(ref[0]))
     print(f"rank {rank}/{world} method {method} t={t}: sharded==single==fused: {same} (nonzero effects {nz})", flush=True)
     ok = ok and same and nz > 0
