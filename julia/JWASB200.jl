@@ -53,9 +53,9 @@ function GpuBackend(packed::Matrix{UInt8}, nObs::Integer, ntraits::Integer; devi
     means = Vector{Float32}(undef, p); xpx = Vector{Float32}(undef, p)
     check(ccall((:jwas_get_marker_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), h[], means, xpx))
     b = GpuBackend(h[], nObs, p, ntraits, means, xpx, nothing)
-    # backend tuning (no effect on results): persistent fused kernel, lagged exact schedule, chain pipelined over
-    # two chain CTAs -- the configuration bench.py measures.  Must precede set_blocks!.
-    for (key, val) in (("engine", 1), ("lag", 1), ("chain_ctas", 2))
+    # backend tuning (no effect on results): persistent fused kernel, lag-2 exact schedule, chain pipelined over
+    # six chain CTAs -- the configuration bench.py measures (panels of 4096 markers).  Must precede set_blocks!.
+    for (key, val) in (("engine", 1), ("lag", 2), ("chain_ctas", 6))
         check(ccall((:jwas_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), h[], key, val))
     end
     finalizer(x -> ccall((:jwas_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), b)   # like streaming_genotypes.jl:966-968
@@ -92,6 +92,35 @@ function BayesABC_gpu!(b::GpuBackend, vare, varEffects::Vector{Float64}, π::Vec
     b.last_stats = st[]
     return nothing
 end
+
+"""The reference call itself on HOST arrays: BayesABC!(xArray, xRinvArray, xpRinvx, yCorr, α, β, δ, vare, varEffects, π)
+mutates yCorr, α, β, δ in place (BayesABC.jl:60-63).  One ccall: copies in, the sweep, copies out."""
+function BayesC_host!(b::GpuBackend, yCorr::Vector{Float32}, α::Vector{Float32}, β::Vector{Float32}, δ::Vector{Int32},
+                      vare, varEffect, π; schedule=SCHED_EXACT, seed::UInt64=UInt64(0), iter::Integer=1)
+    st = Ref{SweepStats}()
+    GC.@preserve yCorr α β δ check(ccall((:jwas_sweep_bayesc_host, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cdouble, UInt64, UInt32, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32},
+         Ref{SweepStats}),
+        b.handle, schedule, Float64(vare), Float64(varEffect), Float64(π), seed, UInt32(iter), yCorr, α, β, δ, st))
+    b.last_stats = st[]
+    return nothing
+end
+
+"""Centre on the means get_genotypes computed on ALL genotyped individuals (readgenotypes.jl:372-385) when the rows
+uploaded are the phenotyped subset (JWAS.jl:381-402).  Before set_blocks!."""
+set_marker_means!(b::GpuBackend, means::Vector{Float32}) =
+    (check(ccall((:jwas_set_marker_means, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}), b.handle, means));
+     check(ccall((:jwas_get_marker_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), b.handle, b.marker_means, b.xpRinvx)))
+
+"""Rows [first, last) (0-based) of the packed columns that rank `rank` of `world` GPU processes stores
+(one process per GPU; Distributed / MPI.jl move the 128-byte NCCL id and the 64-byte IPC handles)."""
+function shard_range(nObs::Integer, rank::Integer, world::Integer)
+    b = Ref{Int64}(0); e = Ref{Int64}(0)
+    check(ccall((:jwas_shard_range, LIB), Cint, (Int64, Cint, Cint, Ref{Int64}, Ref{Int64}), nObs, rank, world, b, e))
+    return b[], e[]
+end
+init_sharding!(b::GpuBackend, rank::Integer, world::Integer, nccl_id::Vector{UInt8}) =
+    check(ccall((:jwas_init_sharding, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), b.handle, rank, world, nccl_id))
 
 "BayesC with scalar σ²α and π (MCMC_BayesianAlphabet.jl:231 fills the vector on the host; here the fill is on the device)"
 function BayesC_gpu!(b::GpuBackend, vare, varEffect, π; schedule=SCHED_EXACT, seed::UInt64=UInt64(0), iter::Integer=1)

@@ -410,6 +410,9 @@ __device__ __forceinline__ int jw_chain_unit(const jw_chain_args& A, const jw_pi
     JW_CT(2);
 
     // ---- speculative rounds (one barrier each), every commit published at once ----
+    // (Measured and dropped: evaluating only a 32/64/128-marker window per round in units with many markers in the model
+    // -- 46.1 vs 46.1 ms per sweep with pi fixed at 0.95.  A round costs ~1 us because all 32 warps of the CTA run the
+    // loop's ~150 instructions of bookkeeping every round, whatever they evaluate; see DESIGN.md, dense regime.)
     unsigned long long my_active = 0, my_rounds = 0;
     int parity = 0, ncommit = 0, pos = 0;
     while (true) {
