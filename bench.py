@@ -463,10 +463,10 @@ def main():
                                            "fixed costs before HBM (DESIGN.md section 5)")
     if (args.config, n, p, world, args.schedule) == ("cfg2", 50000, 600000, 1, "exact"):
         try:        # DRAM bytes of one `ncu --set full` capture of this kernel (tracked under profiles/), per launch
-            rd = {l.split(",")[0]: l.strip().split(",") for l in open(os.path.join(ROOT, "profiles", "r1_fused_kernel_ncu_summary.csv"))}
+            rd = {l.split(",")[0]: l.strip().split(",") for l in open(os.path.join(ROOT, "profiles", "r2_fused_kernel_ncu_summary.csv"))}
             sc = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             roof["traffic"] = sum(float(rd[k][2]) * sc[rd[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            roof["traffic_source"] = "profiles/r1_fused_kernel_ncu_summary.csv (ncu --set full capture, not measured in this run)"
+            roof["traffic_source"] = "profiles/r2_fused_kernel_ncu_summary.csv (ncu --set full capture of this kernel, not measured in this run)"
         except Exception:
             pass
     value = units * res["sweeps_per_s"]
