@@ -177,6 +177,24 @@ def cpu_reference_leg(name, n, p, steps, warmup, nthreads, p_cpu=None, variants=
     return base, t_sample
 
 
+def cpu_leg_subprocess(name, n, p, steps, warmup, p_cpu=None, variants=False, world=1):
+    """cpu_reference_leg in a fresh interpreter: inside the GPU arm the OpenMP runtime is shared with torch, which
+    torchrun has told to use ONE thread (OMP_NUM_THREADS=1) -- 24 oracle threads then crawl (measured: 22x slower than one
+    thread).  A clean process with OMP_NUM_THREADS = all cores gives the same number as `--impl reference`."""
+    # under torchrun the other ranks stay alive (spinning in the final barrier): leave them their cores, or every OpenMP
+    # barrier of the 24-thread team waits for a pre-empted thread (measured: 1.0 s instead of 12 ms per sampled sweep)
+    nthreads = max(1, (os.cpu_count() or 1) - (2 * world if world > 1 else 0))
+    env = dict(os.environ, OMP_NUM_THREADS=str(nthreads))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_PROC_BIND", "GOMP_CPU_AFFINITY"):
+        env.pop(k, None)
+    spec = json.dumps(dict(name=name, n=n, p=p, steps=steps, warmup=warmup, p_cpu=p_cpu, variants=variants, nthreads=nthreads))
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", spec], capture_output=True, text=True,
+                         timeout=600, env=env)
+    if out.returncode != 0:
+        raise RuntimeError("cpu leg failed: " + out.stderr[-300:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
 # ---------------------------------------------------------------------------------------------- GPU workload
 class Workload:
     """One chain on one configuration: device-resident genotypes (this rank's rows), simulated phenotypes, the
@@ -404,8 +422,20 @@ def main():
     ap.add_argument("--cpu-markers", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (jwas_set_option), repeatable")
+    ap.add_argument("--cpu-leg", default=None, help=argparse.SUPPRESS)       # internal: one CPU leg in a clean process
     ap.add_argument("--no-extras", action="store_true", help="main line only (no nested regimes / schedules / configs)")
     args = ap.parse_args()
+    if args.cpu_leg:
+        a = json.loads(args.cpu_leg)
+        try:        # the parent (a GPU rank) may carry a narrowed CPU affinity mask (NCCL / launcher): use every core
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except Exception:
+            pass
+        base, _ = cpu_reference_leg(a["name"], a["n"], a["p"], a["steps"], a["warmup"], a.get("nthreads") or os.cpu_count() or 1,
+                                    p_cpu=a["p_cpu"], variants=a["variants"])
+        base["affinity_cores"] = len(os.sched_getaffinity(0))
+        print(json.dumps(base))
+        return
     if args.warmup < 3:
         args.warmup = 3
     cfg = CONFIGS[args.config]
@@ -515,14 +545,18 @@ def main():
             guard(cfgs, name, lambda c=c, name=name: nested(name, c["n"], c["p"], rank, world, device, args, 30, 8, peak, peak_src))
         line["configs"] = cfgs
     if rank == 0 and not args.no_cpu:
-        base, _ = cpu_reference_leg(args.config, n, p, 2, 1, ncpu, p_cpu=args.cpu_markers or None, variants=True)
-        base["value"] *= units; base["unit"] = UNIT
-        line["cpu_baseline"] = base
-        if "configs" in line and world == 1:
-            for name in ("cfg3", "cfg4"):
-                if isinstance(line["configs"].get(name), dict) and "error" not in line["configs"][name]:
-                    c = CONFIGS[name]
-                    line["configs"][name]["cpu_baseline"] = cpu_reference_leg(name, c["n"], c["p"], 1, 1, ncpu, p_cpu=1500 if c["t"] == 1 else 600)[0]
+        try:
+            base = cpu_leg_subprocess(args.config, n, p, 2, 1, p_cpu=args.cpu_markers or None, variants=True, world=world)
+            base["value"] *= units; base["unit"] = UNIT
+            line["cpu_baseline"] = base
+            if "configs" in line and world == 1:
+                for name in ("cfg3", "cfg4"):
+                    if isinstance(line["configs"].get(name), dict) and "error" not in line["configs"][name]:
+                        c = CONFIGS[name]
+                        line["configs"][name]["cpu_baseline"] = cpu_leg_subprocess(name, c["n"], c["p"], 1, 1,
+                                                                                   p_cpu=1500 if c["t"] == 1 else 600)
+        except Exception as e:                                       # the CPU leg never takes the GPU line down
+            line.setdefault("cpu_baseline", {"error": str(e)[:300]})
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
