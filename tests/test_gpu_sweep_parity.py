@@ -373,7 +373,7 @@ def test_fused_lagged_schedule(jw, oracle, n, p, b, missing):
 @pytest.mark.parametrize("chain_ctas", [2, 3])
 @pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (501, 333, 64, 0.03), (67, 50, 1, 0.0),
                                            (1030, 700, 700, 0.03), (60013, 150, 64, 0.0), (160, 3100, 1500, 0.0),
-                                           (300, 9000, 4096, 0.0), (200, 2500, 2048, 0.0), (160, 3100, 1500, 0.03)])
+                                           (128, 8500, 4096, 0.0), (200, 2500, 2048, 0.0), (160, 3100, 1500, 0.03)])
 def test_fused_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas):
     """option chain_ctas: the chain of the lagged schedule walks units of <= 1024 markers on several chain CTAs
     that hand each other commit records (jw_chain_pipe.cuh).  Same sums in the same order: bit-exact against
@@ -386,7 +386,7 @@ def test_fused_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas):
 @pytest.mark.parametrize("chain_ctas,gather", [(1, 0), (4, 0), (2, 1)])
 @pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (501, 333, 64, 0.03), (67, 50, 1, 0.0),
                                            (1030, 700, 700, 0.03), (60013, 150, 64, 0.0), (160, 3100, 1500, 0.0),
-                                           (300, 9000, 4096, 0.0), (200, 2500, 2048, 0.0), (160, 3100, 1500, 0.03),
+                                           (128, 8500, 4096, 0.0), (200, 2500, 2048, 0.0), (160, 3100, 1500, 0.03),
                                            (300, 4100, 1024, 0.0)])
 def test_fused_lag2_pipelined_chain(jw, oracle, n, p, b, missing, chain_ctas, gather):
     """option lag=2: the stream of block k carries the updates of blocks <= k-3; the chain corrects the rhs with the
@@ -426,7 +426,7 @@ def test_fused_pipelined_chain_other_methods(jw, oracle, chain_ctas):
                 chain_ctas=chain_ctas)
 
 
-@pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (1030, 700, 700, 0.03), (300, 9000, 4096, 0.0)])
+@pytest.mark.parametrize("n,p,b,missing", [(500, 2000, 256, 0.0), (1030, 700, 700, 0.03), (128, 8500, 4096, 0.0)])
 def test_pipelined_chain_inline_replay(jw, oracle, n, p, b, missing):
     """option gather=0: the streaming CTAs replay the commit records in line (kernel mode 1) instead of on a
     gather warp (mode 2, the default when every streaming CTA owns one slice)."""
@@ -634,7 +634,7 @@ def test_host_array_sweep_call(jw, oracle):
 
 @pytest.mark.parametrize("lag,chain_ctas", [(1, 2), (2, 4)])
 @pytest.mark.parametrize("n,p,b", [(500, 2000, 256), (501, 333, 64), (67, 50, 1), (1030, 700, 700), (60013, 150, 64),
-                                   (160, 3100, 1500), (300, 9000, 4096), (200, 2500, 2048), (52000, 1344, 448)])
+                                   (160, 3100, 1500), (128, 8500, 4096), (200, 2500, 2048), (52000, 460, 224)])
 def test_fused_warp_specialised_stream(jw, oracle, n, p, b, lag, chain_ctas):
     """option ws=1 (kernel MODE 3, jw_fused_ws.cuh): builder warps rebuild one table set while the streaming warps
     run through the other; per-warp release of the panel, no CTA barrier.  Same sums, same order of the per-row
