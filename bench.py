@@ -20,7 +20,8 @@ NESTED RESULTS (same JSON line, so nothing hides behind the headline):
   schedules (N = 1) cfg2 exact / exact-block (nreps = b) / independent-block with b = 223 (fast_blocks=true);
             one outer iteration counts as b sweeps (JWAS.jl:312)
   configs   cfg3 (BayesR) and cfg4 (2-trait BayesC-pi) on N GPUs; cfg5 (BayesB 400,000 x 1,000,000) when N = 8
-  strong    (N > 1) cfg2 itself, rows sharded over the N GPUs (fixed total work), with state_crc
+  strong    (N > 1) cfg2 itself, rows sharded over the N GPUs (fixed total work); same burn-in / warm-up / step counts
+            as the main line, so its state_crc equals the N = 1 line's state_crc (bit-identical chains at any N)
 --impl reference : the reference algorithm on the host cores (oracle restatement, dense Float32 dot + axpy per
   marker, all cores) on a bounded marker sample of the same workload; ms_per_step is the time of the sampled step,
   value the rate extrapolated linearly in p (the reference's own method, docs/src/manual/benchmark.md:74-77).
@@ -379,14 +380,14 @@ def e2e_leg(w, steps, units):
 UNIT = "sweeps/s (per 50,000-row shard, summed over GPUs; N=1: plain sweeps/s)"
 
 
-def nested(name, n, p, rank, world, device, args, burnin, steps, peak, peak_src, **kw):
+def nested(name, n, p, rank, world, device, args, burnin, steps, peak, peak_src, warm=3, **kw):
     """One more configuration / regime / schedule, reported inside the main line."""
     w = Workload(name, n, p, rank, world, device, engine=args.engine, lag=args.lag, chain_ctas=args.chain_ctas,
                  panel=args.panel, **kw)
     try:
         if burnin:
             w.advance(burnin)
-        w.advance(3)
+        w.advance(warm)
         res = w.timed(steps)
         out = {"workload": workload_config(name, n, p, world)["workload"], "sweeps_per_s": res["sweeps_per_s"],
                "ms_per_step": res["ms_per_step"], "device_ms_per_step": res["device_ms_per_step"], "steps": steps,
@@ -538,7 +539,9 @@ def main():
                                                     schedule=s_, block=223))
             line["schedules"] = sch
         else:
-            guard(line, "strong", lambda: nested("cfg2", c2["n"], c2["p"], rank, world, device, args, 40, 10, peak, peak_src))
+            # same burn-in / warm-up / step counts as the main line, so that its state_crc equals the N = 1 line's
+            guard(line, "strong", lambda: nested("cfg2", c2["n"], c2["p"], rank, world, device, args, args.burnin, args.steps,
+                                                 peak, peak_src, warm=args.warmup))
         cfgs = {}
         for name in ("cfg3", "cfg4") + (("cfg5",) if world == 8 else ()):
             c = CONFIGS[name]

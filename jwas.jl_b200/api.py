@@ -546,11 +546,20 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     # marker-effect sample files (output.jl:411, 467): <output_folder>/MCMC_samples_marker_effects_<geno>_<trait>.txt,
     # header of marker IDs + one row per saved iteration -- what GWAS() (and the reference's GWAS) reads.  Off by
     # default here: a row is p numbers per saved iteration and trait.
-    sample_rows = [[] for _ in range(t)] if output_marker_effect_samples else None
+    sample_files = None
+    if output_marker_effect_samples:              # rows are streamed to the files as they are produced (output.jl:467)
+        os.makedirs(output_folder, exist_ok=True)
+        model.sample_files = {}
+        sample_files = []
+        for tr in model.lhsVec:
+            path = os.path.join(output_folder, f"MCMC_samples_marker_effects_{Mi.name}_{tr}.txt")
+            f = open(path, "w")
+            f.write(",".join(str(m) for m in Mi.markerID) + "\n")
+            sample_files.append(f); model.sample_files[tr] = path
 
     def sink(alpha):
         for k in range(t):
-            sample_rows[k].append(np.array(alpha[k * p:(k + 1) * p], dtype=np.float32))
+            sample_files[k].write(",".join(repr(float(x)) for x in np.asarray(alpha[k * p:(k + 1) * p], dtype=np.float32)) + "\n")
 
     out = mcmc.run_chain(backend, n=n, p=p, ntraits=t, method=Mi.method, schedule=schedule,
                          sample_sink=(sink if output_marker_effect_samples else None),
@@ -606,13 +615,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         for k, tr in enumerate(model.lhsVec):
             em, ev = out["ebv_mean"][k], out["ebv_var"][k]
             output["EBV_" + tr] = _frame([[i, float(a), float(v)] for i, a, v in zip(ids, em, ev)], ["ID", "EBV", "PEV"])
-    if output_marker_effect_samples:
-        from .gwas import write_samples
-        model.sample_files = {}
-        for k, tr in enumerate(model.lhsVec):
-            path = os.path.join(output_folder, f"MCMC_samples_marker_effects_{Mi.name}_{tr}.txt")
-            write_samples(path, Mi.markerID, sample_rows[k])
-            model.sample_files[tr] = path
+    if sample_files is not None:
+        for f in sample_files:
+            f.close()
     model.output = output
     model.sol = out["mu"]
     return output

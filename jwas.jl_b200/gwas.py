@@ -100,11 +100,14 @@ class _Columns:
 
     def __init__(self, geno):
         self.packed = geno.packed; self.n = geno.nObs; self.means = np.asarray(geno.marker_means, dtype=np.float32)
-        self.cache = {}
+        self.cache = {}                      # bounded (LRU-ish): dense samples (RR-BLUP / BayesL) must not
+        self.cache_cap = max(64, int(2 ** 28 // max(8 * self.n, 1)))   # materialise an n x p Float64 matrix (256 MB cap)
 
     def col(self, j):
         x = self.cache.get(j)
         if x is None:
+            if len(self.cache) >= self.cache_cap:
+                self.cache.pop(next(iter(self.cache)))
             b = self.packed[j]
             codes = np.stack([(b >> s) & 3 for s in (0, 2, 4, 6)], axis=1).reshape(-1)[:self.n]
             # Float32(code) - mean in Float32, 0 where missing: the centred Float32 genotypes of the reference
@@ -151,7 +154,8 @@ def GWAS(model_or_file, map_file=None, *marker_effects_files, window_size="1 Mb"
         mp_ids = [str(x) for x in mp.iloc[:, 0]]
         mp_chr = mp.iloc[:, 1].astype(str).to_numpy(); mp_pos = mp.iloc[:, 2].to_numpy(dtype=np.int64)
     window_size_bp = int(float(window_size.split()[0]) * 1_000_000)
-    keep = np.array([m in set(snp_id) for m in mp_ids])
+    known = set(snp_id)
+    keep = np.array([m in known for m in mp_ids])
     if not keep.any():
         error("Please check the 1st column of the mapfile (i.e., marker ID)")
     chr_, pos = mp_chr[keep], mp_pos[keep]
@@ -209,6 +213,8 @@ def GWAS(model_or_file, map_file=None, *marker_effects_files, window_size="1 Mb"
                 "estimateGenVar": vmean[order], "stdGenVar": vstd[order], "prGenVar": prop[order],
                 "WPPA": wppa[order], "PPA_t": np.cumsum(wppa[order]) / (np.arange(nwin) + 1)})
             out.append(tab)
+            if write_files and local_EBV:                         # GWAS.jl: localEBV<i>.txt, one column per window
+                np.savetxt(f"localEBV{fi}.txt", local, delimiter=",")
             if write_files and pd is not None:
                 np.savetxt(f"MCMC_samples_local_genomic_variance{fi}.txt", win_var, delimiter=",")
                 tab.to_csv("GWAS_" + str(path).replace("/", "_"), index=False)
