@@ -64,7 +64,6 @@ __device__ __forceinline__ void jw_stream_ws(const jw_fused_args& F, int* jw_sme
     int* yqs = jw_smem + (3 * 65536) / 4;                                   // [R] (builder-private between its barriers)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(yqs + 4 * 96);   // full[2], empty[2]
     unsigned long long* full = bars; unsigned long long* empty = bars + 2;
-    const int64_t n = F.C.n, p = F.C.p;
     const int64_t nloc = F.nloc;
     float* const ycorr_l = F.ycorr + F.row_off;
     const int lag = F.lag;
