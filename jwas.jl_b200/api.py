@@ -8,9 +8,10 @@ backend seam is the one the reference itself uses for `storage=:stream`
 genotypes 2-bit packed in HBM behind a libjwasb200 handle and every sweep runs there.
 
 Only what the sweep needs is implemented: `y = intercept + <genotypes>` models (single- or
-multi-trait), BayesA/B/C, BayesR, RR-BLUP and BayesL (single-trait), multi-trait BayesC samplers I / II.
+multi-trait), BayesA/B/C, BayesR, RR-BLUP and BayesL (single-trait), multi-trait BayesC samplers I / II, and the
+annotation-aware priors of BayesC / BayesR / 2-trait BayesC (annotations.py).
 Everything else the reference offers (pedigree, covariates, random terms, SEM, RRM, categorical traits,
-annotations, GBLUP) is outside this backend's scope and raises JwasError with a message saying so.
+GBLUP) is outside this backend's scope and raises JwasError with a message saying so.
 """
 import math
 import os
@@ -18,6 +19,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import annotations as annot
 from . import mcmc
 from ._lib import GpuSweeper, JwasError, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT
 
@@ -75,6 +77,8 @@ class Genotypes:                     # types.jl:98-165 (fields this path uses)
     storage_mode: str = "gpu"
     stream_backend: object = None    # GpuSweeper once the chain starts
     starting_value: object = False
+    annotations: object = False      # annotations.MarkerAnnotations (types.jl:167-216)
+    annotation_start_pi: object = 0.0
 
 
 @dataclass
@@ -164,8 +168,6 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         error("storage must be :gpu in this backend (:dense and :stream live in JWAS.jl).")
     if method not in ("BayesA", "BayesB", "BayesC", "BayesR", "RR-BLUP", "BayesL"):
         error(f"method {method} is outside the GPU marker-sweep path (BayesA/B/C, BayesR, RR-BLUP and BayesL only).")
-    if annotations is not False:
-        error("annotations are outside the GPU marker-sweep path.")
     if double_precision:
         error("double_precision=true is not supported with storage=:gpu.")
     if not center:
@@ -202,6 +204,15 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
             error("Genotype data is empty.")
         codes = _codes_from_matrix(X, missing_value)
 
+    try:                                    # readgenotypes.jl:254-258: one annotation row per RAW marker
+        ann_matrix = annot.validate_annotations_input(annotations, codes.shape[1], method)
+    except annot.AnnotationError as e:
+        error(str(e))
+    if ann_matrix is not False and not estimatePi:
+        import warnings
+        warnings.warn(f"estimatePi=false is ignored when annotations are provided; Annotated {method} requires "
+                      "estimatePi=true.")
+        estimatePi = True
     means, nn, s = _column_stats(codes)
     af = (means / np.float32(2.0)).astype(np.float32)
     if quality_control:                     # readgenotypes.jl:388-399: MAF filter + fixed loci
@@ -213,6 +224,8 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
             error("No markers remain after streaming genotype quality control.")
         codes = codes[:, keep]; means = means[keep]; af = af[keep]
         mk = [m for m, k in zip(mk, keep) if k]
+        if ann_matrix is not False:
+            ann_matrix = ann_matrix[keep]   # annotations follow the markers that survive QC (readgenotypes.jl:256)
     n, p = codes.shape
     g = Genotypes(name=name, obsID=obs, markerID=mk, nObs=n, nMarkers=p, alleleFreq=af,
                   sum2pq=float((2.0 * af.astype(np.float64) * (1 - af.astype(np.float64))).sum()),
@@ -227,6 +240,14 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         g.method = "BayesB"; g.π = 0.0; g.estimatePi = False
     if method in ("RR-BLUP", "BayesL"):    # input_data_validation.jl:24-31: "runs with π = false / estimatePi = false"
         g.π = 0.0; g.estimatePi = False
+    if ann_matrix is not False:            # readgenotypes.jl:127-150, :111-125
+        try:
+            g.annotation_start_pi = annot.annotation_starting_pi(method, g.π, p)
+            g.annotations = annot.build_marker_annotations(ann_matrix, method, g.π)
+        except annot.AnnotationError as e:
+            error(str(e))
+        if method == "BayesC":
+            g.π = g.annotation_start_pi
     return g
 
 
@@ -320,6 +341,10 @@ def build_model(model_equations, R=False, *, df=4.0, genotypes=None, estimate_va
             error(f"{nm} is not a genotype term known to this backend: covariates, factors, pedigree and "
                   "random terms are outside the GPU marker-sweep path.")
         gi = genotypes[nm]; gi.name = nm; gi.ntraits = len(lhs)
+        try:                                                 # build_MME.jl -> annotation_setup.jl:141-153
+            annot.finalize_marker_annotation_setup(gi)
+        except annot.AnnotationError as e:
+            error(str(e))
         if len(lhs) != 1 and not getattr(gi, "_df_bumped", False):
             gi.G.df = gi.G.df + len(lhs)                     # build_MME.jl:108-110
             gi._df_bumped = True
@@ -396,6 +421,13 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         error("burnin must be smaller than chain_length.")
     Mi = model.M[0]
     t = model.nModels
+    annotated = Mi.annotations is not False and Mi.annotations is not None
+    if annotated and t > 1 and not (Mi.method == "BayesC" and t == 2 and not Mi.G.constraint):
+        # MCMC_BayesianAlphabet.jl:19-25
+        error("Annotated multi-trait BayesC currently supports exactly 2 traits with storage=:dense and "
+              "constraint=false.")
+    if annotated and t > 1 and Mi.multi_trait_sampler == "II":
+        error("annotated 2-trait BayesC runs sampler I with storage=:gpu (jwas_sweep_mt2 takes no per-marker prior).")
     if t > 1 and Mi.method != "BayesC":
         error("multi-trait analysis with storage=:gpu supports BayesC (sampler I) only.")
     mt_sampler = "I"
@@ -455,6 +487,15 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             if len(pi) != 4:
                 error("BayesR Pi must have length 4.")
             denom = Mi.sum2pq * float(mcmc.BAYESR_GAMMA @ pi)
+        elif Mi.annotations is not False:
+            # marker-level starting pi (genetic2marker, tools4genotypes.jl:468-475)
+            pi = np.array(Mi.π, dtype=np.float64)
+            if len(pi) != p:
+                error(f"BayesC marker-level Pi must have length {p}.")
+            af64 = Mi.alleleFreq.astype(np.float64)
+            denom = float(np.sum(2.0 * af64 * (1.0 - af64) * (1.0 - np.clip(pi, 0.0, 1.0))))
+            if not denom > 0:
+                error("BayesC implied variance denominator must be positive.")
         else:
             pi = float(Mi.π)
             denom = (1 - pi) * Mi.sum2pq
@@ -493,6 +534,18 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             big = np.array(Mi.π, dtype=np.float64)
         if not Mi.G.constraint and abs(big.sum() - 1.0) > 1e-8:
             error("Summation of probabilities of Pi is not equal to one.")
+        if Mi.G.val is False and annotated:
+            # genetic2marker with the marker-level joint priors (tools4genotypes.jl:440-455)
+            gv = np.array(Mi.genetic_variance.val, float) if Mi.genetic_variance.val is not False else np.diag(vary * 0.5)
+            af64 = Mi.alleleFreq.astype(np.float64)
+            twopq = 2.0 * af64 * (1.0 - af64)
+            sp = Mi.annotations.snp_pi
+            d12 = float(np.sum(twopq * sp[:, 3]))
+            denom = np.array([[float(np.sum(twopq * (sp[:, 1] + sp[:, 3]))), d12],
+                              [d12, float(np.sum(twopq * (sp[:, 2] + sp[:, 3])))]])
+            if np.any(denom <= 0):
+                error("Annotated multi-trait BayesC implied covariance denominator must be positive.")
+            Mi.G.val = gv / denom
         if Mi.G.val is False:
             gv = np.array(Mi.genetic_variance.val, float) if Mi.genetic_variance.val is not False else np.diag(vary * 0.5)
             denom = np.zeros((t, t))
@@ -573,7 +626,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          R=model.R.val if t > 1 else None, G=Mi.G.val if t > 1 else None,
                          big_pi=Mi.π if t > 1 else None, scale_G=Mi.G.scale if t > 1 else None,
                          scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler,
-                         constraint_G=bool(t > 1 and Mi.G.constraint), constraint_R=bool(t > 1 and model.R.constraint))
+                         constraint_G=bool(t > 1 and Mi.G.constraint), constraint_R=bool(t > 1 and model.R.constraint),
+                         annotations=(Mi.annotations if annotated else None))
 
     # ---- output dictionary (output.jl:108-212)
     ma, ma2, md = backend.get_means()
@@ -600,7 +654,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     output["marker effects " + Mi.name] = _frame(rows_me, ["Trait", "Marker_ID", "Estimate", "SD", "Model_Frequency"])
     if Mi.estimatePi:
         pm = np.atleast_1d(out["pi_mean"]); pm2 = np.atleast_1d(out["pi_mean2"])
-        if t == 1 and Mi.method != "BayesR":
+        if t == 1 and Mi.method != "BayesR" and annotated:
+            labels = [str(j + 1) for j in range(p)]          # marker-level pi_j (output.jl:256-266)
+        elif t == 1 and Mi.method != "BayesR":
             labels = ["π"]
         elif t == 1:
             labels = [f"class{c + 1}" for c in range(len(pm))]
@@ -611,6 +667,19 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         output["pi_" + Mi.name] = _frame([[l, pm[i], math.sqrt(abs(pm2[i] - pm[i] ** 2))] for i, l in enumerate(labels)],
                                          ["π", "Estimate", "SD"])
         Mi.mean_pi = out["pi_mean"]
+    if annotated:                                            # output.jl:151-177
+        ann = Mi.annotations
+        asd = np.sqrt(np.abs(ann.mean_coefficients2 - ann.mean_coefficients ** 2))
+        if ann.nsteps == 1:
+            output["annotation coefficients " + Mi.name] = _frame(
+                [[nm, float(e), float(s_)] for nm, e, s_ in zip(ann.names(), ann.mean_coefficients, asd)],
+                ["Annotation", "Estimate", "SD"])
+        else:
+            steps = annot.STEP_LABELS["BayesR" if Mi.method == "BayesR" else "BayesC2"]
+            output["annotation coefficients " + Mi.name] = _frame(
+                [[nm, steps[c], float(ann.mean_coefficients[k, c]), float(asd[k, c])]
+                 for k, nm in enumerate(ann.names()) for c in range(ann.nsteps)],
+                ["Annotation", "Step", "Estimate", "SD"])
     if outputEBV and out.get("ebv_mean") is not None:
         for k, tr in enumerate(model.lhsVec):
             em, ev = out["ebv_mean"][k], out["ebv_var"][k]

@@ -9,6 +9,7 @@ import math
 
 import numpy as np
 
+from . import annotations as annot
 from ._lib import GpuSweeper, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT
 
 BAYESR_GAMMA = np.array([0.0, 0.01, 0.1, 1.0])      # JWAS.jl:12
@@ -141,13 +142,15 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
               mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False,
-              sample_sink=None):
+              sample_sink=None, annotations=None):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
       [1] intercept Gibbs (:207-220, solver.jl:143-151)  [2] marker sweep (:224-290)
       [3] pi (:294-317, Pi.jl)  [4] marker variance (:321-326, variance_components.jl:151-189)
       [5] residual variance (:355-371)  [6] posterior means every saved iteration (:399-413).
+    With `annotations` (annotations.MarkerAnnotations) step [3] is update_marker_annotation_priors! (:296-305) and the
+    sweep takes the marker-level priors it produces.
     Float32 re-casts of the variances follow :323-325, :368-370.
     """
     rng = HostRng([seed, iter0])
@@ -167,6 +170,20 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
         out["pi_mean"] = np.zeros_like(big_pi); out["pi_mean2"] = np.zeros_like(big_pi)
     ebv_m = ebv_s = None
     gamma_arr = None
+    ann = annotations
+    ann_prior = None                      # what the sweep takes: (p,) pi_j for BayesC, (p, 4) class / joint-state priors
+    if ann is not None:
+        if t == 1 and method == "BayesC":
+            pi = np.array(pi, dtype=np.float64)
+            if pi.shape != (p,):
+                raise ValueError("BayesABC: pi vector length must match the number of markers")   # BayesABC.jl:17-23
+            ann_prior = pi
+            out["pi_mean"] = np.zeros(p); out["pi_mean2"] = np.zeros(p)
+        elif (t == 1 and method == "BayesR") or (t == 2 and method == "BayesC" and not constraint_G and mt_sampler == "I"):
+            ann_prior = ann.snp_pi
+        else:
+            raise ValueError("Unsupported annotation configuration.")
+        estimate_pi = True                # normalize_annotation_estimatePi (readgenotypes.jl:152-158)
     if method == "BayesL":
         # Bayesian Lasso (BayesC0L.jl:25-47): marker j has variance var_effect * gamma_j; gamma ~ Gamma(1, 8) to
         # start with (MCMC_BayesianAlphabet.jl:72-77; api.runMCMC has already divided var_effect and its scale by 8)
@@ -198,7 +215,10 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
         # [2] marker effects
         if method in ("BayesC", "BayesB", "BayesA"):
             if t == 1:
-                if method == "BayesC":
+                if ann is not None:
+                    # bayesabc_pi_vector (BayesABC.jl:17-23): one common variance, marker-level pi_j
+                    st = backend.sweep_bayesabc(schedule, vare, np.full(p, float(var_effect)), ann_prior, seed, it)
+                elif method == "BayesC":
                     st = backend.sweep_bayesc(schedule, vare, var_effect, pi, seed, it)
                 else:
                     # BayesB/BayesA: G.val is a per-marker vector kept on the device
@@ -212,10 +232,13 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                 # megaBayesABC! (MCMC_BayesianAlphabet.jl:233-234): per-trait pi vector, diagonal variances
                 st = backend.sweep_mega(schedule, np.diag(R).copy(), np.diag(G).copy(), big_pi, seed, it)
             else:
-                st = (backend.sweep_mt2 if mt_sampler == "II" else backend.sweep_mt1)(schedule, R, G, big_pi, seed, it)
+                # annotated: MarkerSpecificPiPrior(snp_pi) (MTBayesABC.jl:28-30), columns 00, 10, 01, 11
+                st = (backend.sweep_mt2 if mt_sampler == "II" else backend.sweep_mt1)(
+                    schedule, R, G, big_pi if ann is None else ann_prior, seed, it)
         elif method == "BayesR":
             full = 1 if it > burnin else 0          # bayesr_block_nreps, BayesR.jl:22-25
-            st = backend.sweep_bayesr(schedule, full, vare, var_effect, pi, BAYESR_GAMMA, seed, it)
+            st = backend.sweep_bayesr(schedule, full, vare, var_effect, pi if ann is None else ann_prior,   # BayesR.jl:28
+                                      BAYESR_GAMMA, seed, it)
         elif method == "RR-BLUP" and t == 1:
             # BayesC0! = BayesL! with gamma = [1.0] (BayesC0L.jl:19-23): every marker in the model with the common
             # variance, i.e. the BayesC step with pi = 0 (log pi = -inf: the inclusion test always passes)
@@ -226,7 +249,14 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
         else:
             raise ValueError(method)
         # [3] pi
-        if estimate_pi:
+        if ann is not None:
+            delta = np.asarray(backend.get_state()[2]).reshape(t, p)
+            ann_prior, summary = annot.update_marker_annotation_priors(rng, ann, method, t, delta if t > 1 else delta[0])
+            if t == 1:
+                pi = summary
+            else:
+                big_pi = summary
+        elif estimate_pi:
             if t == 1 and method == "BayesR":
                 pi = rng.dirichlet(st["class_counts"][:len(pi)] + 1.0)          # Pi.jl:11-17
             elif t == 1:
@@ -292,6 +322,8 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                 pi_now = pi if t == 1 else big_pi
                 out["pi_mean"] = out["pi_mean"] + (pi_now - out["pi_mean"]) / nsamples
                 out["pi_mean2"] = out["pi_mean2"] + (pi_now ** 2 - out["pi_mean2"]) / nsamples
+            if ann is not None:             # output.jl:597-600
+                ann.accumulate(nsamples)
             if sample_sink is not None:     # marker-effect sample rows (output.jl:467)
                 sample_sink(backend.get_state()[0])
             if want_ebv:                    # getEBV per saved sample (output.jl:281-306, 489-495)

@@ -1,0 +1,95 @@
+"""GPU parity for the marker-level priors that the annotation update feeds to the sweep (BayesR.jl:28,
+MTBayesABC.jl:28-30, BayesABC.jl:17-23): `jwas_sweep_bayesr` / `jwas_sweep_mt1` with per_marker_pi against the
+oracle's contract sweep, bit-exact, and whole annotated chains through runMCMC on the B200 backend against the same
+host logic over the oracle backend.  (File sorts last on purpose: it was written after the round's GPU minutes
+were spent and has only been run on the CPU side -- oracle backend -- so far)"""
+import numpy as np
+import pytest
+
+from helpers import Problem, uniform_starts
+from test_gpu_sweep_parity import GAMMA, PI_R, jw  # noqa: F401  (jw: module fixture)
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [dict(engine=0, lag=0, chain_ctas=0), dict(engine=1, lag=2, chain_ctas=4)]
+
+
+def _opts(g, o):
+    for k, v in o.items():
+        g.set_option(k, v)
+
+
+@pytest.mark.parametrize("o", ENGINES)
+def test_bayesr_marker_level_class_priors(jw, oracle, o):
+    prob = Problem(oracle, 500, 1000, seed=131, missing=0.02)
+    n, p = prob.n, prob.p
+    starts = uniform_starts(p, 256)
+    g = jw.GpuSweeper(prob.packed, n, 1)
+    g.set_blocks(starts); _opts(g, o)
+    yc, al, be, de = prob.fresh_state(); de[:] = 1
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    rng = np.random.default_rng(5)
+    snp_pi = rng.dirichlet([30.0, 2.0, 1.0, 0.5], size=p)
+    vare = prob.vary * 0.5
+    sigma = prob.vary * 0.5 / (prob.xpx.mean() / n * p * float(GAMMA @ PI_R))
+    for it in range(1, 4):
+        rc, _ = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, None, de,
+                                      method=oracle.METHOD_R, nreps_mode=0, independent=False, vare=vare,
+                                      sigmaSq=sigma, pi=snp_pi, gamma=GAMMA, seed=3, it=it, lag=o["lag"])
+        assert rc == 0
+        g.sweep_bayesr(jw.SCHED_EXACT, 1, vare, sigma, snp_pi, GAMMA, 3, it)
+        ga, _, gd = g.get_state()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(g.get_ycorr().view(np.uint32), yc.view(np.uint32))
+        snp_pi = rng.dirichlet([30.0, 2.0, 1.0, 0.5], size=p)      # the priors change every iteration
+    assert (de > 1).sum() > 0
+    g.close()
+
+
+@pytest.mark.parametrize("o", ENGINES)
+def test_two_trait_marker_level_joint_priors(jw, oracle, o):
+    prob = Problem(oracle, 403, 600, seed=141, ntraits=2)
+    n, p = prob.n, prob.p
+    starts = uniform_starts(p, 200)
+    g = jw.GpuSweeper(prob.packed, n, 2)
+    g.set_blocks(starts); _opts(g, o)
+    yc, al, be, de = prob.fresh_state()
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    R = np.array([[1.0, 0.3], [0.3, 1.2]]) * prob.vary * 0.5
+    G = np.array([[1.0, 0.4], [0.4, 0.8]]) * prob.vary * 0.5 / (0.2 * prob.xpx.mean() / n * p)
+    rng = np.random.default_rng(6)
+    for it in range(1, 4):
+        snp_pi = rng.dirichlet([7.0, 1.0, 1.0, 1.0], size=p)       # columns 00, 10, 01, 11
+        rc, _ = oracle.sweep_contract(prob.packed, n, prob.means, prob.xpx, starts, yc, al, be, de,
+                                      method=oracle.METHOD_MT1, nreps_mode=0, independent=False, R=R, G=G,
+                                      bigPi=snp_pi, seed=9, it=it, lag=o["lag"])
+        assert rc == 0
+        g.sweep_mt1(jw.SCHED_EXACT, R, G, snp_pi, 9, it)
+        ga, gb, gd = g.get_state()
+        np.testing.assert_array_equal(gd, de)
+        np.testing.assert_array_equal(ga.view(np.uint32), al.view(np.uint32))
+        np.testing.assert_array_equal(gb.view(np.uint32), be.view(np.uint32))
+        np.testing.assert_array_equal(g.get_ycorr().view(np.uint32), yc.view(np.uint32))
+    assert de.sum() > 0
+    g.close()
+
+
+@pytest.mark.parametrize("case", ["BayesC", "BayesR", "BayesC2"])
+def test_annotated_chain_matches_oracle_chain(case):
+    import jwas_b200
+    from oracle_backend import factory
+    from test_annotations import _annotated_data
+    from test_gpu_chain import assert_same
+    two = case == "BayesC2"
+    codes, ids, ph, A = _annotated_data(n=250, p=320, seed=51, ntraits=2 if two else 1)
+    eqs = "y1 = intercept + geno\ny2 = intercept + geno" if two else "y1 = intercept + geno"
+    Pi = {(0.0, 0.0): 0.45, (1.0, 0.0): 0.20, (0.0, 1.0): 0.15, (1.0, 1.0): 0.20} if two else (0.9 if case == "BayesC" else 0.0)
+    outs = []
+    for bf in (None, factory):
+        geno = jwas_b200.get_genotypes(codes, False, method="BayesR" if case == "BayesR" else "BayesC", Pi=Pi,
+                                       annotations=A, obsID=ids)
+        model = jwas_b200.build_model(eqs, False, genotypes={"geno": geno})
+        outs.append(jwas_b200.runMCMC(model, ph, chain_length=30, burnin=6, seed=77, _backend_factory=bf))
+    assert_same(outs[0], outs[1])
+    assert "annotation coefficients geno" in outs[0]
