@@ -196,6 +196,26 @@ void jwo_bayesabc_ref(const float* X, int64_t n, int64_t p, const float* xpx,
     }
 }
 
+/* BayesC0L.jl:25-47 BayesL! (and BayesC0! = the same routine with gammaArray = [1.0], :19-23).
+ * Julia's promotion: xpRinvx, alpha, yCorr, vRes, vEff Float32; gammaArray Float64 (rand(Gamma(1,8)),
+ * MCMC_BayesianAlphabet.jl:72-77); the literal 1.0 makes invLhs Float64 either way. */
+void jwo_bayesl_ref(const float* X, int64_t n, int64_t p, const float* xpx,
+                    float* ycorr, float* alpha, const double* gamma, int64_t ngamma,
+                    float vRes, float vEff, const double* z, int nthreads) {
+    float lambda = vRes / vEff;                                      /* :30 */
+    for (int64_t j = 0; j < p; ++j) {
+        const float* x = X + j * n;
+        float rhs = jwo_sdot(x, ycorr, n, nthreads) + xpx[j] * alpha[j];   /* :39 */
+        double invLhs;
+        if (ngamma > 1) invLhs = 1.0 / ((double)xpx[j] + (double)lambda / gamma[j]);   /* :32, :40-41 */
+        else invLhs = 1.0 / (double)(xpx[j] + lambda);               /* :33: Float32 sum, then 1.0/ */
+        double mean = invLhs * (double)rhs;                          /* :42 */
+        float oldAlpha = alpha[j];
+        alpha[j] = (float)(mean + z[j] * sqrt(invLhs * (double)vRes));   /* :44 */
+        jwo_saxpy(oldAlpha - alpha[j], x, ycorr, n, nthreads);       /* :45 */
+    }
+}
+
 /* BayesABC.jl:88-108 BayesABC_streaming! */
 void jwo_bayesabc_streaming_ref(const uint8_t* packed, int64_t n, int64_t p, int64_t stride,
                                 const float* means, const float* xpx,

@@ -48,6 +48,11 @@ void jwo_gram_block(const uint8_t* packed, int64_t n, int64_t stride, const floa
                     int64_t j0, int64_t b, float* G);
 
 /* ---- reference-arithmetic samplers (dense Float32, draws replayed from u[], z[]) ---- */
+/* BayesC0L.jl:25-47 BayesL! ; ngamma == 1 is BayesC0! (RR-BLUP, :19-23) */
+void jwo_bayesl_ref(const float* X, int64_t n, int64_t p, const float* xpx,
+                    float* ycorr, float* alpha, const double* gamma, int64_t ngamma,
+                    float vRes, float vEff, const double* z, int nthreads);
+
 /* BayesABC.jl:24-80.  nthreads parallelises the n-long dot/axpy only (BLAS threads). */
 void jwo_bayesabc_ref(const float* X, int64_t n, int64_t p, const float* xpx,
                       float* ycorr, float* alpha, float* beta, float* delta,

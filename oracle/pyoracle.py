@@ -17,8 +17,12 @@ METHOD_ABC, METHOD_R, METHOD_MT1, METHOD_MT2, METHOD_MEGA = 0, 1, 2, 3, 4
 
 
 def build(force=False):
-    if force or not os.path.exists(_SO):
+    # make is mtime-aware: a library older than its sources is rebuilt, an up-to-date one costs nothing
+    try:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    except (OSError, subprocess.CalledProcessError):
+        if force or not os.path.exists(_SO):
+            raise
     return _SO
 
 
@@ -139,6 +143,16 @@ def bayesabc_ref(X, xpx, ycorr, alpha, beta, delta, vare, varEffects, pi, u, z, 
     lib().jwo_bayesabc_ref(_p(X), C.c_int64(n), C.c_int64(p), _p(_f32(xpx)), _p(ycorr), _p(alpha), _p(beta),
                            _p(delta), C.c_float(vare), _p(_f32(varEffects)), _p(_f64(pi)), _p(_f64(u)),
                            _p(_f64(z)), C.c_int(nthreads))
+
+
+def bayesl_ref(X, xpx, ycorr, alpha, gamma, v_res, v_eff, z, nthreads=1):
+    """BayesL! (BayesC0L.jl:25-47); gamma = [1.0] is BayesC0! (RR-BLUP)."""
+    n, p = X.shape
+    assert X.flags.f_contiguous and X.dtype == np.float32
+    g = _f64(gamma)
+    assert len(g) in (1, p)
+    lib().jwo_bayesl_ref(_p(X), C.c_int64(n), C.c_int64(p), _p(_f32(xpx)), _p(ycorr), _p(alpha), _p(g),
+                         C.c_int64(len(g)), C.c_float(v_res), C.c_float(v_eff), _p(_f64(z)), C.c_int(nthreads))
 
 
 def bayesabc_streaming_ref(packed, n, means, xpx, ycorr, alpha, beta, delta, vare, varEffects, pi, u, z):

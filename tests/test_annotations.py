@@ -1,6 +1,6 @@
 """Annotation-aware priors (MCMC/annotation_updates.jl, markers/annotation_setup.jl): validation, start-up state, the
 probit Gibbs steps and whole annotated chains through runMCMC (driven over the CPU oracle backend here; the same host
-code drives the B200 backend, see test_zz_gpu_annotations.py).  The cases follow the reference's own
+code drives the B200 backend, see test_zz_gpu_late.py).  The cases follow the reference's own
 test/unit/test_annotated_bayesc.jl and test_annotated_bayesr.jl; its expected values are built from its own random
 stream, so "update == manual composition of the documented steps under one generator" is asserted the same way here."""
 import math

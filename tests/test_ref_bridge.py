@@ -76,3 +76,33 @@ def test_block_refs_with_one_repetition_equal_dense_refs(oracle, probs):
                                     hyp.big_pi, u, z)
         np.testing.assert_array_equal(s1[3], s2[3])
         np.testing.assert_allclose(s2[1], s1[1], atol=2e-6 * np.abs(s1[1]).max())
+
+
+@pytest.mark.parametrize("lasso", [False, True])
+def test_contract_tracks_reference_bayesl(oracle, probs, lasso):
+    """BayesL! / BayesC0! (BayesC0L.jl:19-47) against the way this backend runs them: the BayesC step with pi = 0 and
+    marker variances sigma^2 * gamma_j (mcmc.run_chain).  Every marker is in the model, so there is no
+    indicator to compare: effects and ycorr within 1e-5 relative after every sweep, default lagged panels and plain."""
+    prob = probs[1]
+    rng = np.random.default_rng(21)
+    sum2pq = float((prob.means.astype(np.float64) * (1 - prob.means / 2)).sum())
+    v_res = float(np.float32(prob.vary / 2))
+    v_eff = float(np.float32((prob.vary / 2) / sum2pq / (8 if lasso else 1)))     # MCMC_BayesianAlphabet.jl:70-74
+    gamma = rng.gamma(1.0, 8.0, P) if lasso else np.array([1.0])
+    ve = np.full(P, v_eff) * gamma
+    for starts, lag in ((np.array(list(range(0, P, 256)) + [P], dtype=np.int64), 2),
+                        (np.array([0, P], dtype=np.int64), 0)):
+        y_r = prob.ycorr0.copy(); a_r = np.zeros(P, np.float32)
+        yc, al, be, de = prob.fresh_state()
+        zr = np.random.default_rng(4)
+        for it in range(1, 4):
+            u, z = zr.random(P), zr.standard_normal(P)
+            oracle.bayesl_ref(prob.X, prob.xpx, y_r, a_r, gamma, v_res, v_eff, z)
+            rc, _ = oracle.sweep_contract(prob.packed, N, prob.means, prob.xpx, starts, yc, al, be, de,
+                                          method=oracle.METHOD_ABC, nreps_mode=0, independent=False, vare=v_res,
+                                          varEffects=ve, pi=np.zeros(P), seed=1, it=it, u=u, z=z, lag=lag)
+            assert rc == 0
+            assert de.sum() == P
+            ra = np.abs(al.astype(np.float64) - a_r).max() / np.abs(a_r).max()
+            ry = np.abs(yc.astype(np.float64) - y_r).max() / np.abs(y_r).max()
+            assert ra <= REL and ry <= REL, (lasso, lag, it, ra, ry)

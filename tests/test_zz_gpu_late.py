@@ -1,8 +1,12 @@
-"""GPU parity for the marker-level priors that the annotation update feeds to the sweep (BayesR.jl:28,
-MTBayesABC.jl:28-30, BayesABC.jl:17-23): `jwas_sweep_bayesr` / `jwas_sweep_mt1` with per_marker_pi against the
-oracle's contract sweep, bit-exact, and whole annotated chains through runMCMC on the B200 backend against the same
-host logic over the oracle backend.  (File sorts last on purpose: it was written after the round's GPU minutes
-were spent and has only been run on the CPU side -- oracle backend -- so far)"""
+"""GPU parity tests written after the round's GPU minutes were spent (the file sorts last on purpose: they have
+only been exercised on the CPU side -- oracle backend / oracle arms -- so far).
+
+1. Marker-level priors that the annotation update feeds to the sweep (BayesR.jl:28, MTBayesABC.jl:28-30,
+   BayesABC.jl:17-23): `jwas_sweep_bayesr` / `jwas_sweep_mt1` with per_marker_pi against the oracle's contract
+   sweep, bit-exact, and whole annotated chains through runMCMC on the B200 backend against the same host logic
+   over the oracle backend.
+2. BayesL! / BayesC0! (BayesC0L.jl:19-47) reference arithmetic (`jwo_bayesl_ref`) against the CUDA library run the
+   way this backend runs them (BayesC step, pi = 0, marker variances sigma^2 * gamma_j): 1e-5 relative."""
 import numpy as np
 import pytest
 
@@ -93,3 +97,32 @@ def test_annotated_chain_matches_oracle_chain(case):
         outs.append(jwas_b200.runMCMC(model, ph, chain_length=30, burnin=6, seed=77, _backend_factory=bf))
     assert_same(outs[0], outs[1])
     assert "annotation coefficients geno" in outs[0]
+
+
+@pytest.mark.parametrize("lasso", [False, True])
+def test_cuda_default_vs_reference_bayesl(jw, oracle, lasso):
+    N, P = 500, 2000
+    prob = Problem(oracle, N, P, seed=2026)
+    rng = np.random.default_rng(21)
+    sum2pq = float((prob.means.astype(np.float64) * (1 - prob.means / 2)).sum())
+    v_res = float(np.float32(prob.vary / 2))
+    v_eff = float(np.float32((prob.vary / 2) / sum2pq / (8 if lasso else 1)))     # MCMC_BayesianAlphabet.jl:70-74
+    gamma = rng.gamma(1.0, 8.0, P) if lasso else np.array([1.0])
+    ve = np.full(P, v_eff) * gamma
+    g = jw.GpuSweeper(prob.packed, N, 1)
+    _opts(g, dict(engine=1, lag=2, chain_ctas=4))
+    g.set_blocks(uniform_starts(P, 256))
+    yc, al, be, de = prob.fresh_state()
+    g.put_ycorr(yc); g.put_state(al, be, de)
+    y_r = prob.ycorr0.copy(); a_r = np.zeros(P, np.float32)
+    zr = np.random.default_rng(4)
+    for it in range(1, 4):
+        u, z = zr.random(P), zr.standard_normal(P)
+        oracle.bayesl_ref(prob.X, prob.xpx, y_r, a_r, gamma, v_res, v_eff, z)
+        g.sweep_bayesabc(jw.SCHED_EXACT, v_res, ve, np.zeros(P), 1, it, u, z)
+        ga, _, gd = g.get_state()
+        assert gd.sum() == P
+        ra = np.abs(ga.astype(np.float64) - a_r).max() / np.abs(a_r).max()
+        ry = np.abs(g.get_ycorr().astype(np.float64) - y_r).max() / np.abs(y_r).max()
+        assert ra <= 1e-5 and ry <= 1e-5, (lasso, it, ra, ry)
+    g.close()
