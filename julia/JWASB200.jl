@@ -119,8 +119,25 @@ function shard_range(nObs::Integer, rank::Integer, world::Integer)
     check(ccall((:jwas_shard_range, LIB), Cint, (Int64, Cint, Cint, Ref{Int64}, Ref{Int64}), nObs, rank, world, b, e))
     return b[], e[]
 end
+"""One rank's shard: `packed_rows` holds only rows [row_begin, row_end) of every column (cld(rows, 4) bytes each);
+the marker statistics are completed by init_sharding! (integer code counts summed over the ranks)."""
+function GpuBackendShard(packed_rows::Matrix{UInt8}, nObs::Integer, ntraits::Integer, row_begin::Integer, row_end::Integer;
+                         device::Integer=0)
+    stride, p = size(packed_rows)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve packed_rows check(ccall((:jwas_create_shard, LIB), Cint,
+        (Int64, Int64, Cint, Int64, Int64, Ptr{UInt8}, Int64, Cint, Ref{Ptr{Cvoid}}),
+        nObs, p, ntraits, row_begin, row_end, packed_rows, stride, device, h))
+    b = GpuBackend(h[], nObs, p, ntraits, Vector{Float32}(undef, p), Vector{Float32}(undef, p), nothing)
+    for (key, val) in (("engine", 1), ("lag", 2), ("chain_ctas", 6))
+        check(ccall((:jwas_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), h[], key, val))
+    end
+    finalizer(x -> ccall((:jwas_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), b)
+    return b        # marker_means / xpRinvx are filled by init_sharding!
+end
 init_sharding!(b::GpuBackend, rank::Integer, world::Integer, nccl_id::Vector{UInt8}) =
-    check(ccall((:jwas_init_sharding, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), b.handle, rank, world, nccl_id))
+    (check(ccall((:jwas_init_sharding, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), b.handle, rank, world, nccl_id));
+     check(ccall((:jwas_get_marker_stats, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), b.handle, b.marker_means, b.xpRinvx)))
 
 "BayesC with scalar σ²α and π (MCMC_BayesianAlphabet.jl:231 fills the vector on the host; here the fill is on the device)"
 function BayesC_gpu!(b::GpuBackend, vare, varEffect, π; schedule=SCHED_EXACT, seed::UInt64=UInt64(0), iter::Integer=1)
@@ -132,30 +149,78 @@ function BayesC_gpu!(b::GpuBackend, vare, varEffect, π; schedule=SCHED_EXACT, s
     return nothing
 end
 
-"Drop-in for BayesR!(genotypes, ycorr, vare) / BayesR_block! (BayesR.jl:27-43)"
-function BayesR_gpu!(b::GpuBackend, vare, sigmaSq, π::Vector{Float64}, gamma::Vector{Float64};
+# marker-level priors (annotated runs: genotypes.annotations.snp_pi, nMarkers x K, BayesR.jl:28, MTBayesABC.jl:28-30)
+# go to the C side row-major; a K-vector is the usual global prior
+prior_arg(π::Vector{Float64}) = (π, Cint(0))
+prior_arg(snp_pi::Matrix{Float64}) = (collect(permutedims(snp_pi)), Cint(1))
+
+"""Drop-in for BayesR!(genotypes, ycorr, vare) / BayesR_block! (BayesR.jl:27-43); `π` is the 4-vector, or the
+nMarkers x 4 matrix `genotypes.annotations.snp_pi` of an annotated run (BayesR.jl:28)."""
+function BayesR_gpu!(b::GpuBackend, vare, sigmaSq, π::Union{Vector{Float64},Matrix{Float64}}, gamma::Vector{Float64};
                      schedule=SCHED_EXACT, iter::Integer=1, burnin::Integer=0, seed::UInt64=UInt64(0))
     st = Ref{SweepStats}()
     full = iter <= burnin ? Cint(0) : Cint(1)                     # bayesr_block_nreps, BayesR.jl:22-25
-    check(ccall((:jwas_sweep_bayesr, LIB), Cint,
+    pr, per_marker = prior_arg(π)
+    GC.@preserve pr gamma check(ccall((:jwas_sweep_bayesr, LIB), Cint,
         (Ptr{Cvoid}, Cint, Cint, Cdouble, Cdouble, Ptr{Float64}, Cint, Ptr{Float64}, Cint, UInt64, UInt32,
          Ptr{Float64}, Ptr{Float64}, Ref{SweepStats}),
-        b.handle, schedule, full, Float64(vare), Float64(sigmaSq), π, Cint(0), gamma, Cint(length(gamma)), seed,
+        b.handle, schedule, full, Float64(vare), Float64(sigmaSq), pr, per_marker, gamma, Cint(length(gamma)), seed,
         UInt32(iter), C_NULL, C_NULL, st))
     b.last_stats = st[]
     return nothing
 end
 
-"Drop-in for MTBayesABC!(genotypes, wArray, vare, locus_effect_variances, nModels) with sampler I (MTBayesABC.jl:37-54)"
-function MTBayesABC_gpu!(b::GpuBackend, R::Matrix{Float64}, G::Matrix{Float64}, bigPi::Vector{Float64};
+"""Drop-in for MTBayesABC!(genotypes, wArray, vare, locus_effect_variances, nModels) with sampler I (MTBayesABC.jl:37-54).
+`bigPi`: the 2^t joint-state priors indexed sum(δ_k << (k-1)) -- for two traits 00, 10, 01, 11, the column order of
+`annotations.snp_pi` (annotation_setup.jl:15), whose nMarkers x 4 matrix is accepted as it is."""
+function MTBayesABC_gpu!(b::GpuBackend, R::Matrix{Float64}, G::Matrix{Float64}, bigPi::Union{Vector{Float64},Matrix{Float64}};
                          schedule=SCHED_EXACT, seed::UInt64=UInt64(0), iter::Integer=1)
     st = Ref{SweepStats}()
     Rr = collect(permutedims(R)); Gr = collect(permutedims(G))     # row-major for the C side
-    check(ccall((:jwas_sweep_mt1, LIB), Cint,
+    pr, per_marker = prior_arg(bigPi)
+    GC.@preserve Rr Gr pr check(ccall((:jwas_sweep_mt1, LIB), Cint,
         (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, UInt64, UInt32, Ptr{Float64}, Ptr{Float64}, Ref{SweepStats}),
-        b.handle, schedule, Rr, Gr, Cint(0), bigPi, Cint(0), seed, UInt32(iter), C_NULL, C_NULL, st))
+        b.handle, schedule, Rr, Gr, Cint(0), pr, per_marker, seed, UInt32(iter), C_NULL, C_NULL, st))
     b.last_stats = st[]
     return nothing
+end
+
+"Sampler II, two traits (MTBayesABC.jl:129-210, 439-646); bigPi in the order 00, 10, 01, 11"
+function MTBayesABC_II_gpu!(b::GpuBackend, R::Matrix{Float64}, G::Matrix{Float64}, bigPi::Vector{Float64};
+                            schedule=SCHED_EXACT, seed::UInt64=UInt64(0), iter::Integer=1)
+    st = Ref{SweepStats}()
+    Rr = collect(permutedims(R)); Gr = collect(permutedims(G))
+    GC.@preserve Rr Gr bigPi check(ccall((:jwas_sweep_mt2, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, Ptr{Float64}, Ptr{Float64}, Ref{SweepStats}),
+        b.handle, schedule, Rr, Gr, bigPi, seed, UInt32(iter), C_NULL, C_NULL, st))
+    b.last_stats = st[]
+    return nothing
+end
+
+"megaBayesABC! (BayesABC.jl:1-7; constraint=true): per-trait vare, σ²α, π -- the traits share one column read"
+function megaBayesABC_gpu!(b::GpuBackend, vare::Vector{Float64}, varEffects::Vector{Float64}, π::Vector{Float64};
+                           schedule=SCHED_EXACT, seed::UInt64=UInt64(0), iter::Integer=1)
+    st = Ref{SweepStats}()
+    GC.@preserve vare varEffects π check(ccall((:jwas_sweep_mega, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, Ptr{Float64}, Ptr{Float64}, Ref{SweepStats}),
+        b.handle, schedule, vare, varEffects, π, seed, UInt32(iter), C_NULL, C_NULL, st))
+    b.last_stats = st[]
+    return nothing
+end
+
+"BayesB: G.val stays a device vector (MCMC_BayesianAlphabet.jl:67-69); its χ² update runs there (variance_components.jl:169-172)"
+fill_var_effects!(b::GpuBackend, v) = check(ccall((:jwas_fill_hyper, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble), b.handle, Cint(0), Float64(v)))
+fill_pi!(b::GpuBackend, π) = check(ccall((:jwas_fill_hyper, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble), b.handle, Cint(1), Float64(π)))
+sample_bayesb_variances!(b::GpuBackend, df, scale; seed::UInt64=UInt64(0), iter::Integer=1) =
+    check(ccall((:jwas_sample_bayesb_variances, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, UInt64, UInt32, Ptr{Float64}),
+                b.handle, Float64(df), Float64(scale), seed, UInt32(iter), C_NULL))
+
+"ycorr -= M*α for the α on the device (MCMC_BayesianAlphabet.jl:137-143); EBV = M*α of one trait (output.jl:302)"
+ycorr_sub_malpha!(b::GpuBackend) = check(ccall((:jwas_ycorr_sub_malpha, LIB), Cint, (Ptr{Cvoid},), b.handle))
+function mul_alpha(b::GpuBackend, trait::Integer)
+    out = Vector{Float32}(undef, b.nObs)
+    check(ccall((:jwas_mul_alpha, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}), b.handle, Cint(trait - 1), out))
+    return out
 end
 
 "intercept-only location update without moving ycorr (MCMC_BayesianAlphabet.jl:207-220)"
@@ -169,5 +234,28 @@ end
 "output_posterior_mean_variance for α, α², δ (output.jl:568-577)"
 accumulate!(b::GpuBackend, nsamples; bayesr::Bool=false) =
     check(ccall((:jwas_accumulate, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cint), b.handle, Float64(nsamples), Cint(bayesr)))
+
+function get_means(b::GpuBackend)
+    tp = b.ntraits * b.nMarkers
+    m = Vector{Float32}(undef, tp); m2 = Vector{Float32}(undef, tp); md = Vector{Float32}(undef, tp)
+    check(ccall((:jwas_get_means, LIB), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), b.handle, m, m2, md))
+    return m, m2, md
+end
+
+# ---- several GPUs, one Julia process per GPU (Distributed / MPI.jl carry the two small byte strings) ----
+"rank 0 makes the 128-byte NCCL id; broadcast it, then every rank calls init_sharding!"
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:jwas_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+"after set_blocks!: export this rank's 64-byte exchange-buffer handle, all-gather them in rank order, import"
+function ipc_export(b::GpuBackend)
+    hd = Vector{UInt8}(undef, 64)
+    check(ccall((:jwas_ipc_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), b.handle, hd))
+    return hd
+end
+ipc_import!(b::GpuBackend, handles::Vector{UInt8}) =
+    check(ccall((:jwas_ipc_import, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), b.handle, handles))
 
 end # module
