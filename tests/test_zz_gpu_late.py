@@ -1,5 +1,5 @@
-"""GPU parity tests written after the round's GPU minutes were spent (the file sorts last on purpose: they have
-only been exercised on the CPU side -- oracle backend / oracle arms -- so far).
+"""GPU parity tests added at the very end of round 2 (run once on a B200 on their own, 9 passed:
+profiles/r2_late_gpu_tests.log -- the file sorts last because the full suite was not re-run with it).
 
 1. Marker-level priors that the annotation update feeds to the sweep (BayesR.jl:28, MTBayesABC.jl:28-30,
    BayesABC.jl:17-23): `jwas_sweep_bayesr` / `jwas_sweep_mt1` with per_marker_pi against the oracle's contract
