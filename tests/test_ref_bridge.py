@@ -106,3 +106,43 @@ def test_contract_tracks_reference_bayesl(oracle, probs, lasso):
             ra = np.abs(al.astype(np.float64) - a_r).max() / np.abs(a_r).max()
             ry = np.abs(yc.astype(np.float64) - y_r).max() / np.abs(y_r).max()
             assert ra <= REL and ry <= REL, (lasso, lag, it, ra, ry)
+
+
+@pytest.mark.parametrize("method", ["BayesC", "BayesR", "MT1"])
+def test_contract_tracks_reference_with_marker_level_priors(oracle, probs, method):
+    """Annotated runs (BayesABC.jl:17-23 pi vector; BayesR.jl:28 and MTBayesABC.jl:28-30 snp_pi matrices): the
+    contract sweep with marker-level priors against the `*_ref` samplers given the same priors, lag-2 panels."""
+    t = 2 if method == "MT1" else 1
+    prob = probs[t]
+    hyp = B.Hyper(prob, method, 5)
+    rng = np.random.default_rng(31)
+    if method == "BayesC":
+        hyp.pi = np.clip(rng.beta(30, 2, size=P), 0.5, 0.999)                 # pi_j
+    elif method == "BayesR":
+        prior = rng.dirichlet([60.0, 2.0, 1.0, 0.4], size=P)
+    else:
+        prior = rng.dirichlet([18.0, 1.0, 1.0, 1.0], size=P)                   # columns 00, 10, 01, 11
+    starts = np.array(list(range(0, P, 256)) + [P], dtype=np.int64)
+    sr = B.ref_state(prob, method)
+    yc, al, be, de = prob.fresh_state()
+    for it in range(1, 4):
+        u, z = rng.random(t * P), rng.standard_normal(t * P)
+        kw = dict(nreps_mode=0, independent=False, seed=1, it=it, u=u, z=z, lag=2)
+        if method == "BayesC":
+            B.ref_sweep(oracle, prob, hyp, "exact", None, sr, u, z)
+            B.contract_sweep(oracle, prob, hyp, "exact", starts, (yc, al, be, de), u, z, it, lag=2)
+        elif method == "BayesR":
+            oracle.bayesr_ref(prob.X, prob.xpx, sr[0], sr[1], sr[3], hyp.vare, hyp.sigma_sq, prior, B.GAMMA, u, z)
+            rc, _ = oracle.sweep_contract(prob.packed, N, prob.means, prob.xpx, starts, yc, al, be, de,
+                                          method=oracle.METHOD_R, vare=hyp.vare, sigmaSq=hyp.sigma_sq, pi=prior,
+                                          gamma=B.GAMMA, **kw)
+            assert rc == 0
+        else:
+            oracle.mtbayesabc_I_ref(prob.X, prob.xpx, sr[0], sr[1], sr[2], sr[3], hyp.R, hyp.G, prior, u, z)
+            rc, _ = oracle.sweep_contract(prob.packed, N, prob.means, prob.xpx, starts, yc, al, be, de,
+                                          method=oracle.METHOD_MT1, R=hyp.R, G=hyp.G, bigPi=prior, **kw)
+            assert rc == 0
+        eq, ra, ry = B.compare(sr, (yc, al, be, de), method)
+        assert eq, f"{method}: delta forks from the reference arithmetic at sweep {it}"
+        assert ra <= REL and ry <= REL, (method, it, ra, ry)
+    assert np.count_nonzero(al) > 5
