@@ -9,11 +9,11 @@ from ._lib import (GpuSweeper, JwasError, SweepStats, SCHED_EXACT, SCHED_BLOCK, 
 
 __all__ = ["GpuSweeper", "JwasError", "SweepStats", "SCHED_EXACT", "SCHED_BLOCK", "SCHED_INDEPENDENT",
            "device_count", "shard_range", "SO_PATH"]
-from .api import (get_genotypes, build_model, set_covariate, set_random, runMCMC, prepare_streaming_genotypes,
+from .api import (get_genotypes, build_model, set_covariate, set_random, runMCMC, outputEBV, prepare_streaming_genotypes,
                   load_streaming_backend, Genotypes, MME, MCMCinfo, Variance, resolve_fast_blocks,
                   validate_fast_block_starts)
 from . import mcmc
 from .gwas import GWAS
 
-__all__ += ["get_genotypes", "build_model", "set_covariate", "set_random", "runMCMC", "prepare_streaming_genotypes",
+__all__ += ["get_genotypes", "build_model", "set_covariate", "set_random", "runMCMC", "outputEBV", "prepare_streaming_genotypes",
             "load_streaming_backend", "Genotypes", "MME", "MCMCinfo", "Variance", "mcmc", "GWAS"]

@@ -104,6 +104,7 @@ class MME:                           # types.jl:264-346 (fields this path uses)
     R: Variance = field(default_factory=Variance)
     MCMCinfo: MCMCinfo = None
     obsID: list = None
+    output_ID: object = False        # outputEBV(model, IDs) (output.jl:60-69); default: all genotyped (check_outputID)
     sol: np.ndarray = None
     output: dict = None
 
@@ -356,6 +357,11 @@ def build_model(model_equations, R=False, *, df=4.0, genotypes=None, estimate_va
                R=Variance(val=R, df=df_R, estimate_variance=estimate_variance, constraint=constraint))
 
 
+def outputEBV(model, IDs):
+    """output.jl:60-69: estimated breeding values and prediction error variances for these IDs."""
+    model.output_ID = [str(x) for x in np.asarray(IDs).reshape(-1)]
+
+
 def set_covariate(*a, **k):
     error("set_covariate: covariates are outside the GPU marker-sweep path.")
 
@@ -586,6 +592,30 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         sw.set_blocks(starts)
         backend = mcmc.GpuBackend(sw)
         Mi.stream_backend = sw
+    # ---- EBV output IDs (check_outputID, input_data_validation.jl:143-196): every genotyped individual unless
+    #      outputEBV(model, IDs) named others; IDs without genotypes are dropped.  When they are not exactly the training
+    #      rows, a second handle holds their rows (centred on the same full-sample means, align_genotypes,
+    #      tools4genotypes.jl:288-296) and serves the getEBV product M_out * alpha (output.jl:300-304)
+    ebv_backend = None
+    ebv_ids = ids
+    if outputEBV:
+        want_ids = list(Mi.obsID) if model.output_ID is False else list(model.output_ID)
+        if any(i not in pos for i in want_ids):
+            import warnings
+            warnings.warn("Testing individuals are not a subset of genotyped individuals (complete genomic data,"
+                          "non-single-step). Only output EBV for tesing individuals with genotypes.")
+            want_ids = [i for i in want_ids if i in pos]
+        if want_ids != ids:
+            ebv_ids = want_ids
+            out_rows = np.array([pos[i] for i in want_ids], dtype=np.int64)
+            out_packed = _pack_codes(_unpack_codes(Mi.packed, Mi.nObs)[out_rows])
+            out_means = np.asarray(Mi.marker_means, dtype=np.float32)
+            if _backend_factory is not None:
+                ebv_backend = _backend_factory(out_packed, len(want_ids), t, np.array([0, p], dtype=np.int64), means=out_means)
+            else:
+                sw_out = GpuSweeper(out_packed, len(want_ids), t, device=device)
+                sw_out.set_marker_means(out_means)
+                ebv_backend = mcmc.GpuBackend(sw_out)
     mu0 = Y.mean(axis=1)
     alpha0 = np.zeros(t * p, np.float32)
     if Mi.starting_value is not False:
@@ -627,7 +657,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          big_pi=Mi.π if t > 1 else None, scale_G=Mi.G.scale if t > 1 else None,
                          scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler,
                          constraint_G=bool(t > 1 and Mi.G.constraint), constraint_R=bool(t > 1 and model.R.constraint),
-                         annotations=(Mi.annotations if annotated else None))
+                         annotations=(Mi.annotations if annotated else None), ebv_backend=ebv_backend)
 
     # ---- output dictionary (output.jl:108-212)
     ma, ma2, md = backend.get_means()
@@ -683,7 +713,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     if outputEBV and out.get("ebv_mean") is not None:
         for k, tr in enumerate(model.lhsVec):
             em, ev = out["ebv_mean"][k], out["ebv_var"][k]
-            output["EBV_" + tr] = _frame([[i, float(a), float(v)] for i, a, v in zip(ids, em, ev)], ["ID", "EBV", "PEV"])
+            output["EBV_" + tr] = _frame([[i, float(a), float(v)] for i, a, v in zip(ebv_ids, em, ev)], ["ID", "EBV", "PEV"])
     if sample_files is not None:
         for f in sample_files:
             f.close()

@@ -142,7 +142,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
               mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False,
-              sample_sink=None, annotations=None):
+              sample_sink=None, annotations=None, ebv_backend=None):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -327,7 +327,11 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
             if sample_sink is not None:     # marker-effect sample rows (output.jl:467)
                 sample_sink(backend.get_state()[0])
             if want_ebv:                    # getEBV per saved sample (output.jl:281-306, 489-495)
-                e = np.array([backend.mul_alpha(k) for k in range(t)], dtype=np.float64)
+                eb = backend
+                if ebv_backend is not None:     # output IDs other than the training rows: M_out * alpha (output.jl:302)
+                    eb = ebv_backend
+                    eb.put_state(*backend.get_state())
+                e = np.array([eb.mul_alpha(k) for k in range(t)], dtype=np.float64)
                 if ebv_m is None:
                     ebv_m = np.zeros_like(e); ebv_s = np.zeros_like(e)
                 d = e - ebv_m

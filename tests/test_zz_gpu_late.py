@@ -6,7 +6,8 @@ profiles/r2_late_gpu_tests.log -- the file sorts last because the full suite was
    sweep, bit-exact, and whole annotated chains through runMCMC on the B200 backend against the same host logic
    over the oracle backend.
 2. BayesL! / BayesC0! (BayesC0L.jl:19-47) reference arithmetic (`jwo_bayesl_ref`) against the CUDA library run the
-   way this backend runs them (BayesC step, pi = 0, marker variances sigma^2 * gamma_j): 1e-5 relative."""
+   way this backend runs them (BayesC step, pi = 0, marker variances sigma^2 * gamma_j): 1e-5 relative.
+3. (added after that run, not yet executed on a B200) EBVs for genotyped individuals without phenotypes."""
 import numpy as np
 import pytest
 
@@ -126,3 +127,29 @@ def test_cuda_default_vs_reference_bayesl(jw, oracle, lasso):
         ry = np.abs(g.get_ycorr().astype(np.float64) - y_r).max() / np.abs(y_r).max()
         assert ra <= 1e-5 and ry <= 1e-5, (lasso, it, ra, ry)
     g.close()
+
+
+def test_ebv_for_unphenotyped_individuals_matches_oracle_chain():
+    """check_outputID / align_genotypes / getEBV (input_data_validation.jl:143-196, tools4genotypes.jl:288-296,
+    output.jl:300-304): training on a phenotyped subset, EBVs for every genotyped individual through a second handle
+    that holds their rows (not yet run on a B200; everything it calls -- jwas_set_marker_means, jwas_put_state,
+    jwas_mul_alpha -- is covered by GPU-verified tests)."""
+    import jwas_b200
+    from oracle_backend import factory
+    from test_api_chain import make_data
+    from test_gpu_chain import assert_same
+    codes, ids, ph = make_data(n=260, p=300, seed=29, missing=0.01)
+    sub = ph.iloc[::-1].iloc[:200].reset_index(drop=True)
+    outs = []
+    for bf in (None, factory):
+        geno = jwas_b200.get_genotypes(codes, 1.0, method="BayesC", Pi=0.9, obsID=ids)
+        model = jwas_b200.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+        outs.append(jwas_b200.runMCMC(model, sub, chain_length=20, burnin=4, seed=77, _backend_factory=bf))
+    assert list(outs[0]["EBV_y1"]["ID"]) == ids
+    g, o = outs[0]["EBV_y1"], outs[1]["EBV_y1"]
+    # the device product sums its rows in another order than the oracle's: equal to Float32 rounding
+    np.testing.assert_allclose(g["EBV"].to_numpy(float), o["EBV"].to_numpy(float), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(g["PEV"].to_numpy(float), o["PEV"].to_numpy(float), rtol=1e-3, atol=1e-6)
+    for key in outs[0]:
+        if not key.startswith("EBV_"):
+            assert_same({key: outs[0][key]}, {key: outs[1][key]})
