@@ -19,6 +19,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import _io
 from . import annotations as annot
 from . import mcmc
 from ._lib import GpuSweeper, JwasError, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT
@@ -141,16 +142,31 @@ def _codes_from_matrix(X, missing_value):
     return codes
 
 
-def _column_stats(codes):
-    """Means over observed calls and allele frequencies (readgenotypes.jl:372-385,
-    streaming_genotypes.jl:560-585), Float32 like the reference."""
-    valid = codes != 3
-    nn = valid.sum(axis=0)
+def _call_counts(packed, n):
+    """(p, 3) int64: 1s, 2s and missing calls per marker, from the packed image (libjwasio when built)."""
+    if _io.available():
+        return _io.packed_counts(packed, n)
+    codes = _unpack_codes(packed, n)
+    return np.stack([(codes == 1).sum(axis=0), (codes == 2).sum(axis=0), (codes == 3).sum(axis=0)], axis=1).astype(np.int64)
+
+
+def _select_rows(packed, n, rows):
+    """Rows `rows` of every packed column as a new image (aligning genotypes to other individuals, JWAS.jl:381-402)."""
+    if _io.available():
+        return _io.packed_rows(packed, rows)
+    return _pack_codes(_unpack_codes(packed, n)[np.asarray(rows)])
+
+
+def _stats_from_counts(counts, n):
+    """Means over observed calls (Float32 like the reference, readgenotypes.jl:372-385, streaming_genotypes.jl:560-585),
+    number of observed calls, their sum and their sum of squares."""
+    n1, n2, nm = counts[:, 0], counts[:, 1], counts[:, 2]
+    nn = n - nm
     if np.any(nn == 0):
         error("Marker %d has only missing values." % int(np.argmin(nn) + 1))
-    s = np.where(valid, codes, 0).sum(axis=0, dtype=np.int64)
+    s = n1 + 2 * n2
     means = (s.astype(np.float32) / nn.astype(np.float32)).astype(np.float32)
-    return means, nn, s
+    return means, nn, s, (n1 + 4 * n2)
 
 
 def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_is_marker_variance=False,
@@ -180,9 +196,15 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
 
     if isinstance(file, str) and (os.path.exists(file + ".meta") or file.endswith((".jgb2", ".meta"))):
         be = load_streaming_backend(file)
-        codes = _unpack_codes(be["packed"], be["nObs"])
+        packed, n = be["packed"], be["nObs"]
         obs, mk = be["obsID"], be["markerID"]
         quality_control = False            # QC happened when the backend was prepared
+    elif isinstance(file, str) and _io.available() and len(separator) == 1:
+        # text file -> 2-bit image in one parallel pass, no dense matrix (libjwasio, include/jwas_io.h)
+        if not os.path.isfile(file):
+            error(f"genotype file {file} is not found.")
+        obs, mk, packed = _io.read_genotype_text(file, separator, header, missing_value)
+        n = len(obs)
     else:
         if isinstance(file, str):
             if pd is None:
@@ -204,9 +226,11 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         if X.size == 0:
             error("Genotype data is empty.")
         codes = _codes_from_matrix(X, missing_value)
+        packed, n = _pack_codes(codes), codes.shape[0]
+        del codes
 
     try:                                    # readgenotypes.jl:254-258: one annotation row per RAW marker
-        ann_matrix = annot.validate_annotations_input(annotations, codes.shape[1], method)
+        ann_matrix = annot.validate_annotations_input(annotations, packed.shape[0], method)
     except annot.AnnotationError as e:
         error(str(e))
     if ann_matrix is not False and not estimatePi:
@@ -214,23 +238,22 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         warnings.warn(f"estimatePi=false is ignored when annotations are provided; Annotated {method} requires "
                       "estimatePi=true.")
         estimatePi = True
-    means, nn, s = _column_stats(codes)
+    # per-marker statistics from the call counts of the packed image (never from a dense matrix)
+    means, nn, s, sq = _stats_from_counts(_call_counts(packed, n), n)
     af = (means / np.float32(2.0)).astype(np.float32)
     if quality_control:                     # readgenotypes.jl:388-399: MAF filter + fixed loci
-        valid = codes != 3
-        cm = np.where(valid, codes, 0).astype(np.float64)
-        ss = (cm ** 2).sum(axis=0) - (s.astype(np.float64) ** 2) / nn
+        ss = sq.astype(np.float64) - (s.astype(np.float64) ** 2) / nn
         keep = (af > MAF) & (af < 1 - MAF) & (ss > 0)
         if not keep.any():
             error("No markers remain after streaming genotype quality control.")
-        codes = codes[:, keep]; means = means[keep]; af = af[keep]
+        packed = np.ascontiguousarray(packed[keep]); means = means[keep]; af = af[keep]
         mk = [m for m, k in zip(mk, keep) if k]
         if ann_matrix is not False:
             ann_matrix = ann_matrix[keep]   # annotations follow the markers that survive QC (readgenotypes.jl:256)
-    n, p = codes.shape
+    p = packed.shape[0]
     g = Genotypes(name=name, obsID=obs, markerID=mk, nObs=n, nMarkers=p, alleleFreq=af,
                   sum2pq=float((2.0 * af.astype(np.float64) * (1 - af.astype(np.float64))).sum()),
-                  centered=True, packed=_pack_codes(codes), marker_means=means, method=method,
+                  centered=True, packed=np.ascontiguousarray(packed), marker_means=means, method=method,
                   estimatePi=bool(estimatePi), multi_trait_sampler=multi_trait_sampler,
                   starting_value=starting_value)
     g.π = Pi if not isinstance(Pi, (list, tuple)) else np.array(Pi, dtype=np.float64)
@@ -270,10 +293,12 @@ def prepare_streaming_genotypes(file, *, output_prefix=None, separator=",", head
     open(paths["marker_path"], "w").write("".join(x + "\n" for x in g.markerID))
     np.arange(1, g.nMarkers + 1, dtype=np.int32).tofile(paths["selected_path"])
     g.marker_means.astype(np.float32).tofile(paths["mean_path"])
-    codes = _unpack_codes(g.packed, g.nObs)
-    valid = codes != 3
-    x = np.where(valid, codes.astype(np.float32) - g.marker_means[None, :], np.float32(0))
-    (x.astype(np.float64) ** 2).sum(axis=0).astype(np.float32).tofile(paths["xp_path"])
+    # xpRinvx of the centred columns, missing calls at the mean (streaming_genotypes.jl:283-285, 560-585), in closed
+    # form from the call counts: sum (x - m)^2 = (n1 + 4 n2) - 2 m (n1 + 2 n2) + m^2 * (observed calls)
+    cnt = _call_counts(g.packed, g.nObs)
+    m64 = g.marker_means.astype(np.float64)
+    s64 = (cnt[:, 0] + 2 * cnt[:, 1]).astype(np.float64)
+    ((cnt[:, 0] + 4 * cnt[:, 1]) - 2 * m64 * s64 + m64 * m64 * (g.nObs - cnt[:, 2])).astype(np.float32).tofile(paths["xp_path"])
     g.alleleFreq.astype(np.float32).tofile(paths["afreq_path"])
     with open(prefix + ".meta", "w") as io:
         for k, v in [("version", "1")] + list(paths.items()) + [("nObs", g.nObs), ("nMarkers", g.nMarkers),
@@ -459,10 +484,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     if n != Mi.nObs or not np.array_equal(rows, np.arange(n)):
         # the reference centres on ALL genotyped individuals in get_genotypes (readgenotypes.jl:372-385) and only then
         # aligns rows to the phenotyped ones (JWAS.jl:381-402): keep the full-sample means, recompute xpx for them
-        sub = _unpack_codes(Mi.packed, Mi.nObs)[rows]
-        if np.any((sub != 3).sum(axis=0) == 0):
+        packed = _select_rows(Mi.packed, Mi.nObs, rows)
+        if np.any(_call_counts(packed, n)[:, 2] == n):
             error("a marker has no observed genotype among the phenotyped individuals.")
-        packed = _pack_codes(sub)
         subset_means = np.asarray(Mi.marker_means, dtype=np.float32)
 
     if output_samples_frequency is None:                 # evaluated on the user's chain_length (JWAS.jl:168), before :312
@@ -608,7 +632,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         if want_ids != ids:
             ebv_ids = want_ids
             out_rows = np.array([pos[i] for i in want_ids], dtype=np.int64)
-            out_packed = _pack_codes(_unpack_codes(Mi.packed, Mi.nObs)[out_rows])
+            out_packed = _select_rows(Mi.packed, Mi.nObs, out_rows)
             out_means = np.asarray(Mi.marker_means, dtype=np.float32)
             if _backend_factory is not None:
                 ebv_backend = _backend_factory(out_packed, len(want_ids), t, np.array([0, p], dtype=np.int64), means=out_means)
