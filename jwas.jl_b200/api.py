@@ -436,12 +436,29 @@ def _frame(rows, cols):
 
 def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=None, seed=False,
             fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
-            double_precision=False, heterogeneous_residuals=False, output_folder="results", device=0,
+            double_precision=False, heterogeneous_residuals=False, output_folder=None, device=0,
             panel=DEFAULT_PANEL, engine=1, lag=DEFAULT_LAG, chain_ctas=DEFAULT_CHAIN_CTAS, output_marker_effect_samples=False,
             _backend_factory=None, **ignored):
     """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
     Returns the reference's output dictionary keys for this path: "location parameters",
-    "residual variance", "marker effects <name>", "pi_<name>", "EBV_<trait>"."""
+    "residual variance", "marker effects <name>", "pi_<name>", "annotation coefficients <name>", "EBV_<trait>",
+    "genetic_variance" and "heritability" (output_heritability=true, output.jl:196-209, 498-511).
+
+    output_folder: the reference always creates a folder ("results", "results1", ... JWAS.jl:255-262) and writes every
+    output table there as <key with _ for spaces>.txt (JWAS.jl:479-482).  Here that happens when output_folder is
+    given; the default (None) writes nothing but requested sample files (into "results")."""
+    write_results = output_folder is not None
+    if output_folder is None:
+        output_folder = "results"
+    elif os.path.exists(output_folder):          # JWAS.jl:255-262: never write into an existing folder
+        base, k = output_folder, 1
+        while os.path.exists(output_folder):
+            output_folder = base + str(k); k += 1
+    if write_results:
+        os.makedirs(output_folder)
+    if output_heritability:                      # check_outputID (input_data_validation.jl:167-174)
+        outputEBV = True
+        model.output_ID = False
     if heterogeneous_residuals:
         error("heterogeneous_residuals=true is not supported with storage=:gpu (unit weights only).")
     if double_precision:
@@ -681,7 +698,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          big_pi=Mi.π if t > 1 else None, scale_G=Mi.G.scale if t > 1 else None,
                          scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler,
                          constraint_G=bool(t > 1 and Mi.G.constraint), constraint_R=bool(t > 1 and model.R.constraint),
-                         annotations=(Mi.annotations if annotated else None), ebv_backend=ebv_backend)
+                         annotations=(Mi.annotations if annotated else None), ebv_backend=ebv_backend,
+                         want_heritability=bool(output_heritability))
 
     # ---- output dictionary (output.jl:108-212)
     ma, ma2, md = backend.get_means()
@@ -738,9 +756,20 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         for k, tr in enumerate(model.lhsVec):
             em, ev = out["ebv_mean"][k], out["ebv_var"][k]
             output["EBV_" + tr] = _frame([[i, float(a), float(v)] for i, a, v in zip(ebv_ids, em, ev)], ["ID", "EBV", "PEV"])
+    if output_heritability and out.get("gvar_mean") is not None:      # output.jl:196-209
+        names = [f"{a}_{b}" for a in model.lhsVec for b in model.lhsVec] if t > 1 else list(model.lhsVec)
+        gm, gs = np.atleast_1d(out["gvar_mean"]).reshape(-1), np.atleast_1d(out["gvar_sd"]).reshape(-1)
+        output["genetic_variance"] = _frame([[nm, float(a), float(b)] for nm, a, b in zip(names, gm, gs)],
+                                            ["Covariance", "Estimate", "SD"])
+        output["heritability"] = _frame([[tr, float(a), float(b)] for tr, a, b in
+                                         zip(model.lhsVec, np.atleast_1d(out["h2_mean"]), np.atleast_1d(out["h2_sd"]))],
+                                        ["Covariance", "Estimate", "SD"])
     if sample_files is not None:
         for f in sample_files:
             f.close()
+    if write_results and pd is not None:         # JWAS.jl:479-482
+        for key, value in output.items():
+            value.to_csv(os.path.join(output_folder, key.replace(" ", "_") + ".txt"), index=False)
     model.output = output
     model.sol = out["mu"]
     return output

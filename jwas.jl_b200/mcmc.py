@@ -142,7 +142,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
               mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False,
-              sample_sink=None, annotations=None, ebv_backend=None):
+              sample_sink=None, annotations=None, ebv_backend=None, want_heritability=False):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -169,6 +169,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
             out[key] = np.zeros((t, t))
         out["pi_mean"] = np.zeros_like(big_pi); out["pi_mean2"] = np.zeros_like(big_pi)
     ebv_m = ebv_s = None
+    gvar_samples, h2_samples = [], []
     gamma_arr = None
     ann = annotations
     ann_prior = None                      # what the sweep takes: (p,) pi_j for BayesC, (p, 4) class / joint-state priors
@@ -337,6 +338,19 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                 d = e - ebv_m
                 ebv_m += d / nsamples
                 ebv_s += d * (e - ebv_m)
+                if want_heritability:
+                    # output.jl:498-511: genetic (co)variance of this sample's breeding values over the output IDs
+                    # (diagonal when the marker covariance is constrained), h2 = diag(g) / (diag(g) + diag(vare))
+                    gv = np.atleast_2d(np.cov(e))
+                    if constraint_G:
+                        gv = np.diag(np.diag(gv))
+                    vres = np.diag(np.atleast_2d(vare if t == 1 else R))
+                    gvar_samples.append(gv.reshape(-1) if t > 1 else gv[0, 0])
+                    h2_samples.append(np.diag(gv) / (np.diag(gv) + vres))
+    if gvar_samples:                # means and standard deviations over the saved samples (output.jl:201-207)
+        g_, h_ = np.array(gvar_samples, dtype=np.float64), np.array(h2_samples, dtype=np.float64)
+        dd = 1 if len(g_) > 1 else 0
+        out.update(gvar_mean=g_.mean(axis=0), gvar_sd=g_.std(axis=0, ddof=dd), h2_mean=h_.mean(axis=0), h2_sd=h_.std(axis=0, ddof=dd))
     if ebv_m is not None:
         out["ebv_mean"] = ebv_m
         out["ebv_var"] = ebv_s / max(nsamples - 1, 1)

@@ -293,3 +293,36 @@ def test_multitrait_constraint_runs_independent_traits():
     out = jw.runMCMC(model, ph, chain_length=12, burnin=2, seed=5, outputEBV=False, _backend_factory=factory)
     assert len(out["pi_geno"]) == 2 and out["pi_geno"]["Estimate"].between(0, 1).all()
     assert len(out["marker effects geno"]) == 2 * geno.nMarkers
+
+
+def test_heritability_output_and_result_files(tmp_path):
+    """output_heritability (output.jl:196-209, 498-511): per saved sample the (co)variance of the breeding values over
+    all genotyped individuals and h2 = g / (g + vare); result tables written like JWAS.jl:479-482 into a folder that is
+    never an existing one (JWAS.jl:255-262)."""
+    codes, ids, ph = make_data(n=150, p=120, seed=41, ntraits=2)
+    geno = jw.get_genotypes(codes, np.eye(2), method="BayesC", Pi=0.0, obsID=ids)
+    model = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.eye(2), genotypes={"geno": geno})
+    folder = str(tmp_path / "res")
+    os.makedirs(folder)                                  # exists already -> results go to res1
+    out = jw.runMCMC(model, ph.iloc[:100], chain_length=40, burnin=10, output_samples_frequency=2, seed=3,
+                     output_heritability=True, output_folder=folder, _backend_factory=factory)
+    gv, h2 = out["genetic_variance"], out["heritability"]
+    assert list(gv["Covariance"]) == ["y1_y1", "y1_y2", "y2_y1", "y2_y2"] and list(h2["Covariance"]) == ["y1", "y2"]
+    assert h2["Estimate"].between(0, 1).all() and (gv["Estimate"].to_numpy()[[0, 3]] > 0).all()
+    assert gv["Estimate"][1] == pytest.approx(gv["Estimate"][2])
+    assert len(out["EBV_y1"]) == 150                     # heritability uses every genotyped individual
+    # h2 of the posterior-mean breeding values is in the same ballpark as the mean of the per-sample h2
+    rv = out["residual variance"]["Estimate"].to_numpy()[[0, 3]]
+    assert np.all(np.abs(h2["Estimate"].to_numpy() - gv["Estimate"].to_numpy()[[0, 3]] / (gv["Estimate"].to_numpy()[[0, 3]] + rv)) < 0.15)
+    assert os.listdir(folder) == []
+    written = sorted(os.listdir(folder + "1"))
+    assert written == sorted(k.replace(" ", "_") + ".txt" for k in out)
+    back = pd.read_csv(os.path.join(folder + "1", "marker_effects_geno.txt"))
+    assert list(back.columns) == ["Trait", "Marker_ID", "Estimate", "SD", "Model_Frequency"] and len(back) == 2 * geno.nMarkers
+    # single trait: scalar tables
+    codes, ids, ph = make_data(n=90, p=60, seed=42)
+    geno = jw.get_genotypes(codes, 1.0, method="BayesC", Pi=0.5, obsID=ids)
+    model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+    out = jw.runMCMC(model, ph, chain_length=20, seed=3, output_heritability=True, _backend_factory=factory)
+    assert list(out["genetic_variance"]["Covariance"]) == ["y1"] and 0 < out["heritability"]["Estimate"][0] < 1
+    assert not os.path.exists("results")                 # no folder given: nothing is written
