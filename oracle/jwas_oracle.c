@@ -93,9 +93,39 @@ void jwo_marker_stats_ref(const uint8_t* packed, int64_t n, int64_t p, int64_t s
  * cross-product needs when either marker has missing calls. */
 typedef struct { int64_t Nab, Sa_vb, Sb_va, Nvv; } jwo_pair;
 
+/* The four sums for one pair of packed bytes (four individuals each), 16 bits per sum:
+ * bits 0-15 Nab, 16-31 Sa_vb, 32-47 Sb_va, 48-63 Nvv.  Pure integer bookkeeping: the counts are the ones the
+ * per-individual loop gives, only four individuals at a time (this keeps the oracle side of the large parity
+ * cases at seconds instead of minutes). */
+static uint64_t pair_lut[256][256];
+static int pair_lut_ready = 0;
+
+static void pair_lut_init(void) {
+    for (int x = 0; x < 256; ++x)
+        for (int y = 0; y < 256; ++y) {
+            uint64_t nab = 0, sa = 0, sb = 0, nvv = 0;
+            for (int k = 0; k < 4; ++k) {
+                unsigned a = (unsigned)(x >> (2 * k)) & 3u, b = (unsigned)(y >> (2 * k)) & 3u;
+                if (a != 3u && b != 3u) { nab += a * b; sa += a; sb += b; nvv += 1; }
+            }
+            pair_lut[x][y] = nab | (sa << 16) | (sb << 32) | (nvv << 48);
+        }
+    pair_lut_ready = 1;
+}
+
 static jwo_pair pair_counts(const uint8_t* ca, const uint8_t* cb, int64_t n) {
     jwo_pair q = {0, 0, 0, 0};
-    for (int64_t i = 0; i < n; ++i) {
+    if (!pair_lut_ready) pair_lut_init();      /* idempotent: a second initialiser writes the same values */
+    const int64_t full = n >> 2;                 /* whole bytes; the last partial byte goes individual by individual */
+    int64_t bpos = 0;
+    while (bpos < full) {
+        int64_t end = bpos + 4000 < full ? bpos + 4000 : full;      /* 4000 bytes * 16 < 65536: no field overflows */
+        uint64_t acc = 0;
+        for (; bpos < end; ++bpos) acc += pair_lut[ca[bpos]][cb[bpos]];
+        q.Nab += (int64_t)(acc & 0xffffu); q.Sa_vb += (int64_t)((acc >> 16) & 0xffffu);
+        q.Sb_va += (int64_t)((acc >> 32) & 0xffffu); q.Nvv += (int64_t)(acc >> 48);
+    }
+    for (int64_t i = full << 2; i < n; ++i) {
         unsigned a = jw_code(ca, i), b = jw_code(cb, i);
         if (a != 3u && b != 3u) { q.Nab += (int64_t)(a * b); q.Sa_vb += a; q.Sb_va += b; q.Nvv += 1; }
     }
