@@ -80,6 +80,8 @@ class Genotypes:                     # types.jl:98-165 (fields this path uses)
     starting_value: object = False
     annotations: object = False      # annotations.MarkerAnnotations (types.jl:167-216)
     annotation_start_pi: object = 0.0
+    nMarkersAll: int = 0             # markers in the raw file and the (1-based) raw indices of the ones kept by QC:
+    selected_marker_indices: np.ndarray = None     # the raw-marker mapping of the packed backend (streaming_genotypes.jl:913-930)
 
 
 @dataclass
@@ -194,11 +196,15 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
     if method == "BayesR" and not isinstance(Pi, (list, tuple, np.ndarray)) and Pi != 0.0:
         error("BayesR Pi must have length 4.")
 
+    be = None
     if isinstance(file, str) and (os.path.exists(file + ".meta") or file.endswith((".jgb2", ".meta"))):
         be = load_streaming_backend(file)
         packed, n = be["packed"], be["nObs"]
         obs, mk = be["obsID"], be["markerID"]
         quality_control = False            # QC happened when the backend was prepared
+        if annotations is not False and not be["has_raw_marker_mapping"]:      # readgenotypes.jl:251-253
+            error("Annotated storage=:stream requires a backend prepared with the current prepare_streaming_genotypes; "
+                  "rebuild the backend to include raw-marker mapping metadata.")
     elif isinstance(file, str) and _io.available() and len(separator) == 1:
         # text file -> 2-bit image in one parallel pass, no dense matrix (libjwasio, include/jwas_io.h)
         if not os.path.isfile(file):
@@ -229,10 +235,15 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         packed, n = _pack_codes(codes), codes.shape[0]
         del codes
 
+    from_backend = be is not None
+    n_all = be["nMarkersAll"] if from_backend else packed.shape[0]
+    selected = be["selected_marker_indices"] if from_backend else np.arange(1, packed.shape[0] + 1, dtype=np.int32)
     try:                                    # readgenotypes.jl:254-258: one annotation row per RAW marker
-        ann_matrix = annot.validate_annotations_input(annotations, packed.shape[0], method)
+        ann_matrix = annot.validate_annotations_input(annotations, n_all, method)
     except annot.AnnotationError as e:
         error(str(e))
+    if ann_matrix is not False and from_backend:
+        ann_matrix = ann_matrix[np.asarray(selected, dtype=np.int64) - 1]      # rows of the markers the backend kept
     if ann_matrix is not False and not estimatePi:
         import warnings
         warnings.warn(f"estimatePi=false is ignored when annotations are provided; Annotated {method} requires "
@@ -248,6 +259,7 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
             error("No markers remain after streaming genotype quality control.")
         packed = np.ascontiguousarray(packed[keep]); means = means[keep]; af = af[keep]
         mk = [m for m, k in zip(mk, keep) if k]
+        selected = selected[keep]
         if ann_matrix is not False:
             ann_matrix = ann_matrix[keep]   # annotations follow the markers that survive QC (readgenotypes.jl:256)
     p = packed.shape[0]
@@ -255,7 +267,8 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
                   sum2pq=float((2.0 * af.astype(np.float64) * (1 - af.astype(np.float64))).sum()),
                   centered=True, packed=np.ascontiguousarray(packed), marker_means=means, method=method,
                   estimatePi=bool(estimatePi), multi_trait_sampler=multi_trait_sampler,
-                  starting_value=starting_value)
+                  starting_value=starting_value, nMarkersAll=int(n_all),
+                  selected_marker_indices=np.asarray(selected, dtype=np.int32))
     g.π = Pi if not isinstance(Pi, (list, tuple)) else np.array(Pi, dtype=np.float64)
     g.G = Variance(val=G if G_is_marker_variance else False, df=df, estimate_variance=estimate_variance,
                    estimate_scale=estimate_scale, constraint=constraint)
@@ -291,7 +304,7 @@ def prepare_streaming_genotypes(file, *, output_prefix=None, separator=",", head
     g.packed.tofile(paths["data_path"])
     open(paths["obs_path"], "w").write("".join(x + "\n" for x in g.obsID))
     open(paths["marker_path"], "w").write("".join(x + "\n" for x in g.markerID))
-    np.arange(1, g.nMarkers + 1, dtype=np.int32).tofile(paths["selected_path"])
+    g.selected_marker_indices.astype(np.int32).tofile(paths["selected_path"])        # raw (1-based) indices kept by QC
     g.marker_means.astype(np.float32).tofile(paths["mean_path"])
     # xpRinvx of the centred columns, missing calls at the mean (streaming_genotypes.jl:283-285, 560-585), in closed
     # form from the call counts: sum (x - m)^2 = (n1 + 4 n2) - 2 m (n1 + 2 n2) + m^2 * (observed calls)
@@ -302,7 +315,7 @@ def prepare_streaming_genotypes(file, *, output_prefix=None, separator=",", head
     g.alleleFreq.astype(np.float32).tofile(paths["afreq_path"])
     with open(prefix + ".meta", "w") as io:
         for k, v in [("version", "1")] + list(paths.items()) + [("nObs", g.nObs), ("nMarkers", g.nMarkers),
-                                                               ("nMarkersAll", g.nMarkers),
+                                                               ("nMarkersAll", g.nMarkersAll),
                                                                ("stride_bytes", (g.nObs + 3) // 4),
                                                                ("centered", 1), ("sum2pq", repr(g.sum2pq))]:
             io.write(f"{k}\t{v}\n")
@@ -333,8 +346,24 @@ def load_streaming_backend(path):
         error(f"Number of IDs in {meta['obs_path']} does not match nObs in manifest.")
     if len(mk) != p:
         error(f"Number of markers in {meta['marker_path']} does not match nMarkers in manifest.")
+    # raw-marker mapping (streaming_genotypes.jl:913-944): older backends have neither entry
+    if ("nMarkersAll" in meta) != bool(meta.get("selected_path")):
+        error("Streaming backend metadata is inconsistent. Rebuild the backend with prepare_streaming_genotypes.")
+    has_map = "nMarkersAll" in meta and bool(meta.get("selected_path"))
+    n_all = int(meta["nMarkersAll"]) if "nMarkersAll" in meta else p
+    if has_map:
+        if not os.path.isfile(meta["selected_path"]):
+            error("Streaming backend selected-marker metadata is missing. Rebuild the backend with prepare_streaming_genotypes.")
+        sel = np.fromfile(meta["selected_path"], dtype=np.int32)
+        if len(sel) != p:
+            error("Number of selected raw-marker indices does not match nMarkers in manifest.")
+        if len(sel) and (sel.min() < 1 or sel.max() > n_all):
+            error("Selected raw-marker indices are out of bounds for the recorded raw marker count.")
+    else:
+        sel = np.arange(1, p + 1, dtype=np.int32)
     return {"packed": packed, "nObs": n, "nMarkers": p, "obsID": obs, "markerID": mk,
-            "centered": int(meta["centered"]) == 1}
+            "centered": int(meta["centered"]) == 1, "nMarkersAll": n_all, "selected_marker_indices": sel,
+            "has_raw_marker_mapping": has_map}
 
 
 # ------------------------------------------------------------------------------------ model

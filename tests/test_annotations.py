@@ -342,3 +342,31 @@ def test_oracle_marker_level_priors_reduce_to_the_global_ones(oracle):
     for a, b in zip(*res):
         np.testing.assert_array_equal(a, b)
     assert res[0][3].sum() > 0
+
+
+def test_packed_backend_keeps_the_raw_marker_mapping_for_annotations(tmp_path):
+    """test_annotated_bayesc.jl:190-265: annotations are given per RAW marker; a backend prepared with QC records which
+    raw markers it kept (selected.i32, nMarkersAll) and get_genotypes(prefix, annotations=...) filters with it; a
+    legacy backend without the mapping is refused."""
+    path = str(tmp_path / "annotated_stream_qc.csv")
+    open(path, "w").write("ID,m1,m2,m3\na1,0,1,2\na2,1,1,1\na3,2,1,0\na4,1,1,2\n")
+    A = np.array([[10.0], [20.0], [30.0]])
+    prefix = jw.prepare_streaming_genotypes(path, quality_control=True, MAF=0.01)
+    be = jw.load_streaming_backend(prefix)
+    assert be["nMarkers"] == 2 and be["nMarkersAll"] == 3 and be["selected_marker_indices"].tolist() == [1, 3]
+    assert be["has_raw_marker_mapping"]
+    geno = jw.get_genotypes(prefix, 1.0, method="BayesC", annotations=A)
+    X = geno.annotations.design_matrix
+    assert geno.nMarkers == 2 and X.shape == (2, 2) and np.all(X[:, 0] == 1.0)
+    np.testing.assert_array_equal(X[:, 1:], A[[0, 2]])
+    assert "rows" in _err(lambda: jw.get_genotypes(prefix, 1.0, method="BayesC", annotations=A[[0, 2]]))
+    # legacy manifest: no selected_path / nMarkersAll lines
+    meta = prefix + ".meta"
+    lines = [l for l in open(meta) if not l.startswith(("selected_path\t", "nMarkersAll\t"))]
+    open(meta, "w").writelines(lines)
+    assert not jw.load_streaming_backend(prefix)["has_raw_marker_mapping"]
+    assert "rebuild the backend" in _err(lambda: jw.get_genotypes(prefix, 1.0, method="BayesC", annotations=A))
+    assert jw.get_genotypes(prefix, 1.0, method="BayesC").nMarkers == 2          # without annotations it still loads
+    # one of the two entries alone is an inconsistent manifest
+    open(meta, "a").write("nMarkersAll\t3\n")
+    assert "inconsistent" in _err(lambda: jw.load_streaming_backend(prefix))
