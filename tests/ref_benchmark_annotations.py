@@ -140,6 +140,76 @@ def run_case(case, seed, data, args, factory, heldout=None):
     return rows
 
 
+# cross-seed agreement of two runs (seeds 100 and 110; chain_length 5000, burnin 1000, frequency 10) on the single-trait
+# fixture: benchmarks/simulated_annotations_method_matrix.jl, reports/2026-04-02-simulated-annotations-method-matrix-report.md
+# variant -> marker corr, PIP corr, EBV corr, annotation coefficient corr, pi vector corr
+PUBLISHED_MATRIX = {"BayesC_dense": (0.8502, 0.6409, 0.9813, None, None),
+                    "Annotated_BayesC_dense": (0.9911, 0.9932, 0.9997, 0.9956, 0.99997),
+                    "BayesR_dense": (0.9760, 0.8255, 0.9995, None, 0.99992),
+                    "Annotated_BayesR_dense": (0.9985, 0.9982, 0.9997, 0.9844, 0.999996)}
+
+
+def matrix_mode(args, factory):
+    """simulated_annotations_method_matrix.jl:78-198 (dense variants): BayesC starts from Pi = 0, BayesR from
+    (0.99, 0.006, 0.003, 0.001); every pair of seeds gives one set of cross-seed correlations (summarize_pair)."""
+    import itertools
+    geno_df = pd.read_csv(os.path.join(args.data, "genotypes.csv"))
+    ph = pd.read_csv(os.path.join(args.data, "phenotypes.csv"))
+    A = pd.read_csv(os.path.join(args.data, "annotations.csv"))[["functional", "random_anno"]].to_numpy(float)
+    v = float(np.var(ph["y1"].to_numpy(float), ddof=1))
+    seeds = [int(s) for s in args.seeds.split(",")]
+    extra = dict(_backend_factory=factory, lag=0, panel=args.panel) if factory is not None else {}
+    rows = []
+    for variant, method, annotated in (("BayesC_dense", "BayesC", False), ("Annotated_BayesC_dense", "BayesC", True),
+                                       ("BayesR_dense", "BayesR", False), ("Annotated_BayesR_dense", "BayesR", True)):
+        runs = {}
+        for seed in seeds:
+            kw = dict(method=method, estimatePi=True, quality_control=False, Pi=(0.0 if method == "BayesC" else list(ST_BAYESR_PI)))
+            if annotated:
+                kw["annotations"] = A
+            geno = jw.get_genotypes(geno_df, v * args.start_h2, **kw)
+            model = jw.build_model("y1 = intercept + geno", v * (1 - args.start_h2), genotypes={"geno": geno})
+            jw.outputEBV(model, list(geno_df.iloc[:, 0]))
+            t0 = time.time()
+            out = jw.runMCMC(model, ph, chain_length=args.chain_length, burnin=args.burnin, output_samples_frequency=args.freq,
+                             seed=seed, outputEBV=True, **extra)
+            me = out["marker effects geno"]
+            pi = out["pi_geno"]["Estimate"].to_numpy(float)
+            runs[seed] = dict(est=me["Estimate"].to_numpy(float), pip=me["Model_Frequency"].to_numpy(float),
+                              ebv=out["EBV_y1"]["EBV"].to_numpy(float),
+                              ann=(out["annotation coefficients geno"]["Estimate"].to_numpy(float) if annotated else None),
+                              pi=(pi if len(pi) > 1 else None))
+            print(f"{variant:24s} seed {seed}: {time.time() - t0:.0f} s", flush=True)
+
+        def cor(a, b):
+            return float(np.corrcoef(a, b)[0, 1]) if a is not None and np.std(a) > 0 and np.std(b) > 0 else np.nan
+        for sa, sb in itertools.combinations(seeds, 2):
+            ra, rb = runs[sa], runs[sb]
+            rows.append(dict(variant=variant, seed_a=sa, seed_b=sb, marker=cor(ra["est"], rb["est"]), pip=cor(ra["pip"], rb["pip"]),
+                             ebv=cor(ra["ebv"], rb["ebv"]), ann=cor(ra["ann"], rb["ann"]), pi=cor(ra["pi"], rb["pi"])))
+    df = pd.DataFrame(rows)
+    lines = ["| Variant | seed pairs | Marker corr: here min / mean / max (reference) | PIP corr | EBV corr | Annotation coeff corr | pi vector corr |",
+             "|---|---|---|---|---|---|---|"]
+    for variant, g in df.groupby("variant", sort=False):
+        ref = PUBLISHED_MATRIX[variant]
+        cells = []
+        for col, r in zip(("marker", "pip", "ebv", "ann", "pi"), ref):
+            x = g[col].to_numpy(float)
+            if np.all(np.isnan(x)):
+                cells.append("—")
+            else:
+                cells.append(f"{np.nanmin(x):.4f} / {np.nanmean(x):.4f} / {np.nanmax(x):.4f} ({'%.4f' % r if r is not None else 'NA'})")
+        lines.append(f"| `{variant}` | {len(g)} | " + " | ".join(cells) + " |")
+    table = "\n".join(lines)
+    print(table)
+    if args.out:
+        with open(args.out, "w") as f:
+            f.write(f"<!-- python tests/ref_benchmark_annotations.py --matrix --seeds {args.seeds} --chain-length {args.chain_length} "
+                    f"--burnin {args.burnin} --freq {args.freq} --backend {args.backend} -->\n" + table + "\n")
+        df.to_csv(os.path.splitext(args.out)[0] + "_runs.csv", index=False)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--data", default="/root/reference/src/4.Datasets/data/simulated_annotations")
@@ -151,6 +221,8 @@ def main():
     ap.add_argument("--panel", type=int, default=16, help="oracle backend only: small panels keep its Gram work small")
     ap.add_argument("--backend", choices=["oracle", "gpu"], default="oracle")
     ap.add_argument("--variants", default="")
+    ap.add_argument("--matrix", action="store_true", help="cross-seed method matrix on the single-trait fixture "
+                    "(the reference's report: --seeds 100,110 --chain-length 5000 --burnin 1000 --freq 10)")
     ap.add_argument("--cv", type=int, default=0, help="K-fold cross-validation mode (the reference's report: 5 folds, "
                     "--chain-length 1500 --burnin 500 --freq 50, seeds 101,202)")
     ap.add_argument("--out", default="")
@@ -158,6 +230,8 @@ def main():
     factory = None
     if args.backend == "oracle":
         from oracle_backend import factory
+    if args.matrix:
+        return matrix_mode(args, factory)
     geno_df = pd.read_csv(os.path.join(args.data, "genotypes.csv"))
     ph = pd.read_csv(os.path.join(args.data, "phenotypes_mt.csv"))
     ann = pd.read_csv(os.path.join(args.data, "annotations_mt.csv"))
