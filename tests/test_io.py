@@ -120,3 +120,28 @@ def test_prepare_streaming_genotypes_files(tmp_path):
     g = jw.get_genotypes(prefix, 1.0)
     assert g.nObs == 57 and g.nMarkers == 40
     np.testing.assert_array_equal(g.packed, be["packed"])
+
+
+@pytest.mark.parametrize("kw", [dict(trail_nl=False), dict(pad_to=4096), dict(pad_to=4096, trail_nl=False), dict(spaces=True)])
+@pytest.mark.parametrize("n,p", [(1, 1), (3, 1), (5, 2), (4, 20000), (4097, 5)])
+def test_file_shapes_at_the_edges(tmp_path, kw, n, p):
+    """No trailing newline, a file that ends exactly on a page boundary (the mapping has no slack behind the last
+    field), padded fields, one row, one marker, a row count that is not a multiple of four."""
+    rng = np.random.default_rng(n * 31 + p)
+    codes = random_codes(rng, n, p, missing=0.05)
+    lines = ["ID," + ",".join(f"m{j + 1}" for j in range(p))]
+    for i in range(n):
+        lines.append(f"i{i}," + ",".join((" %d " % v if kw.get("spaces") else str(v)) for v in codes[i]))
+    end = "\n" if kw.get("trail_nl", True) else ""
+    txt = "\n".join(lines) + end
+    if kw.get("pad_to"):
+        need = (-len(txt)) % kw["pad_to"]
+        lines[-1] = "i" + "x" * need + lines[-1][1:]
+        txt = "\n".join(lines) + end
+        assert len(txt) % kw["pad_to"] == 0
+    path = str(tmp_path / "f.csv")
+    open(path, "w", newline="").write(txt)
+    obs, names, packed = _io.read_genotype_text(path)
+    c = codes.copy(); c[c == 9] = 3
+    assert len(obs) == n and len(names) == p
+    np.testing.assert_array_equal(packed, api._pack_codes(c.astype(np.uint8)))
