@@ -560,6 +560,15 @@ def main():
                                                                                    p_cpu=1500 if c["t"] == 1 else 600)
         except Exception as e:                                       # the CPU leg never takes the GPU line down
             line.setdefault("cpu_baseline", {"error": str(e)[:300]})
+        if world == 1 and not args.no_extras:
+            # SURVEY 8(f) N2, host only: genotype text file -> .jgb2 through libjwasio at the size the reference documents
+            # (10,000 x 5,000: prepare_streaming_genotypes 11.99 s, docs/src/manual/streaming_genotype_backend.md:178-182)
+            try:
+                out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "ingest_bench.py"),
+                                      "--reps", "2"], capture_output=True, text=True, timeout=180)
+                line["ingest"] = json.loads(out.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                line["ingest"] = {"error": str(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

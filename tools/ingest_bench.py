@@ -7,6 +7,7 @@ text file -> .jgb2 + side-cars through libjwasio (include/jwas_io.h).
 import argparse
 import json
 import os
+import shutil
 import sys
 import tempfile
 import time
@@ -48,6 +49,7 @@ def main():
     res["markers_after_qc"] = g.nMarkers
     res["reference_prepare_s_published"] = 11.99
     res["MB_per_s_all_cores"] = round(size_mb / res["parse_pack_s_all_cores"], 0)
+    shutil.rmtree(d, ignore_errors=True)
     print(json.dumps(res))
 
 
