@@ -20,6 +20,7 @@ NESTED RESULTS (same JSON line, so nothing hides behind the headline):
   schedules (N = 1) cfg2 exact / exact-block (nreps = b) / independent-block with b = 223 (fast_blocks=true);
             one outer iteration counts as b sweeps (JWAS.jl:312)
   configs   cfg3 (BayesR) and cfg4 (2-trait BayesC-pi) on N GPUs; cfg5 (BayesB 400,000 x 1,000,000) when N = 8
+  ingest    (N = 1) host only: genotype text file -> .jgb2 through libjwasio at 10,000 x 5,000 (tools/ingest_bench.py)
   strong    (N > 1) cfg2 itself, rows sharded over the N GPUs (fixed total work); same burn-in / warm-up / step counts
             as the main line, so its state_crc equals the N = 1 line's state_crc (bit-identical chains at any N)
 --impl reference : the reference algorithm on the host cores (oracle restatement, dense Float32 dot + axpy per
