@@ -124,7 +124,7 @@ int jwio_csv_pack(const char* path, int separator, int header, double missing_va
     int64_t bad_row = -1, bad_col = -1;
     volatile int bad_kind = 0;             /* 1 = field count, 2 = value */
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());
 #endif
     (void)n_threads;
     /* One group = four consecutive individuals = one byte of every column.  A thread takes a tile of G consecutive
@@ -230,7 +230,7 @@ int jwio_packed_counts(const uint8_t* packed, int64_t n_rows, int64_t n_markers,
     const int64_t full = n_rows / 4;
     const int tail = (int)(n_rows % 4);
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());
 #endif
     (void)n_threads;
 #pragma omp parallel for schedule(static)
@@ -264,7 +264,7 @@ int jwio_packed_rows(const uint8_t* packed, int64_t n_markers, int64_t stride, c
     if (out_stride < (n_out + 3) / 4) FAIL("jwio_packed_rows: out_stride_bytes below cld(n_out,4)");
     for (int64_t i = 0; i < n_out; ++i) if (rows[i] < 0 || (rows[i] >> 2) >= stride) FAIL("jwio_packed_rows: row index out of range");
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
+    omp_set_num_threads(n_threads > 0 ? n_threads : omp_get_num_procs());
 #endif
     (void)n_threads;
 #pragma omp parallel for schedule(static)
