@@ -189,8 +189,6 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
         error(f"method {method} is outside the GPU marker-sweep path (BayesA/B/C, BayesR, RR-BLUP and BayesL only).")
     if double_precision:
         error("double_precision=true is not supported with storage=:gpu.")
-    if not center:
-        error("storage=:gpu requires center=true.")
     if estimate_scale:
         error("estimate_scale=true is not supported with storage=:gpu.")
     if method == "BayesR" and not isinstance(Pi, (list, tuple, np.ndarray)) and Pi != 0.0:
@@ -250,7 +248,13 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
                       "estimatePi=true.")
         estimatePi = True
     # per-marker statistics from the call counts of the packed image (never from a dense matrix)
-    means, nn, s, sq = _stats_from_counts(_call_counts(packed, n), n)
+    counts = _call_counts(packed, n)
+    means, nn, s, sq = _stats_from_counts(counts, n)
+    centered = bool(center) if be is None else be["centered"]     # a prepared backend keeps its own flag (readgenotypes.jl:259-262)
+    if not centered and np.any(counts[:, 2] > 0):
+        # uncentred columns keep the column mean at missing calls (decode_marker!, streaming_genotypes.jl:993-994); the
+        # device image has no value for a missing call other than "the mean, i.e. 0 after centring"
+        error("center=false with missing genotypes is not supported with storage=:gpu.")
     af = (means / np.float32(2.0)).astype(np.float32)
     if quality_control:                     # readgenotypes.jl:388-399: MAF filter + fixed loci
         ss = sq.astype(np.float64) - (s.astype(np.float64) ** 2) / nn
@@ -265,7 +269,7 @@ def get_genotypes(file, G=False, *, method="BayesC", Pi=0.0, estimatePi=True, G_
     p = packed.shape[0]
     g = Genotypes(name=name, obsID=obs, markerID=mk, nObs=n, nMarkers=p, alleleFreq=af,
                   sum2pq=float((2.0 * af.astype(np.float64) * (1 - af.astype(np.float64))).sum()),
-                  centered=True, packed=np.ascontiguousarray(packed), marker_means=means, method=method,
+                  centered=centered, packed=np.ascontiguousarray(packed), marker_means=means, method=method,
                   estimatePi=bool(estimatePi), multi_trait_sampler=multi_trait_sampler,
                   starting_value=starting_value, nMarkersAll=int(n_all),
                   selected_marker_indices=np.asarray(selected, dtype=np.int32))
@@ -295,7 +299,8 @@ def prepare_streaming_genotypes(file, *, output_prefix=None, separator=",", head
     :520-660): <prefix>.jgb2 + .meta and the Float32/Int32/text side-cars, readable by JWAS.jl's
     storage=:stream and by get_genotypes(prefix) here."""
     g = get_genotypes(file, 1.0, separator=separator, header=header, quality_control=quality_control, MAF=MAF,
-                      missing_value=missing_value, center=center)
+                      missing_value=missing_value, center=True)
+    g.centered = bool(center)        # recorded in the manifest; the image itself holds codes either way
     prefix = os.path.abspath(output_prefix or (os.path.splitext(file)[0] + "_stream"))
     paths = {k: prefix + ext for k, ext in (("data_path", ".jgb2"), ("obs_path", ".obsid.txt"),
                                             ("marker_path", ".markerid.txt"), ("selected_path", ".selected.i32"),
@@ -306,18 +311,23 @@ def prepare_streaming_genotypes(file, *, output_prefix=None, separator=",", head
     open(paths["marker_path"], "w").write("".join(x + "\n" for x in g.markerID))
     g.selected_marker_indices.astype(np.int32).tofile(paths["selected_path"])        # raw (1-based) indices kept by QC
     g.marker_means.astype(np.float32).tofile(paths["mean_path"])
-    # xpRinvx of the centred columns, missing calls at the mean (streaming_genotypes.jl:283-285, 560-585), in closed
-    # form from the call counts: sum (x - m)^2 = (n1 + 4 n2) - 2 m (n1 + 2 n2) + m^2 * (observed calls)
+    # xpRinvx, missing calls at the mean (streaming_genotypes.jl:283-285, 560-585), in closed form from the call counts:
+    # centred   sum (x - m)^2 = (n1 + 4 n2) - 2 m (n1 + 2 n2) + m^2 * (observed calls)
+    # uncentred sum x^2       = (n1 + 4 n2) + m^2 * (missing calls)
     cnt = _call_counts(g.packed, g.nObs)
     m64 = g.marker_means.astype(np.float64)
     s64 = (cnt[:, 0] + 2 * cnt[:, 1]).astype(np.float64)
-    ((cnt[:, 0] + 4 * cnt[:, 1]) - 2 * m64 * s64 + m64 * m64 * (g.nObs - cnt[:, 2])).astype(np.float32).tofile(paths["xp_path"])
+    if g.centered:
+        xp = (cnt[:, 0] + 4 * cnt[:, 1]) - 2 * m64 * s64 + m64 * m64 * (g.nObs - cnt[:, 2])
+    else:
+        xp = (cnt[:, 0] + 4 * cnt[:, 1]) + m64 * m64 * cnt[:, 2]
+    xp.astype(np.float32).tofile(paths["xp_path"])
     g.alleleFreq.astype(np.float32).tofile(paths["afreq_path"])
     with open(prefix + ".meta", "w") as io:
         for k, v in [("version", "1")] + list(paths.items()) + [("nObs", g.nObs), ("nMarkers", g.nMarkers),
                                                                ("nMarkersAll", g.nMarkersAll),
                                                                ("stride_bytes", (g.nObs + 3) // 4),
-                                                               ("centered", 1), ("sum2pq", repr(g.sum2pq))]:
+                                                               ("centered", int(g.centered)), ("sum2pq", repr(g.sum2pq))]:
             io.write(f"{k}\t{v}\n")
     return prefix
 
@@ -534,6 +544,10 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
         if np.any(_call_counts(packed, n)[:, 2] == n):
             error("a marker has no observed genotype among the phenotyped individuals.")
         subset_means = np.asarray(Mi.marker_means, dtype=np.float32)
+    if not Mi.centered:
+        # center=false (no missing calls, checked in get_genotypes): the device centres on the means it is given, so
+        # means of zero make x_ij the code itself -- xpRinvx = sum of squared codes, EBV = M * alpha uncentred
+        subset_means = np.zeros(p, dtype=np.float32)
 
     if output_samples_frequency is None:                 # evaluated on the user's chain_length (JWAS.jl:168), before :312
         output_samples_frequency = chain_length // 1000 if chain_length > 1000 else 1
@@ -679,7 +693,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             ebv_ids = want_ids
             out_rows = np.array([pos[i] for i in want_ids], dtype=np.int64)
             out_packed = _select_rows(Mi.packed, Mi.nObs, out_rows)
-            out_means = np.asarray(Mi.marker_means, dtype=np.float32)
+            out_means = np.asarray(Mi.marker_means, dtype=np.float32) if Mi.centered else np.zeros(p, dtype=np.float32)
             if _backend_factory is not None:
                 ebv_backend = _backend_factory(out_packed, len(want_ids), t, np.array([0, p], dtype=np.int64), means=out_means)
             else:

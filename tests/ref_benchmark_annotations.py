@@ -87,7 +87,7 @@ def run_case(case, seed, data, args, factory, heldout=None):
     variant, method, annotated, multitrait, trait, sampler = case
     geno_df, ph_all, A, truth = data
     ph = ph_all if heldout is None else ph_all[~ph_all["ID"].isin(heldout)].reset_index(drop=True)
-    kw = dict(method=method, estimatePi=True, quality_control=False)
+    kw = dict(method=method, estimatePi=True, quality_control=False, center=not args.uncentred)
     if annotated:
         kw["annotations"] = A
     if multitrait:
@@ -172,7 +172,8 @@ def matrix_mode(args, factory):
                                                    ("Annotated_BayesR_dense", "BayesR", True, False)):
         runs = {}
         for seed in seeds:
-            kw = dict(method=method, estimatePi=True, quality_control=False, Pi=(0.0 if method == "BayesC" else list(ST_BAYESR_PI)))
+            kw = dict(method=method, estimatePi=True, quality_control=False, center=not args.uncentred,
+                      Pi=(0.0 if method == "BayesC" else list(ST_BAYESR_PI)))
             if annotated:
                 kw["annotations"] = A
             geno = jw.get_genotypes(geno_df, v * args.start_h2, **kw)
@@ -210,7 +211,7 @@ def matrix_mode(args, factory):
                 cells.append("—")
             else:
                 cells.append(f"{np.nanmin(x):.4f} / {np.nanmean(x):.4f} / {np.nanmax(x):.4f} ({'%.4f' % r if r is not None else 'NA'})")
-        lines.append(f"| `{variant}` | {len(g)} | " + " | ".join(cells) + " |")
+        lines.append(f"| `{variant}`{' (center=false)' if args.uncentred else ''} | {len(g)} | " + " | ".join(cells) + " |")
     table = "\n".join(lines)
     print(table)
     if args.out:
@@ -234,6 +235,7 @@ def main():
     ap.add_argument("--variants", default="")
     ap.add_argument("--matrix", action="store_true", help="cross-seed method matrix on the single-trait fixture "
                     "(the reference's report: --seeds 100,110 --chain-length 5000 --burnin 1000 --freq 10)")
+    ap.add_argument("--uncentred", action="store_true", help="center=false, as the reference's benchmark scripts pass it")
     ap.add_argument("--cv", type=int, default=0, help="K-fold cross-validation mode (the reference's report: 5 folds, "
                     "--chain-length 1500 --burnin 500 --freq 50, seeds 101,202)")
     ap.add_argument("--out", default="")

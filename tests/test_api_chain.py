@@ -326,3 +326,47 @@ def test_heritability_output_and_result_files(tmp_path):
     out = jw.runMCMC(model, ph, chain_length=20, seed=3, output_heritability=True, _backend_factory=factory)
     assert list(out["genetic_variance"]["Covariance"]) == ["y1"] and 0 < out["heritability"]["Estimate"][0] < 1
     assert not os.path.exists("results")                 # no folder given: nothing is written
+
+
+def test_uncentred_genotypes(tmp_path):
+    """center=false (readgenotypes.jl:384; decode_marker!, streaming_genotypes.jl:993-994): x_ij is the code itself,
+    xpRinvx the sum of squared codes, EBV = M * alpha without centring.  Supported when no call is missing (a missing
+    call would have to carry the column mean); the reference's own benchmark scripts run this way."""
+    codes, ids, ph = make_data(n=140, p=90, seed=51)
+    geno = jw.get_genotypes(codes, 1.0, method="BayesC", Pi=0.9, obsID=ids, center=False)
+    assert geno.centered is False
+    np.testing.assert_allclose(geno.marker_means, codes.mean(axis=0), rtol=1e-6)      # still the allele-frequency source
+    model = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+    seen = {}
+
+    def fac(packed, n, t, starts, means=None):
+        seen["b"] = factory(packed, n, t, starts, means=means)
+        return seen["b"]
+
+    out = jw.runMCMC(model, ph, chain_length=200, burnin=50, seed=4, _backend_factory=fac)
+    b = seen["b"]
+    assert np.all(b.means == 0.0)
+    np.testing.assert_allclose(b.xpx, (codes.astype(np.float64) ** 2).sum(axis=0), rtol=1e-6)
+    np.testing.assert_allclose(b.mul_alpha(0), codes @ b.alpha.astype(np.float64), rtol=1e-4, atol=1e-4)
+    # same model, centred: the intercept absorbs the column means, the marker effects agree statistically
+    g2 = jw.get_genotypes(codes, 1.0, method="BayesC", Pi=0.9, obsID=ids)
+    m2 = jw.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": g2})
+    out2 = jw.runMCMC(m2, ph, chain_length=200, burnin=50, seed=4, _backend_factory=factory)
+    e1 = out["EBV_y1"]["EBV"].to_numpy(float); e2 = out2["EBV_y1"]["EBV"].to_numpy(float)
+    assert np.corrcoef(e1, e2)[0, 1] > 0.97
+    assert abs((e1 - e1.mean()).std() / (e2 - e2.mean()).std() - 1) < 0.2
+    # missing calls cannot be represented uncentred
+    codes[3, 5] = 9
+    with pytest.raises(jw.JwasError, match="center=false with missing genotypes"):
+        jw.get_genotypes(codes, 1.0, obsID=ids, center=False)
+    # a prepared backend records its flag and xpRinvx follows it (test_streaming_prepare_lowmem.jl:22-66)
+    path = str(tmp_path / "g.csv")
+    df = pd.DataFrame(codes.astype(int), columns=[f"m{j + 1}" for j in range(90)]); df.insert(0, "ID", ids)
+    df.to_csv(path, index=False)
+    prefix = jw.prepare_streaming_genotypes(path, quality_control=False, center=False)
+    be = jw.load_streaming_backend(prefix)
+    assert be["centered"] is False
+    x = np.where(codes == 9, np.nan, codes)
+    m = np.nanmean(x, axis=0)
+    raw = np.where(np.isnan(x), m, x)
+    np.testing.assert_allclose(np.fromfile(prefix + ".xpRinvx.f32", np.float32), (raw * raw).sum(axis=0), rtol=2e-6)
