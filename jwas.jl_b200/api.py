@@ -515,9 +515,11 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
               "constraint=false.")
     if annotated and t > 1 and Mi.multi_trait_sampler == "II":
         error("annotated 2-trait BayesC runs sampler I with storage=:gpu (jwas_sweep_mt2 takes no per-marker prior).")
-    if t > 1 and Mi.method != "BayesC":
-        error("multi-trait analysis with storage=:gpu supports BayesC (sampler I) only.")
+    if t > 1 and Mi.method not in ("BayesC", "RR-BLUP"):
+        error("multi-trait analysis with storage=:gpu supports BayesC (samplers I / II) and RR-BLUP only.")
     mt_sampler = "I"
+    if Mi.multi_trait_sampler == "II" and Mi.method != "BayesC":       # build_MME.jl:104-107
+        error("multi_trait_sampler overrides are supported for BayesC only.")
     if t > 1 and Mi.multi_trait_sampler == "II":
         if t != 2:
             error("multi_trait_sampler=:II is supported for exactly 2 traits with storage=:gpu.")

@@ -214,7 +214,9 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                 ssum[k] += n * (mu[k] - new_mu)              # later traits see this trait's updated residual sum
                 mu[k] = new_mu
         # [2] marker effects
-        if method in ("BayesC", "BayesB", "BayesA"):
+        if method in ("BayesC", "BayesB", "BayesA") or (method == "RR-BLUP" and t > 1):
+            # multi-trait RR-BLUP: MTBayesC0! (MTBayesC0L.jl:6-58) is sampler I with all the prior mass on the all-traits
+            # state, megaBayesC0! (BayesC0L.jl:13-17) is megaBayesABC! with pi = 0 per trait -- api.runMCMC sets big_pi so
             if t == 1:
                 if ann is not None:
                     # bayesabc_pi_vector (BayesABC.jl:17-23): one common variance, marker-level pi_j

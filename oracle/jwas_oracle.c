@@ -410,6 +410,41 @@ static void inv_small(const double* A, int t, double* Ai) {
     for (int i = 0; i < t; ++i) for (int j = 0; j < t; ++j) Ai[i * t + j] = M[i][t + j];
 }
 
+/* MTBayesC0L.jl:11-58 MTBayesL! ; ngamma == 1 is MTBayesC0! (multi-trait RR-BLUP, :6-9).
+ * Every marker stays in the model: per marker the traits are drawn one after the other from their full conditionals
+ * given the other traits' current effects (:44-51), all axpys after the trait loop (:52-54).  R, G arrive as the
+ * Float32-valued matrices the reference holds; their inverses are taken in binary64 here (Julia: Float32 LU). */
+void jwo_mtbayesl_ref(const float* X, int64_t n, int64_t p, int t, const float* xpx,
+                      float* ycorr, float* alpha, const double* gamma, int64_t ngamma,
+                      const double* R, const double* G, const double* z) {
+    double Rinv[64], Ginv[64];
+    inv_small(R, t, Rinv);                                           /* :17 */
+    inv_small(G, t, Ginv);                                           /* :18 */
+    double Rhs[8], rr[8], Lhs[64];
+    float newa[8], olda[8];
+    for (int64_t m = 0; m < p; ++m) {
+        const float* x = X + m * n;
+        for (int k = 0; k < t; ++k) {                                /* :36-39 */
+            olda[k] = newa[k] = alpha[k * p + m];
+            Rhs[k] = (double)(jwo_sdot(x, ycorr + k * n, n, 1) + xpx[m] * olda[k]);
+        }
+        for (int k = 0; k < t; ++k) {                                /* :40 Rhs = invR0*Rhs */
+            rr[k] = 0.0;
+            for (int q = 0; q < t; ++q) rr[k] += Rinv[k * t + q] * Rhs[q];
+        }
+        const double g = ngamma > 1 ? gamma[m] : 1.0;
+        for (int q = 0; q < t * t; ++q) Lhs[q] = (double)xpx[m] * Rinv[q] + Ginv[q] / g;   /* :41, :27-30 */
+        for (int k = 0; k < t; ++k) {                                /* :42-51 */
+            double lhs = Lhs[k * t + k], ilhs = 1.0 / lhs, dot = 0.0;
+            for (int q = 0; q < t; ++q) dot += Lhs[k * t + q] * (double)newa[q];
+            double mu = ilhs * (rr[k] - dot) + (double)newa[k];
+            newa[k] = (float)(mu + z[k * p + m] * sqrt(ilhs));
+            alpha[k * p + m] = newa[k];
+        }
+        for (int k = 0; k < t; ++k) jwo_saxpy(olda[k] - newa[k], x, ycorr + k * n, n, 1);   /* :52-54 */
+    }
+}
+
 /* MTBayesABC.jl:57-127 _MTBayesABC_samplerI! */
 void jwo_mtbayesabc_I_ref(const float* X, int64_t n, int64_t p, int t, const float* xpx,
                           float* ycorr, float* alpha, float* beta, float* delta,

@@ -53,6 +53,11 @@ void jwo_bayesl_ref(const float* X, int64_t n, int64_t p, const float* xpx,
                     float* ycorr, float* alpha, const double* gamma, int64_t ngamma,
                     float vRes, float vEff, const double* z, int nthreads);
 
+/* MTBayesC0L.jl:11-58 MTBayesL! ; ngamma == 1 is MTBayesC0! (multi-trait RR-BLUP).  alpha (t, p), ycorr (t*n) */
+void jwo_mtbayesl_ref(const float* X, int64_t n, int64_t p, int t, const float* xpx,
+                      float* ycorr, float* alpha, const double* gamma, int64_t ngamma,
+                      const double* R, const double* G, const double* z);
+
 /* BayesABC.jl:24-80.  nthreads parallelises the n-long dot/axpy only (BLAS threads). */
 void jwo_bayesabc_ref(const float* X, int64_t n, int64_t p, const float* xpx,
                       float* ycorr, float* alpha, float* beta, float* delta,

@@ -155,6 +155,16 @@ def bayesl_ref(X, xpx, ycorr, alpha, gamma, v_res, v_eff, z, nthreads=1):
                          C.c_int64(len(g)), C.c_float(v_res), C.c_float(v_eff), _p(_f64(z)), C.c_int(nthreads))
 
 
+def mtbayesl_ref(X, xpx, ycorr, alpha, gamma, R, G, z):
+    """MTBayesL! (MTBayesC0L.jl:11-58); gamma = [1.0] is MTBayesC0! (multi-trait RR-BLUP).  alpha: (t, p) Float32."""
+    n, p = X.shape
+    t = alpha.shape[0]
+    g = _f64(gamma)
+    assert len(g) in (1, p) and alpha.dtype == np.float32 and alpha.flags.c_contiguous
+    lib().jwo_mtbayesl_ref(_p(X), C.c_int64(n), C.c_int64(p), C.c_int(t), _p(_f32(xpx)), _p(ycorr), _p(alpha), _p(g),
+                           C.c_int64(len(g)), _p(_f64(R)), _p(_f64(G)), _p(_f64(z)))
+
+
 def bayesabc_streaming_ref(packed, n, means, xpx, ycorr, alpha, beta, delta, vare, varEffects, pi, u, z):
     p, stride = packed.shape
     lib().jwo_bayesabc_streaming_ref(_p(packed), C.c_int64(n), C.c_int64(p), C.c_int64(stride),

@@ -87,9 +87,11 @@ def test_dense_methods_run_and_predict(method):
     assert out["residual variance"]["Estimate"][0] > 0
 
 
-def test_rrblup_multitrait_is_rejected():
+def test_bayesl_multitrait_is_rejected():
+    """Multi-trait BayesL (MTBayesL!, per-marker gamma) is outside this backend; multi-trait RR-BLUP is not
+    (test_multitrait_rrblup_chain)."""
     codes, ids, ph = make_data(ntraits=2, seed=4)
-    geno = jw.get_genotypes(codes, np.eye(2), method="RR-BLUP", obsID=ids, quality_control=False)
+    geno = jw.get_genotypes(codes, np.eye(2), method="BayesL", obsID=ids, quality_control=False)
     model = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.eye(2), genotypes={"geno": geno})
     with pytest.raises(jw.JwasError, match="multi-trait"):
         jw.runMCMC(model, ph, chain_length=4, seed=1, _backend_factory=factory)
@@ -370,3 +372,22 @@ def test_uncentred_genotypes(tmp_path):
     m = np.nanmean(x, axis=0)
     raw = np.where(np.isnan(x), m, x)
     np.testing.assert_allclose(np.fromfile(prefix + ".xpRinvx.f32", np.float32), (raw * raw).sum(axis=0), rtol=2e-6)
+
+
+@pytest.mark.parametrize("constraint", [False, True])
+def test_multitrait_rrblup_chain(constraint):
+    """Multi-trait RR-BLUP: MTBayesC0! / megaBayesC0! (MCMC_BayesianAlphabet.jl:259-268) through the sampler-I and
+    megaBayesABC sweeps with every marker in the model for every trait."""
+    codes, ids, ph = make_data(n=160, p=120, seed=61, ntraits=2)
+    G = np.array([[1.0, 0.0 if constraint else 0.4], [0.0 if constraint else 0.4, 1.0]])
+    geno = jw.get_genotypes(codes, G, method="RR-BLUP", obsID=ids, constraint=constraint)
+    model = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.eye(2), genotypes={"geno": geno}, constraint=constraint)
+    out = jw.runMCMC(model, ph, chain_length=120, burnin=30, seed=8, _backend_factory=factory)
+    me = out["marker effects geno"]
+    assert (me["Model_Frequency"] == 1.0).all() and "pi_geno" not in out
+    for tr in ("y1", "y2"):
+        assert np.corrcoef(out["EBV_" + tr]["EBV"].to_numpy(float), ph[tr].to_numpy(float))[0, 1] > 0.6
+    g2 = jw.get_genotypes(codes, G, method="RR-BLUP", obsID=ids, multi_trait_sampler="II")
+    m2 = jw.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.eye(2), genotypes={"geno": g2})
+    with pytest.raises(jw.JwasError, match="supported for BayesC only"):
+        jw.runMCMC(m2, ph, chain_length=5, _backend_factory=factory)

@@ -146,3 +146,43 @@ def test_contract_tracks_reference_with_marker_level_priors(oracle, probs, metho
         assert eq, f"{method}: delta forks from the reference arithmetic at sweep {it}"
         assert ra <= REL and ry <= REL, (method, it, ra, ry)
     assert np.count_nonzero(al) > 5
+
+
+def test_contract_tracks_reference_multitrait_rrblup(oracle, probs):
+    """MTBayesC0! = MTBayesL! with gamma = [1.0] (MTBayesC0L.jl:6-58): every marker in the model for every trait.  This
+    backend runs it as sampler I with all the prior mass on the all-traits state (constraint=false) and as
+    megaBayesABC! with pi = 0 per trait (constraint=true: megaBayesC0!, BayesC0L.jl:13-17 = single-trait BayesL! per
+    trait).  Effects and ycorr within 1e-5 relative of the reference arithmetic."""
+    prob = probs[2]
+    hyp = B.Hyper(prob, "MT1", 5)
+    G = hyp.G * 0.05                        # all 2,000 markers carry the variance: a smaller per-marker share
+    big = np.array([0.0, 0.0, 0.0, 1.0])
+    starts = np.array(list(range(0, P, 256)) + [P], dtype=np.int64)
+    y_r = prob.ycorr0.copy(); a_r = np.zeros((2, P), np.float32)
+    yc, al, be, de = prob.fresh_state(); de[:] = 1
+    zr = np.random.default_rng(4)
+    for it in range(1, 4):
+        u, z = zr.random(2 * P), zr.standard_normal(2 * P)
+        oracle.mtbayesl_ref(prob.X, prob.xpx, y_r, a_r, [1.0], hyp.R, G, z)
+        rc, _ = oracle.sweep_contract(prob.packed, N, prob.means, prob.xpx, starts, yc, al, be, de, method=oracle.METHOD_MT1,
+                                      nreps_mode=0, independent=False, R=hyp.R, G=G, bigPi=big, seed=1, it=it, u=u, z=z, lag=2)
+        assert rc == 0 and de.sum() == 2 * P
+        ra = np.abs(al.astype(np.float64) - a_r.reshape(-1)).max() / np.abs(a_r).max()
+        ry = np.abs(yc.astype(np.float64) - y_r).max() / np.abs(y_r).max()
+        assert ra <= REL and ry <= REL, (it, ra, ry)
+    # constraint=true: one single-trait BayesL! per trait with the diagonal variances
+    vare = np.diag(hyp.R).copy(); ve = np.diag(G).copy()
+    y_r = prob.ycorr0.copy(); a_r = np.zeros((2, P), np.float32)
+    yc, al, be, de = prob.fresh_state(); de[:] = 1
+    for it in range(1, 3):
+        u, z = zr.random(2 * P), zr.standard_normal(2 * P)
+        for k in range(2):
+            oracle.bayesl_ref(prob.X, prob.xpx, y_r[k * N:(k + 1) * N], a_r[k], [1.0], float(np.float32(vare[k])),
+                              float(np.float32(ve[k])), z[k * P:(k + 1) * P])
+        rc, _ = oracle.sweep_contract(prob.packed, N, prob.means, prob.xpx, starts, yc, al, be, de, method=oracle.METHOD_MEGA,
+                                      nreps_mode=0, independent=False, R=np.diag(vare), G=np.diag(ve), bigPi=np.zeros(2),
+                                      seed=1, it=it, u=u, z=z, lag=2)
+        assert rc == 0 and de.sum() == 2 * P
+        ra = np.abs(al.astype(np.float64) - a_r.reshape(-1)).max() / np.abs(a_r).max()
+        ry = np.abs(yc.astype(np.float64) - y_r).max() / np.abs(y_r).max()
+        assert ra <= REL and ry <= REL, ("mega", it, ra, ry)

@@ -7,7 +7,8 @@ profiles/r2_late_gpu_tests.log -- the file sorts last because the full suite was
    over the oracle backend.
 2. BayesL! / BayesC0! (BayesC0L.jl:19-47) reference arithmetic (`jwo_bayesl_ref`) against the CUDA library run the
    way this backend runs them (BayesC step, pi = 0, marker variances sigma^2 * gamma_j): 1e-5 relative.
-3. (added after that run, not yet executed on a B200) EBVs for genotyped individuals without phenotypes."""
+3. (added after that run, not yet executed on a B200) EBVs for genotyped individuals without phenotypes; multi-trait
+   RR-BLUP chains."""
 import numpy as np
 import pytest
 
@@ -153,3 +154,24 @@ def test_ebv_for_unphenotyped_individuals_matches_oracle_chain():
     for key in outs[0]:
         if not key.startswith("EBV_"):
             assert_same({key: outs[0][key]}, {key: outs[1][key]})
+
+
+@pytest.mark.parametrize("constraint", [False, True])
+def test_multitrait_rrblup_chain_matches_oracle_chain(constraint):
+    """MTBayesC0! / megaBayesC0! through sampler I with the prior mass on the all-traits state / megaBayesABC with pi = 0
+    (log prior of the other states = -inf on both sides).  Not yet run on a B200; the CPU bridge to `jwo_mtbayesl_ref`
+    is tests/test_ref_bridge.py::test_contract_tracks_reference_multitrait_rrblup."""
+    import jwas_b200
+    from oracle_backend import factory
+    from test_api_chain import make_data
+    from test_gpu_chain import assert_same
+    codes, ids, ph = make_data(n=220, p=260, seed=63, ntraits=2)
+    G = np.array([[1.0, 0.0 if constraint else 0.4], [0.0 if constraint else 0.4, 1.0]])
+    outs = []
+    for bf in (None, factory):
+        geno = jwas_b200.get_genotypes(codes, G, method="RR-BLUP", obsID=ids, constraint=constraint)
+        model = jwas_b200.build_model("y1 = intercept + geno\ny2 = intercept + geno", np.eye(2), genotypes={"geno": geno},
+                                      constraint=constraint)
+        outs.append(jwas_b200.runMCMC(model, ph, chain_length=16, burnin=4, seed=77, _backend_factory=bf))
+    assert_same(outs[0], outs[1])
+    assert (outs[0]["marker effects geno"]["Model_Frequency"] == 1.0).all()
