@@ -8,7 +8,8 @@ backend seam is the one the reference itself uses for `storage=:stream`
 genotypes 2-bit packed in HBM behind a libjwasb200 handle and every sweep runs there.
 
 Only what the sweep needs is implemented: `y = intercept + <genotypes>` models (single- or
-multi-trait), BayesA/B/C, BayesR, RR-BLUP and BayesL (single-trait), multi-trait BayesC samplers I / II, and the
+multi-trait), BayesA/B/C, BayesR and BayesL (single-trait), RR-BLUP (single- and multi-trait), multi-trait BayesC
+samplers I / II, and the
 annotation-aware priors of BayesC / BayesR / 2-trait BayesC (annotations.py).
 Everything else the reference offers (pedigree, covariates, random terms, SEM, RRM, categorical traits,
 GBLUP) is outside this backend's scope and raises JwasError with a message saying so.
