@@ -486,7 +486,8 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
 
     output_folder: the reference always creates a folder ("results", "results1", ... JWAS.jl:255-262) and writes every
     output table there as <key with _ for spaces>.txt (JWAS.jl:479-482).  Here that happens when output_folder is
-    given; the default (None) writes nothing but requested sample files (into "results")."""
+    given -- together with the MCMC sample files of the hyper-parameters, EBVs, genetic variance and heritability
+    (output.jl:318-515); the default (None) writes nothing but requested marker-effect sample files (into "results")."""
     write_results = output_folder is not None
     if output_folder is None:
         output_folder = "results"
@@ -727,6 +728,53 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             f.write(",".join(str(m) for m in Mi.markerID) + "\n")
             sample_files.append(f); model.sample_files[tr] = path
 
+    # hyper-parameter and EBV sample files (output_MCMC_samples_setup / output_MCMC_samples, output.jl:318-515), written
+    # when an output folder was asked for: residual variance, marker effect variances, pi, EBVs, genetic variance and
+    # heritability.  (BayesB's per-marker variances stay on the device and are not written.)
+    hyper_files = {}
+    if write_results:
+        def _open(name, header=None):
+            f = open(os.path.join(output_folder, f"MCMC_samples_{name}.txt"), "w")
+            if header is not None:
+                f.write(",".join(header) + "\n")
+            hyper_files[name] = f
+        pairs = [f"{a}_{b}" for a in model.lhsVec for b in model.lhsVec]
+        _open("residual_variance", list(model.lhsVec) if (t == 1 or model.R.constraint) else pairs)
+        if Mi.method not in ("BayesB", "BayesA"):
+            _open("marker_effects_variances_" + Mi.name)
+        if Mi.estimatePi:
+            _open("pi_" + Mi.name)
+        if outputEBV:
+            for tr in model.lhsVec:
+                _open("EBV_" + tr, list(ebv_ids))
+            if output_heritability:
+                _open("genetic_variance", pairs if t > 1 else list(model.lhsVec))
+                _open("heritability", list(model.lhsVec))
+
+    def _row(x):
+        return ",".join(repr(float(v)) for v in np.atleast_1d(np.asarray(x, dtype=np.float64)).reshape(-1)) + "\n"
+
+    def hyper_sink(smp):
+        ve = np.atleast_2d(smp["vare"])
+        hyper_files["residual_variance"].write(_row(np.diag(ve) if (t > 1 and model.R.constraint) else ve))
+        f = hyper_files.get("marker_effects_variances_" + Mi.name)
+        if f is not None and smp["vara"] is not None:
+            for line in np.atleast_2d(smp["vara"]):          # a scalar, or the t x t matrix row by row (writedlm)
+                f.write(_row(line))
+        f = hyper_files.get("pi_" + Mi.name)
+        if f is not None and smp["pi"] is not None:
+            pv = np.atleast_1d(smp["pi"])
+            for v in pv:                                      # one value per line, a blank line after a vector
+                f.write(repr(float(v)) + "\n")
+            if len(pv) > 1:
+                f.write("\n")
+        if smp["ebv"] is not None:
+            for k, tr in enumerate(model.lhsVec):
+                hyper_files["EBV_" + tr].write(_row(smp["ebv"][k]))
+        if smp["gvar"] is not None:
+            hyper_files["genetic_variance"].write(_row(smp["gvar"]))
+            hyper_files["heritability"].write(_row(smp["h2"]))
+
     def sink(alpha):
         for k in range(t):
             sample_files[k].write(",".join(repr(float(x)) for x in np.asarray(alpha[k * p:(k + 1) * p], dtype=np.float32)) + "\n")
@@ -745,7 +793,9 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
                          scale_R=model.R.scale if t > 1 else None, mu0=mu0, want_ebv=outputEBV, mt_sampler=mt_sampler,
                          constraint_G=bool(t > 1 and Mi.G.constraint), constraint_R=bool(t > 1 and model.R.constraint),
                          annotations=(Mi.annotations if annotated else None), ebv_backend=ebv_backend,
-                         want_heritability=bool(output_heritability))
+                         want_heritability=bool(output_heritability), hyper_sink=(hyper_sink if write_results else None))
+    for f in hyper_files.values():
+        f.close()
 
     # ---- output dictionary (output.jl:108-212)
     ma, ma2, md = backend.get_means()

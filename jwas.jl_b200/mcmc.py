@@ -142,7 +142,7 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
               estimate_pi=True, estimate_variance=True, estimate_vare=True, block_size=1,
               R=None, G=None, big_pi=None, scale_G=None, scale_R=None, sample_intercept=True,
               mu0=None, iter0=0, want_ebv=False, mt_sampler="I", constraint_G=False, constraint_R=False,
-              sample_sink=None, annotations=None, ebv_backend=None, want_heritability=False):
+              sample_sink=None, annotations=None, ebv_backend=None, want_heritability=False, hyper_sink=None):
     """One MCMC run over an already-initialised backend (ycorr = y - mu0 - M*alpha on entry).
 
     Mirrors MCMC_BayesianAlphabet.jl:184-421 for `y = intercept + markers`:
@@ -349,6 +349,13 @@ def run_chain(backend, *, n, p, ntraits, method, schedule, chain_length, burnin,
                     vres = np.diag(np.atleast_2d(vare if t == 1 else R))
                     gvar_samples.append(gv.reshape(-1) if t > 1 else gv[0, 0])
                     h2_samples.append(np.diag(gv) / (np.diag(gv) + vres))
+            if hyper_sink is not None:      # output_MCMC_samples (output.jl:444-515): this saved sample's hyper-parameters
+                hyper_sink(dict(vare=(vare if t == 1 else R),
+                                vara=(None if method in ("BayesB", "BayesA") else (var_effect if t == 1 else G)),
+                                pi=((pi if t == 1 else big_pi) if estimate_pi else None),
+                                ebv=(e if want_ebv else None),
+                                gvar=(gvar_samples[-1] if want_ebv and want_heritability else None),
+                                h2=(h2_samples[-1] if want_ebv and want_heritability else None)))
     if gvar_samples:                # means and standard deviations over the saved samples (output.jl:201-207)
         g_, h_ = np.array(gvar_samples, dtype=np.float64), np.array(h2_samples, dtype=np.float64)
         dd = 1 if len(g_) > 1 else 0

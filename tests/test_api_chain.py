@@ -318,7 +318,24 @@ def test_heritability_output_and_result_files(tmp_path):
     assert np.all(np.abs(h2["Estimate"].to_numpy() - gv["Estimate"].to_numpy()[[0, 3]] / (gv["Estimate"].to_numpy()[[0, 3]] + rv)) < 0.15)
     assert os.listdir(folder) == []
     written = sorted(os.listdir(folder + "1"))
-    assert written == sorted(k.replace(" ", "_") + ".txt" for k in out)
+    samples = ["MCMC_samples_" + x + ".txt" for x in ("residual_variance", "marker_effects_variances_geno", "pi_geno", "EBV_y1",
+                                                         "EBV_y2", "genetic_variance", "heritability")]
+    assert written == sorted([k.replace(" ", "_") + ".txt" for k in out] + samples)
+    # sample files (output.jl:318-515): header + one row per saved sample; their means are the tables of the output
+    ns = (40 - 10) // 2
+    ebv_s = pd.read_csv(os.path.join(folder + "1", "MCMC_samples_EBV_y1.txt"))
+    assert list(ebv_s.columns) == ids and len(ebv_s) == ns
+    np.testing.assert_allclose(ebv_s.mean(axis=0).to_numpy(), out["EBV_y1"]["EBV"].to_numpy(float), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(ebv_s.var(axis=0, ddof=1).to_numpy(), out["EBV_y1"]["PEV"].to_numpy(float), rtol=1e-5, atol=1e-9)
+    h2_s = pd.read_csv(os.path.join(folder + "1", "MCMC_samples_heritability.txt"))
+    assert list(h2_s.columns) == ["y1", "y2"] and len(h2_s) == ns
+    np.testing.assert_allclose(h2_s.mean(axis=0).to_numpy(), h2["Estimate"].to_numpy(float), rtol=1e-9)
+    rv_s = pd.read_csv(os.path.join(folder + "1", "MCMC_samples_residual_variance.txt"))
+    assert list(rv_s.columns) == ["y1_y1", "y1_y2", "y2_y1", "y2_y2"] and len(rv_s) == ns
+    np.testing.assert_allclose(rv_s.mean(axis=0).to_numpy(), out["residual variance"]["Estimate"].to_numpy(float), rtol=1e-6)
+    lines = open(os.path.join(folder + "1", "MCMC_samples_pi_geno.txt")).read().split("\n")
+    assert len(lines) == ns * 5 + 1 and lines[4] == ""              # four joint-state probabilities, then a blank line
+    assert len(open(os.path.join(folder + "1", "MCMC_samples_marker_effects_variances_geno.txt")).readlines()) == 2 * ns
     back = pd.read_csv(os.path.join(folder + "1", "marker_effects_geno.txt"))
     assert list(back.columns) == ["Trait", "Marker_ID", "Estimate", "SD", "Model_Frequency"] and len(back) == 2 * geno.nMarkers
     # single trait: scalar tables
