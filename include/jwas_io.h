@@ -44,6 +44,22 @@ int jwio_packed_select(uint8_t* packed, int64_t n_markers, int64_t stride_bytes,
 int jwio_packed_rows(const uint8_t* packed, int64_t n_markers, int64_t stride_bytes, const int64_t* rows, int64_t n_out,
                      uint8_t* out, int64_t out_stride_bytes, int n_threads);
 
+/* ---- annotation prior update (MCMC/annotation_updates.jl): the O(markers x annotations) part, threaded ----------
+ * One binary probit step (:43-123) on the markers listed in active[0..n_active) (NULL: all m markers).
+ * Xc: m x k design matrix, COLUMN-major (first column = intercept).  response (m): the step's indicator (non-zero = 1).
+ * mu (m): linear predictor on entry (read at the active markers), Xc * coeffs for ALL markers on exit.
+ * liability (m): written at the active markers.  coeffs (k): updated in place.  uniforms (n_active) and normals (k)
+ * come from the host's generator (one uniform per truncated-normal draw, one normal per coefficient, in this order).
+ * Deterministic for any thread count (fixed chunks, partial sums added in chunk order). */
+int jwann_probit_step(int64_t m, int k, const double* Xc, const int64_t* active, int64_t n_active,
+                      const int32_t* response, double* coeffs, double prior_var,
+                      const double* uniforms, const double* normals,
+                      double* liability, double* mu, int n_threads);
+/* prob[j] = clamp(Phi(mu[j]), eps, 1 - eps), or clamp(1 - Phi(mu[j]), ...) with complement (:177-189, :260-304) */
+int jwann_probit_probability(const double* mu, int64_t m, int complement, double* prob, int n_threads);
+double jwann_phi_inv(double p);
+double jwann_phi_cdf(double x);
+
 #ifdef __cplusplus
 }
 #endif

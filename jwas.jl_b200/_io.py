@@ -26,6 +26,8 @@ def lib():
         L.jwio_packed_counts.argtypes = [vp, i64, i64, i64, vp, i32]
         L.jwio_packed_select.argtypes = [vp, i64, i64, vp, i64]
         L.jwio_packed_rows.argtypes = [vp, i64, i64, vp, i64, vp, i64, i32]
+        L.jwann_probit_step.argtypes = [i64, i32, vp, vp, i64, vp, vp, C.c_double, vp, vp, vp, vp, i32]
+        L.jwann_probit_probability.argtypes = [vp, i64, i32, vp, i32]
         _lib = L
     return _lib
 
@@ -88,4 +90,33 @@ def packed_rows(packed, rows, nthreads=0):
     p, stride = packed.shape
     out = np.empty((p, (len(rows) + 3) // 4), np.uint8)
     _check(lib().jwio_packed_rows(_p(packed), p, stride, _p(rows), len(rows), _p(out), out.shape[1], int(nthreads)))
+    return out
+
+
+def probit_step(Xc, active, response, coeffs, prior_var, uniforms, normals, liability, mu, nthreads=0):
+    """jwann_probit_step (include/jwas_io.h): one binary probit step of the annotation update.  Xc (m, k) with contiguous
+    columns; active: int64 indices or None; response int32 (m); coeffs (k), liability (m), mu (m) float64, updated in
+    place."""
+    m, k = Xc.shape
+    assert Xc.flags.f_contiguous and Xc.dtype == np.float64
+    for a in (coeffs, liability, mu):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+    assert response.dtype == np.int32 and response.flags.c_contiguous and len(response) == m
+    act = None if active is None else np.ascontiguousarray(active, dtype=np.int64)
+    n_act = m if act is None else len(act)
+    u = np.ascontiguousarray(uniforms, dtype=np.float64); z = np.ascontiguousarray(normals, dtype=np.float64)
+    assert len(u) >= n_act and len(z) >= k
+    rc = lib().jwann_probit_step(m, k, _p(Xc), None if act is None else _p(act), n_act, _p(response), _p(coeffs),
+                                 float(prior_var), _p(u), _p(z), _p(liability), _p(mu), int(nthreads))
+    if rc:
+        raise JwasError("jwann_probit_step failed (code %d)" % rc)
+
+
+def probit_probability(mu, complement=False, nthreads=0):
+    """clamp(Phi(mu)) (or of 1 - Phi(mu)) to [eps, 1 - eps]."""
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    out = np.empty_like(mu)
+    rc = lib().jwann_probit_probability(_p(mu), mu.size, int(bool(complement)), _p(out), int(nthreads))
+    if rc:
+        raise JwasError("jwann_probit_probability failed (code %d)" % rc)
     return out

@@ -21,6 +21,19 @@ from scipy.special import ndtr, ndtri
 
 EPS = float(np.finfo(np.float64).eps)
 
+# The O(markers x annotations) part of the update runs in libjwasio (jwann_probit_step, threaded C) when the library is
+# built; the numpy statements below are the same algorithm and the fall-back.  Both consume the host generator in the
+# same order (the uniforms of a step, then one normal per coefficient, then the chi-square), so a chain does not depend
+# on which one runs beyond the last bits of the special functions.
+USE_NATIVE = True
+
+
+def _native():
+    if not USE_NATIVE:
+        return None
+    from . import _io
+    return _io if _io.available() else None
+
 # joint states of 2-trait BayesC in the column order of snp_pi (annotation_setup.jl:15): 00, 10, 01, 11 --
 # which is also the sweep's index sum(delta_k << k), so snp_pi is passed to jwas_sweep_mt1 as it is
 MT_STATES = ((0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (1.0, 1.0))
@@ -108,6 +121,7 @@ class MarkerAnnotations:
         self.upper_bound = np.full(shape_l, np.inf)
         self.snp_pi = False if snp_pi is None else np.array(snp_pi, dtype=np.float64)
         self.col_ss = (X * X).sum(axis=0)            # x_k'x_k of every column (the diagonal of lhs = X'X)
+        self.design_cols = np.asfortranarray(X)      # the same matrix with contiguous columns (coordinate updates)
 
     def accumulate(self, nsamples):                  # output.jl:597-600
         self.mean_coefficients += (self.coefficients - self.mean_coefficients) / nsamples
@@ -228,6 +242,8 @@ def gibbs_update_binary_probit_annotation_coefficients(rng, coeffs, X, latent_re
     ahat = inv_lhs * (latent_residual.sum() + m * old)
     coeffs[0] = rng.normal() * math.sqrt(inv_lhs) + ahat
     latent_residual += old - coeffs[0]
+    if not X.flags.f_contiguous and X.shape[1] > 1:
+        X = np.asfortranarray(X)                     # contiguous columns: the dots below run at memory speed
     for k in range(1, X.shape[1]):
         old = coeffs[k]
         xk = X[:, k]
@@ -247,11 +263,29 @@ def clamp_prob(x):
     return np.clip(x, EPS, 1.0 - EPS)
 
 
+def _bounds(response):
+    one = np.asarray(response) != 0
+    return np.where(one, 0.0, -np.inf), np.where(one, np.inf, 0.0)
+
+
 def update_bayesc_binary_priors(rng, ann, delta):
     """annotation_updates.jl:177-189.  Returns the per-marker pi (probability of a ZERO effect)."""
+    nat = _native()
+    if nat is not None:
+        m, k = ann.design_cols.shape
+        u = rng.uniform(m)
+        zn = np.array([rng.normal() for _ in range(k)])
+        ann.lower_bound, ann.upper_bound = _bounds(delta)
+        ann.liability = np.ascontiguousarray(ann.liability, dtype=np.float64)
+        ann.mu = np.ascontiguousarray(ann.mu, dtype=np.float64)
+        nat.probit_step(ann.design_cols, None, np.ascontiguousarray(delta, dtype=np.int32), ann.coefficients, ann.variance,
+                        u, zn, ann.liability, ann.mu)
+        if k > 1:
+            ann.variance = sample_annotation_effect_variance(rng, ann.coefficients)
+        return nat.probit_probability(ann.mu, complement=True)
     ann.liability, ann.lower_bound, ann.upper_bound = sample_binary_annotation_liabilities(rng, ann.mu, delta)
     resid = ann.liability - ann.mu
-    gibbs_update_binary_probit_annotation_coefficients(rng, ann.coefficients, ann.design_matrix, resid,
+    gibbs_update_binary_probit_annotation_coefficients(rng, ann.coefficients, ann.design_cols, resid,
                                                        ann.variance, ann.col_ss)
     ann.mu = ann.design_matrix @ ann.coefficients
     if len(ann.coefficients) > 1:
@@ -267,6 +301,24 @@ def sample_nested_annotation_probit_step(rng, ann, step, response, active):
     ann.lower_bound[:, step] = -np.inf
     ann.upper_bound[:, step] = np.inf
     if len(active) == 0:
+        return
+    nat = _native()
+    if nat is not None:
+        m, k = X.shape
+        u = rng.uniform(len(active))
+        zn = np.array([rng.normal() for _ in range(k)])
+        resp = np.ascontiguousarray(response, dtype=np.int32)
+        lo, up = _bounds(resp[active])
+        ann.lower_bound[active, step] = lo
+        ann.upper_bound[active, step] = up
+        liab = np.ascontiguousarray(ann.liability[:, step]); mu = np.ascontiguousarray(ann.mu[:, step])
+        nat.probit_step(ann.design_cols, (None if len(active) == m else active), resp, coeffs, ann.variance[step], u, zn,
+                        liab, mu)
+        ann.liability[:, step] = liab
+        if k > 1:
+            ann.variance[step] = sample_annotation_effect_variance(rng, coeffs)
+        ann.coefficients[:, step] = coeffs
+        ann.mu[:, step] = mu
         return
     Xa = X[active]
     mu_a = ann.mu[active, step]
@@ -289,9 +341,16 @@ def bayesr_nested_step_indicators(delta):
     return z, [np.arange(len(delta)), np.flatnonzero(z[0]), np.flatnonzero(z[1])]
 
 
+def _step_probabilities(mu):
+    nat = _native()
+    if nat is not None:
+        return nat.probit_probability(mu).reshape(mu.shape)
+    return clamp_prob(ndtr(mu))
+
+
 def rebuild_bayesr_nested_priors(ann):
     """annotation_updates.jl:260-267."""
-    pr = clamp_prob(ndtr(ann.mu))
+    pr = _step_probabilities(ann.mu)
     ann.snp_pi[:, 0] = 1.0 - pr[:, 0]
     ann.snp_pi[:, 1] = pr[:, 0] * (1.0 - pr[:, 1])
     ann.snp_pi[:, 2] = pr[:, 0] * pr[:, 1] * (1.0 - pr[:, 2])
@@ -308,7 +367,7 @@ def bayesc_mt_tree_step_indicators(d1, d2):
 
 def rebuild_bayesc_mt_tree_priors(ann):
     """annotation_updates.jl:294-304."""
-    pr = clamp_prob(ndtr(ann.mu))
+    pr = _step_probabilities(ann.mu)
     p1, p2, p3 = pr[:, 0], pr[:, 1], pr[:, 2]
     ann.snp_pi[:, 0] = 1.0 - p1
     ann.snp_pi[:, 1] = p1 * (1.0 - p2) * p3

@@ -17,6 +17,7 @@ SRC = os.path.join(HERE, "csrc", "jwas_b200.cu")
 
 IO_SO = os.path.join(HERE, "libjwasio.so")
 IO_SRC = os.path.join(HERE, "csrc", "io", "jw_io.c")
+IO_SRCS = [IO_SRC, os.path.join(HERE, "csrc", "io", "jw_annot.c")]
 
 
 def _newest_source_mtime():
@@ -31,11 +32,11 @@ def _newest_source_mtime():
 def build_io(force=False):
     """libjwasio.so: plain C + OpenMP, no CUDA."""
     hdr = os.path.join(os.path.dirname(HERE), "include", "jwas_io.h")
-    if not force and os.path.exists(IO_SO) and os.path.getmtime(IO_SO) >= max(os.path.getmtime(IO_SRC), os.path.getmtime(hdr)):
+    if not force and os.path.exists(IO_SO) and os.path.getmtime(IO_SO) >= max([os.path.getmtime(f) for f in IO_SRCS + [hdr]]):
         return IO_SO
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.check_call([gcc, "-O3", "-march=x86-64-v3", "-fopenmp", "-shared", "-fPIC", "-Wall", "-Wextra",
-                           "-o", IO_SO, IO_SRC, "-lm"])
+                           "-o", IO_SO] + IO_SRCS + ["-lm"])
     return IO_SO
 
 

@@ -121,7 +121,24 @@ def test_two_trait_startup_from_joint_pi_and_rejections():
 
 
 # ---------------------------------------------------------------------------------- the sampler
-def test_update_is_the_documented_composition_standard_probit():
+@pytest.fixture(params=[False, True], ids=["numpy", "native"])
+def native(request):
+    """The update runs in libjwasio (jwann_probit_step) when built, else in numpy: both paths, same expectations (the
+    native special functions differ from scipy's in the last bits: equal to 1e-12)."""
+    old = an.USE_NATIVE
+    an.USE_NATIVE = request.param
+    yield request.param
+    an.USE_NATIVE = old
+
+
+def same(actual, desired, native):
+    if native:
+        np.testing.assert_allclose(actual, desired, rtol=1e-12, atol=1e-13)
+    else:
+        np.testing.assert_array_equal(actual, desired)
+
+
+def test_update_is_the_documented_composition_standard_probit(native):
     """annotation sampler uses the standard probit latent variance (test_annotated_bayesc.jl:336-375)."""
     ann = an.MarkerAnnotations(np.ones((1, 1)), variance=4.0)
     ann.mu[0] = 0.3
@@ -131,14 +148,14 @@ def test_update_is_the_documented_composition_standard_probit():
     assert lo[0] == 0.0 and up[0] == np.inf and liab[0] >= 0.0
     coeffs = np.zeros(1); resid = liab - 0.3
     an.gibbs_update_binary_probit_annotation_coefficients(rng, coeffs, np.ones((1, 1)), resid, 4.0)
-    np.testing.assert_array_equal(ann.liability, liab)
-    np.testing.assert_array_equal(ann.coefficients, coeffs)
-    np.testing.assert_array_equal(ann.mu, coeffs)
-    np.testing.assert_array_equal(prior, np.clip(1.0 - ndtr(coeffs), an.EPS, 1 - an.EPS))
+    same(ann.liability, liab, native)
+    same(ann.coefficients, coeffs, native)
+    same(ann.mu, coeffs, native)
+    same(prior, np.clip(1.0 - ndtr(coeffs), an.EPS, 1 - an.EPS), native)
     assert prior is summary and ann.variance == 4.0            # intercept only: slope variance untouched
 
 
-def test_update_coordinate_probit_with_shrunken_slopes():
+def test_update_coordinate_probit_with_shrunken_slopes(native):
     """test_annotated_bayesc.jl:377-433."""
     X = np.array([[1.0, 0.0], [1.0, 1.0], [1.0, 2.0]])
     delta = np.array([0, 1, 0])
@@ -161,9 +178,9 @@ def test_update_coordinate_probit_with_shrunken_slopes():
     inv = 1.0 / (xx + 1 / 0.25)
     c1 = z1 * math.sqrt(inv) + inv * (X[:, 1] @ resid + xx * coeffs[1])
     var = (c1 ** 2 + 2.0) / rng.chisq(3.0)
-    np.testing.assert_array_equal(ann.liability, liab)
-    np.testing.assert_allclose(ann.coefficients, [c0, c1], rtol=0, atol=1e-15)
-    assert ann.variance == pytest.approx(var, rel=1e-14)
+    same(ann.liability, liab, native)
+    np.testing.assert_allclose(ann.coefficients, [c0, c1], rtol=0, atol=(1e-12 if native else 1e-15))
+    assert ann.variance == pytest.approx(var, rel=(1e-11 if native else 1e-14))
     np.testing.assert_allclose(ann.mu, X @ ann.coefficients)
     np.testing.assert_allclose(prior, np.clip(1 - ndtr(ann.mu), an.EPS, 1 - an.EPS))
     np.testing.assert_array_equal(ann.lower_bound, lo); np.testing.assert_array_equal(ann.upper_bound, up)
@@ -185,7 +202,7 @@ def test_truncated_liabilities_have_the_right_law():
     assert np.isfinite(l).all() and l[0] >= 0 and l[1] <= 0
 
 
-def test_probit_gibbs_recovers_the_generating_coefficients():
+def test_probit_gibbs_recovers_the_generating_coefficients(native):
     rng0 = np.random.default_rng(3)
     m = 20000
     A = np.column_stack([rng0.integers(0, 2, m).astype(float), rng0.normal(size=m)])
@@ -225,7 +242,7 @@ def test_nested_indicators_and_prior_rebuild():
     np.testing.assert_allclose(ann.snp_pi[0], [0.5, 0.5 * (1 - pr[0, 1]) * pr[0, 2], 0.5 * (1 - pr[0, 1]) * (1 - pr[0, 2]), 0.5 * pr[0, 1]])
 
 
-def test_nested_step_only_touches_active_markers():
+def test_nested_step_only_touches_active_markers(native):
     X = np.column_stack([np.ones(6), [0.0, 1.0, 0.0, 1.0, 0.0, 1.0]])
     ann = an.MarkerAnnotations(X, nsteps=3, nclasses=4, coefficients=np.zeros((2, 3)), snp_pi=np.full((6, 4), 0.25))
     delta = np.array([1, 2, 3, 4, 1, 4])
@@ -370,3 +387,41 @@ def test_packed_backend_keeps_the_raw_marker_mapping_for_annotations(tmp_path):
     # one of the two entries alone is an inconsistent manifest
     open(meta, "a").write("nMarkersAll\t3\n")
     assert "inconsistent" in _err(lambda: jw.load_streaming_backend(prefix))
+
+
+@pytest.mark.parametrize("kind", ["BayesC", "BayesR", "BayesC2"])
+def test_native_update_equals_numpy_update(kind):
+    """jwann_probit_step (threaded C, include/jwas_io.h) against the numpy statements of annotations.py on the same
+    generator: several updates in a row, coefficients / liabilities / priors equal to the last bits of the special
+    functions, for one thread and for all of them."""
+    rng0 = np.random.default_rng(9)
+    m = 30011
+    X = np.column_stack([np.ones(m), (rng0.random(m) < 0.15).astype(float), rng0.normal(size=m), rng0.random(m)])
+    outs = []
+    for use in (False, True):
+        old = an.USE_NATIVE
+        an.USE_NATIVE = use
+        try:
+            if kind == "BayesC":
+                ann = an.MarkerAnnotations(X); ann.coefficients[0] = -1.0; ann.mu[:] = X @ ann.coefficients
+            else:
+                ann = an.MarkerAnnotations(X, nsteps=3, nclasses=4, coefficients=np.zeros((4, 3)), snp_pi=np.full((m, 4), 0.25))
+            rng = HostRng([3, 4])
+            r2 = np.random.default_rng(5)
+            for it in range(4):
+                if kind == "BayesC":
+                    delta = (r2.random(m) < 0.2).astype(np.int32)
+                    prior, _ = an.update_marker_annotation_priors(rng, ann, "BayesC", 1, delta)
+                elif kind == "BayesR":
+                    delta = r2.choice([1, 2, 3, 4], size=m, p=[0.8, 0.1, 0.06, 0.04]).astype(np.int32)
+                    prior, _ = an.update_marker_annotation_priors(rng, ann, "BayesR", 1, delta)
+                else:
+                    delta = (r2.random((2, m)) < 0.15).astype(np.int32)
+                    prior, _ = an.update_marker_annotation_priors(rng, ann, "BayesC", 2, delta)
+            outs.append((ann.coefficients.copy(), np.array(ann.variance, dtype=float), ann.liability.copy(), ann.mu.copy(),
+                         np.array(prior).copy(), rng.normal()))
+        finally:
+            an.USE_NATIVE = old
+    for a, b in zip(*outs):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-10)
+    assert outs[0][5] == outs[1][5]                     # both paths consumed the generator identically
