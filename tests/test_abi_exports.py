@@ -34,8 +34,8 @@ def test_io_library_exports_every_declared_symbol():
     """include/jwas_io.h <-> libjwasio.so (host C, the genotype-file side of the path)."""
     from jwas_b200 import _io
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "jwas_io.h")).read(), flags=re.S)
-    syms = sorted(set(re.findall(r"\b(jwio_[a-z0-9_]+)\s*\(", src)))
-    assert len(syms) >= 6
+    syms = sorted(set(re.findall(r"\b(jw(?:io|ann)_[a-z0-9_]+)\s*\(", src)))
+    assert len(syms) >= 10 and "jwann_probit_step" in syms
     L = ctypes.CDLL(_io.SO_PATH)
     for s_ in syms:
         assert hasattr(L, s_), f"{s_} declared in include/jwas_io.h but not exported"
