@@ -556,6 +556,10 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     if output_samples_frequency is None:                 # evaluated on the user's chain_length (JWAS.jl:168), before :312
         output_samples_frequency = chain_length // 1000 if chain_length > 1000 else 1
     starts, chain_length = resolve_fast_blocks(fast_blocks, chain_length, n, p)
+    if burnin >= chain_length:
+        # fast_blocks divides chain_length by the block size (JWAS.jl:312) but leaves burnin alone: nothing would be saved
+        error(f"burnin ({burnin}) must be smaller than the number of outer iterations ({chain_length}) that fast_blocks "
+              "leaves of chain_length.")
     # seed=false: unseeded run (JWAS.jl:239-241 only seeds when a number is given)
     seed_v = int.from_bytes(os.urandom(4), "little") if seed is False else int(seed)
     model.MCMCinfo = MCMCinfo(chain_length=chain_length, burnin=burnin, output_samples_frequency=output_samples_frequency,

@@ -425,3 +425,22 @@ def test_native_update_equals_numpy_update(kind):
     for a, b in zip(*outs):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-10)
     assert outs[0][5] == outs[1][5]                     # both paths consumed the generator identically
+
+
+@pytest.mark.parametrize("kw", [dict(fast_blocks=True), dict(fast_blocks=[1, 40, 41, 100], independent_blocks=True)])
+@pytest.mark.parametrize("method,t", [("BayesC", 1), ("BayesR", 1), ("BayesC", 2)])
+def test_annotated_chains_on_the_block_schedules(method, t, kw):
+    """The reference runs its annotated samplers on the block and independent-block schedules too (CHANGELOG:
+    "Independent-block sampler coverage across ... annotated BayesC/BayesR ... dense 2-trait annotated BayesC")."""
+    codes, ids, ph, A = _annotated_data(n=120, p=150, seed=71, ntraits=t, nqtl=10)
+    eqs = "y1 = intercept + geno" + ("\ny2 = intercept + geno" if t == 2 else "")
+    Pi = {(0.0, 0.0): 0.45, (1.0, 0.0): 0.2, (0.0, 1.0): 0.15, (1.0, 1.0): 0.2} if t == 2 else (0.9 if method == "BayesC" else 0.0)
+    geno = jw.get_genotypes(codes, False, method=method, Pi=Pi, annotations=A, obsID=ids, center=False)
+    model = jw.build_model(eqs, False, genotypes={"geno": geno})
+    out = jw.runMCMC(model, ph.iloc[:100], chain_length=200, burnin=2, seed=3, _backend_factory=factory,
+                     output_heritability=True, **kw)
+    assert "annotation coefficients geno" in out and len(out["EBV_y1"]) == 120
+    assert np.isfinite(out["marker effects geno"]["Estimate"].to_numpy(float)).all()
+    assert 0 < out["heritability"]["Estimate"][0] < 1
+    with pytest.raises(jw.JwasError, match="outer iterations"):
+        jw.runMCMC(model, ph.iloc[:100], chain_length=60, burnin=10, seed=3, _backend_factory=factory, fast_blocks=True)
