@@ -15,7 +15,8 @@
 
 static inline double phi_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
 
-/* inverse of the standard normal CDF: rational start (Acklam), two Halley steps on Phi(x) - p */
+/* inverse of the standard normal CDF: rational start (Acklam, relative error 1.2e-9), one Halley step on Phi(x) - p
+ * (third-order: the step leaves ~1e-16) */
 static double phi_inv(double p) {
     static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
                                 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
@@ -41,8 +42,7 @@ static double phi_inv(double p) {
         x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
              ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
     }
-    for (int it = 0; it < 2; ++it) {
-        if (fabs(x) > 37.0) break;                       /* exp(x^2/2) would overflow; the start is good to 1e-9 there */
+    if (fabs(x) <= 37.0) {                               /* beyond, exp(x^2/2) would overflow; the start is good to 1e-9 */
         double e = phi_cdf(x) - p;
         double u = e * 2.50662827463100050242 * exp(0.5 * x * x);
         x -= u / (1.0 + 0.5 * x * u);

@@ -444,3 +444,21 @@ def test_annotated_chains_on_the_block_schedules(method, t, kw):
     assert 0 < out["heritability"]["Estimate"][0] < 1
     with pytest.raises(jw.JwasError, match="outer iterations"):
         jw.runMCMC(model, ph.iloc[:100], chain_length=60, burnin=10, seed=3, _backend_factory=factory, fast_blocks=True)
+
+
+def test_native_special_functions_against_scipy():
+    """jwann_phi_cdf / jwann_phi_inv (csrc/io/jw_annot.c) in the regime the sampler uses them: p = u * Phi(s)."""
+    import ctypes as C
+    from jwas_b200 import _io
+    L = _io.lib()
+    L.jwann_phi_inv.restype = C.c_double; L.jwann_phi_inv.argtypes = [C.c_double]
+    L.jwann_phi_cdf.restype = C.c_double; L.jwann_phi_cdf.argtypes = [C.c_double]
+    rng = np.random.default_rng(0)
+    s = rng.normal(size=20000) * 4; u = rng.random(20000)
+    p = u * ndtr(s)
+    mine = np.array([L.jwann_phi_inv(float(v)) for v in p])
+    np.testing.assert_allclose(mine, ndtri(p), rtol=0, atol=1e-11)
+    xs = np.linspace(-37.5, 9, 4000)
+    np.testing.assert_allclose([L.jwann_phi_cdf(float(x)) for x in xs], ndtr(xs), rtol=1e-12)
+    assert L.jwann_phi_inv(0.0) == -np.inf and L.jwann_phi_inv(1.0) == np.inf
+    assert abs(L.jwann_phi_inv(1e-300) - ndtri(1e-300)) < 1e-6        # far tail: the rational start alone
