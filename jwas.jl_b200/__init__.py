@@ -13,7 +13,9 @@ from .api import (get_genotypes, build_model, set_covariate, set_random, runMCMC
                   load_streaming_backend, Genotypes, MME, MCMCinfo, Variance, resolve_fast_blocks,
                   validate_fast_block_starts)
 from . import mcmc
+from .memory import estimate_marker_memory, check_marker_memory_guard, format_bytes_human
 from .gwas import GWAS
 
 __all__ += ["get_genotypes", "build_model", "set_covariate", "set_random", "runMCMC", "outputEBV", "prepare_streaming_genotypes",
-            "load_streaming_backend", "Genotypes", "MME", "MCMCinfo", "Variance", "mcmc", "GWAS"]
+            "load_streaming_backend", "Genotypes", "MME", "MCMCinfo", "Variance", "mcmc", "GWAS",
+            "estimate_marker_memory", "check_marker_memory_guard", "format_bytes_human"]

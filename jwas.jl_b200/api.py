@@ -23,6 +23,7 @@ import numpy as np
 from . import _io
 from . import annotations as annot
 from . import mcmc
+from .memory import check_marker_memory_guard, device_memory_bytes, estimate_marker_memory, format_bytes_human
 from ._lib import GpuSweeper, JwasError, SCHED_EXACT, SCHED_BLOCK, SCHED_INDEPENDENT
 
 try:  # pandas is what a DataFrame is here
@@ -478,6 +479,7 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
             double_precision=False, heterogeneous_residuals=False, output_folder=None, device=0,
             panel=DEFAULT_PANEL, engine=1, lag=DEFAULT_LAG, chain_ctas=DEFAULT_CHAIN_CTAS, output_marker_effect_samples=False,
+            memory_guard="error", memory_guard_ratio=0.80,
             _backend_factory=None, **ignored):
     """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
     Returns the reference's output dictionary keys for this path: "location parameters",
@@ -670,6 +672,14 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
     use_lag = int(lag) if (schedule == SCHED_EXACT and engine == 1) else 0
     if use_lag >= 2 and not chain_ctas:
         use_lag = 1                                     # lag 2 needs the pipelined chain
+    # marker-memory precheck (JWAS.jl:415-458) against the HBM of the device instead of the host's RAM
+    est = estimate_marker_memory(n, p, element_bytes=4, block_starts=[int(s_) + 1 for s_ in starts[:-1]], storage_mode="gpu",
+                                 n_traits=t, lag=use_lag)
+    check_marker_memory_guard(mode=memory_guard, ratio=memory_guard_ratio, estimated_bytes=est["bytes_total"],
+                              total_memory_bytes=device_memory_bytes(),
+                              context_string=f"geno={Mi.name}, storage=:gpu, nObs={n}, nMarkers={p}, traits={t}, "
+                                             f"packed+tiled={format_bytes_human(est['bytes_packed'] + est['bytes_tiled'])}, "
+                                             f"Gram={format_bytes_human(est['bytes_XpRinvX'] + est['bytes_cross_gram'])}")
     if _backend_factory is not None:
         backend = _backend_factory(packed, n, t, starts) if subset_means is None else \
             _backend_factory(packed, n, t, starts, means=subset_means)
