@@ -476,11 +476,11 @@ def _frame(rows, cols):
 
 
 def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=None, seed=False,
-            fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=False,
+            fast_blocks=False, independent_blocks=False, outputEBV=True, output_heritability=True,
             double_precision=False, heterogeneous_residuals=False, output_folder=None, device=0,
             panel=DEFAULT_PANEL, engine=1, lag=DEFAULT_LAG, chain_ctas=DEFAULT_CHAIN_CTAS, output_marker_effect_samples=False,
             memory_guard="error", memory_guard_ratio=0.80,
-            _backend_factory=None, **ignored):
+            _backend_factory=None, **other):
     """JWAS.jl:161-511 -> MCMC_BayesianAlphabet (MCMC/MCMC_BayesianAlphabet.jl:4) for the GPU backend.
     Returns the reference's output dictionary keys for this path: "location parameters",
     "residual variance", "marker effects <name>", "pi_<name>", "annotation coefficients <name>", "EBV_<trait>",
@@ -499,8 +499,25 @@ def runMCMC(model, df, *, chain_length=100, burnin=0, output_samples_frequency=N
             output_folder = base + str(k); k += 1
     if write_results:
         os.makedirs(output_folder)
-    if output_heritability:                      # check_outputID (input_data_validation.jl:167-174)
-        outputEBV = True
+    # the reference's remaining keyword arguments (JWAS.jl:161-200): the ones that only steer printing or are deprecated
+    # are accepted, the ones that select a model this backend does not run are refused instead of being ignored
+    passive = {"printout_model_info", "printout_frequency", "big_memory", "fitting_J_vector", "methods",
+               "output_samples_for_all_parameters", "Pi", "estimatePi", "estimate_scale", "estimate_variance"}
+    refused = {"starting_value": False, "update_priors_frequency": 0, "single_step_analysis": False, "pedigree": False,
+               "causal_structure": False, "RRM": False, "prediction_equation": False, "missing_phenotypes": True,
+               "categorical_trait": False, "censored_trait": False}
+    for key, value in other.items():
+        if key in passive:
+            continue
+        if key in refused:
+            if not (value is refused[key] or value == refused[key]):
+                error(f"{key}={value!r} is outside the GPU marker-sweep path (storage=:gpu).")
+            continue
+        error(f"runMCMC got an unknown keyword argument: {key}")
+    # output_heritability (default true as in the reference) needs the EBVs; it makes every genotyped individual an
+    # output ID (check_outputID, input_data_validation.jl:167-174) and is skipped when outputEBV is off (output.jl:498)
+    output_heritability = bool(output_heritability) and bool(outputEBV)
+    if output_heritability:
         model.output_ID = False
     if heterogeneous_residuals:
         error("heterogeneous_residuals=true is not supported with storage=:gpu (unit weights only).")

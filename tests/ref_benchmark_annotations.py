@@ -106,7 +106,7 @@ def run_case(case, seed, data, args, factory, heldout=None):
     t0 = time.time()
     extra = dict(_backend_factory=factory, lag=0, panel=args.panel) if factory is not None else {}
     out = jw.runMCMC(model, ph, chain_length=args.chain_length, burnin=args.burnin,
-                     output_samples_frequency=args.freq, seed=seed, outputEBV=True, **extra)
+                     output_samples_frequency=args.freq, seed=seed, outputEBV=True, output_heritability=False, **extra)
     dt = time.time() - t0
     rows = []
     if heldout is not None:                      # summarize_case_cv (:892-903): held-out cor(y, EBV) per trait
@@ -184,7 +184,7 @@ def matrix_mode(args, factory):
                 geno.annotations.mu[:] = 0.0
             t0 = time.time()
             out = jw.runMCMC(model, ph, chain_length=args.chain_length, burnin=args.burnin, output_samples_frequency=args.freq,
-                             seed=seed, outputEBV=True, **extra)
+                             seed=seed, outputEBV=True, output_heritability=False, **extra)
             me = out["marker effects geno"]
             pi = out["pi_geno"]["Estimate"].to_numpy(float)
             runs[seed] = dict(est=me["Estimate"].to_numpy(float), pip=me["Model_Frequency"].to_numpy(float),

@@ -177,17 +177,22 @@ def test_quality_control_and_phenotype_subset():
     last = xall @ seen["b"].alpha.astype(np.float64)
     assert np.corrcoef(out["EBV_y1"]["EBV"].to_numpy(float), last)[0, 1] > 0.5
     np.testing.assert_allclose(seen["out"].mul_alpha(0), last, rtol=1e-4, atol=1e-5)
-    # outputEBV(model, IDs) (output.jl:60-69) names the individuals; IDs without genotypes are dropped with a warning
+    # outputEBV(model, IDs) (output.jl:60-69) names the individuals (honoured with output_heritability=false, as in the
+    # reference); IDs without genotypes are dropped with a warning
     jw.outputEBV(model, ["a3", "a50", "nobody"])
     with pytest.warns(UserWarning, match="not a subset of genotyped individuals"):
-        out2 = jw.runMCMC(model, sub, chain_length=5, seed=1, _backend_factory=factory)
+        out2 = jw.runMCMC(model, sub, chain_length=5, seed=1, output_heritability=False, _backend_factory=factory)
     assert list(out2["EBV_y1"]["ID"]) == ["a3", "a50"]
     full = out["EBV_y1"].set_index("ID")["EBV"]
     np.testing.assert_allclose(out2["EBV_y1"]["EBV"].to_numpy(float), [full["a3"], full["a50"]], rtol=1e-6)
     # the training rows themselves, in training order: no second backend
     jw.outputEBV(model, list(sub["ID"]))
-    out3 = jw.runMCMC(model, sub, chain_length=5, seed=1, _backend_factory=factory)
+    out3 = jw.runMCMC(model, sub, chain_length=5, seed=1, output_heritability=False, _backend_factory=factory)
     assert list(out3["EBV_y1"]["ID"]) == list(sub["ID"])
+    # with output_heritability=true (the default, as in the reference) every genotyped individual is an output ID again
+    # (check_outputID, input_data_validation.jl:167-174)
+    out4 = jw.runMCMC(model, sub, chain_length=5, seed=1, _backend_factory=factory)
+    assert list(out4["EBV_y1"]["ID"]) == ids and "heritability" in out4
     np.testing.assert_allclose(out3["EBV_y1"]["EBV"].to_numpy(float), [full[i] for i in sub["ID"]], rtol=1e-6)
     # centring stays on ALL genotyped individuals (readgenotypes.jl:372-385 runs before the alignment of
     # JWAS.jl:381-402): the backend keeps the full-sample means and xpx is the subset's sum of squares about them
