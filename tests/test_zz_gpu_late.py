@@ -175,3 +175,19 @@ def test_multitrait_rrblup_chain_matches_oracle_chain(constraint):
         outs.append(jwas_b200.runMCMC(model, ph, chain_length=16, burnin=4, seed=77, _backend_factory=bf))
     assert_same(outs[0], outs[1])
     assert (outs[0]["marker effects geno"]["Model_Frequency"] == 1.0).all()
+
+
+def test_uncentred_chain_matches_oracle_chain():
+    """center=false: the handle is given means of zero (jwas_set_marker_means) so that x_ij is the code itself.  Not yet
+    run on a B200 (the external-means path itself is: test_gpu_sweep_parity.py, full-sample means)."""
+    import jwas_b200
+    from oracle_backend import factory
+    from test_api_chain import make_data
+    from test_gpu_chain import assert_same
+    codes, ids, ph = make_data(n=240, p=280, seed=67)
+    outs = []
+    for bf in (None, factory):
+        geno = jwas_b200.get_genotypes(codes, 1.0, method="BayesC", Pi=0.9, obsID=ids, center=False)
+        model = jwas_b200.build_model("y1 = intercept + geno", 1.0, genotypes={"geno": geno})
+        outs.append(jwas_b200.runMCMC(model, ph, chain_length=20, burnin=4, seed=77, _backend_factory=bf))
+    assert_same(outs[0], outs[1])
