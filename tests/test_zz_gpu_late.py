@@ -8,7 +8,7 @@ profiles/r2_late_gpu_tests.log -- the file sorts last because the full suite was
 2. BayesL! / BayesC0! (BayesC0L.jl:19-47) reference arithmetic (`jwo_bayesl_ref`) against the CUDA library run the
    way this backend runs them (BayesC step, pi = 0, marker variances sigma^2 * gamma_j): 1e-5 relative.
 3. (added after that run, not yet executed on a B200) EBVs for genotyped individuals without phenotypes; multi-trait
-   RR-BLUP chains."""
+   RR-BLUP chains; an uncentred chain.  Their Python side runs on the CPU through tests/fake_gpu_plugin.py."""
 import numpy as np
 import pytest
 
